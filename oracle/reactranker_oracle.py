@@ -1,0 +1,386 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the ReactRanker training hot path.
+
+A plain PyTorch (CPU, fp32 or fp64) restatement of the reference algorithm for the
+path named in BASELINE.json.  It is the checker for the CUDA path: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import it; the
+product package ``reactranker_b200`` never does (it raises when its CUDA extension
+is missing -- there is no CPU fallback).
+
+Pinning: the reference ships no tests / golden vectors for this path,
+so this oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, executed in the build
+container (``scripts/make_golden.py`` -> ``tests/golden/*.npz``; checked by
+``tests/test_oracle_golden.py`` and, when ``/root/reference`` is present, live by
+``tests/test_oracle_vs_reference.py``).
+
+Every function cites the reference lines it restates (paths relative to the
+reference root, package ``reactranker/``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ATOM_FDIM = 61      # features/featurization.py:63
+BOND_FDIM = 22      # features/featurization.py:64
+FBOND_TOTAL = ATOM_FDIM + BOND_FDIM   # models/base_model.py:129
+
+
+# ----------------------------------------------------------------------------------------
+# graph batching  (features/featurization.py:246-329)
+# ----------------------------------------------------------------------------------------
+class OracleBatch:
+    """Restates ``BatchMolGraph.__init__`` (featurization.py:246-290): row 0 of atoms and
+    bonds is padding, per-molecule indices are offset by the running totals, ``a2b`` is
+    right-padded with 0 up to ``max_num_bonds = max(1, max in-degree)``."""
+
+    def __init__(self, mols: Sequence):
+        f_atoms = [[0.0] * ATOM_FDIM]
+        f_bonds = [[0.0] * FBOND_TOTAL]
+        a2b: List[List[int]] = [[]]
+        b2a = [0]
+        b2revb = [0]
+        self.a_scope: List[Tuple[int, int]] = []
+        self.b_scope: List[Tuple[int, int]] = []
+        na, nb = 1, 1
+        for m in mols:
+            f_atoms += list(m.f_atoms)
+            f_bonds += list(m.f_bonds)
+            a2b += [[b + nb for b in m.a2b[a]] for a in range(m.n_atoms)]
+            b2a += [na + m.b2a[b] for b in range(m.n_bonds)]
+            b2revb += [nb + m.b2revb[b] for b in range(m.n_bonds)]
+            self.a_scope.append((na, m.n_atoms))
+            self.b_scope.append((nb, m.n_bonds))
+            na += m.n_atoms
+            nb += m.n_bonds
+        self.n_atoms, self.n_bonds, self.n_mols = na, nb, len(mols)
+        self.max_num_bonds = max(1, max(len(x) for x in a2b))
+        W = self.max_num_bonds
+        self.f_atoms = torch.tensor(f_atoms, dtype=torch.float32).reshape(na, ATOM_FDIM)
+        self.f_bonds = torch.tensor(f_bonds, dtype=torch.float32).reshape(nb, FBOND_TOTAL)
+        self.a2b = torch.tensor([row + [0] * (W - len(row)) for row in a2b], dtype=torch.int64).reshape(na, W)
+        self.b2a = torch.tensor(b2a, dtype=torch.int64)
+        self.b2revb = torch.tensor(b2revb, dtype=torch.int64)
+
+    def get_components(self):
+        return self.f_atoms, self.f_bonds, self.a2b, self.b2a, self.b2revb, self.a_scope, self.b_scope
+
+    def get_a2a(self):
+        return self.b2a[self.a2b]          # featurization.py:326-327
+
+
+def gather_sum(source: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """``index_select_ND(source, index).sum(dim=1)`` (utils.py:176-193 + mpn.py:89-90):
+    padded slots hold 0 and therefore add row 0 of ``source``."""
+    return source.index_select(0, index.reshape(-1)).reshape(index.shape + source.shape[1:]).sum(dim=1)
+
+
+# ----------------------------------------------------------------------------------------
+# model  (models/mpn.py:61-240, models/base_model.py:10-171, 235-297)
+# ----------------------------------------------------------------------------------------
+def _lin(x, sd, name):
+    b = sd.get(name + ".bias")
+    return F.linear(x, sd[name + ".weight"], b)
+
+
+def _drop(x, p, training):
+    return F.dropout(x, p=p, training=training) if (training and p > 0) else x
+
+
+def mpn_forward(sd: Dict[str, torch.Tensor], g, depth: int, dropout: float = 0.0, training: bool = False,
+                prefix: str = "encoder", trace: Optional[dict] = None) -> torch.Tensor:
+    """Bond-message D-MPNN returning per-atom hiddens (mpn.py:61-108 with
+    ``return_atom_hiddens=True``, base_model.py:135)."""
+    dt = sd[prefix + ".W_i.weight"].dtype
+    f_atoms, f_bonds, a2b, b2a, b2revb, _, _ = g.get_components()
+    f_atoms, f_bonds = f_atoms.to(dt), f_bonds.to(dt)
+    inp = _lin(f_bonds, sd, prefix + ".W_i")                      # mpn.py:80
+    msg = torch.relu(inp)                                          # mpn.py:81
+    for t in range(depth - 1):                                     # mpn.py:84-97
+        a_msg = gather_sum(msg, a2b)
+        pre = a_msg[b2a] - msg[b2revb]
+        if trace is not None:
+            trace[f"{prefix}.pre{t}"] = pre
+        msg = _drop(torch.relu(inp + _lin(pre, sd, prefix + ".W_h")), dropout, training)
+        if trace is not None:
+            trace[f"{prefix}.msg{t + 1}"] = msg
+    a_msg = gather_sum(msg, a2b)                                   # mpn.py:100-102
+    hid = torch.relu(_lin(torch.cat([f_atoms, a_msg], dim=1), sd, prefix + ".W_o"))   # mpn.py:103-104
+    return _drop(hid, dropout, training)                           # mpn.py:105
+
+
+def mpndiff_forward(sd, diff, g, depth: int, add_features=None, dropout: float = 0.0, training: bool = False,
+                    prefix: str = "diff_encoder", trace: Optional[dict] = None) -> torch.Tensor:
+    """Atom-message encoder over the product graph + scope-mean readout (mpn.py:170-240)."""
+    dt = diff.dtype
+    _, f_bonds, a2b, _, _, a_scope, _ = g.get_components()
+    f_bonds = f_bonds.to(dt)
+    a2a = g.get_a2a()
+    inp = _lin(diff, sd, prefix + ".W_i")                          # mpn.py:194
+    msg = torch.relu(inp)
+    if depth > 0:
+        for _ in range(depth - 1):                                 # mpn.py:199-213
+            nm = gather_sum(msg, a2a)
+            nf = gather_sum(f_bonds, a2b)                          # the [-bond_fdim:] slice keeps all 83 columns
+            msg = _drop(torch.relu(inp + _lin(torch.cat([nm, nf], dim=1), sd, prefix + ".W_h")), dropout, training)
+        a_msg = gather_sum(msg, a2a)                               # mpn.py:215-216
+        hid = _drop(torch.relu(_lin(torch.cat([diff, a_msg], dim=1), sd, prefix + ".W_o")), dropout, training)
+    else:
+        hid = _drop(msg, dropout, training)                        # mpn.py:220-221
+    if trace is not None:
+        trace[prefix + ".atom_hiddens"] = hid
+    vecs = []
+    for (start, size) in a_scope:                                  # mpn.py:224-235
+        if size == 0:
+            vecs.append(sd[prefix + ".cached_zero_vector"].to(dt))
+        else:
+            vecs.append(hid.narrow(0, start, size).sum(dim=0) / size)
+    vecs = torch.stack(vecs, dim=0)
+    if add_features is not None:                                   # mpn.py:237-238 (cast mpn.py:183)
+        vecs = torch.cat([vecs, torch.as_tensor(np.asarray(add_features), dtype=torch.float32).to(dt)], dim=1)
+    return vecs
+
+
+def resolve_task_type(task_num: int, ffn_last_layer: str, task_type: Optional[str]) -> str:
+    """``build_model``'s head-name resolution (base_model.py:252-264)."""
+    if task_type is None:
+        if task_num == 2:
+            return "gaussian_" + ffn_last_layer
+        if task_num == 4:
+            return "evidential_" + ffn_last_layer
+        return ffn_last_layer
+    if task_type == "evidential_ranking":
+        return task_type
+    return task_type + "_" + ffn_last_layer
+
+
+def ffn_forward(sd, x, head: str, ffn_depth: int = 3, dropout: float = 0.0, training: bool = False,
+                prefix: str = "ffn.ffn") -> torch.Tensor:
+    """``FFN`` (base_model.py:10-108): Sequential(drop, Lin, [relu, drop, Lin]*) -> heads."""
+    idx = 1
+    x = _lin(_drop(x, dropout, training), sd, f"{prefix}.{idx}")
+    for _ in range(ffn_depth - 1):
+        idx += 3
+        x = _lin(_drop(torch.relu(x), dropout, training), sd, f"{prefix}.{idx}")
+    out = x.squeeze(-1)                                            # base_model.py:60
+    if head == "evidential_ranking":                               # base_model.py:91-98
+        score, u = torch.split(out, out.shape[1] // 2, dim=1)
+        return torch.stack((score, F.softplus(u) + 1e-6), dim=2).view(out.size())
+    if head in ("gauss_regression_with_softplus", "gaussian_with_softplus"):   # base_model.py:71-83
+        mu, lv = torch.split(out, out.shape[1] // 2, dim=1)
+        return torch.stack((mu, F.softplus(lv)), dim=2).view(out.size())
+    if head in ("listnet_with_softplus",):                         # base_model.py:99-100
+        return F.softplus(out)
+    return out                                                     # base_model.py:105-106
+
+
+def model_forward(sd, r_g, p_g, add_features, *, mpnn_depth=3, mpnn_diff_depth=3, ffn_depth=3, head="with_softplus",
+                  dropout: float = 0.0, training: bool = False, trace: Optional[dict] = None) -> torch.Tensor:
+    """``ReactionModel.forward`` (base_model.py:150-171): shared encoder on both graphs,
+    atom-wise difference, diff encoder on the product graph, FFN."""
+    r = mpn_forward(sd, r_g, mpnn_depth, dropout, training, trace=None)
+    p = mpn_forward(sd, p_g, mpnn_depth, dropout, training, trace=trace)
+    if trace is not None:
+        trace["r_hiddens"], trace["p_hiddens"] = r, p
+    vec = mpndiff_forward(sd, p - r, p_g, mpnn_diff_depth, add_features, dropout, training, trace=trace)
+    if trace is not None:
+        trace["readout"] = vec
+    return ffn_forward(sd, vec, head, ffn_depth, dropout, training)
+
+
+# ----------------------------------------------------------------------------------------
+# losses  (train/loss.py, train/train_pairwise.py)
+# ----------------------------------------------------------------------------------------
+def listmle_loss(score: torch.Tensor, scope: Sequence[int], targets: torch.Tensor) -> torch.Tensor:
+    """``MLEloss`` (loss.py:64-99) with the forward of ``LogCumsumExp`` (loss.py:28-34).
+    Written with autograd-native ops: its gradient equals the reference's hand-written
+    backward (loss.py:57-61) because the upstream gradient of ``mean`` is uniform.
+    Returns shape [1] like the reference."""
+    total = score.new_zeros(1)
+    for s, t in zip(score.split(list(scope)), targets.split(list(scope))):
+        order = torch.argsort(t, descending=True)
+        x = s[order]
+        m = x.max()
+        lcse = torch.log(torch.flip(torch.cumsum(torch.flip(torch.exp(x - m), [0]), 0), [0])) + m
+        total = total + torch.mean(lcse - x)
+    return total / len(scope)
+
+
+def listnet_loss(score, scope, targets) -> torch.Tensor:
+    """``ListnetLoss`` (loss.py:317-352): mean over ALL items of -softmax(t) * log softmax(s)."""
+    parts = []
+    for s, t in zip(score.split(list(scope)), targets.split(list(scope))):
+        parts.append(-F.softmax(t, dim=0) * torch.log(F.softmax(s, dim=0)))
+    return torch.mean(torch.cat(parts))
+
+
+def evidential_ranking_loss(out2, scope, targets) -> torch.Tensor:
+    """``evidential_ranking`` live branch (loss.py:526-554); returns shape [1]."""
+    total = out2.new_zeros(1)
+    for o, t in zip(out2.split(list(scope)), targets.split(list(scope))):
+        mean, var = o[:, 0], o[:, 1]
+        q = F.softmax(mean, dim=0)
+        p = F.softmax(t, dim=0)
+        unc = 0.5 * (torch.log(p) - torch.log(q)) ** 2 / var + 0.5 * torch.log(2 * 3.141592653 * var)
+        total = total + torch.mean(-torch.log(p) + unc + torch.abs(mean - t))
+    return total / len(scope)
+
+
+def gauss_loss(mu, var, targets) -> torch.Tensor:
+    """``GaussDisLoss`` (loss.py:144-162)."""
+    pi = torch.tensor([np.pi], dtype=torch.float32).to(mu.dtype)
+    return torch.mean(0.5 * torch.log(2 * pi) + 0.5 * torch.log(var) + (mu - targets) ** 2 / (2 * var))
+
+
+def mse_loss(out, targets) -> torch.Tensor:
+    """``nn.MSELoss`` default branch (train_listwise.py:166-167, 282-285)."""
+    return F.mse_loss(out, targets)
+
+
+def ranknet_group_cost(y_pred: torch.Tensor, targets: np.ndarray, sigma: float = 1.0):
+    """One group of ``factorized_training_loop``/'sum_session' (train_pairwise.py:98-122).
+    Returns (sum of C over ordered pairs, num_pairs) or (None, 0) for a skipped group."""
+    Y = np.asarray(targets).reshape(-1, 1)
+    rel = Y - Y.T
+    pos = (rel > 0).astype(np.float32)
+    npos = pos.sum()
+    if npos == 0:
+        return None, 0.0
+    neg = (rel < 0).astype(np.float32)
+    pos_t = torch.from_numpy(pos).to(y_pred.dtype)
+    neg_t = torch.from_numpy(neg).to(y_pred.dtype)
+    if y_pred.dim() > 1:
+        y_pred = y_pred[:, 0]
+    y = y_pred.unsqueeze(1)
+    c_pos = torch.log(1 + torch.exp(-sigma * (y - y.t())))
+    c_neg = torch.log(1 + torch.exp(sigma * (y - y.t())))
+    return torch.sum(pos_t * c_pos + neg_t * c_neg), 2.0 * float(npos)
+
+
+def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
+    """Loss dispatch of ``train()`` for the five north-star keys (train_listwise.py:196-285)."""
+    if task_type == "mle":
+        return listmle_loss(output, scope, targets)
+    if task_type == "listnet":
+        return listnet_loss(output, scope, targets)
+    if task_type == "evidential_ranking":
+        return evidential_ranking_loss(output, scope, targets)
+    if task_type == "gauss_regression":
+        return gauss_loss(output[:, 0], output[:, 1], targets)
+    return mse_loss(output, targets)
+
+
+# ----------------------------------------------------------------------------------------
+# batch planners  (data/load_reactions.py:235-273, 336-421)
+# ----------------------------------------------------------------------------------------
+def plan_batch_reactions(df, batch_size: int, seed: int, target_name: str, smiles_list=None,
+                         add_features_name=None, shuffle_query=True, shuffle_batch=True):
+    """``DataProcessor.generate_batch_reactions`` (load_reactions.py:336-421), pandas/sklearn
+    calls kept so the RNG streams are the reference's.  Yields
+    (smiles [n,2], targets [n,1], scope, add_features, row_index)."""
+    from sklearn.utils import shuffle
+    cols = smiles_list if smiles_list is not None else ["rsmi", "psmi"]
+    reactants = df.rsmi.unique()
+    if shuffle_query:
+        reactants = shuffle(reactants, random_state=seed)
+    room = batch_size
+    chunks, scope = [], []
+
+    def flush():
+        part = chunks[0] if len(chunks) == 1 else __import__("pandas").concat(chunks)
+        feats = None
+        if add_features_name is not None:
+            feats = part[add_features_name].values
+            if feats.ndim == 1:
+                feats = feats.reshape(-1, 1)
+        return part[cols].values, part[target_name].values.reshape(-1, 1), list(scope), feats, part.index.values
+
+    for reactant in reactants:
+        grp = df[df.rsmi == reactant]
+        n = grp.shape[0]
+        if room - n >= 0:                                           # load_reactions.py:370-395
+            if shuffle_batch:
+                grp = grp.sample(frac=1, random_state=seed)
+            chunks.append(grp)
+            scope.append(n)
+            room -= n
+            if room < 2:
+                yield flush()
+                room, chunks, scope = batch_size, [], []
+        else:                                                       # load_reactions.py:396-418
+            grp = grp.sample(n=room, random_state=seed)
+            chunks.append(grp)
+            scope.append(room)
+            yield flush()
+            room, chunks, scope = batch_size, [], []
+    if room < batch_size:                                           # load_reactions.py:420-421
+        yield flush()
+
+
+def plan_batch_per_query(df, seed: int, target_name: str, smiles_list=None, add_features_name=None,
+                         shuffle_query=True, shuffle_batch=True):
+    """``DataProcessor.generate_batch_per_query`` (load_reactions.py:235-273).  The quirk at
+    line 264-267 (add_features taken from the TARGET column) is preserved."""
+    from sklearn.utils import shuffle
+    cols = smiles_list if smiles_list is not None else ["rsmi", "psmi"]
+    reactants = df.rsmi.unique()
+    if shuffle_query:
+        reactants = shuffle(reactants, random_state=seed)
+    for reactant in reactants:
+        grp = df[df.rsmi == reactant]
+        if shuffle_batch:
+            grp = grp.sample(frac=1, random_state=seed)
+        feats = None
+        if add_features_name is not None:
+            feats = grp[target_name].values
+            if feats.ndim == 1:
+                feats = feats.reshape(-1, 1)
+        yield grp[cols].values, grp[target_name].values, feats, grp.index.values
+
+
+# ----------------------------------------------------------------------------------------
+# one training step, reference order (train/train_listwise.py:177-290) -- used for parity
+# of updated weights and as the CPU-baseline leg of bench.py
+# ----------------------------------------------------------------------------------------
+def noam_lr(step: int, warmup_steps: int, total_steps: int, init_lr: float, max_lr: float, final_lr: float) -> float:
+    """``NoamLR.step`` (train/utils.py:61-81) after ``step`` calls."""
+    if step <= warmup_steps:
+        return init_lr + step * (max_lr - init_lr) / warmup_steps
+    if step <= total_steps:
+        gamma = (final_lr / max_lr) ** (1 / (total_steps - warmup_steps))
+        return max_lr * gamma ** (step - warmup_steps)
+    return final_lr
+
+
+def init_state_dict(hidden: int, task_num: int, add_features_dim: int, use_bias: bool = True, seed: int = 0,
+                    mpnn_depth: int = 3, mpnn_diff_depth: int = 3, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """State dict with the reference's 20 key names and nn.Linear default
+    init, created in module-construction order (base_model.py:128-148) so that the same
+    torch seed reproduces ``build_model``'s weights."""
+    torch.manual_seed(seed)
+    import torch.nn as nn
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, i, o, bias):
+        l = nn.Linear(i, o, bias=bias)
+        sd[name + ".weight"] = l.weight.detach().to(dtype)
+        if bias:
+            sd[name + ".bias"] = l.bias.detach().to(dtype)
+
+    sd["encoder.cached_zero_vector"] = torch.zeros(hidden, dtype=dtype)
+    lin("encoder.W_i", FBOND_TOTAL, hidden, use_bias)
+    if mpnn_depth > 1:
+        lin("encoder.W_h", hidden, hidden, use_bias)
+    lin("encoder.W_o", ATOM_FDIM + hidden, hidden, True)
+    sd["diff_encoder.cached_zero_vector"] = torch.zeros(hidden, dtype=dtype)
+    lin("diff_encoder.W_i", hidden, hidden, use_bias)
+    if mpnn_diff_depth > 1:
+        lin("diff_encoder.W_h", hidden + FBOND_TOTAL, hidden, use_bias)
+    if mpnn_diff_depth > 0:
+        lin("diff_encoder.W_o", 2 * hidden, hidden, True)
+    lin("ffn.ffn.1", hidden + add_features_dim, hidden, use_bias)
+    lin("ffn.ffn.4", hidden, hidden, use_bias)
+    lin("ffn.ffn.7", hidden, task_num, use_bias)
+    return sd
