@@ -1,0 +1,190 @@
+/* librr_sm100 -- C ABI of the B200-native ReactRanker training hot path.
+ *
+ * The reference (IannLiu/ReactRanker) has no FFI/plugin layer: the path is Python that
+ * launches stock ATen kernels.  This header is therefore the NEW drop-in
+ * boundary; each entry point cites the reference call site it replaces
+ * (paths relative to the reference root, package reactranker/).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer borrowed for the duration of the call unless its
+ *     name starts with h_ ; the library allocates nothing persistent.
+ *   - every function returns 0 on success or a negative rr_status; rr_last_error() gives
+ *     the message (thread-local).  Work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*); asynchronous CUDA faults surface at the caller's next synchronisation.
+ *   - activations are fp32 row-major [rows, ld] with ld a multiple of 4 (16-byte rows);
+ *     the padded hidden width hp = rr_padded(hidden) has its columns [hidden, hp) zero.
+ *   - graph indices are int32.  A launch may concatenate several reference batches
+ *     ("segments", e.g. one per RankNet group); each keeps its own padding rows and its
+ *     own max_num_bonds through rr_atom_meta, which reproduces the reference's
+ *     "a2b right-padded with 0 => row 0 is gathered" semantics (featurization.py:281-286,
+ *     SURVEY.md §0 trap 1) without materialising the padded slots.
+ */
+#ifndef RR_SM100_H
+#define RR_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_ABI_VERSION 1
+#define RR_ATOM_FDIM 61   /* features/featurization.py:63 */
+#define RR_BOND_FDIM 22   /* features/featurization.py:64 */
+#define RR_FBOND_TOTAL 83 /* models/base_model.py:129     */
+#define RR_FA_LD 64       /* padded row stride of f_atoms on the device */
+#define RR_FB_LD 88       /* padded row stride of f_bonds on the device */
+#define RR_MAX_FFN 4
+#define RR_OUT_LD 16      /* padded width of the last FFN layer's output */
+
+typedef enum {
+  RR_OK = 0,
+  RR_ERR_INVALID = -1,     /* bad shape / alignment / argument            */
+  RR_ERR_CUDA = -2,        /* a CUDA runtime call failed                  */
+  RR_ERR_ARCH = -3,        /* device is not sm_100                        */
+  RR_ERR_UNSUPPORTED = -4, /* legal in the reference, not built here yet  */
+  RR_ERR_WORKSPACE = -5    /* workspace too small                         */
+} rr_status;
+
+/* per-atom record (16 bytes, one vector load) */
+typedef struct {
+  int32_t deg_flags; /* bits 0..7 in-degree, bit 8: this row is a segment's padding atom */
+  int32_t pad_count; /* max_num_bonds(segment) - in-degree: multiplicity of the pad row  */
+  int32_t pad_bond;  /* row of the segment's padding bond  (0 in a single batch)         */
+  int32_t pad_atom;  /* row of the segment's padding atom  (0 in a single batch)         */
+} rr_atom_meta;
+
+/* One batched graph = BatchMolGraph.get_components() + get_a2a() (featurization.py:292-329)
+ * in device layout. */
+typedef struct {
+  int32_t n_atoms;    /* rows incl. padding atoms  (BatchMolGraph.n_atoms)              */
+  int32_t n_bonds;    /* rows incl. padding bonds  (BatchMolGraph.n_bonds)              */
+  int32_t n_mols;     /* len(a_scope)                                                   */
+  int32_t wmax;       /* row stride of a2b/a2b_rev/a2a = max in-degree over the launch  */
+  int32_t n_segments; /* reference batches concatenated in this launch                  */
+  const float* f_atoms;        /* [n_atoms, RR_FA_LD]   cols >= 61 zero                 */
+  const float* f_bonds;        /* [n_bonds, RR_FB_LD]   cols >= 83 zero                 */
+  const rr_atom_meta* a_meta;  /* [n_atoms]                                             */
+  const int32_t* a2b;          /* [n_atoms, wmax] incoming bond rows, first deg valid   */
+  const int32_t* a2b_rev;      /* [n_atoms, wmax] b2revb[a2b]                           */
+  const int32_t* a2a;          /* [n_atoms, wmax] b2a[a2b]  (get_a2a)                   */
+  const int32_t* mol_start;    /* [n_mols] a_scope starts                               */
+  const int32_t* mol_size;     /* [n_mols] a_scope sizes                                */
+  const int32_t* pad_bonds;    /* [n_segments] padding bond rows                        */
+  const int32_t* pad_atoms;    /* [n_segments] padding atom rows                        */
+} rr_graph;
+
+typedef enum { RR_HEAD_RAW = 0, RR_HEAD_EVIDENTIAL_RANKING = 1, RR_HEAD_GAUSS_SOFTPLUS = 2, RR_HEAD_SOFTPLUS = 3 } rr_head;
+
+/* build_model(...) (models/base_model.py:235-297) */
+typedef struct {
+  int32_t hidden;       /* hidden_size                                    */
+  int32_t depth;        /* mpnn_depth       (>= 1)                        */
+  int32_t diff_depth;   /* mpnn_diff_depth  (>= 1)                        */
+  int32_t ffn_depth;    /* ffn_depth        (1..RR_MAX_FFN)               */
+  int32_t task_num;     /* width of the last layer (<= RR_OUT_LD)         */
+  int32_t add_features; /* add_features_dim                               */
+  int32_t head;         /* rr_head                                        */
+  int32_t training;     /* nn.Module.training: dropout active             */
+  float dropout;        /* p of every nn.Dropout                          */
+  uint64_t seed;        /* Philox seed of this step's dropout masks       */
+} rr_model_cfg;
+
+/* Parameters in the reference's state_dict layout (row-major [out, in]).
+ * NULL bias = use_bias False.  The same struct with writable pointers receives the
+ * gradients (overwritten, not accumulated). */
+typedef struct {
+  float* enc_Wi; float* enc_bi;   /* encoder.W_i   [h, 83]        mpn.py:50  */
+  float* enc_Wh; float* enc_bh;   /* encoder.W_h   [h, h]         mpn.py:57  */
+  float* enc_Wo; float* enc_bo;   /* encoder.W_o   [h, 61+h]      mpn.py:59  */
+  float* dif_Wi; float* dif_bi;   /* diff_encoder.W_i [h, h]      mpn.py:161 */
+  float* dif_Wh; float* dif_bh;   /* diff_encoder.W_h [h, h+83]   mpn.py:165 */
+  float* dif_Wo; float* dif_bo;   /* diff_encoder.W_o [h, 2h]     mpn.py:168 */
+  float* ffn_W[RR_MAX_FFN];       /* ffn.ffn.{1,4,7,..}           base_model.py:40-56 */
+  float* ffn_b[RR_MAX_FFN];
+} rr_params;
+
+/* ---- library ------------------------------------------------------------------------ */
+int rr_version(void);
+const char* rr_last_error(void);
+/* fails with RR_ERR_ARCH unless `device` is compute capability 10.x */
+int rr_device_check(int device);
+/* padded hidden width used by every activation buffer */
+int rr_padded(int width);
+
+/* ---- message passing (models/mpn.py) -------------------------------------------------- */
+/* mpn.py:89-92   pre[b] = (sum_k m[a2b[b2a[b],k]]) - m[b2revb[b]]   for every bond row.
+ * relu_src != 0 applies relu() to m on load (m0 = relu(input), mpn.py:81). */
+int rr_bond_message_fwd(const rr_graph* g, const float* m, float* pre, int hp, int relu_src, void* stream);
+/* backward of the above: dm from dpre (gather-only; padding rows reduced with atomics) */
+int rr_bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp, void* stream);
+/* mpn.py:100-102 / 201 / 215: out[a] = sum_k src[idx[a,k]] incl. padding multiplicity.
+ * which: 0 = a2b over bond rows (pad row = pad_bond), 1 = a2a over atom rows (pad_atom). */
+int rr_neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out, int ld, int relu_src, void* stream);
+/* backward of which=0: dsrc[b] = dout[atom b points into]; of which=1: symmetric gather */
+int rr_neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, void* stream);
+/* mpn.py:224-238: vec[i] = mean(hid[a_scope[i]])[:hidden] || add_features[i] (zero padded to vp),
+ * then the FFN's first dropout (base_model.py:40).  hid is [n_atoms, hp], vec is [n_mols, vp]. */
+int rr_readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const float* add_features, int n_add,
+                   float* vec, int vp, float dropout, uint64_t seed, uint64_t stream_id, void* stream);
+/* backward, fused with the relu/dropout mask of hid: dz[a] = dvec[mol(a)]/size * [hid!=0]*scale */
+int rr_readout_bwd(const rr_graph* g, const float* dvec, int vp, const float* vec, const float* hid, float* dz,
+                   int hp, float dropout, void* stream);
+
+/* ---- dense layers (nn.Linear call sites of mpn.py / base_model.py) -------------------- */
+/* Y[M,n] = act(X1 W1^T + X2 W2^T + bias + residual), W* row-major [n_pad, k*] zero padded.
+ * flags: bit0 relu, bit1 dropout(p, seed, stream_id) after relu. X2/W2/bias/residual may be NULL. */
+int rr_linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1,
+                  const float* X2, int ldx2, const float* W2, int k2, const float* bias,
+                  const float* residual, int ldr, float* Y, int ldy, int flags, float dropout,
+                  uint64_t seed, uint64_t stream_id, void* stream);
+/* dX[M,k] (+)= dZ[M,n] W[n,k]   (accumulate != 0 adds) */
+int rr_linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw,
+                    float* dX, int lddx, int accumulate, void* stream);
+/* dW[n,k] += dZ^T X ; dbias[n] += colsum(dZ) when dbias != NULL.  Caller zeroes dW/dbias. */
+int rr_linear_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx,
+                    float* dW, int lddw, float* dbias, void* stream);
+/* dz = dy * [y != 0] * scale (relu + inverted-dropout backward); acc (+)= dz when acc != NULL:
+ * acc_mode 0 none, 1 acc = dz, 2 acc += dz.  y_is_preact: mask is [y > 0]. */
+int rr_relu_bwd(int64_t rows, int ld, const float* dy, const float* y, float scale, int y_is_preact,
+                float* dz, float* acc, int acc_mode, void* stream);
+/* out = a - b  (models/base_model.py:168) */
+int rr_sub(int64_t n, const float* a, const float* b, float* out, void* stream);
+
+/* ---- LTR losses (train/loss.py, train/train_pairwise.py) ------------------------------- */
+/* All take scores [N] (or [N,2]), targets [N], seg_off [G+1] (prefix sums of `scope`) and
+ * return the loss in loss[0] and dL/dscore in dscore, normalised exactly like the reference. */
+typedef enum {
+  RR_LOSS_LISTMLE = 0,    /* MLEloss            loss.py:64-99   (+LogCumsumExp 9-61)      */
+  RR_LOSS_LISTNET = 1,    /* ListnetLoss        loss.py:317-352                            */
+  RR_LOSS_EVIDENTIAL = 2, /* evidential_ranking loss.py:477-556 (scores [N,2])             */
+  RR_LOSS_RANKNET = 3,    /* sum_session        train_pairwise.py:98-122,141-147           */
+  RR_LOSS_GAUSS = 4,      /* GaussDisLoss       loss.py:144-162 (scores [N,2])             */
+  RR_LOSS_MSE = 5         /* nn.MSELoss         train_listwise.py:166-167                  */
+} rr_loss_kind;
+/* norm: the divisor the reference applies (G, N or the window's ordered-pair count); sigma: RankNet */
+int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off,
+                   float norm, float sigma, float* loss, float* dscore, void* stream);
+/* largest group the segmented kernels accept */
+int rr_loss_max_group(void);
+
+/* ---- whole model (models/base_model.py:150-171) ---------------------------------------- */
+/* bytes of workspace rr_model_forward/backward need for these sizes */
+int64_t rr_model_workspace_bytes(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p);
+/* scores: [n_mols] if task_num==1 else [n_mols, task_num].  ws must stay untouched until the
+ * matching rr_model_backward has run. */
+int rr_model_forward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p,
+                     const float* add_features, float* scores, void* ws, int64_t ws_bytes, void* stream);
+/* dscores has the shape of scores; grads receives d/d(parameter) in state_dict layout */
+int rr_model_backward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p,
+                      const float* dscores, rr_params* grads, void* ws, int64_t ws_bytes, void* stream);
+/* kernels launched by the last forward+backward on this thread (for bench.py's gpu_launches) */
+int64_t rr_launch_count(void);
+void rr_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_SM100_H */

@@ -1,0 +1,107 @@
+// extern "C" surface of librr_sm100 (include/rr_sm100.h).  No C++ exception crosses it.
+#include <stdarg.h>
+
+#include "rr_common.cuh"
+
+namespace rr {
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+int padded(int);
+int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream_t);
+int bond_message_bwd(const rr_graph*, const float*, float*, int, cudaStream_t);
+int neighbor_sum_fwd(const rr_graph*, int, const float*, float*, int, int, cudaStream_t);
+int neighbor_sum_bwd(const rr_graph*, int, const float*, float*, int, cudaStream_t);
+int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
+int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
+int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);
+int sub(long long, const float*, const float*, float*, cudaStream_t);
+int linear_fwd(int, int, const float*, int, const float*, int, const float*, int, const float*, int, const float*, const float*, int,
+               float*, int, int, float, uint64_t, uint64_t, cudaStream_t);
+int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
+int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
+int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
+int loss_max_group();
+long long model_workspace_bytes(const rr_model_cfg*, const rr_graph*, const rr_graph*);
+int model_forward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, float*, void*, long long, cudaStream_t);
+int model_backward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, rr_params*, void*, long long, cudaStream_t);
+}  // namespace rr
+
+#define S(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int rr_version(void) { return RR_ABI_VERSION; }
+const char* rr_last_error(void) { return rr::g_err; }
+
+int rr_device_check(int device) {
+  cudaDeviceProp prop;
+  RR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return rr::fail(RR_ERR_ARCH, "device %d is sm_%d%d; librr_sm100 contains sm_100a code only", device, prop.major, prop.minor);
+  return RR_OK;
+}
+
+int rr_padded(int width) { return rr::padded(width); }
+
+int rr_bond_message_fwd(const rr_graph* g, const float* m, float* pre, int hp, int relu_src, void* stream) {
+  return rr::bond_message_fwd(g, m, pre, hp, relu_src, S(stream));
+}
+int rr_bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp, void* stream) {
+  return rr::bond_message_bwd(g, dpre, dm, hp, S(stream));
+}
+int rr_neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out, int ld, int relu_src, void* stream) {
+  RR_REQUIRE(which == 0 || which == 1, "which must be 0 (a2b) or 1 (a2a)");
+  return rr::neighbor_sum_fwd(g, which, src, out, ld, relu_src, S(stream));
+}
+int rr_neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, void* stream) {
+  RR_REQUIRE(which == 0 || which == 1, "which must be 0 (a2b) or 1 (a2a)");
+  return rr::neighbor_sum_bwd(g, which, dout, dsrc, ld, S(stream));
+}
+int rr_readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const float* add_features, int n_add, float* vec, int vp,
+                   float dropout, uint64_t seed, uint64_t stream_id, void* stream) {
+  return rr::readout_fwd(g, hid, hp, hidden, add_features, n_add, vec, vp, dropout, seed, stream_id, S(stream));
+}
+int rr_readout_bwd(const rr_graph* g, const float* dvec, int vp, const float* vec, const float* hid, float* dz, int hp, float dropout, void* stream) {
+  return rr::readout_bwd(g, dvec, vp, vec, hid, dz, hp, dropout, S(stream));
+}
+int rr_linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
+                  const float* bias, const float* residual, int ldr, float* Y, int ldy, int flags, float dropout, uint64_t seed,
+                  uint64_t stream_id, void* stream) {
+  return rr::linear_fwd(M, n, X1, ldx1, W1, k1, X2, ldx2, W2, k2, bias, residual, ldr, Y, ldy, flags, dropout, seed, stream_id, S(stream));
+}
+int rr_linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx, int accumulate, void* stream) {
+  return rr::linear_dgrad(M, n, k, dZ, lddz, W, ldw, dX, lddx, accumulate, S(stream));
+}
+int rr_linear_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, void* stream) {
+  return rr::linear_wgrad(M, n, k, dZ, lddz, X, ldx, dW, lddw, dbias, S(stream));
+}
+int rr_relu_bwd(int64_t rows, int ld, const float* dy, const float* y, float scale, int y_is_preact, float* dz, float* acc, int acc_mode, void* stream) {
+  return rr::relu_bwd(rows, ld, dy, y, scale, y_is_preact, dz, acc, acc_mode, S(stream));
+}
+int rr_sub(int64_t n, const float* a, const float* b, float* out, void* stream) { return rr::sub(n, a, b, out, S(stream)); }
+
+int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off, float norm, float sigma,
+                   float* loss, float* dscore, void* stream) {
+  return rr::loss_fwdbwd(kind, N, G, scores, targets, seg_off, norm, sigma, loss, dscore, S(stream));
+}
+int rr_loss_max_group(void) { return rr::loss_max_group(); }
+
+int64_t rr_model_workspace_bytes(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p) {
+  if (!cfg || !r || !p) {
+    rr::fail(RR_ERR_INVALID, "rr_model_workspace_bytes: NULL argument");
+    return -1;
+  }
+  return rr::model_workspace_bytes(cfg, r, p);
+}
+int rr_model_forward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p, const float* add_features,
+                     float* scores, void* ws, int64_t ws_bytes, void* stream) {
+  return rr::model_forward(cfg, w, r, p, add_features, scores, ws, ws_bytes, S(stream));
+}
+int rr_model_backward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p, const float* dscores,
+                      rr_params* grads, void* ws, int64_t ws_bytes, void* stream) {
+  return rr::model_backward(cfg, w, r, p, dscores, grads, ws, ws_bytes, S(stream));
+}
+int64_t rr_launch_count(void) { return rr::g_launches; }
+void rr_launch_count_reset(void) { rr::g_launches = 0; }
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Shared device/host helpers for librr_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rr_sm100.h"
+
+namespace rr {
+
+// ---- error plumbing (no exceptions cross the C ABI) ----------------------------------
+extern thread_local char g_err[512];
+extern thread_local int64_t g_launches;
+
+inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define RR_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return rr::fail(RR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define RR_LAUNCH_CHECK(name)                                                                 \
+  do {                                                                                        \
+    ++rr::g_launches;                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) return rr::fail(RR_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define RR_REQUIRE(cond, ...)                                  \
+  do {                                                         \
+    if (!(cond)) return rr::fail(RR_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define RR_TRY(expr)          \
+  do {                        \
+    int _s = (expr);          \
+    if (_s != RR_OK) return _s; \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- float4 helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 b) {
+  return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
+}
+__device__ __forceinline__ float4 f4_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float4 f4_relu(float4 a) {
+  return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+}
+// streaming (read-once) and default loads of one 16-byte chunk
+__device__ __forceinline__ float4 ld_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld_f4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+  atomicAdd(p + 0, v.x);
+  atomicAdd(p + 1, v.y);
+  atomicAdd(p + 2, v.z);
+  atomicAdd(p + 3, v.w);
+}
+
+// ---- Philox4x32-10: counter-based dropout masks, regenerable from (seed, stream, index) -----
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t stream_id, uint64_t idx) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t c0 = static_cast<uint32_t>(idx), c1 = static_cast<uint32_t>(idx >> 32);
+  uint32_t c2 = static_cast<uint32_t>(stream_id), c3 = static_cast<uint32_t>(stream_id >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask scaling of 4 consecutive elements; idx4 = (linear element index) / 4
+__device__ __forceinline__ float4 dropout4(float4 v, float p, float inv_keep, uint64_t seed, uint64_t stream_id, uint64_t idx4) {
+  const uint4 r = philox4x32(seed, stream_id, idx4);
+  const uint32_t thr = static_cast<uint32_t>(fminf(p, 1.f) * 4294967295.f);
+  v.x = (r.x >= thr) ? v.x * inv_keep : 0.f;
+  v.y = (r.y >= thr) ? v.y * inv_keep : 0.f;
+  v.z = (r.z >= thr) ? v.z * inv_keep : 0.f;
+  v.w = (r.w >= thr) ? v.w * inv_keep : 0.f;
+  return v;
+}
+
+}  // namespace rr

@@ -1,0 +1,317 @@
+// Segmented learning-to-rank losses, forward + backward in one launch.
+// One CTA per candidate group (reactant); the group lives in shared memory, so the
+// reference's Python loop of ~14 tiny launches per group (train/loss.py:86-95) becomes a
+// single kernel that emits the normalised loss and dL/dscore.
+#include <math_constants.h>
+
+#include "rr_common.cuh"
+
+namespace rr {
+
+constexpr int kLossThreads = 256;
+constexpr int kMaxGroup = 2048;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide reductions; `red` is >= 32 floats of shared scratch
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+__device__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -CUDART_INF_F;
+  if (threadIdx.x < 32) r = warp_max(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// inclusive Hillis-Steele scan over buf[0..n) (left to right), ping-pong with tmp; result in buf
+__device__ void block_scan(float* buf, float* tmp, int n) {
+  float* in = buf;
+  float* out = tmp;
+  for (int off = 1; off < n; off <<= 1) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = in[i] + (i >= off ? in[i - off] : 0.f);
+    float* sw = in;
+    in = out;
+    out = sw;
+  }
+  __syncthreads();
+  if (in != buf)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = in[i];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// ListMLE  (MLEloss loss.py:64-99, LogCumsumExp loss.py:9-61)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) k_listmle(const float* __restrict__ scores, const float* __restrict__ targets,
+                                                          const int* __restrict__ seg, float inv_norm, float* __restrict__ loss,
+                                                          float* __restrict__ dscore) {
+  __shared__ float key[kMaxGroup];
+  __shared__ int id[kMaxGroup];
+  __shared__ float a[kMaxGroup];
+  __shared__ float b[kMaxGroup];
+  __shared__ float red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  if (n <= 0) return;
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    key[i] = i < n ? targets[o + i] : -CUDART_INF_F;
+    id[i] = i;
+  }
+  // bitonic sort, descending by target (ties by index; torch.argsort leaves them unspecified)
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool desc = (i & k) == 0;
+          const float ki = key[i], kl = key[l];
+          const int ii = id[i], il = id[l];
+          const bool i_first = (ki > kl) || (ki == kl && ii < il);  // i should precede l in descending order
+          if (desc ? !i_first : i_first) {
+            key[i] = kl; key[l] = ki;
+            id[i] = il; id[l] = ii;
+          }
+        }
+      }
+    }
+  __syncthreads();
+  // x = scores sorted; reuse key[] for x
+  float mx = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = scores[o + id[i]];
+    key[i] = x;
+    mx = fmaxf(mx, x);
+  }
+  mx = block_max(mx, red);
+  // suffix sums of exp(x - m): scan the reversed array
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = expf(key[n - 1 - i] - mx);
+  block_scan(a, b, n);  // a[i] = sum_{k >= n-1-i} e_k
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float suffix = a[n - 1 - i];
+    part += (logf(suffix) + mx) - key[i];
+    b[i] = 1.f / suffix;
+  }
+  __syncthreads();
+  const float total = block_sum(part, red);
+  // prefix sums of 1/suffix  (== exp(m) * cumsum(exp(-lcse)), loss.py:59)
+  // a[] is free again after the loop above has been read by everyone (block_sum synchronised)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = b[i];
+  block_scan(a, b, n);
+  const float gscale = inv_norm / static_cast<float>(n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float e = expf(key[i] - mx);
+    dscore[o + id[i]] = (e * a[i] - 1.f) * gscale;
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, total * gscale);
+}
+
+// ---------------------------------------------------------------------------------------
+// ListNet@1  (ListnetLoss loss.py:317-352): mean over ALL items (norm = N)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) k_listnet(const float* __restrict__ scores, const float* __restrict__ targets,
+                                                          const int* __restrict__ seg, float inv_norm, float* __restrict__ loss,
+                                                          float* __restrict__ dscore) {
+  __shared__ float red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  if (n <= 0) return;
+  float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    ms = fmaxf(ms, scores[o + i]);
+    mt = fmaxf(mt, targets[o + i]);
+  }
+  ms = block_max(ms, red);
+  mt = block_max(mt, red);
+  float zs = 0.f, zt = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    zs += expf(scores[o + i] - ms);
+    zt += expf(targets[o + i] - mt);
+  }
+  zs = block_sum(zs, red);
+  zt = block_sum(zt, red);
+  const float lzs = logf(zs), izt = 1.f / zt, izs = 1.f / zs;
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ds = scores[o + i] - ms;
+    const float p = expf(targets[o + i] - mt) * izt;
+    part -= p * (ds - lzs);
+    dscore[o + i] = (expf(ds) * izs - p) * inv_norm;
+  }
+  part = block_sum(part, red);
+  if (threadIdx.x == 0) atomicAdd(loss, part * inv_norm);
+}
+
+// ---------------------------------------------------------------------------------------
+// UC-Listwise  (evidential_ranking loss.py:526-554): scores [N,2] = (mean, variance)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) k_evidential(const float* __restrict__ scores, const float* __restrict__ targets,
+                                                             const int* __restrict__ seg, float inv_norm, float* __restrict__ loss,
+                                                             float* __restrict__ dscore) {
+  __shared__ float red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  if (n <= 0) return;
+  float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    ms = fmaxf(ms, scores[2 * (o + i)]);
+    mt = fmaxf(mt, targets[o + i]);
+  }
+  ms = block_max(ms, red);
+  mt = block_max(mt, red);
+  float zs = 0.f, zt = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    zs += expf(scores[2 * (o + i)] - ms);
+    zt += expf(targets[o + i] - mt);
+  }
+  zs = block_sum(zs, red);
+  zt = block_sum(zt, red);
+  const float lzs = logf(zs), lzt = logf(zt);
+  float part = 0.f, dsum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float m = scores[2 * (o + i)], v = scores[2 * (o + i) + 1], t = targets[o + i];
+    const float logq = m - ms - lzs, logp = t - mt - lzt;
+    const float d = logp - logq;
+    part += -logp + 0.5f * d * d / v + 0.5f * logf(2.f * 3.141592653f * v) + fabsf(m - t);
+    dsum += d / v;
+  }
+  part = block_sum(part, red);
+  dsum = block_sum(dsum, red);
+  const float gscale = inv_norm / static_cast<float>(n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float m = scores[2 * (o + i)], v = scores[2 * (o + i) + 1], t = targets[o + i];
+    const float logq = m - ms - lzs, logp = t - mt - lzt;
+    const float d = logp - logq;
+    const float sgn = (m > t) ? 1.f : ((m < t) ? -1.f : 0.f);
+    dscore[2 * (o + i)] = (expf(logq) * dsum - d / v + sgn) * gscale;
+    dscore[2 * (o + i) + 1] = (-0.5f * d * d / (v * v) + 0.5f / v) * gscale;
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, part * gscale);
+}
+
+// ---------------------------------------------------------------------------------------
+// RankNet 'sum_session'  (train_pairwise.py:98-122): all ordered intra-group pairs
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kLossThreads) k_ranknet(const float* __restrict__ scores, const float* __restrict__ targets,
+                                                          const int* __restrict__ seg, float inv_norm, float sigma,
+                                                          float* __restrict__ loss, float* __restrict__ dscore) {
+  __shared__ float ss[kMaxGroup];
+  __shared__ float ts[kMaxGroup];
+  __shared__ float red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  if (n <= 0) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    ss[i] = scores[o + i];
+    ts[i] = targets[o + i];
+  }
+  __syncthreads();
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = ss[i], ti = ts[i];
+    float g = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float d = sigma * (si - ss[j]);
+      const float tj = ts[j];
+      if (ti > tj) {          // pos pair: C = log(1 + exp(-sigma (s_i - s_j)))
+        part += softplus_f(-d);
+        g -= sigmoid_f(-d);
+      } else if (ti < tj) {   // neg pair: C = log(1 + exp(+sigma (s_i - s_j)))
+        part += softplus_f(d);
+        g += sigmoid_f(d);
+      }
+    }
+    dscore[o + i] = 2.f * sigma * g * inv_norm;
+  }
+  part = block_sum(part, red);
+  if (threadIdx.x == 0) atomicAdd(loss, part * inv_norm);
+}
+
+// ---------------------------------------------------------------------------------------
+// pointwise: GaussDisLoss (loss.py:144-162) and nn.MSELoss (train_listwise.py:166-167)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) k_pointwise(int kind, int N, const float* __restrict__ scores, const float* __restrict__ targets,
+                                                            float inv_norm, float* __restrict__ loss, float* __restrict__ dscore) {
+  __shared__ float red[32];
+  float part = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const float t = targets[i];
+    if (kind == RR_LOSS_GAUSS) {
+      const float mu = scores[2 * i], v = scores[2 * i + 1];
+      const float d = mu - t;
+      part += 0.5f * logf(2.f * 3.14159274101257324f) + 0.5f * logf(v) + d * d / (2.f * v);
+      dscore[2 * i] = d / v * inv_norm;
+      dscore[2 * i + 1] = (0.5f / v - d * d / (2.f * v * v)) * inv_norm;
+    } else {
+      const float d = scores[i] - t;
+      part += d * d;
+      dscore[i] = 2.f * d * inv_norm;
+    }
+  }
+  part = block_sum(part, red);
+  if (threadIdx.x == 0) atomicAdd(loss, part * inv_norm);
+}
+
+int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int* seg_off, float norm, float sigma,
+                float* loss, float* dscore, cudaStream_t s) {
+  RR_REQUIRE(N > 0 && scores && targets && loss && dscore, "loss: NULL argument or N <= 0");
+  RR_REQUIRE(norm > 0.f, "loss: norm must be positive (got %g)", norm);
+  RR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  const float inv = 1.f / norm;
+  switch (kind) {
+    case RR_LOSS_LISTMLE:
+    case RR_LOSS_LISTNET:
+    case RR_LOSS_EVIDENTIAL:
+    case RR_LOSS_RANKNET:
+      RR_REQUIRE(G > 0 && seg_off, "loss: segmented kinds need seg_off and G > 0");
+      if (kind == RR_LOSS_LISTMLE) k_listmle<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      else if (kind == RR_LOSS_LISTNET) k_listnet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      else if (kind == RR_LOSS_EVIDENTIAL) k_evidential<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      else k_ranknet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
+      break;
+    case RR_LOSS_GAUSS:
+    case RR_LOSS_MSE: {
+      int blocks = (N + kLossThreads - 1) / kLossThreads;
+      if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+      k_pointwise<<<blocks, kLossThreads, 0, s>>>(kind, N, scores, targets, inv, loss, dscore);
+      break;
+    }
+    default:
+      return fail(RR_ERR_INVALID, "unknown loss kind %d", kind);
+  }
+  RR_LAUNCH_CHECK("loss kernel");
+  return RR_OK;
+}
+
+int loss_max_group() { return kMaxGroup; }
+
+}  // namespace rr

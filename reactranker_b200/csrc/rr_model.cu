@@ -1,0 +1,440 @@
+// Whole-model forward / backward of ReactionModel (models/base_model.py:150-171):
+//   MPN(reactants), MPN(products)  ->  p - r  ->  MPNDiff over the product graph
+//   -> scope-mean readout || add_features -> FFN -> head
+// sequenced on one stream out of a caller-provided workspace.  Nothing is allocated here.
+//
+// Parameters arrive in the reference's state_dict layout and are re-packed once per call
+// into zero-padded, 16-byte-aligned matrices; concatenated inputs of the reference
+// ([f_atoms || a_message], [nei_message || nei_f_bonds], [diff || a_message]) are never
+// materialised: their weight matrices are split column-wise and the GEMM accumulates two
+// sources.  Gradients are produced in the padded layout and un-packed at the end.
+#include "rr_common.cuh"
+
+namespace rr {
+
+// launchers implemented in the other translation units
+int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream_t);
+int bond_message_bwd(const rr_graph*, const float*, float*, int, cudaStream_t);
+int neighbor_sum_fwd(const rr_graph*, int, const float*, float*, int, int, cudaStream_t);
+int neighbor_sum_bwd(const rr_graph*, int, const float*, float*, int, cudaStream_t);
+int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
+int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
+int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);
+int sub(long long, const float*, const float*, float*, cudaStream_t);
+int linear_fwd(int, int, const float*, int, const float*, int, const float*, int, const float*, int, const float*, const float*, int,
+               float*, int, int, float, uint64_t, uint64_t, cudaStream_t);
+int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
+int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
+
+static inline int pad16(int x) { return (x + 15) / 16 * 16; }
+int padded(int w) { return pad16(w); }
+
+constexpr int kMaxDepth = 16;
+
+// ---- packed parameter layout (float offsets) ---------------------------------------------
+struct PackedLayout {
+  int h, hp, vp, F;
+  size_t enc_Wi, enc_bi, enc_Wh, enc_bh, enc_Wo_a, enc_Wo_m, enc_bo;
+  size_t dif_Wi, dif_bi, dif_Wh_m, dif_Wh_f, dif_bh, dif_Wo_d, dif_Wo_m, dif_bo;
+  size_t ffn_W[RR_MAX_FFN], ffn_b[RR_MAX_FFN];
+  int ffn_in[RR_MAX_FFN], ffn_out[RR_MAX_FFN];  // padded dims
+  size_t total;
+};
+
+static PackedLayout make_packed(const rr_model_cfg& c) {
+  PackedLayout L{};
+  L.h = c.hidden;
+  L.hp = pad16(c.hidden);
+  L.vp = pad16(c.hidden + c.add_features);
+  L.F = c.ffn_depth;
+  size_t o = 0;
+  auto take = [&](size_t n) {
+    size_t r = o;
+    o += (n + 63) / 64 * 64;
+    return r;
+  };
+  const size_t hp = L.hp;
+  L.enc_Wi = take(hp * RR_FB_LD); L.enc_bi = take(hp);
+  L.enc_Wh = take(hp * hp);       L.enc_bh = take(hp);
+  L.enc_Wo_a = take(hp * RR_FA_LD); L.enc_Wo_m = take(hp * hp); L.enc_bo = take(hp);
+  L.dif_Wi = take(hp * hp);       L.dif_bi = take(hp);
+  L.dif_Wh_m = take(hp * hp);     L.dif_Wh_f = take(hp * RR_FB_LD); L.dif_bh = take(hp);
+  L.dif_Wo_d = take(hp * hp);     L.dif_Wo_m = take(hp * hp);       L.dif_bo = take(hp);
+  for (int l = 0; l < L.F; ++l) {
+    L.ffn_in[l] = (l == 0) ? L.vp : L.hp;
+    L.ffn_out[l] = (l == L.F - 1) ? RR_OUT_LD : L.hp;
+    L.ffn_W[l] = take(static_cast<size_t>(L.ffn_in[l]) * L.ffn_out[l]);
+    L.ffn_b[l] = take(L.ffn_out[l]);
+  }
+  L.total = o;
+  return L;
+}
+
+struct PackEntry {
+  float* ref;        // state_dict-layout tensor (source when packing, destination when un-packing)
+  long long packed;  // float offset in the packed buffer
+  int rows, cols, ref_ld, ref_col0, packed_ld;
+};
+constexpr int kMaxEntries = 32;
+struct PackTable {
+  PackEntry e[kMaxEntries];
+  int n;
+};
+
+static PackTable make_table(const rr_model_cfg& c, const PackedLayout& L, const rr_params& w) {
+  PackTable T{};
+  const int h = c.hidden, hp = L.hp;
+  auto add = [&](float* ref, size_t off, int rows, int cols, int ref_ld, int col0, int pld) {
+    if (ref == nullptr) return;
+    T.e[T.n++] = PackEntry{ref, static_cast<long long>(off), rows, cols, ref_ld, col0, pld};
+  };
+  add(w.enc_Wi, L.enc_Wi, h, RR_FBOND_TOTAL, RR_FBOND_TOTAL, 0, RR_FB_LD);
+  add(w.enc_bi, L.enc_bi, 1, h, h, 0, hp);
+  add(w.enc_Wh, L.enc_Wh, h, h, h, 0, hp);
+  add(w.enc_bh, L.enc_bh, 1, h, h, 0, hp);
+  add(w.enc_Wo, L.enc_Wo_a, h, RR_ATOM_FDIM, RR_ATOM_FDIM + h, 0, RR_FA_LD);
+  add(w.enc_Wo, L.enc_Wo_m, h, h, RR_ATOM_FDIM + h, RR_ATOM_FDIM, hp);
+  add(w.enc_bo, L.enc_bo, 1, h, h, 0, hp);
+  add(w.dif_Wi, L.dif_Wi, h, h, h, 0, hp);
+  add(w.dif_bi, L.dif_bi, 1, h, h, 0, hp);
+  add(w.dif_Wh, L.dif_Wh_m, h, h, h + RR_FBOND_TOTAL, 0, hp);
+  add(w.dif_Wh, L.dif_Wh_f, h, RR_FBOND_TOTAL, h + RR_FBOND_TOTAL, h, RR_FB_LD);
+  add(w.dif_bh, L.dif_bh, 1, h, h, 0, hp);
+  add(w.dif_Wo, L.dif_Wo_d, h, h, 2 * h, 0, hp);
+  add(w.dif_Wo, L.dif_Wo_m, h, h, 2 * h, h, hp);
+  add(w.dif_bo, L.dif_bo, 1, h, h, 0, hp);
+  for (int l = 0; l < L.F; ++l) {
+    const int in = (l == 0) ? h + c.add_features : h;
+    const int out = (l == L.F - 1) ? c.task_num : h;
+    add(w.ffn_W[l], L.ffn_W[l], out, in, in, 0, L.ffn_in[l]);
+    add(w.ffn_b[l], L.ffn_b[l], 1, out, out, 0, L.ffn_out[l]);
+  }
+  return T;
+}
+
+// direction 0: packed <- ref (pack);  1: ref <- packed (un-pack gradients)
+__global__ void k_pack(PackTable T, float* __restrict__ packed, int direction) {
+  const PackEntry e = T.e[blockIdx.y];
+  const long long n = static_cast<long long>(e.rows) * e.cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / e.cols), c = static_cast<int>(i - static_cast<long long>(r) * e.cols);
+    float* pp = packed + e.packed + static_cast<long long>(r) * e.packed_ld + c;
+    float* rp = e.ref + static_cast<long long>(r) * e.ref_ld + e.ref_col0 + c;
+    if (direction == 0) *pp = *rp;
+    else *rp = *pp;
+  }
+}
+
+// ---- head (base_model.py:59-108) -----------------------------------------------------------
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // nn.Softplus(beta=1, threshold=20)
+__global__ void k_head_fwd(int N, int task, int head, const float* __restrict__ z, float* __restrict__ out) {
+  const int half = task >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * task; i += gridDim.x * blockDim.x) {
+    const int r = i / task, c = i - r * task;
+    const float* zr = z + static_cast<size_t>(r) * RR_OUT_LD;
+    float v;
+    if (head == RR_HEAD_RAW) v = zr[c];
+    else if (head == RR_HEAD_SOFTPLUS) v = softplus_t(zr[c]);
+    else {  // stack((first half, f(second half)), dim=2).view(...)  -> interleaved columns
+      const int j = c >> 1;
+      if ((c & 1) == 0) v = zr[j];
+      else v = softplus_t(zr[half + j]) + (head == RR_HEAD_EVIDENTIAL_RANKING ? 1e-6f : 0.f);
+    }
+    out[i] = v;
+  }
+}
+__global__ void k_head_bwd(int N, int task, int head, const float* __restrict__ z, const float* __restrict__ dout, float* __restrict__ dz) {
+  const int half = task >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * RR_OUT_LD; i += gridDim.x * blockDim.x) {
+    const int r = i / RR_OUT_LD, c = i - r * RR_OUT_LD;
+    float v = 0.f;
+    if (c < task) {
+      const float zc = z[i];
+      const float sg = zc > 20.f ? 1.f : 1.f / (1.f + expf(-zc));
+      const float* dr = dout + static_cast<size_t>(r) * task;
+      if (head == RR_HEAD_RAW) v = dr[c];
+      else if (head == RR_HEAD_SOFTPLUS) v = dr[c] * sg;
+      else v = (c < half) ? dr[2 * c] : dr[2 * (c - half) + 1] * sg;
+    }
+    dz[i] = v;
+  }
+}
+
+// ---- workspace layout -----------------------------------------------------------------------
+struct EncBufs {
+  float* inp;
+  float* pre[kMaxDepth];
+  float* m[kMaxDepth + 1];  // m[1..T]
+  float* am;
+  float* hid;
+};
+struct Workspace {
+  PackedLayout L;
+  float* packed;
+  float* dpacked;
+  EncBufs enc[2];  // 0 = reactants, 1 = products
+  float *d, *inp2, *nf, *am2, *hid2, *vec, *zout;
+  float* nm[kMaxDepth];
+  float* m2[kMaxDepth + 1];
+  float* x[RR_MAX_FFN];
+  // backward scratch
+  float *gB1, *gB2, *dinp, *gA1, *gA2, *gA3, *dD, *dI2, *dvec, *gN1, *gN2, *dzout;
+  size_t bytes;
+};
+
+static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, void* base, Workspace* W) {
+  RR_REQUIRE(c.hidden > 0 && c.hidden <= 4096, "hidden %d out of range", c.hidden);
+  RR_REQUIRE(c.depth >= 1 && c.depth <= kMaxDepth && c.diff_depth >= 0 && c.diff_depth <= kMaxDepth, "depth %d / diff_depth %d out of range", c.depth, c.diff_depth);
+  if (c.diff_depth < 1) return fail(RR_ERR_UNSUPPORTED, "mpnn_diff_depth = 0 (mpn.py:220-221) is not built");
+  RR_REQUIRE(c.ffn_depth >= 1 && c.ffn_depth <= RR_MAX_FFN, "ffn_depth %d out of range", c.ffn_depth);
+  RR_REQUIRE(c.task_num >= 1 && c.task_num <= RR_OUT_LD, "task_num %d out of range", c.task_num);
+  RR_REQUIRE(c.add_features >= 0, "add_features < 0");
+  RR_REQUIRE(r.n_atoms == p.n_atoms && r.n_mols == p.n_mols,
+             "reactant and product batches must have identical atom rows (p - r is atom-wise, base_model.py:168): %d vs %d", r.n_atoms, p.n_atoms);
+  W->L = make_packed(c);
+  const size_t hp = W->L.hp, vp = W->L.vp;
+  const size_t A = r.n_atoms, N = p.n_mols;
+  const size_t Bmax = r.n_bonds > p.n_bonds ? r.n_bonds : p.n_bonds;
+  const int T = c.depth - 1, Td = c.diff_depth - 1;
+  char* cur = static_cast<char*>(base);
+  size_t used = 0;
+  auto take = [&](size_t floats) {
+    float* ptr = base ? reinterpret_cast<float*>(cur + used) : nullptr;
+    used += (floats * sizeof(float) + 255) / 256 * 256;
+    return ptr;
+  };
+  W->packed = take(W->L.total);
+  W->dpacked = take(W->L.total);
+  for (int s = 0; s < 2; ++s) {
+    const size_t B = (s == 0 ? r.n_bonds : p.n_bonds);
+    EncBufs& e = W->enc[s];
+    e.inp = take(B * hp);
+    for (int t = 0; t < T; ++t) e.pre[t] = take(B * hp);
+    for (int t = 1; t <= T; ++t) e.m[t] = take(B * hp);
+    e.am = take(A * hp);
+    e.hid = take(A * hp);
+  }
+  W->d = take(A * hp);
+  W->inp2 = take(A * hp);
+  W->nf = take(A * RR_FB_LD);
+  for (int t = 0; t < Td; ++t) W->nm[t] = take(A * hp);
+  for (int t = 1; t <= Td; ++t) W->m2[t] = take(A * hp);
+  W->am2 = take(A * hp);
+  W->hid2 = take(A * hp);
+  W->vec = take(N * vp);
+  for (int l = 0; l + 1 < c.ffn_depth; ++l) W->x[l] = take(N * hp);
+  W->zout = take(N * RR_OUT_LD);
+  W->gB1 = take(Bmax * hp);
+  W->gB2 = take(Bmax * hp);
+  W->dinp = take(Bmax * hp);
+  W->gA1 = take(A * hp);
+  W->gA2 = take(A * hp);
+  W->gA3 = take(A * hp);
+  W->dD = take(A * hp);
+  W->dI2 = take(A * hp);
+  W->dvec = take(N * vp);
+  W->gN1 = take(N * hp);
+  W->gN2 = take(N * hp);
+  W->dzout = take(N * RR_OUT_LD);
+  W->bytes = used;
+  return RR_OK;
+}
+
+long long model_workspace_bytes(const rr_model_cfg* c, const rr_graph* r, const rr_graph* p) {
+  Workspace W;
+  if (carve(*c, *r, *p, nullptr, &W) != RR_OK) return -1;
+  return static_cast<long long>(W.bytes);
+}
+
+static int check_model_args(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, const rr_graph* p, void* ws, long long ws_bytes, Workspace* W) {
+  RR_REQUIRE(c && w && r && p && ws, "model: NULL argument");
+  RR_REQUIRE(aligned16(ws), "workspace must be 16-byte aligned");
+  RR_TRY(carve(*c, *r, *p, ws, W));
+  if (static_cast<long long>(W->bytes) > ws_bytes) return fail(RR_ERR_WORKSPACE, "workspace %lld bytes < required %zu", ws_bytes, W->bytes);
+  RR_REQUIRE(w->enc_Wi && w->enc_Wo && w->enc_bo && w->dif_Wi && w->dif_Wo && w->dif_bo, "model: missing parameter pointer");
+  RR_REQUIRE(c->depth == 1 || w->enc_Wh, "model: encoder.W_h missing for depth > 1");
+  RR_REQUIRE(c->diff_depth == 1 || w->dif_Wh, "model: diff_encoder.W_h missing for diff_depth > 1");
+  for (int l = 0; l < c->ffn_depth; ++l) RR_REQUIRE(w->ffn_W[l], "model: ffn weight %d missing", l);
+  RR_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f, "dropout must be in [0,1)");
+  RR_REQUIRE(r->f_bonds && r->f_atoms && p->f_bonds && p->f_atoms, "model: graph features missing");
+  if (c->head != RR_HEAD_RAW && c->head != RR_HEAD_SOFTPLUS) RR_REQUIRE((c->task_num & 1) == 0, "two-parameter heads need an even task_num");
+  return RR_OK;
+}
+
+static int pack_params(const rr_model_cfg& c, const Workspace& W, const rr_params& w, cudaStream_t s) {
+  RR_CUDA(cudaMemsetAsync(W.packed, 0, W.L.total * sizeof(float), s));
+  PackTable T = make_table(c, W.L, w);
+  k_pack<<<dim3(32, T.n), 256, 0, s>>>(T, W.packed, 0);
+  RR_LAUNCH_CHECK("k_pack");
+  return RR_OK;
+}
+
+int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, const rr_graph* p, const float* addf, float* scores,
+                  void* ws, long long ws_bytes, cudaStream_t s) {
+  Workspace W;
+  RR_TRY(check_model_args(c, w, r, p, ws, ws_bytes, &W));
+  RR_REQUIRE(scores != nullptr, "scores is NULL");
+  RR_REQUIRE(c->add_features == 0 || addf != nullptr, "add_features is NULL but add_features_dim = %d", c->add_features);
+  const PackedLayout& L = W.L;
+  const int hp = L.hp, vp = L.vp;
+  const int T = c->depth - 1, Td = c->diff_depth - 1;
+  const float pdrop = c->training ? c->dropout : 0.f;
+  const int act = 1 | (pdrop > 0.f ? 2 : 0);
+  const float* P = W.packed;
+  uint64_t sid = 1;
+  RR_TRY(pack_params(*c, W, *w, s));
+
+  const rr_graph* gs[2] = {r, p};
+  for (int k = 0; k < 2; ++k) {  // mpn.py:61-108
+    const rr_graph* g = gs[k];
+    EncBufs& e = W.enc[k];
+    RR_TRY(linear_fwd(g->n_bonds, hp, g->f_bonds, RR_FB_LD, P + L.enc_Wi, RR_FB_LD, nullptr, 0, nullptr, 0, P + L.enc_bi, nullptr, 0,
+                      e.inp, hp, 0, 0.f, c->seed, sid++, s));
+    const float* src = e.inp;
+    int relu_src = 1;
+    for (int t = 0; t < T; ++t) {
+      RR_TRY(bond_message_fwd(g, src, e.pre[t], hp, relu_src, s));
+      RR_TRY(linear_fwd(g->n_bonds, hp, e.pre[t], hp, P + L.enc_Wh, hp, nullptr, 0, nullptr, 0, P + L.enc_bh, e.inp, hp, e.m[t + 1], hp,
+                        act, pdrop, c->seed, sid++, s));
+      src = e.m[t + 1];
+      relu_src = 0;
+    }
+    RR_TRY(neighbor_sum_fwd(g, 0, src, e.am, hp, relu_src, s));
+    RR_TRY(linear_fwd(g->n_atoms, hp, g->f_atoms, RR_FA_LD, P + L.enc_Wo_a, RR_FA_LD, e.am, hp, P + L.enc_Wo_m, hp, P + L.enc_bo, nullptr, 0,
+                      e.hid, hp, act, pdrop, c->seed, sid++, s));
+  }
+  const int A = p->n_atoms;
+  RR_TRY(sub(static_cast<long long>(A) * hp, W.enc[1].hid, W.enc[0].hid, W.d, s));  // base_model.py:168
+
+  // mpn.py:170-240 over the product graph
+  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s));
+  if (Td > 0) RR_TRY(neighbor_sum_fwd(p, 0, p->f_bonds, W.nf, RR_FB_LD, 0, s));
+  {
+    const float* src = W.inp2;
+    int relu_src = 1;
+    for (int t = 0; t < Td; ++t) {
+      RR_TRY(neighbor_sum_fwd(p, 1, src, W.nm[t], hp, relu_src, s));
+      RR_TRY(linear_fwd(A, hp, W.nm[t], hp, P + L.dif_Wh_m, hp, W.nf, RR_FB_LD, P + L.dif_Wh_f, RR_FB_LD, P + L.dif_bh, W.inp2, hp, W.m2[t + 1], hp,
+                        act, pdrop, c->seed, sid++, s));
+      src = W.m2[t + 1];
+      relu_src = 0;
+    }
+    RR_TRY(neighbor_sum_fwd(p, 1, src, W.am2, hp, relu_src, s));
+  }
+  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wo_d, hp, W.am2, hp, P + L.dif_Wo_m, hp, P + L.dif_bo, nullptr, 0, W.hid2, hp, act, pdrop, c->seed, sid++, s));
+  RR_TRY(readout_fwd(p, W.hid2, hp, c->hidden, addf, c->add_features, W.vec, vp, pdrop, c->seed, sid++, s));
+
+  // base_model.py:40-60
+  const int N = p->n_mols;
+  const float* x = W.vec;
+  int ldx = vp;
+  for (int l = 0; l < c->ffn_depth; ++l) {
+    const bool last = (l == c->ffn_depth - 1);
+    float* y = last ? W.zout : W.x[l];
+    RR_TRY(linear_fwd(N, L.ffn_out[l], x, ldx, P + L.ffn_W[l], L.ffn_in[l], nullptr, 0, nullptr, 0, P + L.ffn_b[l], nullptr, 0, y, L.ffn_out[l],
+                      last ? 0 : act, pdrop, c->seed, sid++, s));
+    x = y;
+    ldx = L.ffn_out[l];
+  }
+  {
+    const int n = N * c->task_num;
+    k_head_fwd<<<(n + 255) / 256, 256, 0, s>>>(N, c->task_num, c->head, W.zout, scores);
+    RR_LAUNCH_CHECK("k_head_fwd");
+  }
+  return RR_OK;
+}
+
+int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, const rr_graph* p, const float* dscores, rr_params* grads,
+                   void* ws, long long ws_bytes, cudaStream_t s) {
+  Workspace W;
+  RR_TRY(check_model_args(c, w, r, p, ws, ws_bytes, &W));
+  RR_REQUIRE(dscores && grads, "backward: NULL argument");
+  const PackedLayout& L = W.L;
+  const int hp = L.hp, vp = L.vp;
+  const int T = c->depth - 1, Td = c->diff_depth - 1;
+  const float pdrop = c->training ? c->dropout : 0.f;
+  const float keep = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
+  const float* P = W.packed;  // still holds this step's packed weights
+  float* G = W.dpacked;
+  RR_CUDA(cudaMemsetAsync(G, 0, L.total * sizeof(float), s));
+  const int N = p->n_mols, A = p->n_atoms;
+
+  {
+    const int n = N * RR_OUT_LD;
+    k_head_bwd<<<(n + 255) / 256, 256, 0, s>>>(N, c->task_num, c->head, W.zout, dscores, W.dzout);
+    RR_LAUNCH_CHECK("k_head_bwd");
+  }
+  // FFN
+  {
+    const float* g = W.dzout;
+    int ldg = RR_OUT_LD;
+    float* scratch[2] = {W.gN1, W.gN2};
+    for (int l = c->ffn_depth - 1; l >= 0; --l) {
+      const float* x = (l == 0) ? W.vec : W.x[l - 1];
+      RR_TRY(linear_wgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, x, L.ffn_in[l], G + L.ffn_W[l], L.ffn_in[l], G + L.ffn_b[l], s));
+      if (l > 0) {
+        float* dx = scratch[l & 1];
+        RR_TRY(linear_dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], dx, hp, 0, s));
+        RR_TRY(relu_bwd(N, hp, dx, W.x[l - 1], keep, 0, dx, nullptr, 0, s));
+        g = dx;
+        ldg = hp;
+      } else {
+        RR_TRY(linear_dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], W.dvec, vp, 0, s));
+      }
+    }
+  }
+  // readout + W_o of the diff encoder
+  RR_TRY(readout_bwd(p, W.dvec, vp, W.vec, W.hid2, W.gA1, hp, pdrop, s));
+  RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.d, hp, G + L.dif_Wo_d, hp, G + L.dif_bo, s));
+  RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.am2, hp, G + L.dif_Wo_m, hp, nullptr, s));
+  RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, W.dD, hp, 0, s));
+  RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, W.gA2, hp, 0, s));
+  RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
+  if (Td == 0) {
+    RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 1, s));
+  } else {
+    for (int t = Td; t >= 1; --t) {
+      RR_TRY(relu_bwd(A, hp, W.gA3, W.m2[t], keep, 0, W.gA1, W.dI2, t == Td ? 1 : 2, s));
+      RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.nm[t - 1], hp, G + L.dif_Wh_m, hp, G + L.dif_bh, s));
+      RR_TRY(linear_wgrad(A, hp, RR_FB_LD, W.gA1, hp, W.nf, RR_FB_LD, G + L.dif_Wh_f, RR_FB_LD, nullptr, s));
+      RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, W.gA2, hp, 0, s));
+      RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
+    }
+    RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 2, s));
+  }
+  RR_TRY(linear_wgrad(A, hp, hp, W.dI2, hp, W.d, hp, G + L.dif_Wi, hp, G + L.dif_bi, s));
+  RR_TRY(linear_dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, W.dD, hp, 1, s));
+
+  // shared encoder: products (+dD) then reactants (-dD); weight gradients accumulate (base_model.py:155-156)
+  const rr_graph* gs[2] = {r, p};
+  for (int k = 1; k >= 0; --k) {
+    const rr_graph* g = gs[k];
+    EncBufs& e = W.enc[k];
+    const int B = g->n_bonds;
+    const float sign = (k == 1) ? 1.f : -1.f;
+    RR_TRY(relu_bwd(A, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
+    RR_TRY(linear_wgrad(A, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
+    RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
+    RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, W.gA2, hp, 0, s));
+    RR_TRY(neighbor_sum_bwd(g, 0, W.gA2, W.gB1, hp, s));
+    if (T == 0) {
+      RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 1, s));
+    } else {
+      for (int t = T; t >= 1; --t) {
+        RR_TRY(relu_bwd(B, hp, W.gB1, e.m[t], keep, 0, W.gB1, W.dinp, t == T ? 1 : 2, s));
+        RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
+        RR_TRY(linear_dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, W.gB2, hp, 0, s));
+        RR_TRY(bond_message_bwd(g, W.gB2, W.gB1, hp, s));
+      }
+      RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 2, s));
+    }
+    RR_TRY(linear_wgrad(B, hp, RR_FB_LD, W.dinp, hp, g->f_bonds, RR_FB_LD, G + L.enc_Wi, RR_FB_LD, G + L.enc_bi, s));
+  }
+
+  PackTable Tb = make_table(*c, L, *grads);
+  k_pack<<<dim3(32, Tb.n), 256, 0, s>>>(Tb, G, 1);
+  RR_LAUNCH_CHECK("k_pack(grads)");
+  return RR_OK;
+}
+
+}  // namespace rr

@@ -1,0 +1,442 @@
+"""Graph layout contract of the hot path: ``MolGraph`` -> ``BatchMolGraph`` -> device.
+
+Mirrors the public surface of the reference's ``reactranker/features/featurization.py``
+(``ATOM_FDIM``, ``BOND_FDIM``, ``MolGraph``, ``BatchMolGraph.get_components()/get_a2a()``,
+``mol2graph``) with bit-identical index construction (featurization.py:246-329), but is
+built B200-first:
+
+* every molecule keeps numpy arrays already padded to the device row strides, so a batch
+  is a handful of ``np.concatenate(..., out=pinned)`` calls instead of a Python loop over
+  atoms and bonds (the reference spends ~1.2 ms per reaction there);
+* the reference tensors (``f_atoms f_bonds a2b b2a b2revb`` as float32 / int64) are
+  materialised lazily, only if somebody asks for them through the reference API;
+* ``DeviceGraph`` is the int32, 16-byte-aligned, single-H2D-copy form the CUDA kernels
+  read (``rr_graph`` in include/rr_sm100.h).  It carries the "padded a2b gathers row 0"
+  semantics as a per-atom (in-degree, pad multiplicity, pad rows) record, which also lets
+  several reference batches (RankNet groups, data-parallel shards) share one launch while
+  each keeps its own ``max_num_bonds``.
+
+RDKit is only needed by ``MolGraph(smiles)``; it is imported lazily there.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+ATOM_FDIM = 61          # 16+6+6+5+6+6+6 one-hot blocks + aromatic + mass + 8 ring sizes (featurization.py:63)
+BOND_FDIM = 22          # 14 + 8 (featurization.py:64)
+FBOND_TOTAL = ATOM_FDIM + BOND_FDIM
+FA_LD = 64              # RR_FA_LD
+FB_LD = 88              # RR_FB_LD
+
+ELEM_LIST = ['H', 'C', 'N', 'O', 'S', 'F', 'Si', 'P', 'Cl', 'Br', 'Mg', 'Na', 'I', 'B', 'K']
+
+
+def get_atom_fdim() -> int:
+    return ATOM_FDIM
+
+
+def get_bond_fdim() -> int:
+    return BOND_FDIM
+
+
+# ------------------------------------------------------------------------------------------
+# RDKit featurisation (host input stage, semantics of featurization.py:28-132)
+# ------------------------------------------------------------------------------------------
+def onek_encoding_unk(value, choices) -> List[int]:
+    """One-hot with a trailing 'unknown' slot (featurization.py:28-42)."""
+    enc = [0] * (len(choices) + 1)
+    enc[choices.index(value) if value in choices else -1] = 1
+    return enc
+
+
+def _rdkit():
+    try:
+        from rdkit import Chem
+    except ImportError as e:  # pragma: no cover - rdkit is not in the build image
+        raise ImportError("MolGraph(smiles) needs RDKit for featurisation; synthetic graphs use "
+                          "MolGraph.from_arrays / reactranker_b200.synthetic") from e
+    return Chem
+
+
+def str_to_mol(string: str, explicit_hydrogens: bool = True):
+    Chem = _rdkit()
+    if string.startswith('InChI'):
+        mol = Chem.MolFromInchi(string, removeHs=not explicit_hydrogens)
+    else:
+        params = Chem.SmilesParserParams()
+        params.removeHs = not explicit_hydrogens
+        mol = Chem.MolFromSmiles(string, params)
+    return Chem.AddHs(mol) if explicit_hydrogens else Chem.RemoveHs(mol)
+
+
+def atom_features(atom) -> List[float]:
+    Chem = _rdkit()
+    hyb = Chem.rdchem.HybridizationType
+    f = (onek_encoding_unk(atom.GetSymbol(), ELEM_LIST)
+         + onek_encoding_unk(atom.GetTotalDegree(), [0, 1, 2, 3, 4])
+         + onek_encoding_unk(atom.GetFormalCharge(), [-2, -1, 0, 1, 2])
+         + onek_encoding_unk(atom.GetChiralTag(), [0, 1, 2, 3])
+         + onek_encoding_unk(atom.GetTotalNumHs(), [0, 1, 2, 3, 4])
+         + onek_encoding_unk(atom.GetNumRadicalElectrons(), [0, 1, 2, 3, 4])
+         + onek_encoding_unk(atom.GetHybridization(), [hyb.SP, hyb.SP2, hyb.SP3, hyb.SP3D, hyb.SP3D2])
+         + [1 if atom.GetIsAromatic() else 0]
+         + [atom.GetMass() * 0.01])
+    f += [atom.IsInRingSize(k) for k in range(3, 11)]
+    return f
+
+
+def bond_features(bond) -> List[float]:
+    Chem = _rdkit()
+    if bond is None:
+        return [1] + [0] * (BOND_FDIM - 1)
+    bt = bond.GetBondType()
+    f = [0, bt == Chem.BondType.SINGLE, bt == Chem.BondType.DOUBLE, bt == Chem.BondType.TRIPLE,
+         bt == Chem.BondType.AROMATIC,
+         (bond.GetIsConjugated() if bt is not None else 0), (bond.IsInRing() if bt is not None else 0)]
+    f += [(bond.IsInRingSize(k) if bt is not None else 0) for k in range(3, 11)]
+    f += onek_encoding_unk(int(bond.GetStereo()), list(range(6)))
+    return f
+
+
+# ------------------------------------------------------------------------------------------
+# MolGraph
+# ------------------------------------------------------------------------------------------
+class MolGraph:
+    """One molecule (featurization.py:135-210).  Reference attributes (python lists)
+    ``smiles n_atoms n_bonds f_atoms f_bonds a2b b2a b2revb`` are kept; the numpy pack used
+    for batching is built once and cached."""
+
+    def __init__(self, smiles: str, reaction: bool = True, atom_messages: bool = False):
+        if atom_messages:
+            raise NotImplementedError("atom_messages=True is not on the hot path (base_model.py always uses bond messages)")
+        self.smiles = smiles
+        mol = str_to_mol(smiles, explicit_hydrogens=True)
+        self.n_atoms = mol.GetNumAtoms()
+        self.n_bonds = 0
+        atoms = sorted(mol.GetAtoms(), key=lambda a: a.GetAtomMapNum()) if reaction else list(mol.GetAtoms())
+        self.f_atoms = [atom_features(a) for a in atoms]
+        self.f_bonds, self.a2b, self.b2a, self.b2revb = [], [[] for _ in range(self.n_atoms)], [], []
+        for a1 in range(self.n_atoms):
+            for a2 in range(a1 + 1, self.n_atoms):
+                bond = mol.GetBondBetweenAtoms(atoms[a1].GetIdx(), atoms[a2].GetIdx())
+                if bond is None:
+                    continue
+                fb = bond_features(bond)
+                self.f_bonds.append(self.f_atoms[a1] + fb)
+                self.f_bonds.append(self.f_atoms[a2] + fb)
+                b1, b2 = self.n_bonds, self.n_bonds + 1
+                self.a2b[a2].append(b1)     # b1 = a1 -> a2
+                self.b2a.append(a1)
+                self.a2b[a1].append(b2)     # b2 = a2 -> a1
+                self.b2a.append(a2)
+                self.b2revb += [b2, b1]
+                self.n_bonds += 2
+        self._pack = None
+
+    @classmethod
+    def from_arrays(cls, smiles: str, f_atoms: np.ndarray, f_bond: np.ndarray, b2a: np.ndarray,
+                    a2b_flat: np.ndarray, a2b_ptr: np.ndarray, b2revb: Optional[np.ndarray] = None) -> "MolGraph":
+        """Build from arrays (no RDKit): ``f_atoms`` [A,61], ``f_bond`` [B,22] pure bond
+        features, ``b2a`` [B] source atoms, CSR ``a2b`` incoming-bond lists."""
+        g = object.__new__(cls)
+        g.smiles = smiles
+        g.n_atoms, g.n_bonds = int(f_atoms.shape[0]), int(b2a.shape[0])
+        g._pack = _MolPack.build(np.asarray(f_atoms, np.float32), np.asarray(f_bond, np.float32),
+                                 np.asarray(b2a, np.int32), np.asarray(a2b_flat, np.int32),
+                                 np.asarray(a2b_ptr, np.int32),
+                                 (np.arange(g.n_bonds, dtype=np.int32) ^ 1) if b2revb is None else np.asarray(b2revb, np.int32))
+        return g
+
+    @classmethod
+    def from_synthetic(cls, m) -> "MolGraph":
+        return cls.from_arrays(m.smiles, m.f_atoms_np, m.f_bond_np, m.b2a_np, m.a2b_flat, m.a2b_ptr)
+
+    def pack(self) -> "_MolPack":
+        if self._pack is None:
+            A, B = self.n_atoms, self.n_bonds
+            fa = np.asarray(self.f_atoms, np.float32).reshape(A, ATOM_FDIM)
+            fb = np.asarray(self.f_bonds, np.float32).reshape(B, FBOND_TOTAL)
+            ptr = np.zeros(A + 1, np.int32)
+            ptr[1:] = np.cumsum([len(x) for x in self.a2b])
+            flat = np.asarray([b for row in self.a2b for b in row], np.int32)
+            self._pack = _MolPack.build(fa, fb[:, ATOM_FDIM:], np.asarray(self.b2a, np.int32), flat, ptr,
+                                        np.asarray(self.b2revb, np.int32), f_bonds_full=fb)
+        return self._pack
+
+    def __getattr__(self, name):
+        # list views for molecules created from arrays (reference attribute names)
+        if name in ("f_atoms", "f_bonds", "a2b", "b2a", "b2revb") and self.__dict__.get("_pack") is not None:
+            p = self.__dict__["_pack"]
+            if name == "f_atoms":
+                return p.f_atoms[:, :ATOM_FDIM].tolist()
+            if name == "f_bonds":
+                return p.f_bonds[:, :FBOND_TOTAL].tolist()
+            if name == "a2b":
+                return [p.a2b_flat[p.a2b_ptr[a]:p.a2b_ptr[a + 1]].tolist() for a in range(self.n_atoms)]
+            if name == "b2a":
+                return p.b2a.tolist()
+            return p.b2revb.tolist()
+        raise AttributeError(name)
+
+
+class _MolPack:
+    """Per-molecule arrays, already in device row strides."""
+    __slots__ = ("f_atoms", "f_bonds", "b2a", "b2revb", "a2b_flat", "a2b_ptr", "deg", "n_atoms", "n_bonds")
+
+    @staticmethod
+    def build(f_atoms, f_bond, b2a, a2b_flat, a2b_ptr, b2revb, f_bonds_full=None) -> "_MolPack":
+        p = _MolPack()
+        A, B = f_atoms.shape[0], b2a.shape[0]
+        p.n_atoms, p.n_bonds = A, B
+        p.f_atoms = np.zeros((A, FA_LD), np.float32)
+        p.f_atoms[:, :ATOM_FDIM] = f_atoms
+        p.f_bonds = np.zeros((B, FB_LD), np.float32)
+        if f_bonds_full is not None:
+            p.f_bonds[:, :FBOND_TOTAL] = f_bonds_full
+        elif B:
+            p.f_bonds[:, :ATOM_FDIM] = f_atoms[b2a]          # f_bonds[b] = f_atoms[src] || f_bond (featurization.py:198-199)
+            p.f_bonds[:, ATOM_FDIM:FBOND_TOTAL] = f_bond
+        p.b2a, p.b2revb = b2a, b2revb
+        p.a2b_flat, p.a2b_ptr = a2b_flat, a2b_ptr
+        p.deg = np.diff(a2b_ptr).astype(np.int32)
+        return p
+
+
+def _pack_of(m) -> _MolPack:
+    if isinstance(m, MolGraph):
+        return m.pack()
+    cached = getattr(m, "_rr_pack", None)
+    if cached is None:                                   # duck-typed molecules (synthetic.SynthMol, reference MolGraph)
+        if hasattr(m, "f_atoms_np"):
+            cached = MolGraph.from_synthetic(m).pack()
+        else:
+            g = object.__new__(MolGraph)
+            g.__dict__.update(smiles=m.smiles, n_atoms=m.n_atoms, n_bonds=m.n_bonds, f_atoms=m.f_atoms, f_bonds=m.f_bonds,
+                              a2b=m.a2b, b2a=m.b2a, b2revb=m.b2revb, _pack=None)
+            cached = g.pack()
+        try:
+            m._rr_pack = cached
+        except AttributeError:
+            pass
+    return cached
+
+
+# ------------------------------------------------------------------------------------------
+# BatchMolGraph
+# ------------------------------------------------------------------------------------------
+class BatchMolGraph:
+    """Batch of molecules with the reference's index construction (featurization.py:246-290):
+    row 0 of atoms and bonds is padding, per-molecule indices are shifted by the running
+    totals, ``a2b`` is right-padded with 0 to ``max_num_bonds = max(1, max in-degree)``."""
+
+    def __init__(self, mol_graphs: Sequence, atom_messages: bool = False):
+        if atom_messages:
+            raise NotImplementedError("atom_messages=True is not on the hot path")
+        packs = [_pack_of(m) for m in mol_graphs]
+        self.smiles_batch = [m.smiles for m in mol_graphs]
+        self.n_mols = len(packs)
+        self.atom_fdim = ATOM_FDIM
+        self.bond_fdim = FBOND_TOTAL
+        self._packs = packs
+        nA = np.fromiter((p.n_atoms for p in packs), np.int64, len(packs))
+        nB = np.fromiter((p.n_bonds for p in packs), np.int64, len(packs))
+        a_start = 1 + np.concatenate(([0], np.cumsum(nA)[:-1])) if len(packs) else np.zeros(0, np.int64)
+        b_start = 1 + np.concatenate(([0], np.cumsum(nB)[:-1])) if len(packs) else np.zeros(0, np.int64)
+        self.n_atoms = int(1 + nA.sum())
+        self.n_bonds = int(1 + nB.sum())
+        self._a_start, self._a_size = a_start.astype(np.int32), nA.astype(np.int32)
+        self._b_start, self._b_size = b_start.astype(np.int32), nB.astype(np.int32)
+        self.a_scope = list(zip(a_start.tolist(), nA.tolist()))
+        self.b_scope = list(zip(b_start.tolist(), nB.tolist()))
+        deg = np.zeros(self.n_atoms, np.int32)
+        if packs:
+            np.concatenate([p.deg for p in packs], out=deg[1:])
+        self._deg = deg
+        self.max_num_bonds = max(1, int(deg.max())) if self.n_atoms else 1
+        # index tables (int32, reference values)
+        b2a = np.zeros(self.n_bonds, np.int32)
+        b2revb = np.zeros(self.n_bonds, np.int32)
+        if packs:
+            np.concatenate([p.b2a for p in packs], out=b2a[1:])
+            np.concatenate([p.b2revb for p in packs], out=b2revb[1:])
+            b2a[1:] += np.repeat(a_start, nB).astype(np.int32)
+            b2revb[1:] += np.repeat(b_start, nB).astype(np.int32)
+        self._b2a, self._b2revb = b2a, b2revb
+        W = self.max_num_bonds
+        a2b = np.zeros((self.n_atoms, W), np.int32)
+        if packs:
+            nnz = np.fromiter((p.a2b_flat.shape[0] for p in packs), np.int64, len(packs))
+            flat = np.concatenate([p.a2b_flat for p in packs]) + np.repeat(b_start, nnz).astype(np.int32)
+            rows = np.repeat(np.arange(self.n_atoms, dtype=np.int64), deg)
+            first = np.concatenate(([0], np.cumsum(deg, dtype=np.int64)[:-1]))
+            cols = np.arange(flat.shape[0], dtype=np.int64) - np.repeat(first, deg)
+            a2b[rows, cols] = flat
+        self._a2b = a2b
+        self._lazy = {}
+        self.b2b = None
+        self.a2a = None
+
+    # ---- reference tensors, built on demand --------------------------------------------
+    def _feature_tensor(self, which: str) -> torch.Tensor:
+        if which not in self._lazy:
+            if which == "f_atoms":
+                out = np.zeros((self.n_atoms, ATOM_FDIM), np.float32)
+                if self._packs:
+                    np.concatenate([p.f_atoms[:, :ATOM_FDIM] for p in self._packs], out=out[1:])
+            else:
+                out = np.zeros((self.n_bonds, FBOND_TOTAL), np.float32)
+                if self._packs:
+                    np.concatenate([p.f_bonds[:, :FBOND_TOTAL] for p in self._packs], out=out[1:])
+            self._lazy[which] = torch.from_numpy(out)
+        return self._lazy[which]
+
+    f_atoms = property(lambda self: self._feature_tensor("f_atoms"))
+    f_bonds = property(lambda self: self._feature_tensor("f_bonds"))
+    a2b = property(lambda self: torch.from_numpy(self._a2b.astype(np.int64)))
+    b2a = property(lambda self: torch.from_numpy(self._b2a.astype(np.int64)))
+    b2revb = property(lambda self: torch.from_numpy(self._b2revb.astype(np.int64)))
+
+    def get_components(self):
+        """(f_atoms, f_bonds, a2b, b2a, b2revb, a_scope, b_scope) -- featurization.py:292-301."""
+        return self.f_atoms, self.f_bonds, self.a2b, self.b2a, self.b2revb, self.a_scope, self.b_scope
+
+    def get_a2a(self) -> torch.Tensor:
+        """``b2a[a2b]`` (featurization.py:320-329)."""
+        if self.a2a is None:
+            self.a2a = torch.from_numpy(self._b2a[self._a2b].astype(np.int64))
+        return self.a2a
+
+    def get_b2b(self):
+        raise NotImplementedError("get_b2b is unused by the reference models")
+
+    def get_smiles(self):
+        return self.smiles_batch
+
+    # ---- device form -------------------------------------------------------------------
+    def to_device(self, device, max_num_bonds: Optional[int] = None, non_blocking: bool = True) -> "DeviceGraph":
+        key = (str(device), max_num_bonds)
+        dg = self._lazy.get(key)
+        if dg is None:
+            dg = DeviceGraph.from_batches([self], device, [max_num_bonds] if max_num_bonds else None, non_blocking)
+            self._lazy[key] = dg
+        return dg
+
+
+def mol2graph(smiles_batch: List[str]) -> BatchMolGraph:
+    return BatchMolGraph([MolGraph(s) for s in smiles_batch])
+
+
+# ------------------------------------------------------------------------------------------
+# DeviceGraph: the rr_graph the kernels read
+# ------------------------------------------------------------------------------------------
+class RRAtomMeta(ctypes.Structure):
+    _fields_ = [("deg_flags", ctypes.c_int32), ("pad_count", ctypes.c_int32), ("pad_bond", ctypes.c_int32), ("pad_atom", ctypes.c_int32)]
+
+
+class RRGraph(ctypes.Structure):
+    _fields_ = [("n_atoms", ctypes.c_int32), ("n_bonds", ctypes.c_int32), ("n_mols", ctypes.c_int32), ("wmax", ctypes.c_int32),
+                ("n_segments", ctypes.c_int32),
+                ("f_atoms", ctypes.c_void_p), ("f_bonds", ctypes.c_void_p), ("a_meta", ctypes.c_void_p), ("a2b", ctypes.c_void_p),
+                ("a2b_rev", ctypes.c_void_p), ("a2a", ctypes.c_void_p), ("mol_start", ctypes.c_void_p), ("mol_size", ctypes.c_void_p),
+                ("pad_bonds", ctypes.c_void_p), ("pad_atoms", ctypes.c_void_p)]
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class DeviceGraph:
+    """One or more BatchMolGraphs ("segments") laid out for the kernels and shipped with a
+    single host->device copy out of pinned memory."""
+
+    def __init__(self):
+        self.blob = None
+        self.host_blob = None
+        self.c = RRGraph()
+        self.h2d_bytes = 0
+        self.n_atoms = self.n_bonds = self.n_mols = 0
+        self.real_atoms = self.real_bonds = 0
+
+    @staticmethod
+    def from_batches(batches: Sequence[BatchMolGraph], device, w_override: Optional[Sequence[Optional[int]]] = None,
+                     non_blocking: bool = True) -> "DeviceGraph":
+        S = len(batches)
+        nA = sum(b.n_atoms for b in batches)
+        nB = sum(b.n_bonds for b in batches)
+        nM = sum(b.n_mols for b in batches)
+        wmax = max(1, max(int(b._deg.max()) for b in batches))
+        sections = [("f_atoms", nA * FA_LD * 4), ("f_bonds", nB * FB_LD * 4), ("a_meta", nA * 16), ("a2b", nA * wmax * 4),
+                    ("a2b_rev", nA * wmax * 4), ("a2a", nA * wmax * 4), ("mol_start", nM * 4), ("mol_size", nM * 4),
+                    ("pad_bonds", S * 4), ("pad_atoms", S * 4)]
+        offs, total = {}, 0
+        for name, nbytes in sections:
+            offs[name] = total
+            total += _align(max(nbytes, 4))
+        dev = torch.device(device)
+        pin = dev.type == "cuda"
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=pin)
+        hb = host.numpy()
+
+        def view(name, dtype, shape):
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            return hb[offs[name]:offs[name] + n].view(dtype).reshape(shape)
+
+        fa, fb = view("f_atoms", np.float32, (nA, FA_LD)), view("f_bonds", np.float32, (nB, FB_LD))
+        meta = view("a_meta", np.int32, (nA, 4))
+        a2b, a2br, a2a = (view(k, np.int32, (nA, wmax)) for k in ("a2b", "a2b_rev", "a2a"))
+        ms, mz = view("mol_start", np.int32, (nM,)), view("mol_size", np.int32, (nM,))
+        pb, pa = view("pad_bonds", np.int32, (S,)), view("pad_atoms", np.int32, (S,))
+        a0 = b0 = m0 = 0
+        for s, b in enumerate(batches):
+            W = b.max_num_bonds if not (w_override and w_override[s]) else int(w_override[s])
+            if W < b.max_num_bonds:
+                raise ValueError(f"max_num_bonds override {W} < this batch's in-degree {b.max_num_bonds}")
+            A, B = b.n_atoms, b.n_bonds
+            fa[a0] = 0.0
+            fb[b0] = 0.0
+            if b._packs:
+                np.concatenate([p.f_atoms for p in b._packs], out=fa[a0 + 1:a0 + A])
+                np.concatenate([p.f_bonds for p in b._packs], out=fb[b0 + 1:b0 + B])
+            deg = b._deg
+            meta[a0:a0 + A, 0] = deg
+            meta[a0, 0] |= 0x100
+            meta[a0:a0 + A, 1] = W - deg
+            meta[a0:a0 + A, 2] = b0
+            meta[a0:a0 + A, 3] = a0
+            wb = b._a2b.shape[1]
+            valid = np.arange(wb, dtype=np.int32)[None, :] < deg[:, None]
+            a2b[a0:a0 + A, :wb] = np.where(valid, b._a2b + b0, 0)
+            a2br[a0:a0 + A, :wb] = np.where(valid, b._b2revb[b._a2b] + b0, 0)
+            a2a[a0:a0 + A, :wb] = np.where(valid, b._b2a[b._a2b] + a0, 0)
+            if wb < wmax:
+                a2b[a0:a0 + A, wb:] = 0
+                a2br[a0:a0 + A, wb:] = 0
+                a2a[a0:a0 + A, wb:] = 0
+            ms[m0:m0 + b.n_mols] = b._a_start + a0
+            mz[m0:m0 + b.n_mols] = b._a_size
+            pb[s], pa[s] = b0, a0
+            a0 += A
+            b0 += B
+            m0 += b.n_mols
+        g = DeviceGraph()
+        g.host_blob = host
+        g.blob = host.to(dev, non_blocking=non_blocking) if pin else host
+        g.h2d_bytes = total
+        base = g.blob.data_ptr()
+        c = g.c
+        c.n_atoms, c.n_bonds, c.n_mols, c.wmax, c.n_segments = nA, nB, nM, wmax, S
+        for name, _ in sections:
+            setattr(c, name, base + offs[name])
+        g.n_atoms, g.n_bonds, g.n_mols = nA, nB, nM
+        g.real_atoms, g.real_bonds = nA - S, nB - S
+        g._offs = offs
+        return g
+
+    def section(self, name: str, dtype: torch.dtype, shape) -> torch.Tensor:
+        """Typed view of one section of the device blob (tests / kernels' unit harness)."""
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.blob[self._offs[name]:self._offs[name] + n].view(dtype).reshape(shape)

@@ -1,0 +1,178 @@
+"""LTR loss layer with the reference's module names and call signatures
+(train/loss.py:64-99, 144-162, 317-352, 477-556; RankNet: train/train_pairwise.py:98-147).
+
+Each loss is ONE segmented sm_100a kernel (csrc/rr_loss.cu) that returns the normalised
+loss and dL/dscore together; the Python loop over groups of the reference is gone.
+Normalisation follows the reference exactly: ListMLE / UC-Listwise average per group then
+over groups, ListNet averages over all items of the batch, RankNet divides by the ordered
+pair count of the accumulation window.  ``mle`` and ``evidential_ranking`` return shape [1]
+like the reference, the others a 0-d tensor.
+
+Outside the five north-star keys nothing is built; asking for one of
+the experimental losses raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+def _device_of(gpu, like: torch.Tensor) -> torch.device:
+    if not like.is_cuda:
+        raise _lib.RRError("scores live on the CPU: reactranker_b200 losses run on a B200 only (no CPU fallback)")
+    if gpu is not None:
+        _lib.require_device(gpu)
+    return like.device
+
+
+def _to_dev(x, dev, dtype=torch.float32) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        if x.device == dev and x.dtype == dtype:
+            return x.contiguous()
+        return x.to(dtype).pin_memory().to(dev, non_blocking=True) if not x.is_cuda else x.to(dev, dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype).pin_memory().to(dev, non_blocking=True)
+
+
+def segment_offsets(scope: Sequence[int], dev) -> torch.Tensor:
+    """``scope`` (python list of group sizes, as the reference passes it) -> device prefix sums."""
+    off = np.zeros(len(scope) + 1, np.int32)
+    np.cumsum(np.asarray(scope, np.int64), out=off[1:])
+    return torch.from_numpy(off).pin_memory().to(dev, non_blocking=True)
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, targets, seg_off, kind: int, n_items: int, n_groups: int, norm: float, sigma: float, out_shape):
+        L = _lib.lib()
+        scores_c = scores.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=scores.device)
+        dscore = torch.empty_like(scores_c)
+        with torch.cuda.device(scores.device):
+            _lib.check(L.rr_loss_fwdbwd(kind, n_items, n_groups, scores_c.data_ptr(), targets.data_ptr(), _lib.ptr(seg_off),
+                                        float(norm), float(sigma), loss.data_ptr(), dscore.data_ptr(), _lib.stream_ptr()))
+        ctx.save_for_backward(dscore)
+        return loss.reshape(out_shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dscore,) = ctx.saved_tensors
+        return dscore * g.reshape(()), None, None, None, None, None, None, None, None
+
+
+def _segmented(kind, scores, scope, targets, gpu, norm, out_shape, sigma=1.0, check_max=False):
+    dev = _device_of(gpu, scores)
+    scope = [int(s) for s in scope]
+    n_items = int(sum(scope))
+    if n_items != scores.shape[0]:
+        raise _lib.RRError(f"sum(scope)={n_items} does not match the {scores.shape[0]} scores")
+    if check_max and max(scope) > _lib.lib().rr_loss_max_group():
+        raise _lib.RRError(f"group of {max(scope)} candidates exceeds the segmented kernel's limit {_lib.lib().rr_loss_max_group()}")
+    t = _to_dev(targets, dev).reshape(-1)
+    if t.numel() != n_items:
+        raise _lib.RRError(f"{t.numel()} targets for {n_items} scores")
+    seg = segment_offsets(scope, dev)
+    return _LossFn.apply(scores.float(), t, seg, kind, n_items, len(scope), norm, sigma, out_shape)
+
+
+class MLEloss(nn.Module):
+    """ListMLE (loss.py:64-99 with LogCumsumExp 9-61): per group, sort by target descending,
+    ``mean(logcumsumexp_tail(x) - x)``; then the mean over groups.  Returns shape [1]."""
+
+    def forward(self, score, scope, targets_train, gpu: int):
+        return _segmented(_lib.LOSS_LISTMLE, score, scope, targets_train, gpu, norm=len(scope), out_shape=(1,), check_max=True)
+
+
+class ListnetLoss(nn.Module):
+    """ListNet top-1 (loss.py:317-352): ``mean over all items`` of ``-softmax(t) * log softmax(s)``."""
+
+    def forward(self, score, scope, targets, gpu: int):
+        return _segmented(_lib.LOSS_LISTNET, score, scope, targets, gpu, norm=int(sum(scope)), out_shape=())
+
+
+class evidential_ranking(nn.Module):
+    """UC-Listwise (loss.py:477-556, live branch 526-554).  ``max_coeff, epoch, epochs`` are
+    accepted and unused, as in the reference.  Returns shape [1]."""
+
+    def forward(self, possibilities, scope, targets, max_coeff, epoch, epochs, gpu: int):
+        if possibilities.dim() != 2 or possibilities.shape[1] != 2:
+            raise _lib.RRError("evidential_ranking expects model outputs of shape [N, 2] (score, variance)")
+        return _segmented(_lib.LOSS_EVIDENTIAL, possibilities, scope, targets, gpu, norm=len(scope), out_shape=(1,))
+
+
+class _GaussFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, var, targets):
+        both = torch.stack((mean, var), dim=1).contiguous()
+        L = _lib.lib()
+        n = both.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=both.device)
+        d = torch.empty_like(both)
+        with torch.cuda.device(both.device):
+            _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_GAUSS, n, 0, both.data_ptr(), targets.data_ptr(), None, float(n), 1.0,
+                                        loss.data_ptr(), d.data_ptr(), _lib.stream_ptr()))
+        ctx.save_for_backward(d)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        d = d * g
+        return d[:, 0], d[:, 1], None
+
+
+class GaussDisLoss(nn.Module):
+    """Gaussian NLL (loss.py:144-162): ``mean(0.5 log 2pi + 0.5 log v + (mu - t)^2 / (2 v))``."""
+
+    def forward(self, mean_scores, std_scores, targets, gpu: int):
+        dev = _device_of(gpu, mean_scores)
+        return _GaussFn.apply(mean_scores.float(), std_scores.float(), _to_dev(targets, dev).reshape(-1))
+
+
+class MSELoss(nn.Module):
+    """The default 'regression' criterion (``nn.MSELoss``, train_listwise.py:166-167, 282-285)."""
+
+    def forward(self, output, targets):
+        dev = _device_of(None, output)
+        n = output.shape[0]
+        return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_MSE, n, 0, float(n), 1.0, ())
+
+
+def ranknet_window_loss(scores, scope, targets, num_pairs: float, sigma: float = 1.0, gpu: Optional[int] = None):
+    """'sum_session' RankNet cost of one accumulation window (train_pairwise.py:98-122, 141-147):
+    ``sum over groups and ordered pairs of the pairwise logistic cost / num_pairs``; groups of the
+    window are evaluated by one launch.  ``num_pairs`` is the window's ordered-pair count."""
+    if scores.dim() > 1:
+        scores = scores[:, 0]                        # train_pairwise.py:115-116
+    return _segmented(_lib.LOSS_RANKNET, scores, scope, targets, gpu, norm=float(num_pairs), out_shape=(), sigma=sigma, check_max=True)
+
+
+def count_ordered_pairs(targets: np.ndarray) -> float:
+    """``2 * #{(i, j): t_i > t_j}`` of one group (train_pairwise.py:98-106)."""
+    t = np.asarray(targets, np.float64).reshape(-1)
+    _, counts = np.unique(t, return_counts=True)
+    n = t.shape[0]
+    return float(n * n - np.sum(counts.astype(np.float64) ** 2))
+
+
+def _unbuilt(name):
+    class _Missing(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} is one of the reference's experimental losses (SURVEY.md §2 row 6), not on the "
+                                      "north-star path; only mle / listnet / evidential_ranking / gauss_regression / regression are built")
+    _Missing.__name__ = name
+    return _Missing
+
+
+MLEDisLoss = _unbuilt("MLEDisLoss")
+Lognorm = _unbuilt("Lognorm")
+Listnet_For_evidential = _unbuilt("Listnet_For_evidential")
+Listnet_For_Gauss = _unbuilt("Listnet_For_Gauss")
+Listnetlognorm = _unbuilt("Listnetlognorm")
+Listnet_with_uq = _unbuilt("Listnet_with_uq")
+evidential_loss_new = _unbuilt("evidential_loss_new")
+Dirichlet_uq = _unbuilt("Dirichlet_uq")

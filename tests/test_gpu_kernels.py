@@ -1,0 +1,309 @@
+"""GPU parity of every kernel behind the C ABI against the CPU oracle
+(oracle/reactranker_oracle.py) on the same seeded inputs.  fp32 tolerances are stated per test."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reactranker_oracle as O
+from reactranker_b200 import _lib, synthetic
+from reactranker_b200.features.featurization import BatchMolGraph, DeviceGraph
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def graphs(seed=7, sizes=(4, 3, 5), star=None, side="p"):
+    ds = synthetic.make_dataset(seed, list(sizes), star_leaves_in_group=star)
+    col = ds.psmi if side == "p" else ds.rsmi
+    b = BatchMolGraph([ds.mols[t] for t in col])
+    return ds, b, DeviceGraph.from_batches([b], DEV)
+
+
+def rand(rows, hp, h, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, hp, generator=g)
+    x[:, h:] = 0
+    return x
+
+
+def close(got, want, tol=2e-6):
+    got, want = got.double().cpu(), want.double().cpu()
+    scale = max(float(want.abs().max()), 1e-30)
+    err = float((got - want).abs().max()) / scale
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("h,star", [(300, None), (40, {1: 9}), (24, {0: 11})])
+def test_bond_message_fwd_bwd(h, star):
+    L = _lib.lib()
+    ds, b, dg = graphs(star=star, side="r" if star else "p")
+    hp = L.rr_padded(h)
+    for relu in (0, 1):
+        m = rand(b.n_bonds, hp, h, 1).requires_grad_(True)
+        src = torch.relu(m) if relu else m
+        a_msg = O.gather_sum(src.double(), b.a2b)                       # mpn.py:89-90
+        want = a_msg[b.b2a] - src.double()[b.b2revb]                    # mpn.py:91-92
+        pre = torch.empty(b.n_bonds, hp, device=DEV)
+        md = m.detach().to(DEV)
+        _lib.check(L.rr_bond_message_fwd(ctypes.byref(dg.c), md.data_ptr(), pre.data_ptr(), hp, relu, S()))
+        close(pre, want.detach())
+    up = rand(b.n_bonds, hp, h, 2)
+    m = rand(b.n_bonds, hp, h, 3).double().requires_grad_(True)
+    (O.gather_sum(m, b.a2b)[b.b2a] - m[b.b2revb]).backward(up.double())
+    dm = torch.full((b.n_bonds, hp), float("nan"), device=DEV)
+    upd = up.to(DEV)
+    _lib.check(L.rr_bond_message_bwd(ctypes.byref(dg.c), upd.data_ptr(), dm.data_ptr(), hp, S()))
+    close(dm, m.grad, 5e-6)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("h,star", [(300, None), (40, {2: 10})])
+def test_neighbor_sum_fwd_bwd(which, h, star):
+    L = _lib.lib()
+    ds, b, dg = graphs(star=star, side="r" if star else "p")
+    hp = L.rr_padded(h)
+    rows = b.n_atoms if which else b.n_bonds
+    table = b.get_a2a() if which else b.a2b
+    src = rand(rows, hp, h, 4).double().requires_grad_(True)
+    want = O.gather_sum(src, table)
+    out = torch.empty(b.n_atoms, hp, device=DEV)
+    sd = src.detach().float().to(DEV)
+    _lib.check(L.rr_neighbor_sum_fwd(ctypes.byref(dg.c), which, sd.data_ptr(), out.data_ptr(), hp, 0, S()))
+    close(out, want.detach())
+    up = rand(b.n_atoms, hp, h, 5)
+    want.backward(up.double())
+    dsrc = torch.full((rows, hp), float("nan"), device=DEV)
+    upd = up.to(DEV)
+    _lib.check(L.rr_neighbor_sum_bwd(ctypes.byref(dg.c), which, upd.data_ptr(), dsrc.data_ptr(), hp, S()))
+    close(dsrc, src.grad, 5e-6)
+
+
+def test_neighbor_sum_of_bond_features():
+    """nf = sum_k f_bonds[a2b[a,k]] (mpn.py:202-206) over the 88-wide padded feature rows."""
+    L = _lib.lib()
+    ds, b, dg = graphs()
+    out = torch.empty(b.n_atoms, 88, device=DEV)
+    _lib.check(L.rr_neighbor_sum_fwd(ctypes.byref(dg.c), 0, dg.c.f_bonds, out.data_ptr(), 88, 0, S()))
+    close(out[:, :83], O.gather_sum(b.f_bonds.double(), b.a2b))
+    assert not out[:, 83:].any()
+
+
+def test_multi_segment_launch_equals_separate_batches():
+    """Two reference batches with different max_num_bonds (4 and 9) in ONE launch reproduce the two
+    separately-batched results, padding rows included (SURVEY.md §7 'pad-row recurrence')."""
+    L = _lib.lib()
+    ds = synthetic.make_dataset(9, [3, 3], star_leaves_in_group={1: 9})
+    b1 = BatchMolGraph([ds.mols[t] for t in ds.rsmi[:3]])
+    b2 = BatchMolGraph([ds.mols[t] for t in ds.rsmi[3:]])
+    assert b1.max_num_bonds != b2.max_num_bonds
+    dg = DeviceGraph.from_batches([b1, b2], DEV)
+    h, hp = 40, 48
+    m1, m2 = rand(b1.n_bonds, hp, h, 1), rand(b2.n_bonds, hp, h, 2)
+    want = torch.cat([O.gather_sum(m.double(), b.a2b)[b.b2a] - m.double()[b.b2revb] for m, b in ((m1, b1), (m2, b2))])
+    md = torch.cat([m1, m2]).to(DEV)
+    pre = torch.empty_like(md)
+    _lib.check(L.rr_bond_message_fwd(ctypes.byref(dg.c), md.data_ptr(), pre.data_ptr(), hp, 0, S()))
+    close(pre, want)
+    ups = [rand(b1.n_bonds, hp, h, 3), rand(b2.n_bonds, hp, h, 4)]
+    grads = []
+    for m, b, up in ((m1, b1, ups[0]), (m2, b2, ups[1])):
+        x = m.double().requires_grad_(True)
+        (O.gather_sum(x, b.a2b)[b.b2a] - x[b.b2revb]).backward(up.double())
+        grads.append(x.grad)
+    upd = torch.cat(ups).to(DEV)
+    dm = torch.empty_like(upd)
+    _lib.check(L.rr_bond_message_bwd(ctypes.byref(dg.c), upd.data_ptr(), dm.data_ptr(), hp, S()))
+    close(dm, torch.cat(grads), 5e-6)
+    # atom-level (a2a) gather across segments
+    x1, x2 = rand(b1.n_atoms, hp, h, 5), rand(b2.n_atoms, hp, h, 6)
+    want = torch.cat([O.gather_sum(x.double(), b.get_a2a()) for x, b in ((x1, b1), (x2, b2))])
+    xd = torch.cat([x1, x2]).to(DEV)
+    out = torch.empty_like(xd)
+    _lib.check(L.rr_neighbor_sum_fwd(ctypes.byref(dg.c), 1, xd.data_ptr(), out.data_ptr(), hp, 0, S()))
+    close(out, want)
+
+
+def test_max_num_bonds_override_matches_bigger_batch():
+    """A shard packed with the GLOBAL batch's max_num_bonds equals its rows inside the global batch
+    (data-parallel sharding)."""
+    L = _lib.lib()
+    ds = synthetic.make_dataset(10, [2, 2], star_leaves_in_group={1: 8})
+    mols = [ds.mols[t] for t in ds.rsmi]
+    whole, shard = BatchMolGraph(mols), BatchMolGraph(mols[:2])
+    assert whole.max_num_bonds == 8 and shard.max_num_bonds < 8
+    dg = DeviceGraph.from_batches([shard], DEV, [whole.max_num_bonds])
+    h, hp = 24, 32
+    m = rand(whole.n_bonds, hp, h, 1)
+    want = (O.gather_sum(m.double(), whole.a2b)[whole.b2a] - m.double()[whole.b2revb])[:shard.n_bonds]
+    md = m[:shard.n_bonds].contiguous().to(DEV)
+    pre = torch.empty_like(md)
+    _lib.check(L.rr_bond_message_fwd(ctypes.byref(dg.c), md.data_ptr(), pre.data_ptr(), hp, 0, S()))
+    close(pre, want)
+
+
+@pytest.mark.parametrize("M,n,k1,k2", [(1000, 304, 88, 0), (777, 304, 304, 88), (130, 48, 64, 48), (5, 16, 304, 0), (4100, 608, 608, 608)])
+def test_linear_fwd_dgrad_wgrad(M, n, k1, k2):
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(M)
+    X1, W1 = torch.randn(M, k1, generator=g), torch.randn(n, k1, generator=g) / k1 ** 0.5
+    X2 = torch.randn(M, k2, generator=g) if k2 else None
+    W2 = torch.randn(n, k2, generator=g) / k2 ** 0.5 if k2 else None
+    bias, resid = torch.randn(n, generator=g), torch.randn(M, n, generator=g)
+    z = X1.double() @ W1.double().T + bias.double() + resid.double()
+    if k2:
+        z = z + X2.double() @ W2.double().T
+    d = {k: (v.to(DEV) if v is not None else None) for k, v in dict(X1=X1, W1=W1, X2=X2, W2=W2, bias=bias, resid=resid).items()}
+    Y = torch.empty(M, n, device=DEV)
+    for flags, want in ((0, z), (1, torch.relu(z))):
+        _lib.check(L.rr_linear_fwd(M, n, d["X1"].data_ptr(), k1, d["W1"].data_ptr(), k1, _lib.ptr(d["X2"]), k2, _lib.ptr(d["W2"]), k2,
+                                   d["bias"].data_ptr(), d["resid"].data_ptr(), n, Y.data_ptr(), n, flags, 0.0, 0, 0, S()))
+        close(Y, want, 3e-6)
+    dZ = torch.randn(M, n, generator=g)
+    dZd = dZ.to(DEV)
+    dX = torch.empty(M, k1, device=DEV)
+    _lib.check(L.rr_linear_dgrad(M, n, k1, dZd.data_ptr(), n, d["W1"].data_ptr(), k1, dX.data_ptr(), k1, 0, S()))
+    close(dX, dZ.double() @ W1.double(), 3e-6)
+    _lib.check(L.rr_linear_dgrad(M, n, k1, dZd.data_ptr(), n, d["W1"].data_ptr(), k1, dX.data_ptr(), k1, 1, S()))
+    close(dX, 2 * (dZ.double() @ W1.double()), 3e-6)
+    dW = torch.zeros(n, k1, device=DEV)
+    db = torch.zeros(n, device=DEV)
+    _lib.check(L.rr_linear_wgrad(M, n, k1, dZd.data_ptr(), n, d["X1"].data_ptr(), k1, dW.data_ptr(), k1, db.data_ptr(), S()))
+    close(dW, dZ.double().T @ X1.double(), 1e-5)
+    close(db, dZ.double().sum(0), 1e-5)
+
+
+def test_dropout_epilogue_statistics_and_backward_mask():
+    L = _lib.lib()
+    M, n, k, p = 4096, 304, 64, 0.25
+    X = torch.randn(M, k, device=DEV)
+    W = torch.randn(n, k, device=DEV)
+    Y0, Y1, Y2 = (torch.empty(M, n, device=DEV) for _ in range(3))
+    for Y, flags, seed in ((Y0, 1, 0), (Y1, 3, 11), (Y2, 3, 12)):
+        _lib.check(L.rr_linear_fwd(M, n, X.data_ptr(), k, W.data_ptr(), k, None, 0, None, 0, None, None, 0, Y.data_ptr(), n, flags, p, seed, 5, S()))
+    pos = Y0 > 0
+    dropped = (Y1 == 0) & pos
+    frac = float(dropped.sum()) / float(pos.sum())
+    assert abs(frac - p) < 0.01, frac
+    kept = (Y1 != 0)
+    close(Y1[kept], Y0[kept] / (1 - p), 1e-6)
+    assert float(((Y1 == 0) != (Y2 == 0)).float().mean()) > 0.1      # another seed, another mask
+    # relu_bwd regenerates nothing: mask = [y != 0], scale = 1/(1-p)
+    dy = torch.randn(M, n, device=DEV)
+    dz = torch.empty_like(dy)
+    acc = torch.ones_like(dy)
+    _lib.check(L.rr_relu_bwd(M, n, dy.data_ptr(), Y1.data_ptr(), 1 / (1 - p), 0, dz.data_ptr(), acc.data_ptr(), 2, S()))
+    close(dz, dy * kept / (1 - p), 1e-6)
+    close(acc, 1 + dy * kept / (1 - p), 1e-6)
+
+
+def test_readout_fwd_bwd():
+    L = _lib.lib()
+    ds, b, dg = graphs(sizes=(3, 4))
+    h, hp, vp, f = 40, 48, 48, 1
+    hid = torch.relu(rand(b.n_atoms, hp, h, 1)).double().requires_grad_(True)
+    feats = torch.tensor(ds.temp.reshape(-1, 1), dtype=torch.float32)
+    vec = torch.stack([hid[s:s + n].sum(0) / n for s, n in b.a_scope])[:, :h]        # mpn.py:224-235
+    want = torch.cat([vec, feats.double()], 1)                                          # mpn.py:237-238
+    out = torch.full((b.n_mols, vp), float("nan"), device=DEV)
+    hd, fd = hid.detach().float().to(DEV), feats.to(DEV)
+    _lib.check(L.rr_readout_fwd(ctypes.byref(dg.c), hd.data_ptr(), hp, h, fd.data_ptr(), f, out.data_ptr(), vp, 0.0, 0, 0, S()))
+    close(out[:, :h + f], want.detach())
+    assert not out[:, h + f:].any()
+    up = torch.randn(b.n_mols, vp)
+    want.backward(up[:, :h + f].double())
+    dz = torch.full((b.n_atoms, hp), float("nan"), device=DEV)
+    upd = up.to(DEV)
+    _lib.check(L.rr_readout_bwd(ctypes.byref(dg.c), upd.data_ptr(), vp, out.data_ptr(), hd.data_ptr(), dz.data_ptr(), hp, 0.0, S()))
+    mask = (hid.detach() != 0)
+    close(dz[:, :h], (hid.grad * mask)[:, :h], 3e-6)
+    assert not dz[0].any()                                                              # the padding atom gets no gradient
+
+
+LOSSES = [("mle", _lib.LOSS_LISTMLE, 1), ("listnet", _lib.LOSS_LISTNET, 1), ("evidential_ranking", _lib.LOSS_EVIDENTIAL, 2),
+          ("gauss_regression", _lib.LOSS_GAUSS, 2), ("regression", _lib.LOSS_MSE, 1)]
+
+
+@pytest.mark.parametrize("task,kind,cols", LOSSES)
+@pytest.mark.parametrize("scope", [[5, 3, 6], [1, 2, 1], [32] * 8, [50, 100, 200, 500], [2048]])
+def test_losses_match_oracle(task, kind, cols, scope):
+    L = _lib.lib()
+    N, G = sum(scope), len(scope)
+    g = torch.Generator().manual_seed(N + kind)
+    s = torch.randn(N, cols, generator=g)
+    if cols == 2:
+        s[:, 1] = torch.nn.functional.softplus(s[:, 1]) + 1e-3
+    else:
+        s = s[:, 0]
+    t = torch.randn(N, generator=g)
+    sx = s.double().requires_grad_(True)
+    want = O.loss_for_task(task, sx, scope, t.double())
+    want.backward(torch.ones_like(want))
+    norm = {"mle": G, "evidential_ranking": G}.get(task, N)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+    sd, td = s.to(DEV), t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(sd, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd(kind, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), float(norm), 1.0, loss.data_ptr(), ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 2e-6)
+    close(ds_, sx.grad, 2e-5)
+
+
+@pytest.mark.parametrize("scope", [[5, 4, 6], [64] * 4, [3, 500]])
+def test_ranknet_window_matches_oracle(scope):
+    L = _lib.lib()
+    N, G = sum(scope), len(scope)
+    g = torch.Generator().manual_seed(N)
+    s, t = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    t[:3] = 0.5                                                  # a group whose targets tie: no pairs, skipped (train_pairwise.py:103-104)
+    sx = s.double().requires_grad_(True)
+    total, pairs, o = 0, 0.0, 0
+    for n in scope:
+        c, npairs = O.ranknet_group_cost(sx[o:o + n], t[o:o + n].numpy())
+        if c is not None:
+            total = total + c
+            pairs += npairs
+        o += n
+    want = total / pairs
+    want.backward()
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+    sd, td = s.to(DEV), t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.empty_like(sd)
+    _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_RANKNET, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), pairs, 1.0, loss.data_ptr(), ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 2e-6)
+    close(ds_, sx.grad, 2e-5)
+
+
+def test_listmle_sortedness_and_shift_invariance_at_full_size():
+    """Size-independent properties at config-5 scale (82 groups x 50, 8 x 500): the loss is invariant to a
+    per-group shift of the scores, its gradient sums to zero per group, and a perfectly ordered group with
+    widely separated scores has ~zero loss."""
+    L = _lib.lib()
+    for scope in ([50] * 82, [500] * 8):
+        N, G = sum(scope), len(scope)
+        s, t = torch.randn(N, device=DEV), torch.randn(N, device=DEV)
+        seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+        shift = torch.repeat_interleave(torch.randn(G, device=DEV) * 3, torch.tensor(scope, device=DEV))
+        out = []
+        for sc in (s, s + shift, t * 50):
+            loss, d = torch.empty(1, device=DEV), torch.empty(N, device=DEV)
+            _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_LISTMLE, N, G, sc.contiguous().data_ptr(), t.data_ptr(), seg.data_ptr(), float(G), 1.0,
+                                        loss.data_ptr(), d.data_ptr(), S()))
+            out.append((float(loss), d))
+        assert abs(out[0][0] - out[1][0]) < 1e-4 * abs(out[0][0])
+        persum = torch.stack([x.sum() for x in out[0][1].split(scope)])
+        assert float(persum.abs().max()) < 1e-6
+        assert out[2][0] < 0.05
+
+
+def test_argument_errors_are_reported_not_crashed():
+    L = _lib.lib()
+    x = torch.zeros(8, 6, device=DEV)
+    st = L.rr_linear_fwd(8, 6, x.data_ptr(), 6, x.data_ptr(), 6, None, 0, None, 0, None, None, 0, x.data_ptr(), 6, 0, 0.0, 0, 0, S())
+    assert st == -1 and b"multiples of 4" in L.rr_last_error()
+    with pytest.raises(_lib.RRError):
+        _lib.check(L.rr_loss_fwdbwd(99, 4, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), 1.0, 1.0, x.data_ptr(), x.data_ptr(), S()))

@@ -1,0 +1,235 @@
+"""GPU parity of the whole path through the public (reference-shaped) API against
+(1) golden vectors produced by the REAL reference (tests/golden/model.npz, fp32 and fp64 runs) and
+(2) the CPU oracle on fresh inputs.
+
+Tolerances (north star: 1e-4 relative on losses, 1e-3 on gradients): the fp32 SIMT path is held to
+2e-5 on scores/losses and 2e-4 on gradients against the reference's fp64 run -- the reference's own
+fp32 run differs from its fp64 run by ~1e-6 / 1e-5 on the same cases.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reactranker_oracle as O
+from reactranker_b200 import _lib, synthetic
+from reactranker_b200.features.featurization import BatchMolGraph, DeviceGraph
+from reactranker_b200.models.base_model import build_model
+from reactranker_b200.train import loss as RL
+from helpers import dataset_from_golden, sd_from_golden, rel_err, star_dict, grads_close
+
+pytestmark = pytest.mark.gpu
+GPU = 0
+TASKS = {"mle": (1, None), "listnet": (1, None), "evidential_ranking": (2, "evidential_ranking"),
+         "gauss_regression": (2, None), "regression": (1, None)}
+
+
+def product_loss(task, out, scope, targets, gpu=GPU):
+    if task == "mle":
+        return RL.MLEloss()(out, scope, targets, gpu)
+    if task == "listnet":
+        return RL.ListnetLoss()(out, scope, targets, gpu)
+    if task == "evidential_ranking":
+        return RL.evidential_ranking()(out, scope, targets, 0.0001, 0, 1, gpu)
+    if task == "gauss_regression":
+        return RL.GaussDisLoss()(out[:, 0], out[:, 1], targets, gpu)
+    return RL.MSELoss()(out, targets)
+
+
+def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_softplus"):
+    tn, tt = TASKS[task]
+    m = build_model(hidden_size=hidden, mpnn_depth=depth, mpnn_diff_depth=ddepth, ffn_depth=3, use_bias=True, dropout=dropout,
+                    task_num=tn, ffn_last_layer=last, task_type=tt, add_features_dim=1)
+    if sd is not None:
+        m.load_state_dict(sd)
+    return m.cuda(GPU)
+
+
+CASES = ["mle.h40", "listnet.h40", "evidential_ranking.h40", "gauss_regression.h40", "regression.h40", "mle.star.h40",
+         "evidential_ranking.h24d5"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_scores_loss_grads_vs_reference_golden(golden, name):
+    g = golden("model")
+    task = str(g[name + ".task"])
+    ds, sizes, hidden, depth, ddepth = dataset_from_golden(g, name)
+    model = make_model(hidden, task, depth, ddepth, sd_from_golden(g, name + ".sd"))
+    model.train()
+    r_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
+    p_g = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+    targets = torch.FloatTensor(ds.lgk.reshape(-1, 1)).squeeze()          # train_listwise.py:187
+    loss = product_loss(task, out, sizes, targets)
+    model.zero_grad()
+    loss.backward()
+    assert tuple(out.shape) == tuple(g[name + ".f32.scores"].shape)
+    assert tuple(loss.shape) == tuple(g[name + ".f32.loss"].shape)       # [1] for mle/evidential, 0-d otherwise
+    assert rel_err(out.detach().cpu().numpy(), g[name + ".f64.scores"]) < 2e-5
+    assert rel_err(loss.detach().cpu().numpy(), g[name + ".f64.loss"]) < 2e-5
+    got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+    want = {k: g[f"{name}.f64.grad.{k}"] for k in got}
+    assert not grads_close(got, want, 2e-4)
+    assert model.encoder.cached_zero_vector.grad is None
+
+
+def test_h300_against_reference_golden(golden):
+    """hidden 300 (the north-star width): weights re-created from the torch seed (checked bit-exact on CPU in
+    test_host_cpu), outputs/loss/large-gradient checksums from the reference run."""
+    g = golden("model")
+    name = "mle.h300"
+    ds, sizes, hidden, depth, ddepth = dataset_from_golden(g, name)
+    torch.manual_seed(int(g[name + ".meta"][1]))
+    model = make_model(hidden, "mle", depth, ddepth)
+    r_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
+    p_g = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+    loss = RL.MLEloss()(out, sizes, torch.FloatTensor(ds.lgk), GPU)
+    loss.backward()
+    assert rel_err(out.detach().cpu().numpy(), g[name + ".f64.scores"]) < 2e-5
+    assert rel_err(loss.detach().cpu().numpy(), g[name + ".f64.loss"]) < 2e-5
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        v = p.grad.double().cpu().numpy()
+        if f"{name}.f64.grad.{k}" in g.files:
+            w = g[f"{name}.f64.grad.{k}"]
+            assert np.abs(v - w).max() <= 2e-4 * np.abs(w).max() + 1e-9, k
+        else:
+            s = g[f"{name}.f64.gradsum.{k}"]
+            got = np.asarray([v.sum(), np.abs(v).sum(), (v ** 2).sum()])
+            assert abs(got[1] - s[1]) <= 2e-4 * s[1] and abs(got[2] - s[2]) <= 4e-4 * s[2], k
+
+
+def test_ranknet_window_vs_reference_golden(golden):
+    """One accumulation window of factorized_training_loop (train_pairwise.py:81-160): every group keeps its
+    OWN max_num_bonds (one reference forward per group) but all groups share one launch here."""
+    g = golden("ranknet")
+    sizes = [int(x) for x in g["sizes"]]
+    ds = synthetic.make_dataset(int(g["seed"]), sizes, star_leaves_in_group=star_dict(g["star"]))
+    model = build_model(hidden_size=40, mpnn_depth=3, mpnn_diff_depth=3, ffn_depth=3, use_bias=True, dropout=0.0, task_num=1,
+                        ffn_last_layer="no_softplus", add_features_dim=1)
+    model.load_state_dict(sd_from_golden(g, "sd"))
+    model = model.cuda(GPU)
+    dev = torch.device("cuda", GPU)
+    r_batches, p_batches, o = [], [], 0
+    for n in sizes:
+        r_batches.append(BatchMolGraph([ds.mols[t] for t in ds.rsmi[o:o + n]]))
+        p_batches.append(BatchMolGraph([ds.mols[t] for t in ds.psmi[o:o + n]]))
+        o += n
+    rg, pg = DeviceGraph.from_batches(r_batches, dev), DeviceGraph.from_batches(p_batches, dev)
+    y = model(rg, pg, gpu=GPU, add_features=ds.lgk.reshape(-1, 1))       # the target-column leak (load_reactions.py:264-267)
+    pairs = sum(RL.count_ordered_pairs(ds.lgk[a:a + n]) for a, n in zip(np.cumsum([0] + sizes[:-1]), sizes))
+    assert pairs == float(g["f64.pairs"])
+    loss = RL.ranknet_window_loss(y, sizes, ds.lgk.astype(np.float32), pairs, sigma=1.0, gpu=GPU)
+    loss.backward()
+    assert rel_err(y.detach().cpu().numpy(), g["f64.scores"]) < 2e-5
+    assert rel_err(loss.detach().cpu().numpy(), g["f64.loss"]) < 2e-5
+    got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+    assert not grads_close(got, {k: g[f"f64.grad.{k}"] for k in got}, 2e-4)
+
+
+def test_three_optimizer_steps_vs_reference_golden(golden):
+    """Forward, ListMLE, backward, Adam, NoamLR for three steps (train_listwise.py:177-290)."""
+    from reactranker_b200.train.utils import build_lr_scheduler, build_optimizer
+    g = golden("steps")
+    ds = synthetic.make_dataset(51, [6, 5, 4, 6, 3, 6])
+    model = make_model(40, "mle", 3, 3, sd_from_golden(g, "sd0"))
+    opt = build_optimizer(model)
+    sched = build_lr_scheduler(opt, warmup_epochs=2, total_epochs=4, train_data_size=30, batch_size=10, init_lr=1e-4, max_lr=1e-3, final_lr=1e-4)
+    model.train()
+    losses = []
+    for lo, hi, scope in [(0, 11, [6, 5]), (11, 21, [4, 6]), (21, 30, [3, 6])]:
+        r_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi[lo:hi]])
+        p_g = BatchMolGraph([ds.mols[t] for t in ds.psmi[lo:hi]])
+        out = model(r_g, p_g, gpu=GPU, add_features=ds.temp[lo:hi].reshape(-1, 1))
+        loss = RL.MLEloss()(out, scope, torch.FloatTensor(ds.lgk[lo:hi]), GPU)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step()
+        losses.append(float(loss))
+    assert np.allclose(losses, g["losses"], rtol=1e-4)
+    for k, v in model.state_dict().items():
+        w = g["sd3." + k]
+        assert np.abs(v.cpu().numpy() - w).max() <= 1e-3 * max(np.abs(w).max(), 1e-8), k
+
+
+@pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5)])
+def test_vs_oracle_fresh_inputs(task, hidden, depth):
+    """The two north-star widths on inputs the goldens do not cover, oracle run in fp64 on the host."""
+    ds = synthetic.make_dataset(77, [7, 5, 9, 4])
+    sizes = [7, 5, 9, 4]
+    torch.manual_seed(3)
+    model = make_model(hidden, task, depth, depth)
+    sd64 = {k: v.double().cpu() for k, v in model.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if "cached_zero" not in k}
+    full = dict(sd64)
+    full.update(params)
+    r_o = O.OracleBatch([ds.mols[t] for t in ds.rsmi])
+    p_o = O.OracleBatch([ds.mols[t] for t in ds.psmi])
+    tn, tt = TASKS[task]
+    want = O.model_forward(full, r_o, p_o, ds.temp.reshape(-1, 1), mpnn_depth=depth, mpnn_diff_depth=depth,
+                           head=O.resolve_task_type(tn, "with_softplus", tt))
+    targets = torch.tensor(ds.lgk.astype(np.float32))
+    wl = O.loss_for_task(task, want, sizes, targets.double())
+    wl.backward(torch.ones_like(wl))
+    out = model(BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi]), gpu=GPU,
+                add_features=ds.temp.reshape(-1, 1))
+    loss = product_loss(task, out, sizes, targets)
+    loss.backward()
+    assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < 2e-5
+    assert rel_err(loss.detach().cpu().numpy(), wl.detach().numpy()) < 2e-5
+    got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+    assert not grads_close(got, {k: params[k].grad.numpy() for k in got}, 2e-4)
+
+
+def test_eval_mode_is_deterministic_and_dropout_is_unbiased():
+    ds = synthetic.make_dataset(5, [16] * 8)
+    torch.manual_seed(0)
+    model = make_model(300, "mle", 3, 3, dropout=0.1)
+    r_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
+    p_g = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    feats = ds.temp.reshape(-1, 1)
+    model.eval()
+    with torch.no_grad():
+        a = model(r_g, p_g, gpu=GPU, add_features=feats)
+        b = model(r_g, p_g, gpu=GPU, add_features=feats)
+    assert torch.equal(a, b)
+    model.train()
+    with torch.no_grad():
+        runs = torch.stack([model(r_g, p_g, gpu=GPU, add_features=feats) for _ in range(64)])
+    assert not torch.equal(runs[0], runs[1])
+    # inverted dropout keeps the first moment: the mean over masks approaches the eval output
+    assert float((runs.mean(0) - a).abs().mean()) < 0.35 * float(runs.std(0).mean())
+
+
+def test_full_batch_properties_at_config2_size():
+    """Config-2 scale (4096 reactions = 128 groups x 32, hidden 300): size-independent checks --
+    (a) a data-parallel shard packed with the global max_num_bonds reproduces its rows of the global batch,
+    (b) scores are invariant to the order of the groups in the batch, (c) everything is finite."""
+    G, n = 128, 32
+    ds = synthetic.make_dataset(123, [n] * G)
+    torch.manual_seed(1)
+    model = make_model(300, "listnet", 3, 3).eval()
+    feats = ds.temp.reshape(-1, 1)
+    r_all = [ds.mols[t] for t in ds.rsmi]
+    p_all = [ds.mols[t] for t in ds.psmi]
+    dev = torch.device("cuda", GPU)
+    with torch.no_grad():
+        r_g, p_g = BatchMolGraph(r_all), BatchMolGraph(p_all)
+        full = model(r_g, p_g, gpu=GPU, add_features=feats)
+        assert bool(torch.isfinite(full).all())
+        half = G // 2 * n
+        rs, ps = BatchMolGraph(r_all[:half]), BatchMolGraph(p_all[:half])
+        shard = model(DeviceGraph.from_batches([rs], dev, [r_g.max_num_bonds]), DeviceGraph.from_batches([ps], dev, [p_g.max_num_bonds]),
+                      gpu=GPU, add_features=feats[:half])
+        assert rel_err(shard.cpu().numpy(), full[:half].cpu().numpy()) < 1e-6
+        perm = np.concatenate([np.arange(half, G * n), np.arange(half)])
+        swapped = model(BatchMolGraph([r_all[i] for i in perm]), BatchMolGraph([p_all[i] for i in perm]), gpu=GPU, add_features=feats[perm])
+        assert rel_err(swapped.cpu().numpy(), full.cpu().numpy()[perm]) < 1e-5
+    model.train()
+    out = model(r_g, p_g, gpu=GPU, add_features=feats)
+    loss = RL.ListnetLoss()(out, [n] * G, torch.FloatTensor(ds.lgk), GPU)
+    loss.backward()
+    assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
+    assert float(loss) > 0

@@ -1,0 +1,158 @@
+"""CPU tests of the host-side mirror: bit-exact batching vs the reference goldens, the device
+packing, the C-ABI surface (symbols only -- no compute without a GPU) and the schedule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from reactranker_b200 import _lib, synthetic
+from reactranker_b200.features.featurization import BatchMolGraph, DeviceGraph, MolGraph
+from helpers import star_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_batching_bit_exact_vs_reference_golden(golden):
+    g = golden("batching")
+    for name in ("plain", "star"):
+        ds = synthetic.make_dataset(int(g[name + ".seed"]), [int(x) for x in g[name + ".sizes"]],
+                                    star_leaves_in_group=star_dict(g[name + ".star"]))
+        for side, col in (("r", ds.rsmi), ("p", ds.psmi)):
+            b = BatchMolGraph([ds.mols[t] for t in col])
+            pre = f"{name}.{side}."
+            fa, fb, a2b, b2a, b2revb, a_scope, b_scope = b.get_components()
+            for got, key in ((fa, "f_atoms"), (fb, "f_bonds"), (a2b, "a2b"), (b2a, "b2a"), (b2revb, "b2revb"), (b.get_a2a(), "a2a")):
+                want = g[pre + key]
+                assert got.numpy().dtype == want.dtype and np.array_equal(got.numpy(), want), key
+            assert np.array_equal(np.asarray(a_scope), g[pre + "a_scope"])
+            assert np.array_equal(np.asarray(b_scope), g[pre + "b_scope"])
+            assert b.max_num_bonds == int(g[pre + "max_num_bonds"])
+            assert b.n_atoms == want_rows(g, pre, "f_atoms") and b.n_bonds == want_rows(g, pre, "f_bonds")
+
+
+def want_rows(g, pre, key):
+    return g[pre + key].shape[0]
+
+
+def test_molgraph_list_roundtrip():
+    """A molecule given as python lists (the reference's MolGraph attributes) batches identically."""
+    ds = synthetic.make_dataset(3, [2, 2])
+    class Lists:  # what a reference MolGraph looks like
+        pass
+    mols = []
+    for t in ds.psmi:
+        m = ds.mols[t]
+        o = Lists()
+        o.smiles, o.n_atoms, o.n_bonds = m.smiles, m.n_atoms, m.n_bonds
+        o.f_atoms, o.f_bonds, o.a2b, o.b2a, o.b2revb = m.f_atoms, m.f_bonds, m.a2b, m.b2a, m.b2revb
+        mols.append(o)
+    a = BatchMolGraph(mols)
+    b = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    for x, y in zip(a.get_components()[:5], b.get_components()[:5]):
+        assert torch.equal(x, y)
+
+
+def test_empty_and_degenerate_batches():
+    rng = np.random.default_rng(0)
+    single = synthetic.make_molecule(rng, 1, "lonely")        # one atom, no bonds
+    b = BatchMolGraph([single])
+    assert b.n_atoms == 2 and b.n_bonds == 1 and b.max_num_bonds == 1
+    assert b.a2b.shape == (2, 1) and int(b.a2b.abs().sum()) == 0
+    e = BatchMolGraph([])
+    assert e.n_atoms == 1 and e.n_bonds == 1 and e.a_scope == []
+
+
+def test_device_graph_layout_single_and_multi_segment():
+    ds = synthetic.make_dataset(5, [3, 2], star_leaves_in_group={1: 6})
+    b1 = BatchMolGraph([ds.mols[t] for t in ds.psmi[:3]])
+    b2 = BatchMolGraph([ds.mols[t] for t in ds.rsmi[3:]])       # the star reactant, repeated per candidate
+    one = DeviceGraph.from_batches([b1], "cpu")
+    meta = one.section("a_meta", torch.int32, (b1.n_atoms, 4)).numpy()
+    assert meta[0, 0] == 0x100 and meta[0, 1] == b1.max_num_bonds
+    assert np.array_equal(meta[1:, 0], b1._deg[1:]) and np.array_equal(meta[:, 1], b1.max_num_bonds - b1._deg)
+    a2b = one.section("a2b", torch.int32, (b1.n_atoms, one.c.wmax)).numpy()
+    assert np.array_equal(a2b, b1.a2b.numpy()[:, :one.c.wmax])
+    fb = one.section("f_bonds", torch.float32, (b1.n_bonds, 88)).numpy()
+    assert np.array_equal(fb[:, :83], b1.f_bonds.numpy()) and not fb[:, 83:].any()
+    both = DeviceGraph.from_batches([b1, b2], "cpu")
+    assert both.c.n_segments == 2 and both.n_atoms == b1.n_atoms + b2.n_atoms
+    meta = both.section("a_meta", torch.int32, (both.n_atoms, 4)).numpy()
+    assert meta[b1.n_atoms, 0] == 0x100 and meta[b1.n_atoms, 2] == b1.n_bonds and meta[b1.n_atoms, 3] == b1.n_atoms
+    assert meta[b1.n_atoms, 1] == b2.max_num_bonds == 6           # each segment keeps ITS max_num_bonds
+    a2a = both.section("a2a", torch.int32, (both.n_atoms, both.c.wmax)).numpy()
+    d2 = b2._deg
+    want = b2.get_a2a().numpy() + b1.n_atoms
+    for a in range(b2.n_atoms):
+        assert np.array_equal(a2a[b1.n_atoms + a, :d2[a]], want[a, :d2[a]])
+    with pytest.raises(ValueError):
+        DeviceGraph.from_batches([b2], "cpu", [3])
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rr_sm100.h")).read()
+    declared = set(re.findall(r"\b(rr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    _lib.build()
+    L = ctypes.CDLL(_lib.SO_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.rr_version() == 1
+    assert L.rr_padded(300) == 304 and L.rr_padded(600) == 608 and L.rr_padded(40) == 48
+    L.rr_loss_max_group.restype = ctypes.c_int
+    assert L.rr_loss_max_group() >= 500           # config 5 sweeps groups of 50..500 candidates
+
+
+def test_no_cpu_fallback():
+    from reactranker_b200.models.base_model import build_model
+    ds = synthetic.make_dataset(1, [2])
+    m = build_model(hidden_size=16, task_num=1, add_features_dim=0, dropout=0.0)
+    b = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    with pytest.raises(_lib.RRError):
+        m(b, b, gpu=None)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.RRError):
+            m(b, b, gpu=0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "reactranker_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_noam_matches_reference_golden(golden):
+    from reactranker_b200.train.utils import build_lr_scheduler, build_optimizer
+    g = golden("steps")
+    lin = torch.nn.Linear(2, 2)
+    opt = build_optimizer(lin)
+    sched = build_lr_scheduler(opt, warmup_epochs=2, total_epochs=4, train_data_size=30, batch_size=10,
+                               init_lr=1e-4, max_lr=1e-3, final_lr=1e-4)
+    lrs = [opt.param_groups[0]["lr"]]
+    for _ in range(3):
+        sched.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    assert np.allclose(lrs, g["lrs"], rtol=1e-12)
+    assert opt.defaults["weight_decay"] == 0 and opt.param_groups[0]["weight_decay"] == 0
+
+
+def test_state_dict_keys_and_init_match_reference_golden(golden):
+    """Same 20 keys/shapes as the reference and, under the same torch seed, the same default init."""
+    from reactranker_b200.models.base_model import build_model
+    g = golden("model")
+    name = "mle.h40"
+    hidden, seed, depth, ddepth = (int(x) for x in g[name + ".meta"])
+    torch.manual_seed(seed)
+    m = build_model(hidden_size=hidden, mpnn_depth=depth, mpnn_diff_depth=ddepth, ffn_depth=3, use_bias=True, dropout=0.0,
+                    task_num=1, ffn_last_layer="with_softplus", add_features_dim=1)
+    sd = m.state_dict()
+    want = {k[len(name) + 4:]: g[k] for k in g.files if k.startswith(name + ".sd.")}
+    assert set(sd) == set(want) and len(sd) == 20
+    for k, v in want.items():
+        assert np.array_equal(sd[k].numpy(), v), k
