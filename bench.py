@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the ReactRanker training hot path (D-MPNN reaction encoder + LTR loss) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c2|c4]
+
+One "step" = one training step over one batch of synthetic reaction graphs: forward, loss,
+backward, (gradient all-reduce,) Adam, NoamLR.  Prints ONE JSON line (rank 0).
+
+* ``value``  : reactions/s with the batch already resident in HBM (device path).
+* ``e2e``    : reactions/s through the reference-shaped public API from HOST buffers -- per step
+               ``Parsing_features.parsing_reactions`` (batch assembly from the warm MolGraph cache),
+               the pinned host->device copy of both graphs, forward/loss/backward/Adam, and a
+               device->host read of the loss.
+* ``roofline``: the dominant kernel class of the step, timed with CUDA events on the launching
+               stream inside the timed region (rr_profile_begin/end of librr_sm100).
+* ``cpu_baseline`` / ``--impl reference``: the CPU restatement of the reference path
+               (oracle/reactranker_oracle.py; the reference is Python and /root/reference does not
+               travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[4] (the metric's own: D-MPNN + ListMLE, 1/2/4/8 GPUs), first sweep point: 50 candidates/group
+    "c5": dict(task="mle", hidden=300, depth=3, diff_depth=3, task_num=1, task_type=None, last="with_softplus", dropout=0.1,
+               group=50, groups=82, desc="ListMLE D-MPNN h300 d3/3/3, 82 groups x 50 candidates = 4100 reactions per GPU per step (configs[4])"),
+    "c5-500": dict(task="mle", hidden=300, depth=3, diff_depth=3, task_num=1, task_type=None, last="with_softplus", dropout=0.1,
+                   group=500, groups=8, desc="ListMLE D-MPNN h300 d3/3/3, 8 groups x 500 candidates = 4000 reactions per GPU per step (configs[4])"),
+    "c2": dict(task="listnet", hidden=300, depth=3, diff_depth=3, task_num=1, task_type=None, last="with_softplus", dropout=0.1,
+               group=32, groups=128, desc="ListNet@1 D-MPNN h300 d3/3/3, 128 groups x 32 candidates = 4096 reactions per GPU per step (configs[1])"),
+    "c4": dict(task="evidential_ranking", hidden=600, depth=5, diff_depth=5, task_num=2, task_type="evidential_ranking", last="with_softplus",
+               dropout=0.1, group=32, groups=128, desc="UC-Listwise D-MPNN h600 d5/5/3, 128 groups x 32 = 4096 reactions per GPU per step (configs[3])"),
+}
+METRIC = "train reactions/sec, D-MPNN+ListMLE"
+UNIT = "reactions/s"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=float(p["hbm_gbs"]), tensor=float(p["bf16_tflops_sustained"]), src="MEASURED_PEAKS.json (measured; bf16 sustained)")
+    except Exception:
+        return dict(hbm=6650.0, tensor=1400.0, src="fallback of B200_PROFILING.md")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_pool(wl, n_batches, seed):
+    """``n_batches`` distinct batches of synthetic reactions (SURVEY.md §8d generator)."""
+    from reactranker_b200 import synthetic
+    pool = []
+    for b in range(n_batches):
+        ds = synthetic.make_dataset(seed * 1000 + b, [wl["group"]] * wl["groups"])
+        pool.append(ds)
+    return pool
+
+
+def algorithmic_work(wl, rg, pg, n_add=1):
+    """Per-step algorithmic work of each kernel class (forward + backward), SURVEY.md §8(d):
+    compulsory fp32 activation bytes + int32 indices for the gather kernels, 2MNK for the GEMMs with
+    the reference's logical dimensions (83/61/h, not the padded strides)."""
+    h, T, Td = wl["hidden"], wl["depth"] - 1, wl["diff_depth"] - 1
+    s = i = 4
+    N = pg.n_mols
+    out = {}
+    bond = nbr_f = nbr_b = 0.0
+    g_f = g_d = 0.0
+    for g in (rg, pg):
+        A, B, W = g.n_atoms, g.n_bonds, g.c.wmax
+        bond += T * (2 * B * h * s + (A * W + 2 * B) * i)
+        agg = (B + A) * h * s + A * W * i
+        nbr_f += agg
+        nbr_b += agg
+        g_f += 2.0 * B * 83 * h + T * 2.0 * B * h * h + 2.0 * A * (61 + h) * h
+        g_d += T * 2.0 * B * h * h + 2.0 * A * h * h
+    A, B, W = pg.n_atoms, pg.n_bonds, pg.c.wmax
+    a2a = 2 * A * h * s + A * W * i
+    nbr_f += (Td + 1) * a2a + ((B + A) * 83 * s + A * W * i if Td > 0 else 0)
+    nbr_b += (Td + 1) * a2a
+    g_f += 2.0 * A * h * h + Td * 2.0 * A * (h + 83) * h + 2.0 * A * 2 * h * h
+    g_d += 2.0 * A * h * h + Td * 2.0 * A * h * h + 2.0 * A * 2 * h * h
+    ffn = 2.0 * N * ((h + n_add) * h + h * h + h * wl["task_num"])
+    g_f += ffn
+    g_d += ffn
+    out["bond_fwd"] = (bond, "B")
+    out["bond_bwd"] = (bond, "B")
+    out["nbr_fwd"] = (nbr_f, "B")
+    out["nbr_bwd"] = (nbr_b, "B")
+    out["gemm_fwd"] = (g_f, "FLOP")
+    out["gemm_dgrad"] = (g_d, "FLOP")
+    out["gemm_wgrad"] = (g_f, "FLOP")
+    return out
+
+
+def build(wl, dev_index, world):
+    from reactranker_b200.models.base_model import build_model
+    from reactranker_b200.train import loss as RL
+    from reactranker_b200.train.utils import build_lr_scheduler, build_optimizer
+    torch.manual_seed(0)
+    model = build_model(hidden_size=wl["hidden"], mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], ffn_depth=3, use_bias=True,
+                        dropout=wl["dropout"], task_num=wl["task_num"], ffn_last_layer=wl["last"], task_type=wl["task_type"], add_features_dim=1)
+    model = model.cuda(dev_index).train()
+    opt = build_optimizer(model)
+    rows = wl["group"] * wl["groups"]
+    sched = build_lr_scheduler(opt, warmup_epochs=2, total_epochs=30, train_data_size=100 * rows, batch_size=rows, init_lr=1e-4, max_lr=1e-3, final_lr=1e-4)
+    G, N = wl["groups"] * world, rows * world
+    task = wl["task"]
+    if task == "mle":
+        lm = RL.MLEloss(global_norm=G if world > 1 else None)
+        loss_fn = lambda out, scope, t: lm(out, scope, t, dev_index)  # noqa: E731
+    elif task == "listnet":
+        lm = RL.ListnetLoss(global_norm=N if world > 1 else None)
+        loss_fn = lambda out, scope, t: lm(out, scope, t, dev_index)  # noqa: E731
+    else:
+        lm = RL.evidential_ranking(global_norm=G if world > 1 else None)
+        loss_fn = lambda out, scope, t: lm(out, scope, t, 0.0001, 0, 1, dev_index)  # noqa: E731
+    return model, opt, sched, loss_fn
+
+
+def ours(args):
+    from reactranker_b200 import _lib
+    from reactranker_b200.data.load_reactions import Parsing_features
+    from reactranker_b200.features.featurization import BatchMolGraph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    _lib.require_device(local)
+    model, opt, sched, loss_fn = build(wl, local, world)
+    params = [p for p in model.parameters() if p.requires_grad]
+    scope = [wl["group"]] * wl["groups"]
+    rows = sum(scope)
+
+    pool = make_pool(wl, args.pool, seed=1 + rank)
+    fz = Parsing_features()
+    for ds in pool:
+        for tok, m in ds.mols.items():
+            fz.add(tok, m)
+    # device-resident copies for the device-path measurement
+    resident = []
+    for ds in pool:
+        r_b = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
+        p_b = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+        resident.append((r_b.to_device(dev), p_b.to_device(dev), torch.tensor(ds.temp.reshape(-1, 1), dtype=torch.float32, device=dev),
+                         torch.tensor(ds.lgk, dtype=torch.float32, device=dev)))
+    torch.cuda.synchronize()
+
+    def reduce_grads():
+        if dist is None:
+            return
+        flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        torch._foreach_copy_([p.grad for p in params], torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params]))
+
+    def step_resident(i):
+        rg, pg, feats, targets = resident[i % len(resident)]
+        out = model(rg, pg, gpu=local, add_features=feats)
+        loss = loss_fn(out, scope, targets)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reduce_grads()
+        opt.step()
+        sched.step()
+        return loss
+
+    h2d = [0]
+    d2h = 4
+
+    def step_e2e(i):
+        ds = pool[i % len(pool)]
+        reactions = np.stack([ds.rsmi, ds.psmi], axis=1)                      # what generate_batch_reactions yields
+        r_b, p_b = fz.parsing_reactions(reactions)                           # batch assembly from the warm MolGraph cache
+        out = model(r_b, p_b, gpu=local, add_features=ds.temp.reshape(-1, 1))  # pinned H2D of both graphs inside
+        targets = torch.FloatTensor(ds.lgk.reshape(-1, 1)).squeeze()
+        loss = loss_fn(out, scope, targets)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reduce_grads()
+        opt.step()
+        sched.step()
+        h2d[0] = model.last_h2d_bytes + targets.numel() * 4
+        return float(loss.detach().cpu().reshape(-1)[0])                     # D2H read of the step's result
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        if profile:
+            _lib.profile_begin()
+        _lib.lib().rr_launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = int(_lib.lib().rr_launch_count())
+        prof = _lib.profile_end() if profile else None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, prof
+
+    with ClockSampler(local) as clocks:
+        ms, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    clk = clocks.summary()
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _, _ = timed(step_e2e, e2e_steps, 3)
+
+    value = rows * world * args.steps / (ms / 1e3)
+    e2e_value = rows * world * e2e_steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    rg, pg = resident[0][0], resident[0][1]
+    work = algorithmic_work(wl, rg, pg)
+    kernels = {}
+    for cls, (tot_ms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        ent = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps, "share_of_step": tot_ms / ms}
+        if cls in work:
+            w, unit = work[cls]
+            rate = w / (tot_ms / args.steps / 1e3)
+            if unit == "B":
+                ent.update(bound="hbm", achieved=rate / 1e9, peak=pk["hbm"], unit="GB/s", frac=rate / 1e9 / pk["hbm"])
+            else:
+                ent.update(bound="tensor", achieved=rate / 1e12, peak=pk["tensor"], unit="TFLOP/s", frac=rate / 1e12 / pk["tensor"])
+        kernels[cls] = ent
+    top = max((c for c in kernels if "frac" in kernels[c]), key=lambda c: kernels[c]["ms_per_step"])
+    roof = {k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+    roof.update(kernel=top, traffic=None, peak_source=pk["src"], avg_launch_ms=kernels[top]["ms_per_step"] / kernels[top]["launches_per_step"])
+    mp = [c for c in ("bond_fwd", "bond_bwd", "nbr_fwd", "nbr_bwd") if c in kernels]
+    mp_bytes = sum(work[c][0] for c in mp)
+    mp_ms = sum(kernels[c]["ms_per_step"] for c in mp)
+    roof_mp = {"bound": "hbm", "achieved": mp_bytes / (mp_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+               "frac": mp_bytes / (mp_ms / 1e3) / 1e9 / pk["hbm"], "kernels": mp, "ms_per_step": mp_ms}
+
+    cpu = cpu_baseline(wl, steps=2, warmup=1) if world == 1 and not args.no_cpu else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": f"synthetic reaction graphs (SURVEY.md 8d generator), pool of {len(pool)} distinct batches per rank cycled; random-init weights",
+        "config": {"workload": wl["desc"], "name": args.workload, "reactions_per_gpu_per_step": rows, "global_batch": rows * world,
+                   "parallelism": f"dp{world}" if world > 1 else "single", "optimizer": "Adam(fused)+NoamLR",
+                   "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roof, "roofline_message_passing": roof_mp, "kernels": kernels,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the oracle port of the reference path -- the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_training_steps(wl, groups, steps, warmup, seed=99):
+    from oracle import reactranker_oracle as O
+    from reactranker_b200 import synthetic
+    torch.manual_seed(0)
+    sd = O.init_state_dict(wl["hidden"], wl["task_num"], 1, True, seed=0, mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"])
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "cached_zero" not in k}
+    full = dict(sd)
+    full.update(params)
+    opt = torch.optim.Adam([{"params": list(params.values()), "lr": 1e-4, "weight_decay": 0}])
+    head = O.resolve_task_type(wl["task_num"], wl["last"], wl["task_type"])
+    scope = [wl["group"]] * groups
+    pool = [synthetic.make_dataset(seed + b, scope) for b in range(2)]
+    for ds in pool:                                     # warm MolGraph cache, as the reference's Parsing_features
+        for m in ds.mols.values():
+            m._mk_lists()
+    times = []
+    for i in range(warmup + steps):
+        ds = pool[i % len(pool)]
+        t0 = time.perf_counter()
+        r_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi])          # BatchMolGraph build per step (featurization.py:246-290)
+        p_g = O.OracleBatch([ds.mols[t] for t in ds.psmi])
+        out = O.model_forward(full, r_g, p_g, ds.temp.reshape(-1, 1), mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], head=head,
+                              dropout=wl["dropout"], training=True)
+        loss = O.loss_for_task(wl["task"], out, scope, torch.tensor(ds.lgk.astype(np.float32)))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    return times[warmup:], sum(scope)
+
+
+def cpu_baseline(wl, steps, warmup):
+    groups = max(2, min(wl["groups"], 500 // wl["group"]))       # bounded sample: ~500 reactions per step
+    times, rows = cpu_training_steps(wl, groups, steps, warmup)
+    return {"value": rows * len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{len(times)} training steps of {groups} groups x {wl['group']} = {rows} reactions (same model/loss/optimizer; "
+                      f"oracle restatement of the reference PyTorch CPU path incl. per-step BatchMolGraph build), {sum(times):.1f} s"}
+
+
+def reference(args):
+    """``--impl reference``: the reference's own CPU implementation of the path (oracle port; the reference is
+    Python and cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    groups = max(2, min(wl["groups"], 500 // wl["group"]))
+    times, rows = cpu_training_steps(wl, groups, args.steps, args.warmup)
+    value = rows * len(times) / sum(times)
+    cpu = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+           "sample": f"each step = {groups} groups x {wl['group']} = {rows} reactions of the workload on the host CPU"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic reaction graphs (SURVEY.md 8d generator); random-init weights",
+        "config": {"workload": wl["desc"], "name": args.workload, "reactions_per_step_sample": rows},
+        "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches per rank")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference(a)
+    else:
+        if a.warmup < 3:
+            a.warmup = 3
+        ours(a)

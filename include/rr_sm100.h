@@ -180,7 +180,13 @@ int rr_model_forward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph
 /* dscores has the shape of scores; grads receives d/d(parameter) in state_dict layout */
 int rr_model_backward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p,
                       const float* dscores, rr_params* grads, void* ws, int64_t ws_bytes, void* stream);
-/* kernels launched by the last forward+backward on this thread (for bench.py's gpu_launches) */
+/* Per-kernel-class device timing for bench.py's roofline: between begin and end every launch is bracketed by
+ * CUDA events on its own stream; end() waits for them and returns summed milliseconds / launch counts per class
+ * (0 gemm_fwd 1 gemm_dgrad 2 gemm_wgrad 3 bond_fwd 4 bond_bwd 5 nbr_fwd 6 nbr_bwd 7 readout 8 elementwise 9 loss 10 misc). */
+int rr_profile_begin(void);
+int rr_profile_end(double* h_ms_by_class, int64_t* h_launches_by_class, int n_classes);
+int rr_profile_classes(void);
+/* kernels launched on this thread since the last reset (for bench.py's gpu_launches) */
 int64_t rr_launch_count(void);
 void rr_launch_count_reset(void);
 

@@ -47,7 +47,9 @@ EXPORTS = [
     "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
     "rr_loss_fwdbwd", "rr_loss_max_group",
     "rr_model_workspace_bytes", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
+    "rr_profile_begin", "rr_profile_end", "rr_profile_classes",
 ]
+KERNEL_CLASSES = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "bond_fwd", "bond_bwd", "nbr_fwd", "nbr_bwd", "readout", "elementwise", "loss", "misc"]
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
@@ -109,6 +111,7 @@ def lib() -> ctypes.CDLL:
                 L.rr_model_workspace_bytes.argtypes = [vp, vp, vp]
                 L.rr_model_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
                 L.rr_model_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
+                L.rr_profile_end.argtypes = [vp, vp, i32]
                 _lib = L
     return _lib
 
@@ -144,3 +147,16 @@ def ptr(t) -> Optional[int]:
 def stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_begin() -> None:
+    check(lib().rr_profile_begin())
+
+
+def profile_end() -> dict:
+    """{class: (milliseconds, launches)} of every kernel launched since profile_begin()."""
+    n = lib().rr_profile_classes()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(lib().rr_profile_end(ms, cnt, n))
+    return {KERNEL_CLASSES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -1,11 +1,26 @@
 // extern "C" surface of librr_sm100 (include/rr_sm100.h).  No C++ exception crosses it.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "rr_common.cuh"
 
 namespace rr {
 thread_local char g_err[512] = "";
-thread_local int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
+ProfState g_prof;
+std::mutex g_prof_mutex;
+void prof_push(int cls, cudaEvent_t a, cudaEvent_t b) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  ProfState& p = g_prof;
+  if (p.n == p.cap) {
+    const int cap = p.cap ? p.cap * 2 : 4096;
+    ProfState::Rec* r = static_cast<ProfState::Rec*>(realloc(p.recs, cap * sizeof(ProfState::Rec)));
+    if (!r) return;
+    p.recs = r;
+    p.cap = cap;
+  }
+  p.recs[p.n++] = ProfState::Rec{cls, a, b};
+}
 
 int padded(int);
 int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream_t);
@@ -101,7 +116,36 @@ int rr_model_backward(const rr_model_cfg* cfg, const rr_params* w, const rr_grap
                       rr_params* grads, void* ws, int64_t ws_bytes, void* stream) {
   return rr::model_backward(cfg, w, r, p, dscores, grads, ws, ws_bytes, S(stream));
 }
-int64_t rr_launch_count(void) { return rr::g_launches; }
-void rr_launch_count_reset(void) { rr::g_launches = 0; }
+int rr_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(rr::g_prof_mutex);
+  rr::g_prof.enabled = true;
+  rr::g_prof.n = 0;
+  return RR_OK;
+}
+int rr_profile_end(double* ms_by_class, int64_t* launches_by_class, int n_classes) {
+  std::lock_guard<std::mutex> lock(rr::g_prof_mutex);
+  rr::ProfState& p = rr::g_prof;
+  p.enabled = false;
+  RR_REQUIRE(ms_by_class && launches_by_class && n_classes >= rr::KC_COUNT, "rr_profile_end: need %d classes", rr::KC_COUNT);
+  for (int i = 0; i < n_classes; ++i) {
+    ms_by_class[i] = 0.0;
+    launches_by_class[i] = 0;
+  }
+  int status = RR_OK;
+  for (int i = 0; i < p.n; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.recs[i].b) != cudaSuccess || cudaEventElapsedTime(&ms, p.recs[i].a, p.recs[i].b) != cudaSuccess)
+      status = rr::fail(RR_ERR_CUDA, "rr_profile_end: event %d not complete", i);
+    ms_by_class[p.recs[i].cls] += ms;
+    launches_by_class[p.recs[i].cls] += 1;
+    cudaEventDestroy(p.recs[i].a);
+    cudaEventDestroy(p.recs[i].b);
+  }
+  p.n = 0;
+  return status;
+}
+int rr_profile_classes(void) { return rr::KC_COUNT; }
+int64_t rr_launch_count(void) { return rr::g_launches.load(); }
+void rr_launch_count_reset(void) { rr::g_launches.store(0); }
 
 }  // extern "C"

@@ -1,6 +1,8 @@
 // Shared device/host helpers for librr_sm100 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -12,7 +14,7 @@ namespace rr {
 
 // ---- error plumbing (no exceptions cross the C ABI) ----------------------------------
 extern thread_local char g_err[512];
-extern thread_local int64_t g_launches;
+extern std::atomic<int64_t> g_launches;   // process-wide: autograd runs backward on its own thread
 
 inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 inline int fail(int code, const char* fmt, ...) {
@@ -35,6 +37,37 @@ inline int fail(int code, const char* fmt, ...) {
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) return rr::fail(RR_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
+
+// ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py) ----
+enum KernelClass { KC_GEMM_FWD = 0, KC_GEMM_DGRAD, KC_GEMM_WGRAD, KC_BOND_FWD, KC_BOND_BWD, KC_NBR_FWD, KC_NBR_BWD, KC_READOUT,
+                   KC_ELEMENTWISE, KC_LOSS, KC_MISC, KC_COUNT };
+struct ProfState {
+  bool enabled = false;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  Rec* recs = nullptr;
+  int n = 0, cap = 0;
+};
+extern ProfState g_prof;  // process-wide, guarded by g_prof_mutex
+extern std::mutex g_prof_mutex;
+void prof_push(int cls, cudaEvent_t a, cudaEvent_t b);
+struct ProfScope {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  int cls;
+  ProfScope(int cls_, cudaStream_t s_) : s(s_), cls(cls_) {
+    if (g_prof.enabled) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+    }
+  }
+  ~ProfScope() {
+    if (a) {
+      cudaEventRecord(b, s);
+      prof_push(cls, a, b);
+    }
+  }
+};
 
 #define RR_REQUIRE(cond, ...)                                  \
   do {                                                         \

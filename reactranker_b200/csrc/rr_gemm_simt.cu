@@ -183,6 +183,7 @@ static int check_mat(const char* what, const void* p, int ld) {
 int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
                const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed, uint64_t stream_id,
                cudaStream_t s) {
+  ProfScope prof_scope(KC_GEMM_FWD, s);
   RR_REQUIRE(M >= 0 && n > 0 && (n & 3) == 0 && k1 > 0 && (k1 & 3) == 0 && (k2 & 3) == 0, "linear_fwd: M %d n %d k1 %d k2 %d (n, k multiples of 4)", M, n, k1, k2);
   RR_TRY(check_mat("X1", X1, ldx1));
   RR_TRY(check_mat("W1", W1, k1));
@@ -221,6 +222,7 @@ int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1,
 }
 
 int linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx, int accumulate, cudaStream_t s) {
+  ProfScope prof_scope(KC_GEMM_DGRAD, s);
   RR_REQUIRE(M >= 0 && n > 0 && k > 0 && (n & 3) == 0 && (k & 3) == 0, "linear_dgrad: M %d n %d k %d", M, n, k);
   RR_TRY(check_mat("dZ", dZ, lddz));
   RR_TRY(check_mat("W", W, ldw));
@@ -241,6 +243,7 @@ int linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W,
 }
 
 int linear_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s) {
+  ProfScope prof_scope(KC_GEMM_WGRAD, s);
   RR_REQUIRE(M >= 0 && n > 0 && k > 0 && (n & 3) == 0 && (k & 3) == 0, "linear_wgrad: M %d n %d k %d", M, n, k);
   RR_TRY(check_mat("dZ", dZ, lddz));
   RR_TRY(check_mat("X", X, ldx));

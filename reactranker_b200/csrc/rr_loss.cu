@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(kLossThreads) k_pointwise(int kind, int N, con
 
 int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int* seg_off, float norm, float sigma,
                 float* loss, float* dscore, cudaStream_t s) {
+  ProfScope prof_scope(KC_LOSS, s);
   RR_REQUIRE(N > 0 && scores && targets && loss && dscore, "loss: NULL argument or N <= 0");
   RR_REQUIRE(norm > 0.f, "loss: norm must be positive (got %g)", norm);
   RR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));

@@ -325,6 +325,7 @@ static void atom_launch_dims(int n_atoms, int ld, dim3* grid, dim3* block) {
 }
 
 int bond_message_fwd(const rr_graph* g, const float* m, float* pre, int hp, int relu_src, cudaStream_t s) {
+  ProfScope prof_scope(KC_BOND_FWD, s);
   RR_TRY(check_graph(g, hp));
   RR_REQUIRE(m && pre && aligned16(m) && aligned16(pre), "m/pre must be non-NULL and 16-byte aligned");
   dim3 grid, block;
@@ -342,6 +343,7 @@ static int zero_rows(float* base, const int* rows, int n, int ld, cudaStream_t s
 }
 
 int bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp, cudaStream_t s) {
+  ProfScope prof_scope(KC_BOND_BWD, s);
   RR_TRY(check_graph(g, hp));
   RR_REQUIRE(dpre && dm && aligned16(dpre) && aligned16(dm), "dpre/dm must be non-NULL and 16-byte aligned");
   RR_REQUIRE(g->pad_bonds && g->n_segments > 0, "graph needs pad_bonds/n_segments");
@@ -354,6 +356,7 @@ int bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp, cu
 }
 
 int neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out, int ld, int relu_src, cudaStream_t s) {
+  ProfScope prof_scope(KC_NBR_FWD, s);
   RR_TRY(check_graph(g, ld));
   RR_REQUIRE(src && out && aligned16(src) && aligned16(out), "src/out must be non-NULL and 16-byte aligned");
   dim3 grid, block;
@@ -364,6 +367,7 @@ int neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out,
 }
 
 int neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, cudaStream_t s) {
+  ProfScope prof_scope(KC_NBR_BWD, s);
   RR_TRY(check_graph(g, ld));
   RR_REQUIRE(dout && dsrc && aligned16(dout) && aligned16(dsrc), "dout/dsrc must be non-NULL and 16-byte aligned");
   RR_REQUIRE(g->pad_bonds && g->pad_atoms && g->n_segments > 0, "graph needs pad rows/n_segments");
@@ -383,6 +387,7 @@ int neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsr
 
 int readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const float* addf, int n_add, float* vec, int vp, float p,
                 uint64_t seed, uint64_t stream_id, cudaStream_t s) {
+  ProfScope prof_scope(KC_READOUT, s);
   RR_REQUIRE(g && g->n_mols > 0 && g->mol_start && g->mol_size, "graph has no molecule scope");
   RR_REQUIRE((hp & 3) == 0 && (vp & 3) == 0 && vp >= hidden + n_add && hidden <= hp, "readout widths hp %d vp %d hidden %d n_add %d", hp, vp, hidden, n_add);
   RR_REQUIRE(n_add == 0 || addf != nullptr, "add_features is NULL");
@@ -396,6 +401,7 @@ int readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const f
 }
 
 int readout_bwd(const rr_graph* g, const float* dvec, int vp, const float* vec, const float* hid, float* dz, int hp, float p, cudaStream_t s) {
+  ProfScope prof_scope(KC_READOUT, s);
   RR_REQUIRE(g && g->n_mols > 0 && g->mol_start && g->mol_size && g->pad_atoms, "graph has no molecule scope");
   RR_REQUIRE((hp & 3) == 0 && (vp & 3) == 0 && vp >= hp, "readout_bwd needs vp >= hp (vp %d hp %d)", vp, hp);
   RR_TRY(zero_rows(dz, g->pad_atoms, g->n_segments, hp, s));
@@ -408,6 +414,7 @@ int readout_bwd(const rr_graph* g, const float* dvec, int vp, const float* vec, 
 }
 
 int relu_bwd(long long rows, int ld, const float* dy, const float* y, float scale, int preact, float* dz, float* acc, int acc_mode, cudaStream_t s) {
+  ProfScope prof_scope(KC_ELEMENTWISE, s);
   RR_REQUIRE((ld & 3) == 0 && rows >= 0, "relu_bwd: ld %d must be a multiple of 4", ld);
   RR_REQUIRE(dy && y && (dz || acc_mode), "relu_bwd: NULL argument");
   RR_REQUIRE(acc_mode == 0 || acc != nullptr, "relu_bwd: acc is NULL");
@@ -421,6 +428,7 @@ int relu_bwd(long long rows, int ld, const float* dy, const float* y, float scal
 }
 
 int sub(long long n, const float* a, const float* b, float* out, cudaStream_t s) {
+  ProfScope prof_scope(KC_ELEMENTWISE, s);
   RR_REQUIRE((n & 3) == 0 && a && b && out, "sub: n %lld must be a multiple of 4", n);
   const long long n4 = n / 4;
   if (n4 == 0) return RR_OK;

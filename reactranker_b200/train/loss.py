@@ -38,11 +38,23 @@ def _to_dev(x, dev, dtype=torch.float32) -> torch.Tensor:
     return torch.as_tensor(np.asarray(x), dtype=dtype).pin_memory().to(dev, non_blocking=True)
 
 
+_SEG_CACHE: dict = {}
+
+
 def segment_offsets(scope: Sequence[int], dev) -> torch.Tensor:
-    """``scope`` (python list of group sizes, as the reference passes it) -> device prefix sums."""
+    """``scope`` (python list of group sizes, as the reference passes it) -> device prefix sums.
+    A few recent scopes are kept on the device so a repeated batch shape costs no copy."""
+    key = (tuple(scope), str(dev))
+    hit = _SEG_CACHE.get(key)
+    if hit is not None:
+        return hit
     off = np.zeros(len(scope) + 1, np.int32)
     np.cumsum(np.asarray(scope, np.int64), out=off[1:])
-    return torch.from_numpy(off).pin_memory().to(dev, non_blocking=True)
+    t = torch.from_numpy(off).pin_memory().to(dev, non_blocking=True)
+    if len(_SEG_CACHE) >= 64:
+        _SEG_CACHE.pop(next(iter(_SEG_CACHE)))
+    _SEG_CACHE[key] = t
+    return t
 
 
 class _LossFn(torch.autograd.Function):
@@ -79,29 +91,42 @@ def _segmented(kind, scores, scope, targets, gpu, norm, out_shape, sigma=1.0, ch
     return _LossFn.apply(scores.float(), t, seg, kind, n_items, len(scope), norm, sigma, out_shape)
 
 
-class MLEloss(nn.Module):
+class _DPNorm(nn.Module):
+    """Data-parallel hook: when reaction groups are sharded over ranks, every rank divides by the GLOBAL
+    normaliser (groups / items of the whole batch) and the gradients are SUM-all-reduced, which
+    reproduces the single-device loss exactly.  ``global_norm=None`` = single device."""
+
+    def __init__(self, global_norm=None):
+        super().__init__()
+        self.global_norm = global_norm
+
+    def _norm(self, local):
+        return local if self.global_norm is None else self.global_norm
+
+
+class MLEloss(_DPNorm):
     """ListMLE (loss.py:64-99 with LogCumsumExp 9-61): per group, sort by target descending,
     ``mean(logcumsumexp_tail(x) - x)``; then the mean over groups.  Returns shape [1]."""
 
     def forward(self, score, scope, targets_train, gpu: int):
-        return _segmented(_lib.LOSS_LISTMLE, score, scope, targets_train, gpu, norm=len(scope), out_shape=(1,), check_max=True)
+        return _segmented(_lib.LOSS_LISTMLE, score, scope, targets_train, gpu, norm=self._norm(len(scope)), out_shape=(1,), check_max=True)
 
 
-class ListnetLoss(nn.Module):
+class ListnetLoss(_DPNorm):
     """ListNet top-1 (loss.py:317-352): ``mean over all items`` of ``-softmax(t) * log softmax(s)``."""
 
     def forward(self, score, scope, targets, gpu: int):
-        return _segmented(_lib.LOSS_LISTNET, score, scope, targets, gpu, norm=int(sum(scope)), out_shape=())
+        return _segmented(_lib.LOSS_LISTNET, score, scope, targets, gpu, norm=self._norm(int(sum(scope))), out_shape=())
 
 
-class evidential_ranking(nn.Module):
+class evidential_ranking(_DPNorm):
     """UC-Listwise (loss.py:477-556, live branch 526-554).  ``max_coeff, epoch, epochs`` are
     accepted and unused, as in the reference.  Returns shape [1]."""
 
     def forward(self, possibilities, scope, targets, max_coeff, epoch, epochs, gpu: int):
         if possibilities.dim() != 2 or possibilities.shape[1] != 2:
             raise _lib.RRError("evidential_ranking expects model outputs of shape [N, 2] (score, variance)")
-        return _segmented(_lib.LOSS_EVIDENTIAL, possibilities, scope, targets, gpu, norm=len(scope), out_shape=(1,))
+        return _segmented(_lib.LOSS_EVIDENTIAL, possibilities, scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,))
 
 
 class _GaussFn(torch.autograd.Function):

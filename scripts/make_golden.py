@@ -24,7 +24,7 @@ os.makedirs(OUT, exist_ok=True)
 
 
 def np_sd(sd):
-    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+    return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}   # copy: Adam updates in place
 
 
 def build_ref_model(hidden, task_num, ffn_last_layer, task_type, seed, depth=3, diff_depth=3, dropout=0.0, dtype=torch.float32):
@@ -282,8 +282,7 @@ def golden_steps():
 
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
-    golden_batching()
-    golden_planner()
-    golden_model()
-    golden_ranknet()
-    golden_steps()
+    only = sys.argv[1:]
+    for fn in (golden_batching, golden_planner, golden_model, golden_ranknet, golden_steps):
+        if not only or fn.__name__[len("golden_"):] in only:
+            fn()

@@ -156,3 +156,46 @@ def test_state_dict_keys_and_init_match_reference_golden(golden):
     assert set(sd) == set(want) and len(sd) == 20
     for k, v in want.items():
         assert np.array_equal(sd[k].numpy(), v), k
+
+
+def test_planner_bit_exact_vs_reference_golden(golden):
+    """DataProcessor.generate_batch_reactions / generate_batch_per_query reproduce the row order and
+    scope the reference produced (incl. the truncating `sample(n=idx)` branch) for several seeds."""
+    from reactranker_b200.data.load_reactions import DataProcessor
+    g = golden("planner")
+    ds = synthetic.make_dataset(int(g["seed"]), [int(x) for x in g["sizes"]], atoms_lo=3, atoms_hi=4)
+    df = ds.to_dataframe()
+    row_of = {p: i for i, p in enumerate(ds.psmi)}
+    dp = DataProcessor(df)
+    for bs in (50, 24, 64):
+        for seed in (0, 1, 5):
+            rows, scopes, steps = [], [], []
+            for smiles, targets, scope, feats in dp.generate_batch_reactions(
+                    smiles_list=["rsmi_mapped", "psmi_mapped"], target_name="lgk", batch_size=bs, seed=seed, add_features_name="temp"):
+                ids = [row_of[s[1]] for s in smiles]
+                assert targets.shape == (len(ids), 1) and feats.shape == (len(ids), 1)
+                assert np.array_equal(targets[:, 0], ds.lgk[ids]) and np.array_equal(feats[:, 0], ds.temp[ids])
+                rows += ids
+                scopes += list(scope)
+                steps.append((len(ids), len(scope)))
+            key = f"reactions.bs{bs}.seed{seed}."
+            assert np.array_equal(rows, g[key + "rows"]) and np.array_equal(scopes, g[key + "scope"])
+            assert np.array_equal(np.asarray(steps), g[key + "steps"])
+    for seed in (0, 3):
+        rows, lens = [], []
+        for smiles, targets, feats in dp.generate_batch_per_query(smiles_list=["rsmi_mapped", "psmi_mapped"], target_name="lgk",
+                                                                  seed=seed, add_features_name="temp"):
+            ids = [row_of[s[1]] for s in smiles]
+            assert np.array_equal(feats[:, 0], ds.lgk[ids])        # the target-column leak is preserved
+            rows += ids
+            lens.append(len(ids))
+        assert np.array_equal(rows, g[f"per_query.seed{seed}.rows"]) and np.array_equal(lens, g[f"per_query.seed{seed}.lens"])
+
+
+def test_parsing_features_builds_reference_batches():
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(8, [3, 2])
+    fz = Parsing_features(ds.mols)
+    r, p = fz.parsing_reactions(np.stack([ds.rsmi, ds.psmi], 1))
+    assert r.n_mols == p.n_mols == 5 and r.n_atoms == p.n_atoms
+    assert fz.parsing_reactions(None) == [None, None] and fz.parsing_smiles(None) is None
