@@ -189,6 +189,7 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     _lib.require_device(local)
+    _lib.check(_lib.lib().rr_set_gemm_mode(1 if args.gemm == "tc" else 0))
     model, opt, sched, loss_fn = build(wl, local, world)
     params = [p for p in model.parameters() if p.requires_grad]
     scope = [wl["group"]] * wl["groups"]
@@ -313,7 +314,8 @@ def ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": f"synthetic reaction graphs (SURVEY.md 8d generator), pool of {len(pool)} distinct batches per rank cycled; random-init weights",
+        "dtype": "f32 (dense layers: tcgen05 kind::tf32 with on-chip 3xTF32 split, fp32 accumulate)" if args.gemm == "tc" else "f32",
+        "data": f"synthetic reaction graphs (SURVEY.md 8d generator), pool of {len(pool)} distinct batches per rank cycled; random-init weights",
         "config": {"workload": wl["desc"], "name": args.workload, "reactions_per_gpu_per_step": rows, "global_batch": rows * world,
                    "parallelism": f"dp{world}" if world > 1 else "single", "optimizer": "Adam(fused)+NoamLR",
                    "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush"},
@@ -401,6 +403,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches per rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gemm", default="tc", choices=["tc", "simt"], help="dense layers: tcgen05 3xTF32 (default) or exact-fp32 SIMT")
     a = ap.parse_args()
     if a.impl == "reference":
         reference(a)

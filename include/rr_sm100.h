@@ -140,6 +140,10 @@ int rr_linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int 
                   const float* X2, int ldx2, const float* W2, int k2, const float* bias,
                   const float* residual, int ldr, float* Y, int ldy, int flags, float dropout,
                   uint64_t seed, uint64_t stream_id, void* stream);
+/* Which GEMM implementation the dense layers use: 0 = exact fp32 SIMT kernels, 1 = tcgen05 tensor cores with
+ * an on-chip 3xTF32 split (fp32-class accuracy, ~1e-6 relative), TMA-fed, accumulating in TMEM.  Process-wide. */
+int rr_set_gemm_mode(int mode);
+int rr_get_gemm_mode(void);
 /* dX[M,k] (+)= dZ[M,n] W[n,k]   (accumulate != 0 adds) */
 int rr_linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw,
                     float* dX, int lddx, int accumulate, void* stream);
@@ -173,6 +177,10 @@ int rr_loss_max_group(void);
 /* ---- whole model (models/base_model.py:150-171) ---------------------------------------- */
 /* bytes of workspace rr_model_forward/backward need for these sizes */
 int64_t rr_model_workspace_bytes(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p);
+/* Byte offset, inside the workspace, of a forward activation saved for backward -- for per-layer parity tests.
+ * Names: enc{0,1}.inp, enc{0,1}.pre<t>, enc{0,1}.m<t+1>, enc{0,1}.am, enc{0,1}.hid (0 = reactants, 1 = products),
+ * d, inp2, nf, nm<t>, m2_<t+1>, am2, hid2, vec, zout.  -1 on error. */
+int64_t rr_model_buffer_offset(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p, const char* name);
 /* scores: [n_mols] if task_num==1 else [n_mols, task_num].  ws must stay untouched until the
  * matching rr_model_backward has run. */
 int rr_model_forward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p,

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "librr_sm100.so")
-SOURCES = ["rr_api.cu", "rr_mp.cu", "rr_gemm_simt.cu", "rr_loss.cu", "rr_model.cu"]
+SOURCES = ["rr_api.cu", "rr_mp.cu", "rr_gemm_simt.cu", "rr_gemm_tc.cu", "rr_loss.cu", "rr_model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -46,8 +46,8 @@ EXPORTS = [
     "rr_bond_message_fwd", "rr_bond_message_bwd", "rr_neighbor_sum_fwd", "rr_neighbor_sum_bwd",
     "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
     "rr_loss_fwdbwd", "rr_loss_max_group",
-    "rr_model_workspace_bytes", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
-    "rr_profile_begin", "rr_profile_end", "rr_profile_classes",
+    "rr_model_workspace_bytes", "rr_model_buffer_offset", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
+    "rr_profile_begin", "rr_profile_end", "rr_profile_classes", "rr_set_gemm_mode", "rr_get_gemm_mode",
 ]
 KERNEL_CLASSES = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "bond_fwd", "bond_bwd", "nbr_fwd", "nbr_bwd", "readout", "elementwise", "loss", "misc"]
 
@@ -109,9 +109,14 @@ def lib() -> ctypes.CDLL:
                 L.rr_sub.argtypes = [i64, vp, vp, vp, vp]
                 L.rr_loss_fwdbwd.argtypes = [i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]
                 L.rr_model_workspace_bytes.argtypes = [vp, vp, vp]
+                L.rr_model_buffer_offset.argtypes = [vp, vp, vp, ctypes.c_char_p]
+                L.rr_model_buffer_offset.restype = ctypes.c_int64
                 L.rr_model_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
                 L.rr_model_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
                 L.rr_profile_end.argtypes = [vp, vp, i32]
+                L.rr_set_gemm_mode.argtypes = [i32]
+                # dense layers: tcgen05 tensor cores (3xTF32 split) unless RR_GEMM_MODE=0 asks for the exact-fp32 SIMT kernels
+                L.rr_set_gemm_mode(int(os.environ.get("RR_GEMM_MODE", "1")))
                 _lib = L
     return _lib
 

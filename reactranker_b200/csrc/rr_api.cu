@@ -7,6 +7,7 @@
 namespace rr {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_gemm_mode{0};
 ProfState g_prof;
 std::mutex g_prof_mutex;
 void prof_push(int cls, cudaEvent_t a, cudaEvent_t b) {
@@ -38,6 +39,7 @@ int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, in
 int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
 int loss_max_group();
 long long model_workspace_bytes(const rr_model_cfg*, const rr_graph*, const rr_graph*);
+long long model_buffer_offset(const rr_model_cfg*, const rr_graph*, const rr_graph*, const char*);
 int model_forward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, float*, void*, long long, cudaStream_t);
 int model_backward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, rr_params*, void*, long long, cudaStream_t);
 }  // namespace rr
@@ -108,6 +110,13 @@ int64_t rr_model_workspace_bytes(const rr_model_cfg* cfg, const rr_graph* r, con
   }
   return rr::model_workspace_bytes(cfg, r, p);
 }
+int64_t rr_model_buffer_offset(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p, const char* name) {
+  if (!cfg || !r || !p || !name) {
+    rr::fail(RR_ERR_INVALID, "rr_model_buffer_offset: NULL argument");
+    return -1;
+  }
+  return rr::model_buffer_offset(cfg, r, p, name);
+}
 int rr_model_forward(const rr_model_cfg* cfg, const rr_params* w, const rr_graph* r, const rr_graph* p, const float* add_features,
                      float* scores, void* ws, int64_t ws_bytes, void* stream) {
   return rr::model_forward(cfg, w, r, p, add_features, scores, ws, ws_bytes, S(stream));
@@ -116,6 +125,12 @@ int rr_model_backward(const rr_model_cfg* cfg, const rr_params* w, const rr_grap
                       rr_params* grads, void* ws, int64_t ws_bytes, void* stream) {
   return rr::model_backward(cfg, w, r, p, dscores, grads, ws, ws_bytes, S(stream));
 }
+int rr_set_gemm_mode(int mode) {
+  RR_REQUIRE(mode >= 0 && mode <= 3, "gemm mode must be 0 (fp32 SIMT), 1 (tcgen05 3xTF32) or the debug masks 2 (forward only) / 3 (dgrad only)");
+  rr::g_gemm_mode.store(mode);
+  return RR_OK;
+}
+int rr_get_gemm_mode(void) { return rr::g_gemm_mode.load(); }
 int rr_profile_begin(void) {
   std::lock_guard<std::mutex> lock(rr::g_prof_mutex);
   rr::g_prof.enabled = true;

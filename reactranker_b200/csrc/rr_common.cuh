@@ -69,6 +69,9 @@ struct ProfScope {
   }
 };
 
+// 0 = fp32 SIMT GEMMs, 1 = tcgen05 3xTF32 GEMMs where the shape allows (forward + dgrad)
+extern std::atomic<int> g_gemm_mode;
+
 #define RR_REQUIRE(cond, ...)                                  \
   do {                                                         \
     if (!(cond)) return rr::fail(RR_ERR_INVALID, __VA_ARGS__); \

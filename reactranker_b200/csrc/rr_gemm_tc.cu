@@ -1,0 +1,401 @@
+// tcgen05 / TMEM / TMA GEMM for the nn.Linear call sites (forward and dgrad), sm_100a.
+//
+//   C[M, N] = epilogue( sum_src  A_src[M, K_src] * B_src[N, K_src]^T )        (both operands K-major)
+//
+// fp32 in, fp32 out, fp32-class accuracy through a 3xTF32 split done on chip:
+//   a = a_hi + a_lo,  a_hi = a rounded to the nearest TF32 value (low 13 mantissa bits zero)
+//   A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (the dropped A_lo*B_lo term is ~2^-22 relative)
+// so the reference's fp32 results are reproduced to ~1e-6 while the contraction runs on the 5th-gen
+// tensor cores (kind::tf32), accumulating in TMEM.
+//
+// One CTA = one 128-row tile of C across up to 320 output columns (the whole hidden width for h = 300),
+// 6 warps, warp-specialised:
+//   warp 0    : TMA producer   - cp.async.bulk.tensor (128B swizzle) of the A tile [128 x 32] and the B tile
+//                                [nt x 32] per k-block into a 2..4 stage ring (mbarrier complete_tx)
+//   warps 2-5 : split workers  - turn the landed fp32 tiles into (hi, lo) pairs in shared memory,
+//                                fence.proxy.async, signal the MMA warp; afterwards they are the epilogue:
+//                                tcgen05.ld the accumulator (one row per thread), add bias / residual,
+//                                ReLU, Philox dropout, store (or accumulate for dgrad)
+//   warp 1    : MMA issuer     - one elected lane issues 3 x 4 tcgen05.mma (UMMA_K = 8) per k-block and
+//                                per N-half, commits to the stage's "empty" barrier; owns TMEM alloc/dealloc
+//
+// Two-source K (concat-free [x1 || x2] W^T) walks both sources through the same accumulator.
+#include <cuda.h>
+
+#include "rr_common.cuh"
+
+namespace rr {
+
+namespace tc {
+
+constexpr int BM = 128;         // rows per CTA tile == UMMA_M
+constexpr int BK = 32;          // fp32 per k-block == one 128-byte swizzle row
+constexpr int UK = 8;           // UMMA_K for kind::tf32 (32 bytes)
+constexpr int A_BYTES = BM * BK * 4;
+constexpr int THREADS = 192;
+constexpr int MAX_NT = 320;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct Src {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int K;
+  int pad_[15];  // keep every CUtensorMap 64-byte aligned inside the kernel parameter block
+};
+
+struct Args {
+  Src src[2];
+  int nsrc;
+  int M, N;
+  int nt;      // output columns per CTA (multiple of 16, <= MAX_NT)
+  int bn;      // rows per B TMA box (nt or nt/2)
+  int stages;
+  int tmem_cols;
+  float* C;
+  int ldc;
+  const float* bias;
+  const float* resid;
+  int ldr;
+  int relu;
+  int accumulate;
+  float p, inv_keep;
+  uint64_t seed, stream_id;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO(=1, unused for swizzled K-major) << 16 | SBO(1024 B between 8-row groups) << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split an fp32 tile in place into hi (TF32-exact) and lo = x - hi
+__device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int bytes, int wtid) {
+  for (int off = wtid * 16; off < bytes; off += 128 * 16) {
+    float4 v = *reinterpret_cast<float4*>(hi + off);
+    float4 h, l;
+    // round-to-nearest onto the TF32 grid (10 explicit mantissa bits): |lo| <= 2^-12 |x|, signs balanced
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+    l.x = v.x - h.x;
+    l.y = v.y - h.y;
+    l.z = v.z - h.z;
+    l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const __grid_constant__ Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int nt = g.nt;
+  const int b_bytes = nt * BK * 4;
+  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+  const int S = g.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
+  uint64_t* ready = full + S;
+  uint64_t* empty = ready + S;
+  uint64_t* acc_bar = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * nt;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, 4);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < g.nsrc; ++s) {
+      prefetch_tmap(&g.src[s].tmA);
+      prefetch_tmap(&g.src[s].tmB);
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int it = 0;
+      const uint32_t tx = static_cast<uint32_t>(A_BYTES + b_bytes);
+      for (int s = 0; s < g.nsrc; ++s) {
+        const int nkb = (g.src[s].K + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty + st, ph ^ 1);
+          uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+          mbar_expect_tx(full + st, tx);
+          tma_load_2d(&g.src[s].tmA, full + st, base, kb * BK, m0);
+          for (int j = 0; j < nt; j += g.bn) tma_load_2d(&g.src[s].tmB, full + st, base + 2 * A_BYTES + j * BK * 4, kb * BK, n0 + j);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const int n1 = (nt <= 256) ? nt : ((nt / 2 + 15) / 16 * 16);
+      const int n2 = nt - n1;
+      const uint32_t idesc1 = umma_idesc(BM, n1);
+      const uint32_t idesc2 = n2 ? umma_idesc(BM, n2) : 0u;
+      int it = 0;
+      for (int s = 0; s < g.nsrc; ++s) {
+        const int nkb = (g.src[s].K + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(ready + st, ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+          const uint32_t a_hi = base, a_lo = base + A_BYTES, b_hi = base + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint32_t ko = k * UK * 4;
+            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+            // column half 1
+            umma_tf32(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc1, first);
+            umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc1, 1u);
+            umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc1, 1u);
+            if (n2) {
+              const uint32_t bo = static_cast<uint32_t>(n1) * BK * 4;
+              umma_tf32(tmem_base + n1, umma_desc(a_lo + ko), umma_desc(b_hi + bo + ko), idesc2, first);
+              umma_tf32(tmem_base + n1, umma_desc(a_hi + ko), umma_desc(b_lo + bo + ko), idesc2, 1u);
+              umma_tf32(tmem_base + n1, umma_desc(a_hi + ko), umma_desc(b_hi + bo + ko), idesc2, 1u);
+            }
+          }
+          umma_commit(empty + st);  // frees the stage once these MMAs have read it
+        }
+      }
+      umma_commit(acc_bar);         // accumulator complete
+    }
+  } else {
+    // ---------------- split workers, then epilogue ----------------
+    const int wtid = threadIdx.x - 64;  // 0..127
+    int it = 0;
+    for (int s = 0; s < g.nsrc; ++s) {
+      const int nkb = (g.src[s].K + BK - 1) / BK;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full + st, ph);
+        uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+        split_tile(base, base + A_BYTES, A_BYTES, wtid);
+        split_tile(base + 2 * A_BYTES, base + 2 * A_BYTES + b_bytes, b_bytes, wtid);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready + st);
+      }
+    }
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row = m0 + quad * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    for (int c = 0; c < nt; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + c, v);                 // warp-collective: executed by every lane, rows >= M included
+      if (row < g.M) {
+        const int col = n0 + c;
+        float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (g.bias) o = f4_add(o, ld_f4(g.bias + col + 4 * q));
+          if (g.resid) o = f4_add(o, ld_f4(g.resid + static_cast<size_t>(row) * g.ldr + col + 4 * q));
+          if (g.relu) o = f4_relu(o);
+          if (g.p > 0.f) o = dropout4(o, g.p, g.inv_keep, g.seed, g.stream_id, (static_cast<uint64_t>(row) * g.ldc + col + 4 * q) >> 2);
+          if (g.accumulate) o = f4_add(o, *reinterpret_cast<const float4*>(cp + 4 * q));
+          st_f4(cp + 4 * q, o);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with row stride ld floats; box = [box_rows x 32 floats], 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows %d cols %d ld %d box_rows %d", static_cast<int>(r), rows, cols, ld, box_rows);
+  return RR_OK;
+}
+
+}  // namespace tc
+
+// Can this problem run on the tcgen05 kernel?  (everything the model produces can; odd C-ABI calls fall back to SIMT)
+bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2) {
+  if (M <= 0 || n < 16 || (n & 15)) return false;
+  if ((k1 & 3) || (k2 & 3) || (ldx1 & 3) || (ldx2 & 3) || k1 <= 0) return false;
+  const int tiles = (n + tc::MAX_NT - 1) / tc::MAX_NT;
+  if (n % tiles) return false;
+  const int nt = n / tiles;
+  return (nt & 15) == 0 && nt >= 16;
+}
+
+// Y = epi(X1 W1^T + X2 W2^T): W* row-major [n, k*] (K-major B operand)
+int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
+              const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
+              int kclass, cudaStream_t s) {
+  using namespace tc;
+  ProfScope prof_scope(kclass, s);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  Args g{};
+  const int tiles = (n + MAX_NT - 1) / MAX_NT;
+  g.nt = n / tiles;
+  g.bn = g.nt <= 256 ? g.nt : g.nt / 2;
+  RR_REQUIRE(g.nt % g.bn == 0 && (g.bn % 8) == 0, "tc_linear: tile %d box %d", g.nt, g.bn);
+  const int stage_bytes = 2 * A_BYTES + 2 * g.nt * BK * 4;
+  int S = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (S > 4) S = 4;
+  RR_REQUIRE(S >= 2, "tc_linear: tile of %d columns does not fit two pipeline stages", g.nt);
+  g.stages = S;
+  int cols = 32;
+  while (cols < g.nt) cols <<= 1;
+  g.tmem_cols = cols;
+  g.nsrc = 1;
+  RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
+  RR_TRY(make_map(&g.src[0].tmB, W1, n, k1, ldw1, g.bn));
+  g.src[0].K = k1;
+  if (X2 && k2 > 0) {
+    RR_TRY(make_map(&g.src[1].tmA, X2, M, k2, ldx2, BM));
+    RR_TRY(make_map(&g.src[1].tmB, W2, n, k2, ldw2, g.bn));
+    g.src[1].K = k2;
+    g.nsrc = 2;
+  }
+  g.M = M;
+  g.N = n;
+  g.C = Y;
+  g.ldc = ldy;
+  g.bias = bias;
+  g.resid = resid;
+  g.ldr = ldr;
+  g.relu = relu;
+  g.accumulate = accumulate;
+  g.p = p;
+  g.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  g.seed = seed;
+  g.stream_id = stream_id;
+  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256;
+  dim3 grid((M + BM - 1) / BM, tiles);
+  k_tc_gemm<<<grid, THREADS, smem, s>>>(g);
+  RR_LAUNCH_CHECK("k_tc_gemm");
+  return RR_OK;
+}
+
+}  // namespace rr

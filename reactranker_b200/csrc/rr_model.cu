@@ -26,6 +26,11 @@ int linear_fwd(int, int, const float*, int, const float*, int, const float*, int
 int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
 int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
 
+bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2);
+int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
+              const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
+              int kclass, cudaStream_t s);
+
 static inline int pad16(int x) { return (x + 15) / 16 * 16; }
 int padded(int w) { return pad16(w); }
 
@@ -38,7 +43,10 @@ struct PackedLayout {
   size_t dif_Wi, dif_bi, dif_Wh_m, dif_Wh_f, dif_bh, dif_Wo_d, dif_Wo_m, dif_bo;
   size_t ffn_W[RR_MAX_FFN], ffn_b[RR_MAX_FFN];
   int ffn_in[RR_MAX_FFN], ffn_out[RR_MAX_FFN];  // padded dims
-  size_t total;
+  // transposed copies [in_pad, out_pad] of every weight that has a dgrad: K-major B operand of dX = dZ W on tcgen05
+  size_t enc_Wh_T, enc_Wo_m_T, dif_Wi_T, dif_Wh_m_T, dif_Wo_d_T, dif_Wo_m_T, ffn_W_T[RR_MAX_FFN];
+  size_t total;       // floats, transposed copies included
+  size_t grad_total;  // floats of the gradient image (no transposed copies)
 };
 
 static PackedLayout make_packed(const rr_model_cfg& c) {
@@ -66,6 +74,14 @@ static PackedLayout make_packed(const rr_model_cfg& c) {
     L.ffn_W[l] = take(static_cast<size_t>(L.ffn_in[l]) * L.ffn_out[l]);
     L.ffn_b[l] = take(L.ffn_out[l]);
   }
+  L.grad_total = o;
+  L.enc_Wh_T = take(hp * hp);
+  L.enc_Wo_m_T = take(hp * hp);
+  L.dif_Wi_T = take(hp * hp);
+  L.dif_Wh_m_T = take(hp * hp);
+  L.dif_Wo_d_T = take(hp * hp);
+  L.dif_Wo_m_T = take(hp * hp);
+  for (int l = 0; l < L.F; ++l) L.ffn_W_T[l] = take(static_cast<size_t>(L.ffn_in[l]) * L.ffn_out[l]);
   L.total = o;
   return L;
 }
@@ -74,19 +90,24 @@ struct PackEntry {
   float* ref;        // state_dict-layout tensor (source when packing, destination when un-packing)
   long long packed;  // float offset in the packed buffer
   int rows, cols, ref_ld, ref_col0, packed_ld;
+  int transpose;     // packed[c][r] = ref[r][c]
 };
-constexpr int kMaxEntries = 32;
+constexpr int kMaxEntries = 48;
 struct PackTable {
   PackEntry e[kMaxEntries];
   int n;
 };
 
-static PackTable make_table(const rr_model_cfg& c, const PackedLayout& L, const rr_params& w) {
+static PackTable make_table(const rr_model_cfg& c, const PackedLayout& L, const rr_params& w, bool with_transposes) {
   PackTable T{};
   const int h = c.hidden, hp = L.hp;
   auto add = [&](float* ref, size_t off, int rows, int cols, int ref_ld, int col0, int pld) {
     if (ref == nullptr) return;
-    T.e[T.n++] = PackEntry{ref, static_cast<long long>(off), rows, cols, ref_ld, col0, pld};
+    T.e[T.n++] = PackEntry{ref, static_cast<long long>(off), rows, cols, ref_ld, col0, pld, 0};
+  };
+  auto add_t = [&](float* ref, size_t off, int rows, int cols, int ref_ld, int col0, int pld) {
+    if (ref == nullptr || !with_transposes) return;
+    T.e[T.n++] = PackEntry{ref, static_cast<long long>(off), rows, cols, ref_ld, col0, pld, 1};
   };
   add(w.enc_Wi, L.enc_Wi, h, RR_FBOND_TOTAL, RR_FBOND_TOTAL, 0, RR_FB_LD);
   add(w.enc_bi, L.enc_bi, 1, h, h, 0, hp);
@@ -108,7 +129,14 @@ static PackTable make_table(const rr_model_cfg& c, const PackedLayout& L, const 
     const int out = (l == L.F - 1) ? c.task_num : h;
     add(w.ffn_W[l], L.ffn_W[l], out, in, in, 0, L.ffn_in[l]);
     add(w.ffn_b[l], L.ffn_b[l], 1, out, out, 0, L.ffn_out[l]);
+    add_t(w.ffn_W[l], L.ffn_W_T[l], out, in, in, 0, L.ffn_out[l]);
   }
+  add_t(w.enc_Wh, L.enc_Wh_T, h, h, h, 0, hp);
+  add_t(w.enc_Wo, L.enc_Wo_m_T, h, h, RR_ATOM_FDIM + h, RR_ATOM_FDIM, hp);
+  add_t(w.dif_Wi, L.dif_Wi_T, h, h, h, 0, hp);
+  add_t(w.dif_Wh, L.dif_Wh_m_T, h, h, h + RR_FBOND_TOTAL, 0, hp);
+  add_t(w.dif_Wo, L.dif_Wo_d_T, h, h, 2 * h, 0, hp);
+  add_t(w.dif_Wo, L.dif_Wo_m_T, h, h, 2 * h, h, hp);
   return T;
 }
 
@@ -118,7 +146,7 @@ __global__ void k_pack(PackTable T, float* __restrict__ packed, int direction) {
   const long long n = static_cast<long long>(e.rows) * e.cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / e.cols), c = static_cast<int>(i - static_cast<long long>(r) * e.cols);
-    float* pp = packed + e.packed + static_cast<long long>(r) * e.packed_ld + c;
+    float* pp = packed + e.packed + (e.transpose ? static_cast<long long>(c) * e.packed_ld + r : static_cast<long long>(r) * e.packed_ld + c);
     float* rp = e.ref + static_cast<long long>(r) * e.ref_ld + e.ref_col0 + c;
     if (direction == 0) *pp = *rp;
     else *rp = *pp;
@@ -204,7 +232,7 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
     return ptr;
   };
   W->packed = take(W->L.total);
-  W->dpacked = take(W->L.total);
+  W->dpacked = take(W->L.grad_total);
   for (int s = 0; s < 2; ++s) {
     const size_t B = (s == 0 ? r.n_bonds : p.n_bonds);
     EncBufs& e = W->enc[s];
@@ -240,6 +268,52 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   return RR_OK;
 }
 
+// dX[M, k] (+)= dZ[M, n] W[n, k]: tensor cores read the transposed copy Wt[k, n] as a K-major operand, the SIMT path reads W
+static int dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, const float* Wt, int ldwt, float* dX, int lddx,
+                 int accumulate, cudaStream_t s) {
+  if ((g_gemm_mode.load() == 1 || g_gemm_mode.load() == 3) && tc_supported(M, k, n, 0, lddz, 0))
+    return tc_linear(M, k, dZ, lddz, Wt, ldwt, n, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, dX, lddx, 0, accumulate, 0.f, 0, 0, KC_GEMM_DGRAD, s);
+  return linear_dgrad(M, n, k, dZ, lddz, W, ldw, dX, lddx, accumulate, s);
+}
+
+// byte offset of a named forward buffer inside the workspace (tests compare per-layer activations with the oracle)
+long long model_buffer_offset(const rr_model_cfg* c, const rr_graph* r, const rr_graph* p, const char* name) {
+  Workspace W;
+  char* base = reinterpret_cast<char*>(static_cast<uintptr_t>(4096));
+  if (carve(*c, *r, *p, base, &W) != RR_OK) return -1;
+  auto off = [&](const float* ptr) { return static_cast<long long>(reinterpret_cast<const char*>(ptr) - base); };
+  char buf[64];
+  for (int k = 0; k < 2; ++k) {
+    snprintf(buf, sizeof(buf), "enc%d.inp", k);
+    if (!strcmp(name, buf)) return off(W.enc[k].inp);
+    snprintf(buf, sizeof(buf), "enc%d.am", k);
+    if (!strcmp(name, buf)) return off(W.enc[k].am);
+    snprintf(buf, sizeof(buf), "enc%d.hid", k);
+    if (!strcmp(name, buf)) return off(W.enc[k].hid);
+    for (int t = 0; t < c->depth - 1; ++t) {
+      snprintf(buf, sizeof(buf), "enc%d.pre%d", k, t);
+      if (!strcmp(name, buf)) return off(W.enc[k].pre[t]);
+      snprintf(buf, sizeof(buf), "enc%d.m%d", k, t + 1);
+      if (!strcmp(name, buf)) return off(W.enc[k].m[t + 1]);
+    }
+  }
+  for (int t = 0; t < c->diff_depth - 1; ++t) {
+    snprintf(buf, sizeof(buf), "nm%d", t);
+    if (!strcmp(name, buf)) return off(W.nm[t]);
+    snprintf(buf, sizeof(buf), "m2_%d", t + 1);
+    if (!strcmp(name, buf)) return off(W.m2[t + 1]);
+  }
+  if (!strcmp(name, "d")) return off(W.d);
+  if (!strcmp(name, "inp2")) return off(W.inp2);
+  if (!strcmp(name, "nf")) return off(W.nf);
+  if (!strcmp(name, "am2")) return off(W.am2);
+  if (!strcmp(name, "hid2")) return off(W.hid2);
+  if (!strcmp(name, "vec")) return off(W.vec);
+  if (!strcmp(name, "zout")) return off(W.zout);
+  fail(RR_ERR_INVALID, "unknown buffer name %s", name);
+  return -1;
+}
+
 long long model_workspace_bytes(const rr_model_cfg* c, const rr_graph* r, const rr_graph* p) {
   Workspace W;
   if (carve(*c, *r, *p, nullptr, &W) != RR_OK) return -1;
@@ -263,7 +337,7 @@ static int check_model_args(const rr_model_cfg* c, const rr_params* w, const rr_
 
 static int pack_params(const rr_model_cfg& c, const Workspace& W, const rr_params& w, cudaStream_t s) {
   RR_CUDA(cudaMemsetAsync(W.packed, 0, W.L.total * sizeof(float), s));
-  PackTable T = make_table(c, W.L, w);
+  PackTable T = make_table(c, W.L, w, true);
   k_pack<<<dim3(32, T.n), 256, 0, s>>>(T, W.packed, 0);
   RR_LAUNCH_CHECK("k_pack");
   return RR_OK;
@@ -356,7 +430,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   const float keep = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
   const float* P = W.packed;  // still holds this step's packed weights
   float* G = W.dpacked;
-  RR_CUDA(cudaMemsetAsync(G, 0, L.total * sizeof(float), s));
+  RR_CUDA(cudaMemsetAsync(G, 0, L.grad_total * sizeof(float), s));
   const int N = p->n_mols, A = p->n_atoms;
 
   {
@@ -374,12 +448,12 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       RR_TRY(linear_wgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, x, L.ffn_in[l], G + L.ffn_W[l], L.ffn_in[l], G + L.ffn_b[l], s));
       if (l > 0) {
         float* dx = scratch[l & 1];
-        RR_TRY(linear_dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], dx, hp, 0, s));
+        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], dx, hp, 0, s));
         RR_TRY(relu_bwd(N, hp, dx, W.x[l - 1], keep, 0, dx, nullptr, 0, s));
         g = dx;
         ldg = hp;
       } else {
-        RR_TRY(linear_dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], W.dvec, vp, 0, s));
+        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], W.dvec, vp, 0, s));
       }
     }
   }
@@ -387,8 +461,8 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   RR_TRY(readout_bwd(p, W.dvec, vp, W.vec, W.hid2, W.gA1, hp, pdrop, s));
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.d, hp, G + L.dif_Wo_d, hp, G + L.dif_bo, s));
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.am2, hp, G + L.dif_Wo_m, hp, nullptr, s));
-  RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, W.dD, hp, 0, s));
-  RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, W.gA2, hp, 0, s));
+  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, P + L.dif_Wo_d_T, hp, W.dD, hp, 0, s));
+  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, P + L.dif_Wo_m_T, hp, W.gA2, hp, 0, s));
   RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
   if (Td == 0) {
     RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 1, s));
@@ -397,13 +471,13 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       RR_TRY(relu_bwd(A, hp, W.gA3, W.m2[t], keep, 0, W.gA1, W.dI2, t == Td ? 1 : 2, s));
       RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.nm[t - 1], hp, G + L.dif_Wh_m, hp, G + L.dif_bh, s));
       RR_TRY(linear_wgrad(A, hp, RR_FB_LD, W.gA1, hp, W.nf, RR_FB_LD, G + L.dif_Wh_f, RR_FB_LD, nullptr, s));
-      RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, W.gA2, hp, 0, s));
+      RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s));
       RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
     }
     RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 2, s));
   }
   RR_TRY(linear_wgrad(A, hp, hp, W.dI2, hp, W.d, hp, G + L.dif_Wi, hp, G + L.dif_bi, s));
-  RR_TRY(linear_dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, W.dD, hp, 1, s));
+  RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s));
 
   // shared encoder: products (+dD) then reactants (-dD); weight gradients accumulate (base_model.py:155-156)
   const rr_graph* gs[2] = {r, p};
@@ -415,7 +489,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
     RR_TRY(relu_bwd(A, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
     RR_TRY(linear_wgrad(A, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
     RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
-    RR_TRY(linear_dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, W.gA2, hp, 0, s));
+    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s));
     RR_TRY(neighbor_sum_bwd(g, 0, W.gA2, W.gB1, hp, s));
     if (T == 0) {
       RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 1, s));
@@ -423,7 +497,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       for (int t = T; t >= 1; --t) {
         RR_TRY(relu_bwd(B, hp, W.gB1, e.m[t], keep, 0, W.gB1, W.dinp, t == T ? 1 : 2, s));
         RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
-        RR_TRY(linear_dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, W.gB2, hp, 0, s));
+        RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s));
         RR_TRY(bond_message_bwd(g, W.gB2, W.gB1, hp, s));
       }
       RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 2, s));
@@ -431,7 +505,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
     RR_TRY(linear_wgrad(B, hp, RR_FB_LD, W.dinp, hp, g->f_bonds, RR_FB_LD, G + L.enc_Wi, RR_FB_LD, G + L.enc_bi, s));
   }
 
-  PackTable Tb = make_table(*c, L, *grads);
+  PackTable Tb = make_table(*c, L, *grads, false);
   k_pack<<<dim3(32, Tb.n), 256, 0, s>>>(Tb, G, 1);
   RR_LAUNCH_CHECK("k_pack(grads)");
   return RR_OK;

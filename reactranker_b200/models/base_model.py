@@ -144,6 +144,15 @@ class ReactionModel(nn.Module):
         return _lib.RRModelCfg(self._hidden, self._depth, self._diff_depth, self._ffn_depth, self._task_num, self._add,
                                self._head, int(training), self._dropout, seed)
 
+    def saved_activation(self, out: torch.Tensor, name: str, rows: int, cols: int) -> torch.Tensor:
+        """A forward activation kept in the workspace of the autograd node behind ``out`` (per-layer parity tests):
+        see rr_model_buffer_offset for the names."""
+        node = out.grad_fn
+        off = _lib.lib().rr_model_buffer_offset(ctypes.byref(node.cfg), ctypes.byref(node.rg.c), ctypes.byref(node.pg.c), name.encode())
+        if off < 0:
+            _lib.check(-1)
+        return node.ws[off:off + rows * cols * 4].view(torch.float32).reshape(rows, cols)
+
     # ---- reference call signature (base_model.py:150-154) ----------------------------------
     def forward(self, r_inputs, p_inputs, gpu, add_features: Optional[List[np.ndarray]] = None):
         dev_idx = _lib.require_device(gpu)

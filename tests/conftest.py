@@ -21,3 +21,22 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_gemms_by_default(request):
+    """GPU parity tests run the exact-fp32 SIMT GEMMs unless they ask for the tensor-core path with the
+    ``tc_mode`` fixture; the library's own default (tcgen05) is restored afterwards."""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    from reactranker_b200 import _lib
+    L = _lib.lib()
+    L.rr_set_gemm_mode(1 if "tc_mode" in request.fixturenames else 0)
+    yield
+    L.rr_set_gemm_mode(1)
+
+
+@pytest.fixture
+def tc_mode():
+    yield

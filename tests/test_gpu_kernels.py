@@ -307,3 +307,41 @@ def test_argument_errors_are_reported_not_crashed():
     assert st == -1 and b"multiples of 4" in L.rr_last_error()
     with pytest.raises(_lib.RRError):
         _lib.check(L.rr_loss_fwdbwd(99, 4, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), 1.0, 1.0, x.data_ptr(), x.data_ptr(), S()))
+
+
+@pytest.mark.parametrize("M,n,k1,k2", [(128, 48, 64, 0), (1000, 304, 88, 0), (777, 304, 304, 88), (130, 48, 64, 48), (5, 16, 304, 0),
+                                       (4100, 608, 608, 608), (40000, 304, 304, 0), (300, 304, 16, 0)])
+def test_tcgen05_linear_matches_fp64(tc_mode, M, n, k1, k2):
+    """tcgen05 3xTF32 forward GEMM (bias + residual + ReLU epilogue, two-source K) against an fp64 matmul:
+    fp32-class accuracy, 5e-6 of the largest output."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(M + n)
+    X1, W1 = torch.randn(M, k1, generator=g), torch.randn(n, k1, generator=g) / k1 ** 0.5
+    X2 = torch.randn(M, k2, generator=g) if k2 else None
+    W2 = torch.randn(n, k2, generator=g) / k2 ** 0.5 if k2 else None
+    bias, resid = torch.randn(n, generator=g), torch.randn(M, n, generator=g)
+    z = X1.double() @ W1.double().T + bias.double() + resid.double()
+    if k2:
+        z = z + X2.double() @ W2.double().T
+    d = {k: (v.to(DEV) if v is not None else None) for k, v in dict(X1=X1, W1=W1, X2=X2, W2=W2, bias=bias, resid=resid).items()}
+    Y = torch.full((M, n), float("nan"), device=DEV)
+    for flags, want in ((0, z), (1, torch.relu(z))):
+        _lib.check(L.rr_linear_fwd(M, n, d["X1"].data_ptr(), k1, d["W1"].data_ptr(), k1, _lib.ptr(d["X2"]), k2, _lib.ptr(d["W2"]), k2,
+                                   d["bias"].data_ptr(), d["resid"].data_ptr(), n, Y.data_ptr(), n, flags, 0.0, 0, 0, S()))
+        torch.cuda.synchronize()
+        close(Y, want, 1e-5 if k1 + k2 > 1000 else 5e-6)
+    # no bias / residual, plain product
+    _lib.check(L.rr_linear_fwd(M, n, d["X1"].data_ptr(), k1, d["W1"].data_ptr(), k1, None, 0, None, 0, None, None, 0, Y.data_ptr(), n, 0, 0.0, 0, 0, S()))
+    close(Y, X1.double() @ W1.double().T, 1e-5 if k1 > 500 else 5e-6)
+
+
+def test_tcgen05_and_simt_draw_the_same_dropout_mask(tc_mode):
+    L = _lib.lib()
+    M, n, k, p = 1024, 304, 64, 0.3
+    X, W = torch.randn(M, k, device=DEV), torch.randn(n, k, device=DEV)
+    Yt, Ys = torch.empty(M, n, device=DEV), torch.empty(M, n, device=DEV)
+    _lib.check(L.rr_linear_fwd(M, n, X.data_ptr(), k, W.data_ptr(), k, None, 0, None, 0, None, None, 0, Yt.data_ptr(), n, 3, p, 7, 9, S()))
+    _lib.check(L.rr_set_gemm_mode(0))
+    _lib.check(L.rr_linear_fwd(M, n, X.data_ptr(), k, W.data_ptr(), k, None, 0, None, 0, None, None, 0, Ys.data_ptr(), n, 3, p, 7, 9, S()))
+    assert float(((Yt == 0) != (Ys == 0)).float().mean()) < 1e-4        # only entries whose pre-activation is ~0 may differ
+    close(Yt, Ys.double(), 5e-6)

@@ -154,9 +154,13 @@ def test_three_optimizer_steps_vs_reference_golden(golden):
     # last bias under a shift-invariant loss) is amplified: the reference's own fp32 and fp64 runs differ by 1e-2 relative
     # there.  Weights are therefore held to: typical entry within 1e-6, no entry further than Adam's bound 2*sum(lr).
     lr_sum = float(np.sum(g["lrs"][:3]))
+    # ffn.ffn.4.bias / ffn.ffn.7.bias have an exactly-zero true gradient here (units are on or off for every row of a group and
+    # ListMLE is shift invariant: 1e-18 in the fp64 oracle), so their trajectory is pure rounding noise times Adam.
     for k, v in model.state_dict().items():
         d = np.abs(v.cpu().numpy() - g["sd3." + k])
-        assert float(np.median(d)) <= 1e-6 and float(d.max()) <= 2 * lr_sum, k
+        assert float(d.max()) <= 2 * lr_sum, k
+        if k not in ("ffn.ffn.4.bias", "ffn.ffn.7.bias"):
+            assert float(np.median(d)) <= 1e-6, k
 
 
 @pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5)])
@@ -238,3 +242,55 @@ def test_full_batch_properties_at_config2_size():
     loss.backward()
     assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
     assert float(loss) > 0
+
+
+@pytest.mark.parametrize("name", ["mle.h40", "evidential_ranking.h24d5", "mle.star.h40", "listnet.h40"])
+def test_tcgen05_path_vs_reference_golden(golden, tc_mode, name):
+    """Same parity bar with the dense layers on tcgen05 (3xTF32 split, fp32-class accuracy)."""
+    test_scores_loss_grads_vs_reference_golden(golden, name)
+
+
+@pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5), ("mle", 296, 3)])
+def test_tcgen05_path_vs_oracle(tc_mode, task, hidden, depth):
+    """Dense layers on tcgen05 (3xTF32 split): activations / scores carry ~5e-6 relative error (the tensor core truncates
+    its fp32 accumulator once per MMA).  Gradients are checked in two parts, because this network is ill-conditioned at
+    the ReLU kinks of its padding rows (one padding row collects the gradient of every padded neighbour slot of the batch):
+    perturbing the WEIGHTS of the fp64 oracle by 5e-6 relative moves some gradient tensors by 3e-2 through a single mask
+    flip.  (1) With the forward masks fixed (exact-fp32 forward, tensor-core dgrad: gemm mode 3) gradients match the fp64
+    oracle to 2e-4 like the SIMT path; (2) with everything on tensor cores the scores/loss match to 5e-5 / 1e-5 and each
+    gradient tensor to 5e-2 in relative L2 with a typical (median) entry error below 5e-4 of the tensor's maximum."""
+    ds = synthetic.make_dataset(77, [7, 5, 9, 4])
+    sizes = [7, 5, 9, 4]
+    torch.manual_seed(3)
+    model = make_model(hidden, task, depth, depth)
+    sd64 = {k: v.double().cpu() for k, v in model.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if "cached_zero" not in k}
+    full = dict(sd64)
+    full.update(params)
+    tn, tt = TASKS[task]
+    want = O.model_forward(full, O.OracleBatch([ds.mols[t] for t in ds.rsmi]), O.OracleBatch([ds.mols[t] for t in ds.psmi]),
+                           ds.temp.reshape(-1, 1), mpnn_depth=depth, mpnn_diff_depth=depth, head=O.resolve_task_type(tn, "with_softplus", tt))
+    targets = torch.tensor(ds.lgk.astype(np.float32))
+    wl = O.loss_for_task(task, want, sizes, targets.double())
+    wl.backward(torch.ones_like(wl))
+    wg = {k: v.grad.numpy() for k, v in params.items()}
+    r_g, p_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    L = _lib.lib()
+    for mode in (3, 1):
+        _lib.check(L.rr_set_gemm_mode(mode))
+        model.zero_grad()
+        out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+        loss = product_loss(task, out, sizes, targets)
+        loss.backward()
+        got = {k: p.grad.double().cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+        gscale = max(float(np.abs(v).max()) for v in wg.values())
+        live = {k: w for k, w in wg.items() if float(np.abs(w).max()) >= 1e-6 * gscale}   # drop structurally-zero gradients
+        if mode == 3:
+            assert not grads_close(got, live, 2e-4)
+            continue
+        assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < 5e-5
+        assert rel_err(loss.detach().cpu().numpy(), wl.detach().numpy()) < 1e-5
+        for k, w in live.items():
+            e = got[k] - w
+            assert float(np.linalg.norm(e) / np.linalg.norm(w)) < 5e-2, k
+            assert float(np.median(np.abs(e))) < 5e-4 * float(np.abs(w).max()), k
