@@ -179,6 +179,9 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
               const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
               int kclass, cudaStream_t s);
 
+bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);
+int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s);
+
 static int check_mat(const char* what, const void* p, int ld) {
   RR_REQUIRE(p != nullptr, "%s is NULL", what);
   RR_REQUIRE(aligned16(p) && (ld & 3) == 0, "%s must be 16-byte aligned with a row stride multiple of 4 (ld %d)", what, ld);
@@ -253,6 +256,8 @@ int linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W,
 }
 
 int linear_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s) {
+  if (g_gemm_mode.load() == 1 && M >= 256 && tc_wgrad_supported(M, n, k, lddz, ldx) && aligned16(dZ) && aligned16(X) && aligned16(dW) && (lddw & 3) == 0)
+    return tc_wgrad(M, n, k, dZ, lddz, X, ldx, dW, lddw, dbias, s);
   ProfScope prof_scope(KC_GEMM_WGRAD, s);
   RR_REQUIRE(M >= 0 && n > 0 && k > 0 && (n & 3) == 0 && (k & 3) == 0, "linear_wgrad: M %d n %d k %d", M, n, k);
   RR_TRY(check_mat("dZ", dZ, lddz));

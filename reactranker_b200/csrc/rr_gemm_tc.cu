@@ -301,6 +301,200 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const __grid_constant__ 
   }
 }
 
+
+// ================================================================================================
+// wgrad:  dW[n, k] += sum_m dZ[m, n] * X[m, k]      (+ dbias[n] += sum_m dZ[m, n])
+// The reduction runs over the ROWS of both operands, so both are MN-major for the tensor core:
+// a TMA box [32 rows m x 32 floats] lands as 32 rows of 128 bytes (128B swizzle) = one MN-atom column,
+// UMMA descriptors use LBO = bytes between 32-float column blocks, SBO = 512 (4 rows of the reduction, 32-byte-atom swizzle).
+// One CTA = 128 rows of dW (n) x up to 320 columns (k) x a slab of the m range; partial results are
+// added to dW with vector reductions (split over m like the SIMT kernel).
+// ================================================================================================
+constexpr int WG_BK = 32;                 // rows of the reduction per stage
+constexpr int WG_BOX = WG_BK * 128;       // bytes of one TMA box (32 rows x 128 B)
+constexpr int WG_A_BYTES = 4 * WG_BOX;    // 128 n-columns
+
+struct WgArgs {
+  CUtensorMap tmA;   // dZ [M, n]
+  CUtensorMap tmB;   // X  [M, k]
+  int M, n, k;
+  int kt;            // k columns per CTA (multiple of 16, <= 320)
+  int nb;            // TMA boxes of B per stage = ceil(kt / 32)
+  int stages;
+  int tmem_cols;
+  int m_chunk;       // rows of the reduction per blockIdx.z (multiple of WG_BK)
+  float* dW;
+  int lddw;
+  float* dbias;
+};
+
+// MN-major tf32 operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte atomicity
+// (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1, TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 4 reduction rows x 128 B,
+// so SBO = 512 B between 4-row groups and LBO = bytes between 32-float column blocks.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__ WgArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int b_bytes = g.nb * WG_BOX;
+  const int stage_bytes = 2 * WG_A_BYTES + 2 * b_bytes;
+  const int S = g.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
+  uint64_t* ready = full + S;
+  uint64_t* empty = ready + S;
+  uint64_t* acc_bar = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BM, k0 = blockIdx.y * g.kt;
+  const int m_beg = blockIdx.z * g.m_chunk;
+  const int m_end = min(g.M, m_beg + g.m_chunk);
+  const int nst = (m_end - m_beg + WG_BK - 1) / WG_BK;   // >= 1 by construction of the grid
+
+  if (threadIdx.x < BM) sbias[threadIdx.x] = 0.f;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, 4);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&g.tmA);
+    prefetch_tmap(&g.tmB);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = static_cast<uint32_t>(WG_A_BYTES + b_bytes);
+      for (int it = 0; it < nst; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(empty + st, ph ^ 1);
+        uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+        const int m = m_beg + it * WG_BK;
+        mbar_expect_tx(full + st, tx);
+        for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, full + st, base + j * WG_BOX, n0 + 32 * j, m);
+        for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, full + st, base + 2 * WG_A_BYTES + j * WG_BOX, k0 + 32 * j, m);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const int n1 = (g.kt <= 256) ? g.kt : 160;      // 160 = five 32-float atoms: the second MMA starts on an atom boundary
+      const int n2 = g.kt - n1;
+      const uint32_t mn = (1u << 15) | (1u << 16);    // A and B are MN-major
+      const uint32_t idesc1 = umma_idesc(BM, n1) | mn;
+      const uint32_t idesc2 = n2 ? (umma_idesc(BM, n2) | mn) : 0u;
+      for (int it = 0; it < nst; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(ready + st, ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+        const uint32_t a_hi = base, a_lo = base + WG_A_BYTES, b_hi = base + 2 * WG_A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int k = 0; k < WG_BK / UK; ++k) {
+          const uint32_t ko = k * 1024;                // next 8 rows of the reduction
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, umma_desc_mn(a_lo + ko, WG_BOX), umma_desc_mn(b_hi + ko, WG_BOX), idesc1, first);
+          umma_tf32(tmem_base, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_lo + ko, WG_BOX), idesc1, 1u);
+          umma_tf32(tmem_base, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_hi + ko, WG_BOX), idesc1, 1u);
+          if (n2) {
+            const uint32_t bo = static_cast<uint32_t>(n1 / 32) * WG_BOX;
+            umma_tf32(tmem_base + n1, umma_desc_mn(a_lo + ko, WG_BOX), umma_desc_mn(b_hi + bo + ko, WG_BOX), idesc2, first);
+            umma_tf32(tmem_base + n1, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_lo + bo + ko, WG_BOX), idesc2, 1u);
+            umma_tf32(tmem_base + n1, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_hi + bo + ko, WG_BOX), idesc2, 1u);
+          }
+        }
+        umma_commit(empty + st);
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    const int wtid = threadIdx.x - 64;
+    const bool do_bias = g.dbias != nullptr && blockIdx.y == 0;
+    float4 bsum[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+    for (int it = 0; it < nst; ++it) {
+      const int st = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(full + st, ph);
+      uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+      // A: split + column sums of dZ (each thread always meets the same logical 16-byte column chunk of block j = i >> 1)
+#pragma unroll
+      for (int i = 0; i < WG_A_BYTES / 2048; ++i) {
+        const int off = wtid * 16 + i * 2048;
+        const float4 v = *reinterpret_cast<float4*>(base + off);
+        float4 h, l;
+        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+        l = f4_sub(v, h);
+        *reinterpret_cast<float4*>(base + off) = h;
+        *reinterpret_cast<float4*>(base + WG_A_BYTES + off) = l;
+        bsum[i >> 1] = f4_add(bsum[i >> 1], v);
+      }
+      split_tile(base + 2 * WG_A_BYTES, base + 2 * WG_A_BYTES + b_bytes, b_bytes, wtid);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready + st);
+    }
+    if (do_bias) {
+      // 32-byte-atom swizzle: logical 32 B chunk = physical 32 B chunk ^ (row & 3); the 16 B half inside it is unchanged
+      const int c = ((((wtid & 7) >> 1) ^ ((wtid >> 3) & 3)) << 1) | (wtid & 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(sbias + j * 32 + c * 4 + 0, bsum[j].x);
+        atomicAdd(sbias + j * 32 + c * 4 + 1, bsum[j].y);
+        atomicAdd(sbias + j * 32 + c * 4 + 2, bsum[j].z);
+        atomicAdd(sbias + j * 32 + c * 4 + 3, bsum[j].w);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (n0 + wtid < g.n) atomicAdd(g.dbias + n0 + wtid, sbias[wtid]);
+    }
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int row = n0 + quad * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    for (int c = 0; c < g.kt; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + c, v);
+      if (row < g.n) {
+        float* cp = g.dW + static_cast<size_t>(row) * g.lddw + k0 + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (k0 + c + 4 * q < g.k) red_add_v4(cp + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -319,7 +513,9 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major [rows, cols] with row stride ld floats; box = [box_rows x 32 floats], 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  if (box_rows < 1 || box_rows > 256) return fail(RR_ERR_INVALID, "TMA box of %d rows", box_rows);
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -327,12 +523,64 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
   cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows %d cols %d ld %d box_rows %d", static_cast<int>(r), rows, cols, ld, box_rows);
   return RR_OK;
 }
 
 }  // namespace tc
+
+
+bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx) {
+  if (M <= 0 || n < 4 || k < 4 || (n & 3) || (k & 3) || (lddz & 3) || (ldx & 3)) return false;
+  const int tiles = (k + tc::MAX_NT - 1) / tc::MAX_NT;
+  if (tiles == 1) return true;               // one k-tile: columns are padded to a multiple of 16 with TMA zero fill
+  return (k % tiles) == 0 && ((k / tiles) & 15) == 0;
+}
+
+int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s) {
+  using namespace tc;
+  ProfScope prof_scope(KC_GEMM_WGRAD, s);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  WgArgs g{};
+  const int ktiles = (k + MAX_NT - 1) / MAX_NT;
+  g.kt = ktiles == 1 ? (k + 15) / 16 * 16 : k / ktiles;
+  g.nb = (g.kt + 31) / 32;
+  const int stage_bytes = 2 * WG_A_BYTES + 2 * g.nb * WG_BOX;
+  int S = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (S > 4) S = 4;
+  RR_REQUIRE(S >= 2, "tc_wgrad: %d columns do not fit two pipeline stages", g.kt);
+  g.stages = S;
+  int cols = 32;
+  while (cols < g.kt) cols <<= 1;
+  g.tmem_cols = cols;
+  RR_TRY(make_map(&g.tmA, dZ, M, n, lddz, WG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  RR_TRY(make_map(&g.tmB, X, M, k, ldx, WG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  g.M = M;
+  g.n = n;
+  g.k = k;
+  g.dW = dW;
+  g.lddw = lddw;
+  g.dbias = dbias;
+  const int ntiles = (n + BM - 1) / BM;
+  int splits = (num_sms() + ntiles * ktiles - 1) / (ntiles * ktiles);
+  const int max_splits = (M + 8 * WG_BK - 1) / (8 * WG_BK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int chunk = (M + splits - 1) / splits;
+  chunk = (chunk + WG_BK - 1) / WG_BK * WG_BK;
+  splits = (M + chunk - 1) / chunk;
+  g.m_chunk = chunk;
+  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256 + BM * sizeof(float) + 64;
+  dim3 grid(ntiles, ktiles, splits);
+  k_tc_wgrad<<<grid, THREADS, smem, s>>>(g);
+  RR_LAUNCH_CHECK("k_tc_wgrad");
+  return RR_OK;
+}
 
 // Can this problem run on the tcgen05 kernel?  (everything the model produces can; odd C-ABI calls fall back to SIMT)
 bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2) {

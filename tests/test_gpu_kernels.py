@@ -345,3 +345,21 @@ def test_tcgen05_and_simt_draw_the_same_dropout_mask(tc_mode):
     _lib.check(L.rr_linear_fwd(M, n, X.data_ptr(), k, W.data_ptr(), k, None, 0, None, 0, None, None, 0, Ys.data_ptr(), n, 3, p, 7, 9, S()))
     assert float(((Yt == 0) != (Ys == 0)).float().mean()) < 1e-4        # only entries whose pre-activation is ~0 may differ
     close(Yt, Ys.double(), 5e-6)
+
+
+@pytest.mark.parametrize("M,n,k", [(1000, 304, 304), (4100, 304, 88), (777, 304, 64), (40000, 304, 304), (1000, 608, 608), (300, 16, 304),
+                                   (513, 48, 48)])
+def test_tcgen05_wgrad_matches_fp64(tc_mode, M, n, k):
+    """tcgen05 wgrad (MN-major operands, split over the row range, vector reductions into dW) and its fused bias gradient."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(M + k)
+    dZ, X = torch.randn(M, n, generator=g), torch.randn(M, k, generator=g)
+    dZ[0] *= 50.0
+    dZd, Xd = dZ.to(DEV), X.to(DEV)
+    dW = torch.zeros(n, k, device=DEV)
+    db = torch.zeros(n, device=DEV)
+    _lib.check(L.rr_linear_wgrad(M, n, k, dZd.data_ptr(), n, Xd.data_ptr(), k, dW.data_ptr(), k, db.data_ptr(), S()))
+    close(dW, dZ.double().T @ X.double(), 1e-5)
+    close(db, dZ.double().sum(0), 1e-5)
+    _lib.check(L.rr_linear_wgrad(M, n, k, dZd.data_ptr(), n, Xd.data_ptr(), k, dW.data_ptr(), k, None, S()))   # accumulates
+    close(dW, 2 * (dZ.double().T @ X.double()), 1e-5)
