@@ -16,22 +16,42 @@
 
 namespace rr {
 
-constexpr int kFast = 8;  // neighbours kept in registers; larger degrees take the reload path
+constexpr int kFast = 4;  // neighbours kept in registers; larger in-degrees take the reload path
 
-struct AtomCtx {
+// One atom's gather task.  Everything in it is loaded WITHOUT waiting for the in-degree (the index rows are read
+// unconditionally up to kFast), and the task of the thread's NEXT atom is prefetched while the current rows are in
+// flight: the dependent chain meta -> indices -> rows collapses to one DRAM round trip per atom in steady state.
+struct Task {
   int deg, pad_count, pad_bond, pad_atom;
   bool is_pad;
+  int idx[kFast];
+  int rev[kFast];
 };
 
-__device__ __forceinline__ AtomCtx load_ctx(const rr_atom_meta* meta, int a) {
-  const int4 m = __ldg(reinterpret_cast<const int4*>(meta) + a);
-  AtomCtx c;
-  c.deg = m.x & 0xff;
-  c.is_pad = (m.x >> 8) & 1;
-  c.pad_count = m.y;
-  c.pad_bond = m.z;
-  c.pad_atom = m.w;
-  return c;
+template <bool WITH_REV>
+__device__ __forceinline__ void load_task(Task& t, const rr_graph& g, const int* __restrict__ table, int a) {
+  const int4 m = __ldg(reinterpret_cast<const int4*>(g.a_meta) + a);
+  const int* ib = table + static_cast<size_t>(a) * g.wmax;
+  const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
+  if (g.wmax == 4) {
+    const int4 i4 = __ldg(reinterpret_cast<const int4*>(ib));
+    t.idx[0] = i4.x; t.idx[1] = i4.y; t.idx[2] = i4.z; t.idx[3] = i4.w;
+    if (WITH_REV) {
+      const int4 r4 = __ldg(reinterpret_cast<const int4*>(rb));
+      t.rev[0] = r4.x; t.rev[1] = r4.y; t.rev[2] = r4.z; t.rev[3] = r4.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kFast; ++k) {
+      t.idx[k] = (k < g.wmax) ? __ldg(ib + k) : 0;
+      if (WITH_REV) t.rev[k] = (k < g.wmax) ? __ldg(rb + k) : 0;
+    }
+  }
+  t.deg = m.x & 0xff;
+  t.is_pad = (m.x >> 8) & 1;
+  t.pad_count = m.y;
+  t.pad_bond = m.z;
+  t.pad_atom = m.w;
 }
 
 __device__ __forceinline__ float4 ld_row(const float* base, int row, int ld, int c4, bool relu) {
@@ -39,46 +59,46 @@ __device__ __forceinline__ float4 ld_row(const float* base, int row, int ld, int
   return relu ? f4_relu(v) : v;
 }
 
-// grid-stride helper: block = apb atoms x cpr chunks
-#define RR_ATOM_LOOP(n_atoms)                                                      \
+// block = apb atoms x cpr chunks; grid-stride over atoms with a one-task prefetch
+#define RR_ATOM_SETUP()                                                            \
   const int cpr = ld >> 2;                                                         \
   const int slot = threadIdx.x / cpr;                                              \
   const int c4 = (threadIdx.x - slot * cpr) << 2;                                  \
   const int apb = blockDim.x / cpr;                                                \
   if (slot >= apb) return;                                                         \
-  for (int a = blockIdx.x * apb + slot; a < (n_atoms); a += gridDim.x * apb)
+  const int stride = gridDim.x * apb;                                              \
+  int a = blockIdx.x * apb + slot;                                                 \
+  if (a >= g.n_atoms) return
 
 // ---------------------------------------------------------------------------------------
 // forward: pre = bond_message(m)                                         mpn.py:89-92
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_bond_fwd(rr_graph g, const float* __restrict__ m, float* __restrict__ pre, int ld, int relu) {
-  RR_ATOM_LOOP(g.n_atoms) {
-    const AtomCtx cx = load_ctx(g.a_meta, a);
-    int idx[kFast], rev[kFast];
-    const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
-    const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
-#pragma unroll
-    for (int k = 0; k < kFast; ++k) {
-      idx[k] = (k < cx.deg) ? __ldg(ib + k) : 0;
-      rev[k] = (k < cx.deg) ? __ldg(rb + k) : 0;
-    }
+__global__ void __launch_bounds__(512, 2) k_bond_fwd(rr_graph g, const float* __restrict__ m, float* __restrict__ pre, int ld, int relu) {
+  RR_ATOM_SETUP();
+  Task nx;
+  load_task<true>(nx, g, g.a2b, a);
+  for (; a < g.n_atoms; a += stride) {
+    const Task t = nx;
+    if (a + stride < g.n_atoms) load_task<true>(nx, g, g.a2b, a + stride);
     float4 acc = f4_zero();
-    if (cx.pad_count > 0) acc = f4_scale(static_cast<float>(cx.pad_count), ld_row(m, cx.pad_bond, ld, c4, relu));
+    if (t.pad_count > 0) acc = f4_scale(static_cast<float>(t.pad_count), ld_row(m, t.pad_bond, ld, c4, relu));
     float4 v[kFast];
 #pragma unroll
     for (int k = 0; k < kFast; ++k)
-      if (k < cx.deg) {
-        v[k] = ld_row(m, idx[k], ld, c4, relu);
-        acc = f4_add(acc, v[k]);
-      }
-    for (int k = kFast; k < cx.deg; ++k) acc = f4_add(acc, ld_row(m, __ldg(ib + k), ld, c4, relu));
+      if (k < t.deg) v[k] = ld_row(m, t.idx[k], ld, c4, relu);
 #pragma unroll
     for (int k = 0; k < kFast; ++k)
-      if (k < cx.deg) st_f4(pre + static_cast<size_t>(rev[k]) * ld + c4, f4_sub(acc, v[k]));
-    for (int k = kFast; k < cx.deg; ++k)
+      if (k < t.deg) acc = f4_add(acc, v[k]);
+    const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
+    const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
+    for (int k = kFast; k < t.deg; ++k) acc = f4_add(acc, ld_row(m, __ldg(ib + k), ld, c4, relu));
+#pragma unroll
+    for (int k = 0; k < kFast; ++k)
+      if (k < t.deg) st_f4(pre + static_cast<size_t>(t.rev[k]) * ld + c4, f4_sub(acc, v[k]));
+    for (int k = kFast; k < t.deg; ++k)
       st_f4(pre + static_cast<size_t>(__ldg(rb + k)) * ld + c4, f4_sub(acc, ld_row(m, __ldg(ib + k), ld, c4, relu)));
-    if (cx.is_pad)  // the padding bond: b2a = pad atom, b2revb = itself (featurization.py:262-264)
-      st_f4(pre + static_cast<size_t>(cx.pad_bond) * ld + c4, f4_sub(acc, ld_row(m, cx.pad_bond, ld, c4, relu)));
+    if (t.is_pad)  // the padding bond: b2a = pad atom, b2revb = itself (featurization.py:262-264)
+      st_f4(pre + static_cast<size_t>(t.pad_bond) * ld + c4, f4_sub(acc, ld_row(m, t.pad_bond, ld, c4, relu)));
   }
 }
 
@@ -86,44 +106,42 @@ __global__ void __launch_bounds__(512) k_bond_fwd(rr_graph g, const float* __res
 // backward: dm from dpre.  dm[b_k] = S_a - dpre[rev(b_k)],  S_a = sum_k dpre[rev(b_k)]
 // padding row: dm[pad] += sum_a pad_count_a * S_a - dpre[pad]   (row pre-zeroed by k_zero_rows)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_bond_bwd(rr_graph g, const float* __restrict__ dpre, float* __restrict__ dm, int ld) {
+__global__ void __launch_bounds__(512, 2) k_bond_bwd(rr_graph g, const float* __restrict__ dpre, float* __restrict__ dm, int ld) {
+  RR_ATOM_SETUP();
   float4 pad_acc = f4_zero();
   int pad_row = -1;
-  RR_ATOM_LOOP(g.n_atoms) {
-    const AtomCtx cx = load_ctx(g.a_meta, a);
-    if (cx.pad_bond != pad_row) {
+  Task nx;
+  load_task<true>(nx, g, g.a2b, a);
+  for (; a < g.n_atoms; a += stride) {
+    const Task t = nx;
+    if (a + stride < g.n_atoms) load_task<true>(nx, g, g.a2b, a + stride);
+    if (t.pad_bond != pad_row) {
       if (pad_row >= 0) red_add_f4(dm + static_cast<size_t>(pad_row) * ld + c4, pad_acc);
       pad_acc = f4_zero();
-      pad_row = cx.pad_bond;
-    }
-    int idx[kFast], rev[kFast];
-    const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
-    const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
-#pragma unroll
-    for (int k = 0; k < kFast; ++k) {
-      idx[k] = (k < cx.deg) ? __ldg(ib + k) : 0;
-      rev[k] = (k < cx.deg) ? __ldg(rb + k) : 0;
+      pad_row = t.pad_bond;
     }
     float4 S = f4_zero();
     float4 self = f4_zero();
-    if (cx.is_pad) {
-      self = ld_row(dpre, cx.pad_bond, ld, c4, false);
+    if (t.is_pad) {
+      self = ld_row(dpre, t.pad_bond, ld, c4, false);
       S = self;
     }
     float4 v[kFast];
 #pragma unroll
     for (int k = 0; k < kFast; ++k)
-      if (k < cx.deg) {
-        v[k] = ld_row(dpre, rev[k], ld, c4, false);
-        S = f4_add(S, v[k]);
-      }
-    for (int k = kFast; k < cx.deg; ++k) S = f4_add(S, ld_row(dpre, __ldg(rb + k), ld, c4, false));
+      if (k < t.deg) v[k] = ld_row(dpre, t.rev[k], ld, c4, false);
 #pragma unroll
     for (int k = 0; k < kFast; ++k)
-      if (k < cx.deg) st_f4(dm + static_cast<size_t>(idx[k]) * ld + c4, f4_sub(S, v[k]));
-    for (int k = kFast; k < cx.deg; ++k)
+      if (k < t.deg) S = f4_add(S, v[k]);
+    const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
+    const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
+    for (int k = kFast; k < t.deg; ++k) S = f4_add(S, ld_row(dpre, __ldg(rb + k), ld, c4, false));
+#pragma unroll
+    for (int k = 0; k < kFast; ++k)
+      if (k < t.deg) st_f4(dm + static_cast<size_t>(t.idx[k]) * ld + c4, f4_sub(S, v[k]));
+    for (int k = kFast; k < t.deg; ++k)
       st_f4(dm + static_cast<size_t>(__ldg(ib + k)) * ld + c4, f4_sub(S, ld_row(dpre, __ldg(rb + k), ld, c4, false)));
-    pad_acc = f4_fma(static_cast<float>(cx.pad_count), S, pad_acc);
+    pad_acc = f4_fma(static_cast<float>(t.pad_count), S, pad_acc);
     pad_acc = f4_sub(pad_acc, self);
   }
   if (pad_row >= 0) red_add_f4(dm + static_cast<size_t>(pad_row) * ld + c4, pad_acc);
@@ -132,65 +150,89 @@ __global__ void __launch_bounds__(512) k_bond_bwd(rr_graph g, const float* __res
 // ---------------------------------------------------------------------------------------
 // neighbour sum: out[a] = pad_count*src[pad] + sum_k src[idx[a,k]]       mpn.py:100-102,201-206,215
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_nbr_sum_fwd(rr_graph g, int which, const float* __restrict__ src, float* __restrict__ out, int ld, int relu) {
+__global__ void __launch_bounds__(512, 2) k_nbr_sum_fwd(rr_graph g, int which, const float* __restrict__ src, float* __restrict__ out, int ld, int relu) {
   const int* table = which ? g.a2a : g.a2b;
-  RR_ATOM_LOOP(g.n_atoms) {
-    const AtomCtx cx = load_ctx(g.a_meta, a);
-    const int* ib = table + static_cast<size_t>(a) * g.wmax;
+  RR_ATOM_SETUP();
+  Task nx;
+  load_task<false>(nx, g, table, a);
+  for (; a < g.n_atoms; a += stride) {
+    const Task t = nx;
+    if (a + stride < g.n_atoms) load_task<false>(nx, g, table, a + stride);
     float4 acc = f4_zero();
-    if (cx.pad_count > 0)
-      acc = f4_scale(static_cast<float>(cx.pad_count), ld_row(src, which ? cx.pad_atom : cx.pad_bond, ld, c4, relu));
-    int idx[kFast];
-#pragma unroll
-    for (int k = 0; k < kFast; ++k) idx[k] = (k < cx.deg) ? __ldg(ib + k) : 0;
+    if (t.pad_count > 0) acc = f4_scale(static_cast<float>(t.pad_count), ld_row(src, which ? t.pad_atom : t.pad_bond, ld, c4, relu));
     float4 v[kFast];
 #pragma unroll
     for (int k = 0; k < kFast; ++k)
-      if (k < cx.deg) v[k] = ld_row(src, idx[k], ld, c4, relu);
+      if (k < t.deg) v[k] = ld_row(src, t.idx[k], ld, c4, relu);
 #pragma unroll
     for (int k = 0; k < kFast; ++k)
-      if (k < cx.deg) acc = f4_add(acc, v[k]);
-    for (int k = kFast; k < cx.deg; ++k) acc = f4_add(acc, ld_row(src, __ldg(ib + k), ld, c4, relu));
+      if (k < t.deg) acc = f4_add(acc, v[k]);
+    const int* ib = table + static_cast<size_t>(a) * g.wmax;
+    for (int k = kFast; k < t.deg; ++k) acc = f4_add(acc, ld_row(src, __ldg(ib + k), ld, c4, relu));
     st_f4(out + static_cast<size_t>(a) * ld + c4, acc);
   }
 }
 
 // backward over bond rows (which = 0): dsrc[b_k] = dout[a]; dsrc[pad] += pad_count * dout[a]
-__global__ void __launch_bounds__(512) k_nbr_sum_bwd_bond(rr_graph g, const float* __restrict__ dout, float* __restrict__ dsrc, int ld) {
+__global__ void __launch_bounds__(512, 2) k_nbr_sum_bwd_bond(rr_graph g, const float* __restrict__ dout, float* __restrict__ dsrc, int ld) {
+  RR_ATOM_SETUP();
   float4 pad_acc = f4_zero();
   int pad_row = -1;
-  RR_ATOM_LOOP(g.n_atoms) {
-    const AtomCtx cx = load_ctx(g.a_meta, a);
-    if (cx.pad_bond != pad_row) {
+  Task nx;
+  load_task<false>(nx, g, g.a2b, a);
+  float4 vn = ld_row(dout, a, ld, c4, false);
+  for (; a < g.n_atoms; a += stride) {
+    const Task t = nx;
+    const float4 v = vn;
+    if (a + stride < g.n_atoms) {
+      load_task<false>(nx, g, g.a2b, a + stride);
+      vn = ld_row(dout, a + stride, ld, c4, false);
+    }
+    if (t.pad_bond != pad_row) {
       if (pad_row >= 0) red_add_f4(dsrc + static_cast<size_t>(pad_row) * ld + c4, pad_acc);
       pad_acc = f4_zero();
-      pad_row = cx.pad_bond;
+      pad_row = t.pad_bond;
     }
-    const float4 v = ld_row(dout, a, ld, c4, false);
+#pragma unroll
+    for (int k = 0; k < kFast; ++k)
+      if (k < t.deg) st_f4(dsrc + static_cast<size_t>(t.idx[k]) * ld + c4, v);
     const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
-    for (int k = 0; k < cx.deg; ++k) st_f4(dsrc + static_cast<size_t>(__ldg(ib + k)) * ld + c4, v);
-    pad_acc = f4_fma(static_cast<float>(cx.pad_count), v, pad_acc);
+    for (int k = kFast; k < t.deg; ++k) st_f4(dsrc + static_cast<size_t>(__ldg(ib + k)) * ld + c4, v);
+    pad_acc = f4_fma(static_cast<float>(t.pad_count), v, pad_acc);
   }
   if (pad_row >= 0) red_add_f4(dsrc + static_cast<size_t>(pad_row) * ld + c4, pad_acc);
 }
 
 // backward over atom rows (which = 1): the neighbour relation is symmetric, so
 // dsrc[a] = sum_k dout[a2a[a,k]] (real neighbours only); dsrc[pad_atom] += pad_count_a * dout[a]
-__global__ void __launch_bounds__(512) k_nbr_sum_bwd_atom(rr_graph g, const float* __restrict__ dout, float* __restrict__ dsrc, int ld) {
+__global__ void __launch_bounds__(512, 2) k_nbr_sum_bwd_atom(rr_graph g, const float* __restrict__ dout, float* __restrict__ dsrc, int ld) {
+  RR_ATOM_SETUP();
   float4 pad_acc = f4_zero();
   int pad_row = -1;
-  RR_ATOM_LOOP(g.n_atoms) {
-    const AtomCtx cx = load_ctx(g.a_meta, a);
-    if (cx.pad_atom != pad_row) {
+  Task nx;
+  load_task<false>(nx, g, g.a2a, a);
+  for (; a < g.n_atoms; a += stride) {
+    const Task t = nx;
+    if (a + stride < g.n_atoms) load_task<false>(nx, g, g.a2a, a + stride);
+    if (t.pad_atom != pad_row) {
       if (pad_row >= 0) red_add_f4(dsrc + static_cast<size_t>(pad_row) * ld + c4, pad_acc);
       pad_acc = f4_zero();
-      pad_row = cx.pad_atom;
+      pad_row = t.pad_atom;
     }
-    const int* ib = g.a2a + static_cast<size_t>(a) * g.wmax;
+    float4 self = f4_zero();
+    if (t.pad_count > 0) self = ld_row(dout, a, ld, c4, false);
+    float4 v[kFast];
+#pragma unroll
+    for (int k = 0; k < kFast; ++k)
+      if (k < t.deg) v[k] = ld_row(dout, t.idx[k], ld, c4, false);
     float4 acc = f4_zero();
-    for (int k = 0; k < cx.deg; ++k) acc = f4_add(acc, ld_row(dout, __ldg(ib + k), ld, c4, false));
-    if (!cx.is_pad) st_f4(dsrc + static_cast<size_t>(a) * ld + c4, acc);
-    if (cx.pad_count > 0) pad_acc = f4_fma(static_cast<float>(cx.pad_count), ld_row(dout, a, ld, c4, false), pad_acc);
+#pragma unroll
+    for (int k = 0; k < kFast; ++k)
+      if (k < t.deg) acc = f4_add(acc, v[k]);
+    const int* ib = g.a2a + static_cast<size_t>(a) * g.wmax;
+    for (int k = kFast; k < t.deg; ++k) acc = f4_add(acc, ld_row(dout, __ldg(ib + k), ld, c4, false));
+    if (!t.is_pad) st_f4(dsrc + static_cast<size_t>(a) * ld + c4, acc);
+    pad_acc = f4_fma(static_cast<float>(t.pad_count), self, pad_acc);
   }
   if (pad_row >= 0) red_add_f4(dsrc + static_cast<size_t>(pad_row) * ld + c4, pad_acc);
 }
@@ -316,7 +358,7 @@ static void atom_launch_dims(int n_atoms, int ld, dim3* grid, dim3* block) {
   const int blocks_needed = (n_atoms + apb - 1) / apb;
   int per_sm = 2048 / ((threads + 31) / 32 * 32);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 4) per_sm = 4;   // ~64 registers per thread: 4 resident blocks of ~256 threads, each thread walks several atoms
   int g = num_sms() * per_sm;
   if (g > blocks_needed) g = blocks_needed;
   if (g < 1) g = 1;
