@@ -1,0 +1,73 @@
+"""RankNet epoch driver ``run_train`` with the reference's signature (train/run_train_pairwise.py:18-140): target z-scoring,
+'sum_session' training, ``evaluate_top_scores`` validation, best-metric checkpointing."""
+from __future__ import annotations
+
+import copy
+from logging import Logger
+
+import torch
+import torch.nn as nn
+from pandas import DataFrame
+from torch.optim.lr_scheduler import _LRScheduler
+from tqdm import trange
+
+from .. import _lib
+from ..data.load_reactions import DataProcessor
+from ..utils import save_checkpoint
+from .eval import evaluate_top_scores
+from .train_pairwise import factorized_training_loop
+
+try:
+    from torch.utils.tensorboard import SummaryWriter
+except Exception:  # pragma: no cover
+    SummaryWriter = None
+
+
+def run_train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, val_data_ini: DataFrame, path_checkpoints: str, optimizer,
+              epochs: int, smiles2graph_dic, batch_size: int, seed: int, gpu: int, train_strategy: str = 'baseline', task_type: str = 'baseline',
+              writer=SummaryWriter, logger: Logger = None, smiles_list=None, target_name: str = 'ea', save_metric=None, add_features_name=None):
+    if train_strategy not in ('sum_session',) or task_type != 'baseline':
+        raise NotImplementedError("only train_strategy='sum_session', task_type='baseline' (main_ranknet.py's defaults) is built")
+    gpu = _lib.require_device(gpu)
+    torch.cuda.set_device(gpu)
+    train_data, val_data = copy.deepcopy(train_data_ini), copy.deepcopy(val_data_ini)
+    mean, std = train_data[target_name].mean(), train_data[target_name].std(ddof=0)
+    sign = 1.0 if target_name == 'lgk' else -1.0          # run_train_pairwise.py:40-45
+    train_data['std' + target_name] = train_data[target_name].map(lambda x: sign * (x - mean) / std)
+    val_data['std' + target_name] = val_data[target_name].map(lambda x: sign * (x - mean) / std)
+    print('stds is: ', std)
+    print('mean is: ', mean)
+    train_proc, val_proc = DataProcessor(train_data), DataProcessor(val_data)
+    score_old = [0, 0, 0] if save_metric == 'all' else float(0)
+    for epoch in trange(epochs):
+        lr = optimizer.state_dict()['param_groups'][0]['lr']
+        print('learning rate: ', lr)
+        if logger is not None:
+            logger.info('learning rate is: {}'.format(lr))
+        model.zero_grad()
+        model.train()
+        epoch_loss = factorized_training_loop(epoch, model, None, optimizer, scheduler, smiles2graph_dic, train_proc, batch_size=batch_size, sigma=1.0,
+                                              training_algo=train_strategy, gpu=gpu, smiles_list=smiles_list, target_name='std' + target_name,
+                                              add_features_name=add_features_name)
+        model.eval()
+        average_score, average_pred_in_targ, average_top1_in_pred = evaluate_top_scores(
+            model, gpu, val_proc, smiles2graph_dic, ratio=0.25, show_info=True, smiles_list=smiles_list, target_name='std' + target_name,
+            add_features_name=add_features_name)
+        if save_metric is None or save_metric == 'average_score':
+            if average_score >= score_old:
+                score_old = average_score
+                save_checkpoint(path_checkpoints, model, mean, std)
+                print('Note: the checkpint file is updated')
+        elif save_metric == 'all':
+            for slot, val in enumerate((average_score, average_pred_in_targ, average_top1_in_pred)):
+                if val >= score_old[slot]:
+                    score_old[slot] = val
+                    save_checkpoint(path_checkpoints[slot], model, mean, std)
+                    print('Note: the checkpint file is updated')
+        if logger is not None:
+            logger.info('Epoch [{}/{}],train_loss,{:.4f}, average_score_top1,{:.4f}, average_pred_in_targ_top25%,{:.4f}'.format(
+                epoch + 1, epochs, epoch_loss, average_score, average_top1_in_pred))
+        print('Epoch [{}/{}], average score: {:.4f}'.format(epoch + 1, epochs, average_score))
+        print('Epoch [{}/{}], average_pred_in_targ_top25%: {:.4f}'.format(epoch + 1, epochs, average_pred_in_targ))
+        print('Epoch [{}/{}], average_targtop1_in_predtop25%: {:.4f}'.format(epoch + 1, epochs, average_top1_in_pred))
+        print('Epoch [{}/{}], train loss: {:.4f}'.format(epoch + 1, epochs, epoch_loss))

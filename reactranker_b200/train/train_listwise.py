@@ -1,0 +1,186 @@
+"""``train(...)`` for the listwise / pointwise task keys, with the reference's signature, target normalisation, loss
+dispatch, optimiser stepping and per-epoch checkpointing (train/train_listwise.py:21-373).
+
+Differences, all on purpose:
+* the five north-star keys run on the sm_100a path: ``mle``, ``listnet``, ``evidential_ranking``, ``gauss_regression`` and
+  the default ``regression``; the reference's experimental keys raise ``NotImplementedError``;
+* the reference copies ``encoder.W_i.weight`` to the host EVERY step to look for NaNs (train_listwise.py:190-195); here the
+  check is ``torch.isfinite`` on the device, read back once per epoch together with the loss;
+* ``gpu=None`` raises: there is no CPU path.
+"""
+from __future__ import annotations
+
+import copy
+from logging import Logger
+from typing import Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+from pandas import DataFrame
+from torch.optim.lr_scheduler import _LRScheduler
+from tqdm import trange
+
+from .. import _lib
+from ..data.load_reactions import DataProcessor
+from ..utils import save_checkpoint
+from .eval import calculate_mse, ranking_metrics
+from .loss import GaussDisLoss, ListnetLoss, MLEloss, MSELoss, evidential_ranking
+
+try:  # only used as the default value of ``writer`` in the reference signature
+    from torch.utils.tensorboard import SummaryWriter
+except Exception:  # pragma: no cover
+    SummaryWriter = None
+
+BUILT_TASKS = ("mle", "listnet", "evidential_ranking", "gauss_regression")
+UNBUILT_TASKS = ("mle_gaussian", "mledis_gaussian", "mle_regression", "mle_evidential", "mledis_evidential", "listnet_uq", "listnet_evidential",
+                 "listnet_gauss", "listnetdis_gauss", "listnetdis_lognorm", "dirichlet_uq", "listnet_regression", "regression_exploss",
+                 "evidential", "mle_dirichlet")
+NDCG_METRICS = ['NDCG@1', 'NDCG@2', 'NDCG@25%', 'NDCG@all']
+
+
+def normalized_targets(train_col, val_col, target_name, normalize_target):
+    """Target transform of train_listwise.py:66-115: for every target except ``lgk``/``lgk_bi`` the sign is flipped
+    (a lower barrier is the better candidate); ``normalize_target`` may be a bool, a float scale or a ``"lo,hi"`` range."""
+    mean, std = train_col.mean(), train_col.std(ddof=0)
+    if target_name == 'lgk_bi':
+        return train_col, val_col, mean, std
+    sign = 1.0 if target_name == 'lgk' else -1.0
+    lo_v, hi_v = train_col.min(), train_col.max()
+    if isinstance(normalize_target, float):
+        f = lambda x: sign * (x * normalize_target) / (hi_v - lo_v)  # noqa: E731
+    elif isinstance(normalize_target, str):
+        lo_b, hi_b = (int(v) for v in normalize_target.split(','))
+        f = lambda x: sign * (x - lo_v) * (hi_b - lo_b) / (hi_v - lo_v) + lo_b  # noqa: E731
+    elif normalize_target:
+        f = lambda x: sign * (x - mean) / std  # noqa: E731
+    else:
+        f = lambda x: sign * x  # noqa: E731
+    return train_col.map(f), val_col.map(f), mean, std
+
+
+def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, val_data_ini: DataFrame, path_checkpoints: str, optimizer,
+          epochs: int, smiles2graph_dic, batch_size: int, seed: int, gpu: Union[int, str], task_type: str = 'mle_gaussian',
+          writer=SummaryWriter, logger: Logger = None, target_name: str = 'ea', smiles_list: list = None, save_metric=None,
+          show_info=False, max_coeff=0.0001, normalize_target=True, add_features_name=None):
+    if task_type in UNBUILT_TASKS:
+        raise NotImplementedError(f"task_type '{task_type}' is one of the reference's experimental keys; built: {BUILT_TASKS} and 'regression'")
+    dev_idx = _lib.require_device(gpu)
+    print('Note: Set fixed seed')
+    torch.manual_seed(seed)
+    model = model.cuda(dev_idx)
+    torch.cuda.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+    train_data, val_data = copy.deepcopy(train_data_ini), copy.deepcopy(val_data_ini)
+    score_old = float('inf') if save_metric == 'mse' else ([0, 0, 0] if save_metric == 'all' else float(0))
+    data_len = train_data.shape[0] + val_data.shape[0]
+    if logger is not None:
+        logger.info('Note: the length of training and vailidate data is: {}'.format(data_len))
+    print("Note: the length of training and vailidate data is", data_len)
+
+    train_std, val_std, mean, std = normalized_targets(train_data[target_name], val_data[target_name], target_name, normalize_target)
+    train_data['std' + target_name] = train_std
+    val_data['std' + target_name] = val_data[target_name] if save_metric in NDCG_METRICS else val_std
+    print('stds is: ', std)
+    print('mean is: ', mean)
+
+    if task_type == 'mle':
+        loss_fn = MLEloss()
+    elif task_type == 'listnet':
+        loss_fn = ListnetLoss()
+    elif task_type == 'evidential_ranking':
+        loss_fn = evidential_ranking()
+    elif task_type == 'gauss_regression':
+        loss_fn = GaussDisLoss()
+    else:                                         # default regression (train_listwise.py:166-167)
+        loss_fn = MSELoss()
+
+    train_proc, val_proc = DataProcessor(train_data), DataProcessor(val_data)
+    finite = torch.ones((), dtype=torch.bool, device=torch.device("cuda", dev_idx))
+    for epoch in trange(epochs):
+        lr = optimizer.state_dict()['param_groups'][0]['lr']
+        print('learning rate: ', lr)
+        if logger is not None:
+            logger.info('learning rate is: {}'.format(lr))
+        model.train()
+        loss = torch.zeros(1)
+        for reactions, targets, scope, add_features in train_proc.generate_batch_reactions(
+                smiles_list=smiles_list, target_name='std' + target_name, batch_size=batch_size, seed=epoch, add_features_name=add_features_name):
+            targets_t = torch.FloatTensor(targets).squeeze()                         # train_listwise.py:187
+            r_inputs, p_inputs = smiles2graph_dic.parsing_reactions(reactions)
+            output = model(r_inputs, p_inputs, gpu=dev_idx, add_features=add_features)
+            if task_type == 'mle':
+                loss = loss_fn(output, scope, targets_t, dev_idx)
+            elif task_type == 'listnet':
+                loss = loss_fn(output, scope, targets_t, dev_idx)
+            elif task_type == 'evidential_ranking':
+                loss = loss_fn(output, scope, targets_t, max_coeff, epoch, epochs, dev_idx)
+            elif task_type == 'gauss_regression':
+                loss = loss_fn(output[:, 0], output[:, 1], targets_t, dev_idx)
+            else:
+                loss = loss_fn(output, targets_t)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            scheduler.step()
+            finite &= torch.isfinite(model.encoder.W_i.weight).all()
+        if not bool(finite):                       # the reference prints, it does not abort (train_listwise.py:190-195)
+            print('*' * 40)
+            print('the mean of encoder.W_i.weight is: ', model.state_dict()['encoder.W_i.weight'])
+            print('the ffn.ffn.7.weight is: ', model.state_dict().get('ffn.ffn.7.weight'))
+            print('*' * 40)
+        loss_value = float(loss.detach().reshape(-1)[0])
+        if writer is not None and not isinstance(writer, type):
+            writer.add_scalar('loss_every_epoch', loss_value)
+
+        average_score, average_pred_in_targ, average_top1_in_pred, NDCG_ = ranking_metrics(
+            model, gpu=dev_idx, data_processor=val_proc, smiles2graph_dic=smiles2graph_dic, show_info=show_info, smiles_list=smiles_list,
+            target_name='std' + target_name, add_features_name=add_features_name)
+
+        def improved(new, slot=None):
+            nonlocal score_old
+            old = score_old if slot is None else score_old[slot]
+            if new >= old:
+                if slot is None:
+                    score_old = new
+                else:
+                    score_old[slot] = new
+                return True
+            return False
+
+        if save_metric is None or save_metric == 'average_score':
+            if improved(average_score):
+                save_checkpoint(path_checkpoints, model, mean, std)
+                print('Note: the checkpint file is updated')
+        elif save_metric == 'all':
+            for slot, val in enumerate((average_score, average_pred_in_targ, average_top1_in_pred)):
+                if improved(val, slot):
+                    save_checkpoint(path_checkpoints[slot], model, mean, std)
+                    print('Note: the checkpint file is updated')
+        elif save_metric == 'average_pred_in_targ':
+            if improved(average_pred_in_targ):
+                save_checkpoint(path_checkpoints, model, mean, std)
+        elif save_metric == 'average_top1_in_pred':
+            if improved(average_top1_in_pred):
+                save_checkpoint(path_checkpoints, model, mean, std)
+        elif save_metric in NDCG_METRICS:
+            if improved(NDCG_[NDCG_METRICS.index(save_metric)]):
+                save_checkpoint(path_checkpoints, model, mean, std)
+        elif save_metric == 'mse':
+            calculate_mse()
+        else:
+            raise Exception('Unknown save metric')
+
+        if writer is not None and not isinstance(writer, type):
+            writer.add_scalar("average_score", average_score)
+        msg = 'Epoch [{}/{}], train_loss,{:.4f}, top1,{:.4f}, top1_in_pred_top25%,{:.4f}, pred_top25%_in_targ_top25%,{:.4f}'.format(
+            epoch + 1, epochs, loss_value, average_score, average_top1_in_pred, average_pred_in_targ)
+        if logger is not None:
+            logger.info(msg)
+        print('Epoch [{}/{}], average score: {:.4f}'.format(epoch + 1, epochs, average_score))
+        print('Epoch [{}/{}], targ_top1_in_pred_top25%: {:.4f}'.format(epoch + 1, epochs, average_top1_in_pred))
+        print('Epoch [{}/{}], pred_top25%_in_targ_top25%: {:.4f}'.format(epoch + 1, epochs, average_pred_in_targ))
+        print('Epoch [{}/{}], train loss: {:.4f}'.format(epoch + 1, epochs, loss_value))
+        if save_metric in NDCG_METRICS:
+            print('Epoch [{}/{}], NDCG: {}'.format(epoch + 1, epochs, NDCG_))
