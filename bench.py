@@ -185,6 +185,7 @@ def ours(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries exactly one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]

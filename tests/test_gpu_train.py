@@ -29,9 +29,9 @@ def test_main_trains_every_task_key(tmp_path, task):
 
 
 def test_main_ranknet_trains(tmp_path):
-    out = run(["main_ranknet.py", "--synthetic", "40,8", "--path", str(tmp_path), "--gpu", "0", "--batch_size", "64", "--total_epochs", "2"])
+    out = run(["main_ranknet.py", "--synthetic", "40,8", "--path", str(tmp_path), "--gpu", "0", "--batch_size", "64", "--total_epochs", "3"])
     losses = [float(l.rsplit(":", 1)[1]) for l in out.splitlines() if "train loss" in l]
-    assert len(losses) == 2 and all(np.isfinite(losses)) and 0.3 < losses[0] < 1.5      # ~log 2 per pair at initialisation
+    assert len(losses) == 3 and all(np.isfinite(losses)) and 0.3 < losses[0] < 1.5      # ~log 2 per pair at initialisation
     assert "test score for k_fold vailidation" in out
 
 
