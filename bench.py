@@ -7,9 +7,10 @@ One "step" = one training step over one batch of synthetic reaction graphs: forw
 backward, (gradient all-reduce,) Adam, NoamLR.  Prints ONE JSON line (rank 0).
 
 * ``value``  : reactions/s with the batch already resident in HBM (device path).
-* ``e2e``    : reactions/s through the reference-shaped public API from HOST buffers -- per step
-               ``Parsing_features.parsing_reactions`` (batch assembly from the warm MolGraph cache),
-               the pinned host->device copy of both graphs, forward/loss/backward/Adam, and a
+* ``e2e``    : reactions/s through the reference-shaped public API from HOST buffers -- per step the batch plan
+               (``DataProcessor.generate_batch_reactions``), ``Parsing_features.parsing_reactions`` on the warm
+               MolGraph cache, the pinned host->device copies (molecule ids, row offsets, extra features, targets),
+               on-device batch assembly from the HBM-resident molecule store, forward/loss/backward/Adam, and a
                device->host read of the loss.
 * ``roofline``: the dominant kernel class of the step, timed with CUDA events on the launching
                stream inside the timed region (rr_profile_begin/end of librr_sm100).
@@ -201,6 +202,11 @@ def ours(args):
     for ds in pool:
         for tok, m in ds.mols.items():
             fz.add(tok, m)
+    # the pool as ONE data set for the end-to-end leg: DataProcessor plans the batches like train() does
+    import pandas as pd
+    from reactranker_b200.data.load_reactions import DataProcessor
+    frame = pd.concat([ds.to_dataframe().assign(flag=lambda d, i=i: d.flag + i * wl["groups"]) for i, ds in enumerate(pool)], ignore_index=True)
+    planner = DataProcessor(frame)
     # device-resident copies for the device-path measurement
     resident = []
     for ds in pool:
@@ -231,13 +237,25 @@ def ours(args):
     h2d = [0]
     d2h = 4
 
+    batches = {"it": None, "epoch": 0}
+
+    def next_batch():
+        while True:
+            if batches["it"] is None:
+                batches["it"] = planner.generate_batch_reactions(smiles_list=["rsmi_mapped", "psmi_mapped"], target_name="lgk", batch_size=rows,
+                                                                 seed=batches["epoch"], add_features_name="temp")
+                batches["epoch"] += 1
+            for b in batches["it"]:
+                if sum(b[2]) == rows:
+                    return b
+            batches["it"] = None
+
     def step_e2e(i):
-        ds = pool[i % len(pool)]
-        reactions = np.stack([ds.rsmi, ds.psmi], axis=1)                      # what generate_batch_reactions yields
-        r_b, p_b = fz.parsing_reactions(reactions)                           # batch assembly from the warm MolGraph cache
-        out = model(r_b, p_b, gpu=local, add_features=ds.temp.reshape(-1, 1))  # pinned H2D of both graphs inside
-        targets = torch.FloatTensor(ds.lgk.reshape(-1, 1)).squeeze()
-        loss = loss_fn(out, scope, targets)
+        reactions, tg, sc, feats = next_batch()                               # batch plan (DataProcessor.generate_batch_reactions)
+        r_b, p_b = fz.parsing_reactions(reactions)                           # warm MolGraph cache -> store ids
+        out = model(r_b, p_b, gpu=local, add_features=feats)                  # H2D (ids, offsets, features) + on-device assembly inside
+        targets = torch.FloatTensor(tg).squeeze()
+        loss = loss_fn(out, sc, targets)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         reduce_grads()

@@ -76,6 +76,22 @@ typedef struct {
   const int32_t* pad_atoms;    /* [n_segments] padding atom rows                        */
 } rr_graph;
 
+/* Device-resident molecule store: the MolGraph cache of Parsing_features (load_reactions.py:540-586) kept in HBM.
+ * Molecule i owns atoms [atom_off[i], atom_off[i]+n_atoms[i]) and bonds [bond_off[i], ...) of the concatenated arrays;
+ * indices inside a molecule are local (MolGraph numbering, featurization.py:135-210, b2revb = b xor 1). */
+typedef struct {
+  const float* f_atoms;      /* [sum A, RR_FA_LD]                                   */
+  const float* f_bonds;      /* [sum B, RR_FB_LD]                                   */
+  const int32_t* n_atoms;    /* [n_molecules]                                       */
+  const int32_t* n_bonds;    /* [n_molecules]                                       */
+  const int64_t* atom_off;   /* [n_molecules]                                       */
+  const int64_t* bond_off;   /* [n_molecules]                                       */
+  const int32_t* deg;        /* [sum A] in-degree                                   */
+  const int32_t* a2b_start;  /* [sum A] start of the atom's list in a2b_flat, local */
+  const int32_t* a2b_flat;   /* [sum B] incoming bonds per atom, local bond ids     */
+  const int32_t* b2a;        /* [sum B] source atom of each bond, local             */
+} rr_mol_store;
+
 typedef enum { RR_HEAD_RAW = 0, RR_HEAD_EVIDENTIAL_RANKING = 1, RR_HEAD_GAUSS_SOFTPLUS = 2, RR_HEAD_SOFTPLUS = 3 } rr_head;
 
 /* build_model(...) (models/base_model.py:235-297) */
@@ -113,6 +129,14 @@ const char* rr_last_error(void);
 int rr_device_check(int device);
 /* padded hidden width used by every activation buffer */
 int rr_padded(int width);
+
+/* ---- batch assembly on the device (replaces the host BatchMolGraph build + the per-step feature upload) ---------- */
+/* Writes every array of `out` (whose sizes and device buffers the caller provides) for the molecules mol_ids[0..n_mols)
+ * placed at atom rows a_start[i] / bond rows b_start[i]; mol_W / mol_pad_bond / mol_pad_atom give each molecule's
+ * segment (max_num_bonds and padding rows), seg_* list the segments' padding rows.  Result == the host-packed graph. */
+int rr_graph_assemble(const rr_mol_store* store, int n_mols, const int32_t* mol_ids, const int32_t* a_start, const int32_t* b_start,
+                      const int32_t* mol_W, const int32_t* mol_pad_bond, const int32_t* mol_pad_atom, int n_segments,
+                      const int32_t* seg_pad_atom, const int32_t* seg_pad_bond, const int32_t* seg_W, const rr_graph* out, void* stream);
 
 /* ---- message passing (models/mpn.py) -------------------------------------------------- */
 /* mpn.py:89-92   pre[b] = (sum_k m[a2b[b2a[b],k]]) - m[b2revb[b]]   for every bond row.

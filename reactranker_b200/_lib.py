@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "librr_sm100.so")
-SOURCES = ["rr_api.cu", "rr_mp.cu", "rr_gemm_simt.cu", "rr_gemm_tc.cu", "rr_loss.cu", "rr_model.cu"]
+SOURCES = ["rr_api.cu", "rr_mp.cu", "rr_gemm_simt.cu", "rr_gemm_tc.cu", "rr_assemble.cu", "rr_loss.cu", "rr_model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -35,6 +35,10 @@ class RRModelCfg(ctypes.Structure):
                 ("seed", ctypes.c_uint64)]
 
 
+class RRMolStore(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("f_atoms", "f_bonds", "n_atoms", "n_bonds", "atom_off", "bond_off", "deg", "a2b_start", "a2b_flat", "b2a")]
+
+
 class RRParams(ctypes.Structure):
     _fields_ = [("enc_Wi", c_f32p), ("enc_bi", c_f32p), ("enc_Wh", c_f32p), ("enc_bh", c_f32p), ("enc_Wo", c_f32p), ("enc_bo", c_f32p),
                 ("dif_Wi", c_f32p), ("dif_bi", c_f32p), ("dif_Wh", c_f32p), ("dif_bh", c_f32p), ("dif_Wo", c_f32p), ("dif_bo", c_f32p),
@@ -43,7 +47,7 @@ class RRParams(ctypes.Structure):
 
 EXPORTS = [
     "rr_version", "rr_last_error", "rr_device_check", "rr_padded",
-    "rr_bond_message_fwd", "rr_bond_message_bwd", "rr_neighbor_sum_fwd", "rr_neighbor_sum_bwd",
+    "rr_graph_assemble", "rr_bond_message_fwd", "rr_bond_message_bwd", "rr_neighbor_sum_fwd", "rr_neighbor_sum_bwd",
     "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
     "rr_loss_fwdbwd", "rr_loss_max_group",
     "rr_model_workspace_bytes", "rr_model_buffer_offset", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
@@ -96,6 +100,7 @@ def lib() -> ctypes.CDLL:
                 i32, i64, u64, f32, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
                 L.rr_device_check.argtypes = [i32]
                 L.rr_padded.argtypes = [i32]
+                L.rr_graph_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
                 L.rr_bond_message_fwd.argtypes = [vp, vp, vp, i32, i32, vp]
                 L.rr_bond_message_bwd.argtypes = [vp, vp, vp, i32, vp]
                 L.rr_neighbor_sum_fwd.argtypes = [vp, i32, vp, vp, i32, i32, vp]

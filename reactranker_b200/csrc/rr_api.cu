@@ -38,6 +38,8 @@ int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, in
 int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
 int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
 int loss_max_group();
+int graph_assemble(const rr_mol_store*, int, const int*, const int*, const int*, const int*, const int*, const int*, int, const int*, const int*,
+                   const int*, const rr_graph*, cudaStream_t);
 long long model_workspace_bytes(const rr_model_cfg*, const rr_graph*, const rr_graph*);
 long long model_buffer_offset(const rr_model_cfg*, const rr_graph*, const rr_graph*, const char*);
 int model_forward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, float*, void*, long long, cudaStream_t);
@@ -60,6 +62,12 @@ int rr_device_check(int device) {
 
 int rr_padded(int width) { return rr::padded(width); }
 
+int rr_graph_assemble(const rr_mol_store* store, int n_mols, const int32_t* mol_ids, const int32_t* a_start, const int32_t* b_start,
+                      const int32_t* mol_W, const int32_t* mol_pad_bond, const int32_t* mol_pad_atom, int n_segments, const int32_t* seg_pad_atom,
+                      const int32_t* seg_pad_bond, const int32_t* seg_W, const rr_graph* out, void* stream) {
+  return rr::graph_assemble(store, n_mols, mol_ids, a_start, b_start, mol_W, mol_pad_bond, mol_pad_atom, n_segments, seg_pad_atom, seg_pad_bond,
+                            seg_W, out, S(stream));
+}
 int rr_bond_message_fwd(const rr_graph* g, const float* m, float* pre, int hp, int relu_src, void* stream) {
   return rr::bond_message_fwd(g, m, pre, hp, relu_src, S(stream));
 }

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import pandas as pd
 
-from ..features.featurization import BatchMolGraph, MolGraph
+from ..features.featurization import BatchMolGraph, MolGraph, MoleculeStore, _pack_of
 
 
 def get_time():
@@ -248,32 +248,51 @@ class DataProcessor:
 
 
 class Parsing_features:
-    """SMILES -> MolGraph cache and batch assembly (load_reactions.py:540-586).  Pre-built graphs
-    (synthetic molecules, graphs featurised elsewhere) can be registered with ``add``."""
+    """SMILES -> MolGraph cache and batch assembly (load_reactions.py:540-586).
+
+    The cache doubles as a ``MoleculeStore``: every molecule is registered once and mirrored in HBM the first time a
+    batch goes to the device, after which a batch is a vector of store ids (``parsing_smiles`` = one dict lookup per
+    SMILES) assembled on the GPU.  Pre-built graphs (synthetic molecules, graphs featurised elsewhere) can be registered
+    with ``add``.  ``smiles2graph`` keeps the reference's attribute name and contents."""
 
     def __init__(self, graphs: Optional[dict] = None):
-        self.smiles2graph = dict(graphs) if graphs else {}
+        self.smiles2graph = {}
+        self.store = MoleculeStore()
+        self._sid: Dict[str, int] = {}
+        for k, v in (graphs or {}).items():
+            self.add(k, v)
 
     def add(self, smiles: str, graph) -> None:
         self.smiles2graph[smiles] = graph
+        self._sid.pop(smiles, None)
+
+    def _register(self, smi) -> int:
+        g = self.smiles2graph.get(smi)
+        if g is None:
+            g = self.smiles2graph[smi] = MolGraph(smi, reaction=True, atom_messages=False)
+        sid = self.store.register(_pack_of(g))
+        self._sid[smi] = sid
+        return sid
 
     def parsing_smiles(self, smiles: list = None):
         if smiles is None:
             return None
-        cache = self.smiles2graph
-        graphs = []
-        for smi in smiles:
-            g = cache.get(smi)
-            if g is None:
-                g = cache[smi] = MolGraph(smi, reaction=True, atom_messages=False)
-            graphs.append(g)
-        return BatchMolGraph(graphs)
+        sid_of = self._sid
+        try:
+            ids = [sid_of[s] for s in smiles]
+        except KeyError:
+            ids = [sid_of[s] if s in sid_of else self._register(s) for s in smiles]
+        if ids and min(ids) < 0:                    # a molecule the store cannot hold: host path
+            return BatchMolGraph([self.smiles2graph[s] for s in smiles])
+        return BatchMolGraph.from_store(self.store, np.asarray(ids, dtype=np.int32), smiles)
 
     def parsing_reactions(self, reactions: list = None):
         if reactions is None:
             return [None, None]
         reactions = np.asarray(reactions, dtype=object)
-        return [self.parsing_smiles(reactions[:, 0]), self.parsing_smiles(reactions[:, 1])]
+        return [self.parsing_smiles(reactions[:, 0].tolist()), self.parsing_smiles(reactions[:, 1].tolist())]
 
     def clear_cache(self):
         self.smiles2graph.clear()
+        self._sid.clear()
+        self.store = MoleculeStore()

@@ -185,11 +185,12 @@ class MolGraph:
 
 class _MolPack:
     """Per-molecule arrays, already in device row strides."""
-    __slots__ = ("f_atoms", "f_bonds", "b2a", "b2revb", "a2b_flat", "a2b_ptr", "deg", "n_atoms", "n_bonds")
+    __slots__ = ("f_atoms", "f_bonds", "b2a", "b2revb", "a2b_flat", "a2b_ptr", "deg", "n_atoms", "n_bonds", "sid", "store")
 
     @staticmethod
     def build(f_atoms, f_bond, b2a, a2b_flat, a2b_ptr, b2revb, f_bonds_full=None) -> "_MolPack":
         p = _MolPack()
+        p.sid, p.store = None, None
         A, B = f_atoms.shape[0], b2a.shape[0]
         p.n_atoms, p.n_bonds = A, B
         p.f_atoms = np.zeros((A, FA_LD), np.float32)
@@ -226,59 +227,195 @@ def _pack_of(m) -> _MolPack:
 
 
 # ------------------------------------------------------------------------------------------
+# MoleculeStore: the MolGraph cache, resident in HBM
+# ------------------------------------------------------------------------------------------
+class MoleculeStore:
+    """Per-molecule arrays of every registered molecule, concatenated; mirrored on one CUDA device on demand.
+    With it a batch costs a few bytes per molecule of host->device traffic (ids + row offsets) and one assembly
+    kernel (csrc/rr_assemble.cu) instead of a host rebuild plus ~36 kB per reaction of PCIe traffic."""
+
+    def __init__(self):
+        self.packs: List[_MolPack] = []
+        self.nA = np.zeros(0, np.int32)
+        self.nB = np.zeros(0, np.int32)
+        self.maxdeg = np.zeros(0, np.int32)
+        self.aoff = np.zeros(0, np.int64)
+        self.boff = np.zeros(0, np.int64)
+        self._tot_a = 0
+        self._tot_b = 0
+        self._dev = None
+        self._uploaded = 0
+        self._d = {}
+        self.c = None
+        self.h2d_bytes_total = 0
+
+    def __len__(self):
+        return len(self.packs)
+
+    def register(self, pack: "_MolPack") -> int:
+        """Returns the store id, or -1 for a molecule whose reverse-bond map is not the canonical ``b xor 1``."""
+        sid = getattr(pack, "sid", None)
+        if sid is not None and getattr(pack, "store", None) is self:
+            return sid
+        if pack.n_bonds and not np.array_equal(pack.b2revb, np.arange(pack.n_bonds, dtype=np.int32) ^ 1):
+            return -1
+        sid = len(self.packs)
+        self.packs.append(pack)
+        pack.sid, pack.store = sid, self
+        if sid >= self.nA.shape[0]:
+            cap = max(1024, 2 * self.nA.shape[0])
+            for name in ("nA", "nB", "maxdeg", "aoff", "boff"):
+                old = getattr(self, name)
+                grown = np.zeros(cap, old.dtype)
+                grown[:old.shape[0]] = old
+                setattr(self, name, grown)
+        self.nA[sid], self.nB[sid] = pack.n_atoms, pack.n_bonds
+        self.maxdeg[sid] = int(pack.deg.max()) if pack.n_atoms else 0
+        self.aoff[sid], self.boff[sid] = self._tot_a, self._tot_b
+        self._tot_a += pack.n_atoms
+        self._tot_b += pack.n_bonds
+        return sid
+
+    # ---- device mirror -----------------------------------------------------------------
+    _SPECS = (("f_atoms", torch.float32, FA_LD, "a"), ("f_bonds", torch.float32, FB_LD, "b"), ("deg", torch.int32, 1, "a"),
+              ("a2b_start", torch.int32, 1, "a"), ("a2b_flat", torch.int32, 1, "b"), ("b2a", torch.int32, 1, "b"),
+              ("n_atoms", torch.int32, 1, "m"), ("n_bonds", torch.int32, 1, "m"), ("atom_off", torch.int64, 1, "m"), ("bond_off", torch.int64, 1, "m"))
+
+    def sync(self, device) -> None:
+        """Upload molecules registered since the last call (amortised: capacity doubles)."""
+        dev = torch.device(device)
+        if self._dev is not None and self._dev != dev:
+            raise RuntimeError(f"MoleculeStore already lives on {self._dev}")
+        n = len(self.packs)
+        if self._dev == dev and self._uploaded == n:
+            return
+        from .. import _lib
+        self._dev = dev
+        lo = self._uploaded
+        new = self.packs[lo:n]
+        a_lo, b_lo = int(self.aoff[lo]) if lo < n else self._tot_a, int(self.boff[lo]) if lo < n else self._tot_b
+        need = {"a": self._tot_a, "b": self._tot_b, "m": n}
+        host = {
+            "f_atoms": np.concatenate([p.f_atoms for p in new]) if new else np.zeros((0, FA_LD), np.float32),
+            "f_bonds": np.concatenate([p.f_bonds for p in new]) if new else np.zeros((0, FB_LD), np.float32),
+            "deg": np.concatenate([p.deg for p in new]), "a2b_start": np.concatenate([p.a2b_ptr[:-1] for p in new]).astype(np.int32),
+            "a2b_flat": np.concatenate([p.a2b_flat for p in new]).astype(np.int32), "b2a": np.concatenate([p.b2a for p in new]).astype(np.int32),
+            "n_atoms": self.nA[lo:n], "n_bonds": self.nB[lo:n], "atom_off": self.aoff[lo:n], "bond_off": self.boff[lo:n],
+        }
+        start = {"a": a_lo, "b": b_lo, "m": lo}
+        for name, dtype, width, kind in self._SPECS:
+            cur = self._d.get(name)
+            rows = need[kind]
+            if cur is None or cur.shape[0] < rows:
+                cap = max(rows, 2 * (cur.shape[0] if cur is not None else 0), 1)
+                grown = torch.empty((cap, width) if width > 1 else (cap,), dtype=dtype, device=dev)
+                if cur is not None and start[kind] > 0:
+                    grown[:start[kind]] = cur[:start[kind]]
+                self._d[name] = cur = grown
+            h = torch.from_numpy(np.ascontiguousarray(host[name]))
+            if h.numel():
+                if dev.type == "cuda":
+                    h = h.pin_memory()
+                cur[start[kind]:start[kind] + h.shape[0]].copy_(h, non_blocking=True)
+                self.h2d_bytes_total += h.numel() * h.element_size()
+        self._uploaded = n
+        c = _lib.RRMolStore()
+        for name, *_ in self._SPECS:
+            setattr(c, name, self._d[name].data_ptr())
+        self.c = c
+
+
+# ------------------------------------------------------------------------------------------
 # BatchMolGraph
 # ------------------------------------------------------------------------------------------
 class BatchMolGraph:
-    """Batch of molecules with the reference's index construction (featurization.py:246-290):
-    row 0 of atoms and bonds is padding, per-molecule indices are shifted by the running
-    totals, ``a2b`` is right-padded with 0 to ``max_num_bonds = max(1, max in-degree)``."""
+    """Batch of molecules with the reference's index construction (featurization.py:246-290): row 0 of atoms and
+    bonds is padding, per-molecule indices are shifted by the running totals, ``a2b`` is right-padded with 0 to
+    ``max_num_bonds = max(1, max in-degree)``.
+
+    Only the sizes are computed eagerly.  The reference tensors are built (vectorised) when somebody reads them; the
+    training path never does: ``to_device`` assembles the batch on the GPU from the molecule store when the batch came
+    from ``Parsing_features`` and packs it on the host otherwise."""
 
     def __init__(self, mol_graphs: Sequence, atom_messages: bool = False):
         if atom_messages:
             raise NotImplementedError("atom_messages=True is not on the hot path")
         packs = [_pack_of(m) for m in mol_graphs]
-        self.smiles_batch = [m.smiles for m in mol_graphs]
-        self.n_mols = len(packs)
-        self.atom_fdim = ATOM_FDIM
-        self.bond_fdim = FBOND_TOTAL
-        self._packs = packs
-        nA = np.fromiter((p.n_atoms for p in packs), np.int64, len(packs))
-        nB = np.fromiter((p.n_bonds for p in packs), np.int64, len(packs))
-        a_start = 1 + np.concatenate(([0], np.cumsum(nA)[:-1])) if len(packs) else np.zeros(0, np.int64)
-        b_start = 1 + np.concatenate(([0], np.cumsum(nB)[:-1])) if len(packs) else np.zeros(0, np.int64)
+        self._setup(packs, [m.smiles for m in mol_graphs], None, None)
+
+    @classmethod
+    def from_store(cls, store: MoleculeStore, ids: np.ndarray, smiles) -> "BatchMolGraph":
+        obj = cls.__new__(cls)
+        obj._setup(None, smiles, store, np.asarray(ids, dtype=np.int32))
+        return obj
+
+    def _setup(self, packs, smiles, store, ids):
+        self.smiles_batch = list(smiles)
+        self.atom_fdim, self.bond_fdim = ATOM_FDIM, FBOND_TOTAL
+        self._store, self._ids, self._packs_ = store, ids, packs
+        if ids is not None:
+            nA, nB = store.nA[ids].astype(np.int64), store.nB[ids].astype(np.int64)
+            maxdeg = int(store.maxdeg[ids].max()) if len(ids) else 0
+        else:
+            nA = np.fromiter((p.n_atoms for p in packs), np.int64, len(packs))
+            nB = np.fromiter((p.n_bonds for p in packs), np.int64, len(packs))
+            maxdeg = max((int(p.deg.max()) if p.n_atoms else 0 for p in packs), default=0)
+        self.n_mols = len(nA)
+        a_start = 1 + np.concatenate(([0], np.cumsum(nA)[:-1])) if self.n_mols else np.zeros(0, np.int64)
+        b_start = 1 + np.concatenate(([0], np.cumsum(nB)[:-1])) if self.n_mols else np.zeros(0, np.int64)
         self.n_atoms = int(1 + nA.sum())
         self.n_bonds = int(1 + nB.sum())
         self._a_start, self._a_size = a_start.astype(np.int32), nA.astype(np.int32)
         self._b_start, self._b_size = b_start.astype(np.int32), nB.astype(np.int32)
-        self.a_scope = list(zip(a_start.tolist(), nA.tolist()))
-        self.b_scope = list(zip(b_start.tolist(), nB.tolist()))
-        deg = np.zeros(self.n_atoms, np.int32)
-        if packs:
-            np.concatenate([p.deg for p in packs], out=deg[1:])
-        self._deg = deg
-        self.max_num_bonds = max(1, int(deg.max())) if self.n_atoms else 1
-        # index tables (int32, reference values)
-        b2a = np.zeros(self.n_bonds, np.int32)
-        b2revb = np.zeros(self.n_bonds, np.int32)
-        if packs:
-            np.concatenate([p.b2a for p in packs], out=b2a[1:])
-            np.concatenate([p.b2revb for p in packs], out=b2revb[1:])
-            b2a[1:] += np.repeat(a_start, nB).astype(np.int32)
-            b2revb[1:] += np.repeat(b_start, nB).astype(np.int32)
-        self._b2a, self._b2revb = b2a, b2revb
-        W = self.max_num_bonds
-        a2b = np.zeros((self.n_atoms, W), np.int32)
-        if packs:
-            nnz = np.fromiter((p.a2b_flat.shape[0] for p in packs), np.int64, len(packs))
-            flat = np.concatenate([p.a2b_flat for p in packs]) + np.repeat(b_start, nnz).astype(np.int32)
-            rows = np.repeat(np.arange(self.n_atoms, dtype=np.int64), deg)
-            first = np.concatenate(([0], np.cumsum(deg, dtype=np.int64)[:-1]))
-            cols = np.arange(flat.shape[0], dtype=np.int64) - np.repeat(first, deg)
-            a2b[rows, cols] = flat
-        self._a2b = a2b
+        self._max_deg = maxdeg
+        self.max_num_bonds = max(1, maxdeg)
         self._lazy = {}
+        self._index = None
         self.b2b = None
         self.a2a = None
+
+    @property
+    def _packs(self):
+        if self._packs_ is None:
+            sp = self._store.packs
+            self._packs_ = [sp[i] for i in self._ids.tolist()]
+        return self._packs_
+
+    @property
+    def a_scope(self):
+        return list(zip(self._a_start.tolist(), self._a_size.tolist()))
+
+    @property
+    def b_scope(self):
+        return list(zip(self._b_start.tolist(), self._b_size.tolist()))
+
+    # ---- index tables (int32, reference values), built on first use ------------------------
+    def _build_index(self):
+        if self._index is None:
+            packs = self._packs
+            nB = self._b_size.astype(np.int64)
+            deg = np.zeros(self.n_atoms, np.int32)
+            b2a = np.zeros(self.n_bonds, np.int32)
+            b2revb = np.zeros(self.n_bonds, np.int32)
+            a2b = np.zeros((self.n_atoms, self.max_num_bonds), np.int32)
+            if packs:
+                np.concatenate([p.deg for p in packs], out=deg[1:])
+                np.concatenate([p.b2a for p in packs], out=b2a[1:])
+                np.concatenate([p.b2revb for p in packs], out=b2revb[1:])
+                b2a[1:] += np.repeat(self._a_start, nB)
+                b2revb[1:] += np.repeat(self._b_start, nB)
+                flat = np.concatenate([p.a2b_flat for p in packs]) + np.repeat(self._b_start, nB)     # one incoming entry per bond
+                rows = np.repeat(np.arange(self.n_atoms, dtype=np.int64), deg)
+                first = np.concatenate(([0], np.cumsum(deg, dtype=np.int64)[:-1]))
+                cols = np.arange(flat.shape[0], dtype=np.int64) - np.repeat(first, deg)
+                a2b[rows, cols] = flat
+            self._index = (deg, a2b, b2a, b2revb)
+        return self._index
+
+    _deg = property(lambda self: self._build_index()[0])
+    _a2b = property(lambda self: self._build_index()[1])
+    _b2a = property(lambda self: self._build_index()[2])
+    _b2revb = property(lambda self: self._build_index()[3])
 
     # ---- reference tensors, built on demand --------------------------------------------
     def _feature_tensor(self, which: str) -> torch.Tensor:
@@ -362,16 +499,79 @@ class DeviceGraph:
         self.real_atoms = self.real_bonds = 0
 
     @staticmethod
-    def from_batches(batches: Sequence[BatchMolGraph], device, w_override: Optional[Sequence[Optional[int]]] = None,
-                     non_blocking: bool = True) -> "DeviceGraph":
+    def _sections(nA, nB, nM, wmax, S):
+        return [("f_atoms", nA * FA_LD * 4), ("f_bonds", nB * FB_LD * 4), ("a_meta", nA * 16), ("a2b", nA * wmax * 4),
+                ("a2b_rev", nA * wmax * 4), ("a2a", nA * wmax * 4), ("mol_start", nM * 4), ("mol_size", nM * 4),
+                ("pad_bonds", S * 4), ("pad_atoms", S * 4)]
+
+    @staticmethod
+    def assemble(batches: Sequence[BatchMolGraph], dev, w_override=None) -> "DeviceGraph":
+        """Build the graph ON THE DEVICE from the molecule store: the host sends ids and row offsets only."""
+        from .. import _lib
+        store = batches[0]._store
+        store.sync(dev)
         S = len(batches)
         nA = sum(b.n_atoms for b in batches)
         nB = sum(b.n_bonds for b in batches)
         nM = sum(b.n_mols for b in batches)
-        wmax = max(1, max(int(b._deg.max()) for b in batches))
-        sections = [("f_atoms", nA * FA_LD * 4), ("f_bonds", nB * FB_LD * 4), ("a_meta", nA * 16), ("a2b", nA * wmax * 4),
-                    ("a2b_rev", nA * wmax * 4), ("a2a", nA * wmax * 4), ("mol_start", nM * 4), ("mol_size", nM * 4),
-                    ("pad_bonds", S * 4), ("pad_atoms", S * 4)]
+        wmax = max(1, max(b._max_deg for b in batches))
+        sections = DeviceGraph._sections(nA, nB, nM, wmax, S)
+        offs, total = {}, 0
+        for name, nbytes in sections:
+            offs[name] = total
+            total += _align(max(nbytes, 4))
+        # one small pinned buffer: [ids | a_start | b_start | W | pad_bond | pad_atom] per molecule + 3 per segment
+        ctl = np.empty(6 * nM + 3 * S, np.int32)
+        ids, a_st, b_st, mW, mpb, mpa = (ctl[i * nM:(i + 1) * nM] for i in range(6))
+        seg = ctl[6 * nM:].reshape(3, S)
+        a0 = b0 = m0 = 0
+        for s_i, b in enumerate(batches):
+            W = b.max_num_bonds if not (w_override and w_override[s_i]) else int(w_override[s_i])
+            if W < b.max_num_bonds:
+                raise ValueError(f"max_num_bonds override {W} < this batch's in-degree {b.max_num_bonds}")
+            n = b.n_mols
+            ids[m0:m0 + n] = b._ids
+            a_st[m0:m0 + n] = b._a_start + a0
+            b_st[m0:m0 + n] = b._b_start + b0
+            mW[m0:m0 + n], mpb[m0:m0 + n], mpa[m0:m0 + n] = W, b0, a0
+            seg[0, s_i], seg[1, s_i], seg[2, s_i] = a0, b0, W
+            a0 += b.n_atoms
+            b0 += b.n_bonds
+            m0 += n
+        host = torch.from_numpy(ctl).pin_memory()
+        d_ctl = host.to(dev, non_blocking=True)
+        g = DeviceGraph()
+        g.host_blob = host
+        g.blob = torch.empty(total, dtype=torch.uint8, device=dev)
+        g.h2d_bytes = ctl.nbytes
+        base = g.blob.data_ptr()
+        c = g.c
+        c.n_atoms, c.n_bonds, c.n_mols, c.wmax, c.n_segments = nA, nB, nM, wmax, S
+        for name, _ in sections:
+            setattr(c, name, base + offs[name])
+        p0 = d_ctl.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rr_graph_assemble(ctypes.byref(store.c), nM, p0, p0 + 4 * nM, p0 + 8 * nM, p0 + 12 * nM, p0 + 16 * nM, p0 + 20 * nM,
+                                                    S, p0 + 24 * nM, p0 + 24 * nM + 4 * S, p0 + 24 * nM + 8 * S, ctypes.byref(c),
+                                                    torch.cuda.current_stream().cuda_stream))
+        g._ctl = d_ctl
+        g.n_atoms, g.n_bonds, g.n_mols = nA, nB, nM
+        g.real_atoms, g.real_bonds = nA - S, nB - S
+        g._offs = offs
+        return g
+
+    @staticmethod
+    def from_batches(batches: Sequence[BatchMolGraph], device, w_override: Optional[Sequence[Optional[int]]] = None,
+                     non_blocking: bool = True) -> "DeviceGraph":
+        dev = torch.device(device)
+        if dev.type == "cuda" and all(b._ids is not None and b._store is batches[0]._store for b in batches):
+            return DeviceGraph.assemble(batches, dev, w_override)
+        S = len(batches)
+        nA = sum(b.n_atoms for b in batches)
+        nB = sum(b.n_bonds for b in batches)
+        nM = sum(b.n_mols for b in batches)
+        wmax = max(1, max(b._max_deg for b in batches))
+        sections = DeviceGraph._sections(nA, nB, nM, wmax, S)
         offs, total = {}, 0
         for name, nbytes in sections:
             offs[name] = total

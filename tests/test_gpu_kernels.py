@@ -363,3 +363,29 @@ def test_tcgen05_wgrad_matches_fp64(tc_mode, M, n, k):
     close(db, dZ.double().sum(0), 1e-5)
     _lib.check(L.rr_linear_wgrad(M, n, k, dZd.data_ptr(), n, Xd.data_ptr(), k, dW.data_ptr(), k, None, S()))   # accumulates
     close(dW, 2 * (dZ.double().T @ X.double()), 1e-5)
+
+
+def test_device_assembly_equals_host_packing():
+    """rr_graph_assemble (molecule store in HBM, ids + offsets from the host) writes exactly the arrays the host packer
+    ships, for a single batch, for a multi-segment launch and with a max_num_bonds override."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(17, [5, 3, 6], star_leaves_in_group={1: 8})
+    fz = Parsing_features(ds.mols)
+    cases = []
+    whole_r, whole_p = fz.parsing_reactions(np.stack([ds.rsmi, ds.psmi], 1))
+    cases.append(([whole_r], None))
+    cases.append(([whole_p], [whole_p.max_num_bonds + 2]))
+    groups = [fz.parsing_smiles(list(ds.rsmi[a:b])) for a, b in ((0, 5), (5, 8), (8, 14))]
+    cases.append((groups, None))
+    for batches, w in cases:
+        assert all(b._ids is not None for b in batches)
+        dev_g = DeviceGraph.from_batches(batches, DEV, w)                       # assembled on the GPU
+        host_g = DeviceGraph.from_batches([BatchMolGraph([ds.mols[s] for s in b.smiles_batch]) for b in batches], DEV, w)   # packed on the host
+        assert dev_g.h2d_bytes < host_g.h2d_bytes / 50
+        nA, nB, nM, wmax, S_ = dev_g.n_atoms, dev_g.n_bonds, dev_g.n_mols, dev_g.c.wmax, dev_g.c.n_segments
+        assert (nA, nB, nM, wmax, S_) == (host_g.n_atoms, host_g.n_bonds, host_g.n_mols, host_g.c.wmax, host_g.c.n_segments)
+        for name, dt, shape in (("f_atoms", torch.float32, (nA, 64)), ("f_bonds", torch.float32, (nB, 88)), ("a_meta", torch.int32, (nA, 4)),
+                                ("a2b", torch.int32, (nA, wmax)), ("a2b_rev", torch.int32, (nA, wmax)), ("a2a", torch.int32, (nA, wmax)),
+                                ("mol_start", torch.int32, (nM,)), ("mol_size", torch.int32, (nM,)), ("pad_bonds", torch.int32, (S_,)),
+                                ("pad_atoms", torch.int32, (S_,))):
+            assert torch.equal(dev_g.section(name, dt, shape), host_g.section(name, dt, shape)), name
