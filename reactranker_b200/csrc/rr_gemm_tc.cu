@@ -21,6 +21,7 @@
 //
 // Two-source K (concat-free [x1 || x2] W^T) walks both sources through the same accumulator.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "rr_common.cuh"
 
@@ -301,6 +302,249 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const __grid_constant__ 
   }
 }
 
+
+// ================================================================================================
+// v2 forward / dgrad kernel: persistent, A operand through TENSOR MEMORY (tcgen05.mma "TS" form).
+//
+// v1 re-reads the A tile from shared memory for each of the three TF32 products and writes both halves of the
+// split back to shared memory, so shared-memory bandwidth (128 B/clk) paces it.  Here the four A-split warps read
+// their row of the landed fp32 tile once and store (hi, lo) straight into TMEM with tcgen05.st; the MMAs take A from
+// TMEM and only B from shared memory.  The CTA is persistent (one per SM, static round-robin over tiles), a
+// separate epilogue warpgroup drains the accumulator while the producer and the split warps already work on the
+// next tile, and the epilogue moves 128-byte row segments (tcgen05.ld x32).
+//   warp 0: TMA producer | warp 1: MMA issuer (+TMEM alloc) | warps 2-5: split (A -> TMEM, B -> smem hi/lo) |
+//   warps 6-9: epilogue
+// TMEM columns: [0, 320) accumulator, [320 + 64 s, ...) A stage s = 32 columns hi + 32 columns lo.
+// ================================================================================================
+constexpr int THREADS2 = 320;
+constexpr int TM_A0 = 320;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const Args& g, const float* v, int row, int col) {
+  float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
+#pragma unroll
+  for (int q = 0; q < NV / 4; ++q) {
+    float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    if (g.bias) o = f4_add(o, ld_f4(g.bias + col + 4 * q));
+    if (g.resid) o = f4_add(o, ld_f4_stream(g.resid + static_cast<size_t>(row) * g.ldr + col + 4 * q));
+    if (g.relu) o = f4_relu(o);
+    if (g.p > 0.f) o = dropout4(o, g.p, g.inv_keep, g.seed, g.stream_id, (static_cast<uint64_t>(row) * g.ldc + col + 4 * q) >> 2);
+    if (g.accumulate) o = f4_add(o, *reinterpret_cast<const float4*>(cp + 4 * q));
+    st_f4(cp + 4 * q, o);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant__ Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int nt = g.nt;
+  const int b_bytes = nt * BK * 4;
+  const int stage_bytes = A_BYTES + 2 * b_bytes;       // A raw | B hi | B lo
+  constexpr int S = 2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
+  uint64_t* ready = full + S;
+  uint64_t* empty = ready + S;
+  uint64_t* acc_full = empty + S;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / nt;
+  const int total_tiles = m_tiles * n_tiles;
+  int nkb_total = 0;
+  for (int s = 0; s < g.nsrc; ++s) nkb_total += (g.src[s].K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(ready + s, 4);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < g.nsrc; ++s) {
+      prefetch_tmap(&g.src[s].tmA);
+      prefetch_tmap(&g.src[s].tmB);
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int it = 0;
+      const uint32_t tx = static_cast<uint32_t>(A_BYTES + b_bytes);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * nt;
+        for (int s = 0; s < g.nsrc; ++s) {
+          const int nkb = (g.src[s].K + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int st = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(empty + st, ph ^ 1);
+            uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+            mbar_expect_tx(full + st, tx);
+            tma_load_2d(&g.src[s].tmA, full + st, base, kb * BK, m0);
+            for (int j = 0; j < nt; j += g.bn) tma_load_2d(&g.src[s].tmB, full + st, base + A_BYTES + j * BK * 4, kb * BK, n0 + j);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const int n1 = (nt <= 256) ? nt : ((nt / 2 + 15) / 16 * 16);
+      const int n2 = nt - n1;
+      const uint32_t idesc1 = umma_idesc(BM, n1);
+      const uint32_t idesc2 = n2 ? umma_idesc(BM, n2) : 0u;
+      int it = 0, t_local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_local) {
+        mbar_wait(acc_empty, (t_local & 1) ^ 1);        // epilogue has drained the previous tile's accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < nkb_total; ++kb, ++it) {
+          const int st = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(ready + st, ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
+          const uint32_t b_hi = base + A_BYTES, b_lo = b_hi + b_bytes;
+          const uint32_t a_hi = tmem_base + TM_A0 + st * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint32_t ko = k * UK * 4;
+            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_tf32_ts(tmem_base, a_lo + k * UK, umma_desc(b_hi + ko), idesc1, first);
+            umma_tf32_ts(tmem_base, a_hi + k * UK, umma_desc(b_lo + ko), idesc1, 1u);
+            umma_tf32_ts(tmem_base, a_hi + k * UK, umma_desc(b_hi + ko), idesc1, 1u);
+            if (n2) {
+              const uint32_t bo = static_cast<uint32_t>(n1) * BK * 4;
+              umma_tf32_ts(tmem_base + n1, a_lo + k * UK, umma_desc(b_hi + bo + ko), idesc2, first);
+              umma_tf32_ts(tmem_base + n1, a_hi + k * UK, umma_desc(b_lo + bo + ko), idesc2, 1u);
+              umma_tf32_ts(tmem_base + n1, a_hi + k * UK, umma_desc(b_hi + bo + ko), idesc2, 1u);
+            }
+          }
+          umma_commit(empty + st);
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- split workers ----------------
+    const int wtid = threadIdx.x - 64;       // 0..127
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;          // row of the A tile owned by this thread == its TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb_total; ++kb, ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full + st, ph);
+        uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+        // A: this thread's row of 32 floats (128-byte swizzle: chunk c sits at c ^ (row & 7)) -> hi / lo -> TMEM
+        uint32_t hi[32], lo[32];
+        const uint8_t* rowp = base + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
+            hi[4 * c + j] = h;
+            lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
+          }
+        }
+        tmem_st32(lane_addr + TM_A0 + st * 64, hi);
+        tmem_st32(lane_addr + TM_A0 + st * 64 + 32, lo);
+        // B: elementwise split in shared memory
+        split_tile(base + A_BYTES, base + A_BYTES + b_bytes, b_bytes, wtid);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready + st);
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int quad = warp & 3;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    int t_local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_local) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * nt;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(acc_full, t_local & 1);
+      tc_fence_after();
+      int c = 0;
+      for (; c + 32 <= nt; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        if (c + 32 >= nt) {                   // last read of this accumulator: hand it back before the global traffic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+        if (row < g.M) epilogue_store<32>(g, v, row, n0 + c);
+      }
+      if (c < nt) {                           // 16-column tail (nt is a multiple of 16)
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        if (row < g.M) epilogue_store<16>(g, v, row, n0 + c);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
 
 // ================================================================================================
 // wgrad:  dW[n, k] += sum_m dZ[m, n] * X[m, k]      (+ dbias[n] += sum_m dZ[m, n])
@@ -639,6 +883,21 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   g.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   g.seed = seed;
   g.stream_id = stream_id;
+  static const bool use_v1 = getenv("RR_TC_V1") != nullptr;
+  if (!use_v1) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      attr2_set = true;
+    }
+    const int stage2 = A_BYTES + 2 * g.nt * BK * 4;
+    const size_t smem2 = static_cast<size_t>(2) * stage2 + 1024 + 256;
+    const int total_tiles = ((M + BM - 1) / BM) * tiles;
+    const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
+    k_tc_gemm2<<<ctas, THREADS2, smem2, s>>>(g);
+    RR_LAUNCH_CHECK("k_tc_gemm2");
+    return RR_OK;
+  }
   const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256;
   dim3 grid((M + BM - 1) / BM, tiles);
   k_tc_gemm<<<grid, THREADS, smem, s>>>(g);
