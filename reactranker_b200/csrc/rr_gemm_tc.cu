@@ -141,22 +141,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split an fp32 tile in place into hi (TF32-exact) and lo = x - hi
-__device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int bytes, int wtid) {
-  for (int off = wtid * 16; off < bytes; off += 128 * 16) {
-    float4 v = *reinterpret_cast<float4*>(hi + off);
+// explicit shared-space accesses: pointers carved out of the dynamic shared buffer are generic to the compiler, which
+// otherwise emits LD.E/ST.E (generic, long-scoreboard) instead of LDS/STS in the split loops
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void split4(float4 v, float4& h, float4& l) {
+  // round-to-nearest onto the TF32 grid (10 explicit mantissa bits): |lo| <= 2^-12 |x|, signs balanced
+  h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+  h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+  h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+  h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+  l = f4_sub(v, h);
+}
+
+// split an fp32 tile in place into hi (TF32-exact) and lo = x - hi; 128 threads, 4 independent chunks in flight each
+__device__ __forceinline__ void split_tile(uint8_t* hi_p, uint8_t* lo_p, int bytes, int wtid) {
+  const uint32_t hi = smem_u32(hi_p), lo = smem_u32(lo_p);
+  int off = wtid * 16;
+  for (; off + 3 * 2048 < bytes; off += 4 * 2048) {
+    float4 v[4], h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = lds_f4(hi + off + u * 2048);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) split4(v[u], h[u], l[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sts_f4(hi + off + u * 2048, h[u]);
+      sts_f4(lo + off + u * 2048, l[u]);
+    }
+  }
+  for (; off < bytes; off += 2048) {
     float4 h, l;
-    // round-to-nearest onto the TF32 grid (10 explicit mantissa bits): |lo| <= 2^-12 |x|, signs balanced
-    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-    l.x = v.x - h.x;
-    l.y = v.y - h.y;
-    l.z = v.z - h.z;
-    l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
+    split4(lds_f4(hi + off), h, l);
+    sts_f4(hi + off, h);
+    sts_f4(lo + off, l);
   }
 }
 
@@ -317,7 +341,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const __grid_constant__ 
 // TMEM columns: [0, 320) accumulator, [320 + 64 s, ...) A stage s = 32 columns hi + 32 columns lo.
 // ================================================================================================
 constexpr int THREADS2 = 320;
-constexpr int TM_A0 = 320;
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -368,34 +391,38 @@ __device__ __forceinline__ void epilogue_store(const Args& g, const float* v, in
   }
 }
 
+constexpr int NT2 = 160;                          // output columns per work item (<= 160, multiple of 16)
+constexpr int S2 = 3;                             // pipeline stages (shared memory A/B tiles + TMEM A tiles)
+constexpr int B2_BYTES = NT2 * BK * 4;            // one B box: 160 rows x 128 B
+constexpr int STAGE2 = A_BYTES + 2 * B2_BYTES;    // A raw | B hi | B lo  = 57344 B
+constexpr int TM_A2 = 2 * NT2;                    // TMEM: two accumulators [0,160) [160,320), then 3 x (32 hi + 32 lo) columns of A
+
 __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant__ Args g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int nt = g.nt;
-  const int b_bytes = nt * BK * 4;
-  const int stage_bytes = A_BYTES + 2 * b_bytes;       // A raw | B hi | B lo
-  constexpr int S = 2;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
-  uint64_t* ready = full + S;
-  uint64_t* empty = ready + S;
-  uint64_t* acc_full = empty + S;
-  uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S2) * STAGE2);
+  uint64_t* ready = full + S2;
+  uint64_t* empty = ready + S2;
+  uint64_t* acc_full = empty + S2;     // [2]
+  uint64_t* acc_empty = acc_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / nt;
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + NT2 - 1) / NT2;
   const int total_tiles = m_tiles * n_tiles;
   int nkb_total = 0;
   for (int s = 0; s < g.nsrc; ++s) nkb_total += (g.src[s].K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < S2; ++s) {
       mbar_init(full + s, 1);
       mbar_init(ready + s, 4);
       mbar_init(empty + s, 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full + b, 1);
+      mbar_init(acc_empty + b, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < g.nsrc; ++s) {
       prefetch_tmap(&g.src[s].tmA);
@@ -415,19 +442,19 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
-      const uint32_t tx = static_cast<uint32_t>(A_BYTES + b_bytes);
+      const uint32_t tx = static_cast<uint32_t>(A_BYTES + B2_BYTES);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * nt;
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
         for (int s = 0; s < g.nsrc; ++s) {
           const int nkb = (g.src[s].K + BK - 1) / BK;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int st = it % S;
-            const uint32_t ph = (it / S) & 1;
+            const int st = it % S2;
+            const uint32_t ph = (it / S2) & 1;
             mbar_wait(empty + st, ph ^ 1);
-            uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+            uint8_t* base = smem + static_cast<size_t>(st) * STAGE2;
             mbar_expect_tx(full + st, tx);
             tma_load_2d(&g.src[s].tmA, full + st, base, kb * BK, m0);
-            for (int j = 0; j < nt; j += g.bn) tma_load_2d(&g.src[s].tmB, full + st, base + A_BYTES + j * BK * 4, kb * BK, n0 + j);
+            tma_load_2d(&g.src[s].tmB, full + st, base + A_BYTES, kb * BK, n0);   // rows past N are zero-filled
           }
         }
       }
@@ -435,39 +462,33 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      const int n1 = (nt <= 256) ? nt : ((nt / 2 + 15) / 16 * 16);
-      const int n2 = nt - n1;
-      const uint32_t idesc1 = umma_idesc(BM, n1);
-      const uint32_t idesc2 = n2 ? umma_idesc(BM, n2) : 0u;
-      int it = 0, t_local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_local) {
-        mbar_wait(acc_empty, (t_local & 1) ^ 1);        // epilogue has drained the previous tile's accumulator
+      int it = 0, w = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++w) {
+        const int n0 = (tile % n_tiles) * NT2;
+        const int width = min(NT2, g.N - n0);
+        const uint32_t idesc = umma_idesc(BM, width);
+        const int buf = w & 1;
+        const uint32_t d = tmem_base + buf * NT2;
+        mbar_wait(acc_empty + buf, ((w >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator
         tc_fence_after();
         for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-          const int st = it % S;
-          const uint32_t ph = (it / S) & 1;
+          const int st = it % S2;
+          const uint32_t ph = (it / S2) & 1;
           mbar_wait(ready + st, ph);
           tc_fence_after();
-          const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
-          const uint32_t b_hi = base + A_BYTES, b_lo = b_hi + b_bytes;
-          const uint32_t a_hi = tmem_base + TM_A0 + st * 64, a_lo = a_hi + 32;
+          const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * STAGE2);
+          const uint32_t b_hi = base + A_BYTES, b_lo = b_hi + B2_BYTES;
+          const uint32_t a_hi = tmem_base + TM_A2 + st * 64, a_lo = a_hi + 32;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint32_t ko = k * UK * 4;
-            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_tf32_ts(tmem_base, a_lo + k * UK, umma_desc(b_hi + ko), idesc1, first);
-            umma_tf32_ts(tmem_base, a_hi + k * UK, umma_desc(b_lo + ko), idesc1, 1u);
-            umma_tf32_ts(tmem_base, a_hi + k * UK, umma_desc(b_hi + ko), idesc1, 1u);
-            if (n2) {
-              const uint32_t bo = static_cast<uint32_t>(n1) * BK * 4;
-              umma_tf32_ts(tmem_base + n1, a_lo + k * UK, umma_desc(b_hi + bo + ko), idesc2, first);
-              umma_tf32_ts(tmem_base + n1, a_hi + k * UK, umma_desc(b_lo + bo + ko), idesc2, 1u);
-              umma_tf32_ts(tmem_base + n1, a_hi + k * UK, umma_desc(b_hi + bo + ko), idesc2, 1u);
-            }
+            umma_tf32_ts(d, a_lo + k * UK, umma_desc(b_hi + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_lo + ko), idesc, 1u);
+            umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_hi + ko), idesc, 1u);
           }
           umma_commit(empty + st);
         }
-        umma_commit(acc_full);
+        umma_commit(acc_full + buf);
       }
     }
   } else if (warp < 6) {
@@ -478,18 +499,22 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % n_tiles) * NT2;
+      const int b_used = min(NT2, g.N - n0) * BK * 4;      // only the rows the MMA reads need splitting
       for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-        const int st = it % S;
-        const uint32_t ph = (it / S) & 1;
+        const int st = it % S2;
+        const uint32_t ph = (it / S2) & 1;
         mbar_wait(full + st, ph);
-        uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
+        uint8_t* base = smem + static_cast<size_t>(st) * STAGE2;
         // A: this thread's row of 32 floats (128-byte swizzle: chunk c sits at c ^ (row & 7)) -> hi / lo -> TMEM
         uint32_t hi[32], lo[32];
-        const uint8_t* rowp = base + r * 128;
+        const uint32_t rowp = smem_u32(base) + r * 128;
+        float4 av[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) av[c] = lds_f4(rowp + ((c ^ (r & 7)) << 4));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-          const float e[4] = {v.x, v.y, v.z, v.w};
+          const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
@@ -497,10 +522,10 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
             lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
           }
         }
-        tmem_st32(lane_addr + TM_A0 + st * 64, hi);
-        tmem_st32(lane_addr + TM_A0 + st * 64 + 32, lo);
+        tmem_st32(lane_addr + TM_A2 + st * 64, hi);
+        tmem_st32(lane_addr + TM_A2 + st * 64 + 32, lo);
         // B: elementwise split in shared memory
-        split_tile(base + A_BYTES, base + A_BYTES + b_bytes, b_bytes, wtid);
+        split_tile(base + A_BYTES, base + A_BYTES + B2_BYTES, b_used, wtid);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_proxy_async();
         tc_fence_before();
@@ -511,30 +536,32 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
   } else {
     // ---------------- epilogue ----------------
     const int quad = warp & 3;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    int t_local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t_local) {
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * nt;
+    int w = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++w) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
+      const int width = min(NT2, g.N - n0);
       const int row = m0 + quad * 32 + lane;
-      mbar_wait(acc_full, t_local & 1);
+      const int buf = w & 1;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * NT2;
+      mbar_wait(acc_full + buf, (w >> 1) & 1);
       tc_fence_after();
       int c = 0;
-      for (; c + 32 <= nt; c += 32) {
+      for (; c + 32 <= width; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
-        if (c + 32 >= nt) {                   // last read of this accumulator: hand it back before the global traffic
+        if (c + 32 >= width) {                // last read of this accumulator: hand it back before the global traffic
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty);
+          if (lane == 0) mbar_arrive(acc_empty + buf);
         }
         if (row < g.M) epilogue_store<32>(g, v, row, n0 + c);
       }
-      if (c < nt) {                           // 16-column tail (nt is a multiple of 16)
+      if (c < width) {                        // 16-column tail (widths are multiples of 16)
         float v[16];
         tmem_ld16(taddr + c, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
+        if (lane == 0) mbar_arrive(acc_empty + buf);
         if (row < g.M) epilogue_store<16>(g, v, row, n0 + c);
       }
     }
@@ -686,16 +713,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__
       // A: split + column sums of dZ (each thread always meets the same logical 16-byte column chunk of block j = i >> 1)
 #pragma unroll
       for (int i = 0; i < WG_A_BYTES / 2048; ++i) {
-        const int off = wtid * 16 + i * 2048;
-        const float4 v = *reinterpret_cast<float4*>(base + off);
+        const uint32_t off = smem_u32(base) + wtid * 16 + i * 2048;
+        const float4 v = lds_f4(off);
         float4 h, l;
-        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-        l = f4_sub(v, h);
-        *reinterpret_cast<float4*>(base + off) = h;
-        *reinterpret_cast<float4*>(base + WG_A_BYTES + off) = l;
+        split4(v, h, l);
+        sts_f4(off, h);
+        sts_f4(off + WG_A_BYTES, l);
         bsum[i >> 1] = f4_add(bsum[i >> 1], v);
       }
       split_tile(base + 2 * WG_A_BYTES, base + 2 * WG_A_BYTES + b_bytes, b_bytes, wtid);
@@ -842,20 +865,14 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
               int kclass, cudaStream_t s) {
   using namespace tc;
   ProfScope prof_scope(kclass, s);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
+  static const bool use_v1 = getenv("RR_TC_V1") != nullptr;
   Args g{};
   const int tiles = (n + MAX_NT - 1) / MAX_NT;
   g.nt = n / tiles;
-  g.bn = g.nt <= 256 ? g.nt : g.nt / 2;
-  RR_REQUIRE(g.nt % g.bn == 0 && (g.bn % 8) == 0, "tc_linear: tile %d box %d", g.nt, g.bn);
+  g.bn = use_v1 ? (g.nt <= 256 ? g.nt : g.nt / 2) : NT2;
   const int stage_bytes = 2 * A_BYTES + 2 * g.nt * BK * 4;
   int S = (SMEM_LIMIT - 2048) / stage_bytes;
   if (S > 4) S = 4;
-  RR_REQUIRE(S >= 2, "tc_linear: tile of %d columns does not fit two pipeline stages", g.nt);
   g.stages = S;
   int cols = 32;
   while (cols < g.nt) cols <<= 1;
@@ -883,21 +900,26 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   g.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   g.seed = seed;
   g.stream_id = stream_id;
-  static const bool use_v1 = getenv("RR_TC_V1") != nullptr;
   if (!use_v1) {
     static bool attr2_set = false;
     if (!attr2_set) {
       RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
       attr2_set = true;
     }
-    const int stage2 = A_BYTES + 2 * g.nt * BK * 4;
-    const size_t smem2 = static_cast<size_t>(2) * stage2 + 1024 + 256;
-    const int total_tiles = ((M + BM - 1) / BM) * tiles;
+    const size_t smem2 = static_cast<size_t>(S2) * STAGE2 + 1024 + 256;
+    const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
     const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
     k_tc_gemm2<<<ctas, THREADS2, smem2, s>>>(g);
     RR_LAUNCH_CHECK("k_tc_gemm2");
     return RR_OK;
   }
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  RR_REQUIRE(g.nt % g.bn == 0 && (g.bn % 8) == 0, "tc_linear: tile %d box %d", g.nt, g.bn);
+  RR_REQUIRE(S >= 2, "tc_linear: tile of %d columns does not fit two pipeline stages", g.nt);
   const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256;
   dim3 grid((M + BM - 1) / BM, tiles);
   k_tc_gemm<<<grid, THREADS, smem, s>>>(g);
