@@ -23,27 +23,6 @@ void prof_push(int cls, cudaEvent_t a, cudaEvent_t b) {
   p.recs[p.n++] = ProfState::Rec{cls, a, b};
 }
 
-int padded(int);
-int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream_t);
-int bond_message_bwd(const rr_graph*, const float*, float*, int, cudaStream_t);
-int neighbor_sum_fwd(const rr_graph*, int, const float*, float*, int, int, cudaStream_t);
-int neighbor_sum_bwd(const rr_graph*, int, const float*, float*, int, cudaStream_t);
-int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
-int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
-int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);
-int sub(long long, const float*, const float*, float*, cudaStream_t);
-int linear_fwd(int, int, const float*, int, const float*, int, const float*, int, const float*, int, const float*, const float*, int,
-               float*, int, int, float, uint64_t, uint64_t, cudaStream_t);
-int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
-int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
-int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
-int loss_max_group();
-int graph_assemble(const rr_mol_store*, int, const int*, const int*, const int*, const int*, const int*, const int*, int, const int*, const int*,
-                   const int*, const rr_graph*, cudaStream_t);
-long long model_workspace_bytes(const rr_model_cfg*, const rr_graph*, const rr_graph*);
-long long model_buffer_offset(const rr_model_cfg*, const rr_graph*, const rr_graph*, const char*);
-int model_forward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, float*, void*, long long, cudaStream_t);
-int model_backward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, rr_params*, void*, long long, cudaStream_t);
 }  // namespace rr
 
 #define S(stream) static_cast<cudaStream_t>(stream)

@@ -150,4 +150,37 @@ __device__ __forceinline__ float4 dropout4(float4 v, float p, float inv_keep, ui
   return v;
 }
 
+// ---- launchers shared between translation units ----------------------------------------------
+int padded(int);
+int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream_t);
+int bond_message_bwd(const rr_graph*, const float*, float*, int, cudaStream_t);
+int neighbor_sum_fwd(const rr_graph*, int, const float*, float*, int, int, cudaStream_t);
+int neighbor_sum_bwd(const rr_graph*, int, const float*, float*, int, cudaStream_t);
+int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
+int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
+int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);
+int sub(long long, const float*, const float*, float*, cudaStream_t);
+// hi_off / lo_off: float offsets from W1 / W2 to their pre-split TF32 images (0 = split on chip)
+int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
+               const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed, uint64_t stream_id,
+               cudaStream_t s, ptrdiff_t hi_off = 0, ptrdiff_t lo_off = 0);
+int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
+int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
+int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
+int loss_max_group();
+int graph_assemble(const rr_mol_store*, int, const int*, const int*, const int*, const int*, const int*, const int*, int, const int*, const int*,
+                   const int*, const rr_graph*, cudaStream_t);
+long long model_workspace_bytes(const rr_model_cfg*, const rr_graph*, const rr_graph*);
+long long model_buffer_offset(const rr_model_cfg*, const rr_graph*, const rr_graph*, const char*);
+int model_forward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, float*, void*, long long, cudaStream_t);
+int model_backward(const rr_model_cfg*, const rr_params*, const rr_graph*, const rr_graph*, const float*, rr_params*, void*, long long, cudaStream_t);
+
+// ---- tcgen05 GEMM entry points (rr_gemm_tc.cu) ---------------------------------------------
+bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2);
+int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
+              const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
+              int kclass, cudaStream_t s, const float* W1lo = nullptr, const float* W2lo = nullptr);
+bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);
+int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s);
+
 }  // namespace rr

@@ -174,13 +174,6 @@ __global__ void __launch_bounds__(NT, 2) k_gemm(GemmArgs g) {
   }
 }
 
-bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2);
-int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
-              const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
-              int kclass, cudaStream_t s);
-
-bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);
-int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s);
 
 static int check_mat(const char* what, const void* p, int ld) {
   RR_REQUIRE(p != nullptr, "%s is NULL", what);
@@ -190,12 +183,15 @@ static int check_mat(const char* what, const void* p, int ld) {
 
 int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
                const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed, uint64_t stream_id,
-               cudaStream_t s) {
+               cudaStream_t s, ptrdiff_t hi_off, ptrdiff_t lo_off) {
+  // hi_off / lo_off != 0: TF32-exact (hi, remainder) images of W1 / W2 live at W + hi_off / W + lo_off (the model's packed weights)
+  const bool pre = hi_off != 0 && lo_off != 0;
   if ((g_gemm_mode.load() == 1 || g_gemm_mode.load() == 2) && tc_supported(M, n, k1, X2 ? k2 : 0, ldx1, X2 ? ldx2 : 0) && aligned16(X1) && aligned16(W1) && aligned16(Y) &&
       (!X2 || (aligned16(X2) && aligned16(W2))) && (!resid || (aligned16(resid) && (ldr & 3) == 0)) && (!bias || aligned16(bias)) && (ldy & 3) == 0 &&
       p >= 0.f && p < 1.f)
-    return tc_linear(M, n, X1, ldx1, W1, k1, k1, X2, ldx2, W2, k2, X2 ? k2 : 0, bias, resid, ldr, Y, ldy, flags & 1, 0, (flags & 2) ? p : 0.f, seed,
-                     stream_id, KC_GEMM_FWD, s);
+    return tc_linear(M, n, X1, ldx1, pre ? W1 + hi_off : W1, k1, k1, X2, ldx2, (pre && W2) ? W2 + hi_off : W2, k2, X2 ? k2 : 0, bias, resid, ldr, Y, ldy,
+                     flags & 1, 0, (flags & 2) ? p : 0.f, seed, stream_id, KC_GEMM_FWD, s, pre ? W1 + lo_off : nullptr,
+                     (pre && W2) ? W2 + lo_off : nullptr);
   ProfScope prof_scope(KC_GEMM_FWD, s);
   RR_REQUIRE(M >= 0 && n > 0 && (n & 3) == 0 && k1 > 0 && (k1 & 3) == 0 && (k2 & 3) == 0, "linear_fwd: M %d n %d k1 %d k2 %d (n, k multiples of 4)", M, n, k1, k2);
   RR_TRY(check_mat("X1", X1, ldx1));

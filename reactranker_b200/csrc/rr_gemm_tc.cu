@@ -40,6 +40,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct Src {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmBlo;  // v2 kernel, pre-split weights: the lo image of B (tmB then maps the hi image)
   int K;
   int pad_[15];  // keep every CUtensorMap 64-byte aligned inside the kernel parameter block
 };
@@ -61,6 +62,8 @@ struct Args {
   int accumulate;
   float p, inv_keep;
   uint64_t seed, stream_id;
+  int presplit;  // B arrives as two TF32-exact images (hi, lo) made once per step by the pack kernel: no B split in the main loop
+  int diag;      // RR_TC_DIAG bit mask (timing experiments only, results are wrong): 1 no A split, 2 no B split, 4 no MMA, 8 no epilogue traffic
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const __grid_constant__ 
 //   warps 6-9: epilogue
 // TMEM columns: [0, 320) accumulator, [320 + 64 s, ...) A stage s = 32 columns hi + 32 columns lo.
 // ================================================================================================
-constexpr int THREADS2 = 320;
+constexpr int THREADS2_BASE = 192;   // TMA warp + MMA warp + 4 split warps; the epilogue adds 4 or 8 warps
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -361,6 +364,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+               "r"(r[14]), "r"(r[15])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -376,19 +385,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int NV>
-__device__ __forceinline__ void epilogue_store(const Args& g, const float* v, int row, int col) {
-  float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
+// Epilogue of one [32 rows x 32 columns] block of the accumulator held one row per lane.
+// A lane owning a whole row would touch 32 different rows per global instruction (16 of every 32-byte sector wasted, no coalescing), and that
+// was half of the kernel's time.  The block is therefore transposed through a warp-private, XOR-swizzled 4 KB staging tile: afterwards 8
+// consecutive lanes cover one row's 128 contiguous bytes, so every global load / store instruction moves whole sectors of 4 rows.
+// The residual (or, for dgrad accumulation, the previous value of C) of a block is loaded one block AHEAD of its use (epi_issue), the first
+// block of a tile before the wait for its accumulator, so its latency hides behind the MMAs.
+__device__ __forceinline__ void epi_issue(const Args& g, float4 (&R)[8], int row0, int col0, int lane) {
+  const float* src = g.resid ? g.resid : (g.accumulate ? g.C : nullptr);
+  if (src == nullptr) return;
+  const int ld = g.resid ? g.ldr : g.ldc;
+  const int col = col0 + 4 * (lane & 7);
 #pragma unroll
-  for (int q = 0; q < NV / 4; ++q) {
-    float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    if (g.bias) o = f4_add(o, ld_f4(g.bias + col + 4 * q));
-    if (g.resid) o = f4_add(o, ld_f4_stream(g.resid + static_cast<size_t>(row) * g.ldr + col + 4 * q));
-    if (g.relu) o = f4_relu(o);
-    if (g.p > 0.f) o = dropout4(o, g.p, g.inv_keep, g.seed, g.stream_id, (static_cast<uint64_t>(row) * g.ldc + col + 4 * q) >> 2);
-    if (g.accumulate) o = f4_add(o, *reinterpret_cast<const float4*>(cp + 4 * q));
-    st_f4(cp + 4 * q, o);
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + i * 4 + (lane >> 3);
+    if (row < g.M && col < g.N) R[i] = ld_f4_stream(src + static_cast<size_t>(row) * ld + col);
   }
+}
+__device__ __forceinline__ void epilogue_block(const Args& g, const float (&v)[32], const float4 (&R)[8], uint32_t stage, int row0, int col0, int lane) {
+  const int j = lane & 7, rsub = lane >> 3;
+  const int col = col0 + 4 * j;
+  const bool col_ok = col < g.N;
+  const float4 bs = (g.bias && col_ok) ? ld_f4(g.bias + col) : f4_zero();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    sts_f4(stage + lane * 128 + ((c ^ (lane & 7)) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub, row = row0 + r;
+    float4 o = lds_f4(stage + r * 128 + ((j ^ (r & 7)) << 4));
+    if (row < g.M && col_ok) {
+      float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
+      if (g.bias) o = f4_add(o, bs);
+      if (g.resid) o = f4_add(o, R[i]);
+      if (g.relu) o = f4_relu(o);
+      if (g.p > 0.f) o = dropout4(o, g.p, g.inv_keep, g.seed, g.stream_id, (static_cast<uint64_t>(row) * g.ldc + col) >> 2);
+      if (g.accumulate) o = f4_add(o, g.resid ? *reinterpret_cast<const float4*>(cp) : R[i]);
+      st_f4(cp, o);
+    }
+  }
+  __syncwarp();
 }
 
 constexpr int NT2 = 160;                          // output columns per work item (<= 160, multiple of 16)
@@ -397,7 +434,8 @@ constexpr int B2_BYTES = NT2 * BK * 4;            // one B box: 160 rows x 128 B
 constexpr int STAGE2 = A_BYTES + 2 * B2_BYTES;    // A raw | B hi | B lo  = 57344 B
 constexpr int TM_A2 = 2 * NT2;                    // TMEM: two accumulators [0,160) [160,320), then 3 x (32 hi + 32 lo) columns of A
 
-__global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant__ Args g) {
+template <int EW>
+__global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const __grid_constant__ Args g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S2) * STAGE2);
@@ -421,7 +459,7 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full + b, 1);
-      mbar_init(acc_empty + b, 4);
+      mbar_init(acc_empty + b, EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < g.nsrc; ++s) {
@@ -442,7 +480,7 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
-      const uint32_t tx = static_cast<uint32_t>(A_BYTES + B2_BYTES);
+      const uint32_t tx = static_cast<uint32_t>(A_BYTES + (g.presplit ? 2 : 1) * B2_BYTES);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
         for (int s = 0; s < g.nsrc; ++s) {
@@ -455,6 +493,7 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
             mbar_expect_tx(full + st, tx);
             tma_load_2d(&g.src[s].tmA, full + st, base, kb * BK, m0);
             tma_load_2d(&g.src[s].tmB, full + st, base + A_BYTES, kb * BK, n0);   // rows past N are zero-filled
+            if (g.presplit) tma_load_2d(&g.src[s].tmBlo, full + st, base + A_BYTES + B2_BYTES, kb * BK, n0);
           }
         }
       }
@@ -479,12 +518,14 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
           const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * STAGE2);
           const uint32_t b_hi = base + A_BYTES, b_lo = b_hi + B2_BYTES;
           const uint32_t a_hi = tmem_base + TM_A2 + st * 64, a_lo = a_hi + 32;
+          if (!(g.diag & 4)) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint32_t ko = k * UK * 4;
-            umma_tf32_ts(d, a_lo + k * UK, umma_desc(b_hi + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_lo + ko), idesc, 1u);
-            umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_hi + ko), idesc, 1u);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint32_t ko = k * UK * 4;
+              umma_tf32_ts(d, a_lo + k * UK, umma_desc(b_hi + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_lo + ko), idesc, 1u);
+              umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_hi + ko), idesc, 1u);
+            }
           }
           umma_commit(empty + st);
         }
@@ -507,62 +548,73 @@ __global__ void __launch_bounds__(THREADS2, 1) k_tc_gemm2(const __grid_constant_
         mbar_wait(full + st, ph);
         uint8_t* base = smem + static_cast<size_t>(st) * STAGE2;
         // A: this thread's row of 32 floats (128-byte swizzle: chunk c sits at c ^ (row & 7)) -> hi / lo -> TMEM
-        uint32_t hi[32], lo[32];
-        const uint32_t rowp = smem_u32(base) + r * 128;
-        float4 av[8];
+        if (!(g.diag & 1)) {
+          uint32_t hi[32], lo[32];
+          const uint32_t rowp = smem_u32(base) + r * 128;
+          float4 av[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) av[c] = lds_f4(rowp + ((c ^ (r & 7)) << 4));
+          for (int c = 0; c < 8; ++c) av[c] = lds_f4(rowp + ((c ^ (r & 7)) << 4));
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+          for (int c = 0; c < 8; ++c) {
+            const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
-            hi[4 * c + j] = h;
-            lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
+              hi[4 * c + j] = h;
+              lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
+            }
           }
+          tmem_st32(lane_addr + TM_A2 + st * 64, hi);
+          tmem_st32(lane_addr + TM_A2 + st * 64 + 32, lo);
         }
-        tmem_st32(lane_addr + TM_A2 + st * 64, hi);
-        tmem_st32(lane_addr + TM_A2 + st * 64 + 32, lo);
-        // B: elementwise split in shared memory
-        split_tile(base + A_BYTES, base + A_BYTES + B2_BYTES, b_used, wtid);
+        // B: elementwise split in shared memory (unless the weights arrived pre-split)
+        if (!g.presplit && !(g.diag & 2)) split_tile(base + A_BYTES, base + A_BYTES + B2_BYTES, b_used, wtid);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        fence_proxy_async();
+        if (!g.presplit) fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready + st);
       }
     }
   } else {
-    // ---------------- epilogue ----------------
+    // ---------------- epilogue: EW / 4 warps per TMEM lane quadrant, taking the 32-column blocks of a tile in turn ----------------
+    constexpr int EPQ = EW / 4;
     const int quad = warp & 3;
+    const int eidx = (warp - 6) >> 2;
+    const uint32_t stage = smem_u32(reinterpret_cast<uint8_t*>(full) + 256) + (warp - 6) * 4096;   // warp-private staging tile
     int w = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++w) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
-      const int width = min(NT2, g.N - n0);
-      const int row = m0 + quad * 32 + lane;
+      const int nblk = (min(NT2, g.N - n0) + 31) >> 5;
+      const int row0 = m0 + quad * 32;
       const int buf = w & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * NT2;
+      float4 R[8];
+      int c = eidx;
+      if (c < nblk && !(g.diag & 8)) epi_issue(g, R, row0, n0 + 32 * c, lane);
       mbar_wait(acc_full + buf, (w >> 1) & 1);
       tc_fence_after();
-      int c = 0;
-      for (; c + 32 <= width; c += 32) {
+      if (c >= nblk) {                        // narrow tile: nothing for this warp, but the accumulator hand-back counts every epilogue warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);
+      }
+      for (; c < nblk; c += EPQ) {
         float v[32];
-        tmem_ld32(taddr + c, v);
-        if (c + 32 >= width) {                // last read of this accumulator: hand it back before the global traffic
+        tmem_ld32(taddr + 32 * c, v);         // a 16-column tail reads 16 stale columns past the tile: never stored (col < N guard)
+        const bool last = c + EPQ >= nblk;
+        if (last) {                           // last read of this accumulator: hand it back before the global traffic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + buf);
         }
-        if (row < g.M) epilogue_store<32>(g, v, row, n0 + c);
-      }
-      if (c < width) {                        // 16-column tail (widths are multiples of 16)
-        float v[16];
-        tmem_ld16(taddr + c, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + buf);
-        if (row < g.M) epilogue_store<16>(g, v, row, n0 + c);
+        float4 Rn[8];
+        if (!last && !(g.diag & 8)) epi_issue(g, Rn, row0, n0 + 32 * (c + EPQ), lane);
+        if (!(g.diag & 8)) epilogue_block(g, v, R, stage, row0, n0 + 32 * c, lane);
+        if (!last) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) R[i] = Rn[i];
+        }
       }
     }
   }
@@ -591,12 +643,14 @@ struct WgArgs {
   int M, n, k;
   int kt;            // k columns per CTA (multiple of 16, <= 320)
   int nb;            // TMA boxes of B per stage = ceil(kt / 32)
+  int k_pad;         // k rounded up to 16: the last k-tile may be narrower than kt
+  int tm_a;          // first TMEM column of the A stages (accumulator below it)
   int stages;
-  int tmem_cols;
   int m_chunk;       // rows of the reduction per blockIdx.z (multiple of WG_BK)
   float* dW;
   int lddw;
   float* dbias;
+  int diag;          // RR_TC_DIAG (timing experiments)
 };
 
 // MN-major tf32 operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte atomicity
@@ -615,26 +669,37 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__ WgArgs g) {
+// ================================================================================================
+// wgrad v2: the dZ operand goes through TENSOR MEMORY.
+// v1 splits both operands in shared memory and reads both back for each of the three TF32 products: ~390 KB of shared-memory traffic per
+// 32 rows of the reduction, twice what the MMAs themselves need.  Here the thread that owns TMEM lane n reads column n of the landed
+// dZ tile (one LDS.32 per row: a warp reads 128 contiguous bytes, no swizzle needed), splits it in registers and tcgen05.st's (hi, lo)
+// into TMEM as the [n x m] A operand; only X is split in shared memory (MN-major B, as in v1).  The bias gradient is the same thread's
+// running sum.  BKR = rows of the reduction per pipeline stage (32: 2 stages at 320 columns; 16: 4 stages).
+// TMEM: accumulator from column 0 | stage s: BKR columns hi + BKR columns lo from column tm_a + 2 BKR s.
+// ================================================================================================
+
+template <int BKR>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad2(const __grid_constant__ WgArgs g) {
+  constexpr int BOX = BKR * 128;          // bytes of one [BKR x 32 floats] TMA box
+  constexpr int A_RAW = 4 * BOX;          // 128 n-columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int b_bytes = g.nb * WG_BOX;
-  const int stage_bytes = 2 * WG_A_BYTES + 2 * b_bytes;
+  const int b_bytes = g.nb * BOX;
+  const int stage_bytes = A_RAW + 2 * b_bytes;   // A raw | B hi | B lo
   const int S = g.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
   uint64_t* ready = full + S;
   uint64_t* empty = ready + S;
   uint64_t* acc_bar = empty + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BM, k0 = blockIdx.y * g.kt;
   const int m_beg = blockIdx.z * g.m_chunk;
   const int m_end = min(g.M, m_beg + g.m_chunk);
-  const int nst = (m_end - m_beg + WG_BK - 1) / WG_BK;   // >= 1 by construction of the grid
+  const int nst = (m_end - m_beg + BKR - 1) / BKR;   // >= 1 by construction of the grid
 
-  if (threadIdx.x < BM) sbias[threadIdx.x] = 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -647,7 +712,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__
     prefetch_tmap(&g.tmB);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -657,23 +722,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = static_cast<uint32_t>(WG_A_BYTES + b_bytes);
+      const uint32_t tx = static_cast<uint32_t>(A_RAW + b_bytes);
       for (int it = 0; it < nst; ++it) {
         const int st = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(empty + st, ph ^ 1);
         uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
-        const int m = m_beg + it * WG_BK;
+        const int m = m_beg + it * BKR;
         mbar_expect_tx(full + st, tx);
-        for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, full + st, base + j * WG_BOX, n0 + 32 * j, m);
-        for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, full + st, base + 2 * WG_A_BYTES + j * WG_BOX, k0 + 32 * j, m);
+        for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, full + st, base + j * BOX, n0 + 32 * j, m);
+        for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, full + st, base + A_RAW + j * BOX, k0 + 32 * j, m);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const int n1 = (g.kt <= 256) ? g.kt : 160;      // 160 = five 32-float atoms: the second MMA starts on an atom boundary
-      const int n2 = g.kt - n1;
-      const uint32_t mn = (1u << 15) | (1u << 16);    // A and B are MN-major
+      const int width = min(g.kt, g.k_pad - k0);
+      const int n1 = (width <= 256) ? width : 160;    // 160 = five 32-float atoms: the second MMA starts on an atom boundary
+      const int n2 = width - n1;
+      const uint32_t mn = (1u << 16);                 // B is MN-major; A comes from TMEM
       const uint32_t idesc1 = umma_idesc(BM, n1) | mn;
       const uint32_t idesc2 = n2 ? (umma_idesc(BM, n2) | mn) : 0u;
       for (int it = 0; it < nst; ++it) {
@@ -682,19 +748,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__
         mbar_wait(ready + st, ph);
         tc_fence_after();
         const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
-        const uint32_t a_hi = base, a_lo = base + WG_A_BYTES, b_hi = base + 2 * WG_A_BYTES, b_lo = b_hi + b_bytes;
+        const uint32_t b_hi = base + A_RAW, b_lo = b_hi + b_bytes;
+        const uint32_t a_hi = tmem_base + g.tm_a + st * 2 * BKR, a_lo = a_hi + BKR;
+        if (!(g.diag & 4)) {
 #pragma unroll
-        for (int k = 0; k < WG_BK / UK; ++k) {
-          const uint32_t ko = k * 1024;                // next 8 rows of the reduction
-          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-          umma_tf32(tmem_base, umma_desc_mn(a_lo + ko, WG_BOX), umma_desc_mn(b_hi + ko, WG_BOX), idesc1, first);
-          umma_tf32(tmem_base, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_lo + ko, WG_BOX), idesc1, 1u);
-          umma_tf32(tmem_base, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_hi + ko, WG_BOX), idesc1, 1u);
-          if (n2) {
-            const uint32_t bo = static_cast<uint32_t>(n1 / 32) * WG_BOX;
-            umma_tf32(tmem_base + n1, umma_desc_mn(a_lo + ko, WG_BOX), umma_desc_mn(b_hi + bo + ko, WG_BOX), idesc2, first);
-            umma_tf32(tmem_base + n1, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_lo + bo + ko, WG_BOX), idesc2, 1u);
-            umma_tf32(tmem_base + n1, umma_desc_mn(a_hi + ko, WG_BOX), umma_desc_mn(b_hi + bo + ko, WG_BOX), idesc2, 1u);
+          for (int k = 0; k < BKR / UK; ++k) {
+            const uint32_t ko = k * 1024;                // next 8 rows of the reduction
+            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+            umma_tf32_ts(tmem_base, a_lo + k * UK, umma_desc_mn(b_hi + ko, BOX), idesc1, first);
+            umma_tf32_ts(tmem_base, a_hi + k * UK, umma_desc_mn(b_lo + ko, BOX), idesc1, 1u);
+            umma_tf32_ts(tmem_base, a_hi + k * UK, umma_desc_mn(b_hi + ko, BOX), idesc1, 1u);
+            if (n2) {
+              const uint32_t bo = static_cast<uint32_t>(n1 / 32) * BOX;
+              umma_tf32_ts(tmem_base + n1, a_lo + k * UK, umma_desc_mn(b_hi + bo + ko, BOX), idesc2, first);
+              umma_tf32_ts(tmem_base + n1, a_hi + k * UK, umma_desc_mn(b_lo + bo + ko, BOX), idesc2, 1u);
+              umma_tf32_ts(tmem_base + n1, a_hi + k * UK, umma_desc_mn(b_hi + bo + ko, BOX), idesc2, 1u);
+            }
           }
         }
         umma_commit(empty + st);
@@ -703,51 +772,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__
     }
   } else {
     const int wtid = threadIdx.x - 64;
-    const bool do_bias = g.dbias != nullptr && blockIdx.y == 0;
-    float4 bsum[4] = {f4_zero(), f4_zero(), f4_zero(), f4_zero()};
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                   // TMEM lane == column n0 + r of dZ
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float bsum = 0.f;
     for (int it = 0; it < nst; ++it) {
       const int st = it % S;
       const uint32_t ph = (it / S) & 1;
       mbar_wait(full + st, ph);
       uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
-      // A: split + column sums of dZ (each thread always meets the same logical 16-byte column chunk of block j = i >> 1)
+      if (!(g.diag & 1)) {
+        const uint32_t colp = smem_u32(base) + quad * BOX + lane * 4;
+        float a[BKR];
 #pragma unroll
-      for (int i = 0; i < WG_A_BYTES / 2048; ++i) {
-        const uint32_t off = smem_u32(base) + wtid * 16 + i * 2048;
-        const float4 v = lds_f4(off);
-        float4 h, l;
-        split4(v, h, l);
-        sts_f4(off, h);
-        sts_f4(off + WG_A_BYTES, l);
-        bsum[i >> 1] = f4_add(bsum[i >> 1], v);
+        for (int m = 0; m < BKR; ++m) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[m]) : "r"(colp + m * 128));
+        uint32_t hi[BKR], lo[BKR];
+#pragma unroll
+        for (int m = 0; m < BKR; ++m) {
+          const uint32_t h = (__float_as_uint(a[m]) + 0x1000u) & 0xFFFFE000u;
+          hi[m] = h;
+          lo[m] = __float_as_uint(a[m] - __uint_as_float(h));
+          bsum += a[m];
+        }
+        const uint32_t ta = lane_addr + g.tm_a + st * 2 * BKR;
+        if constexpr (BKR == 32) {
+          tmem_st32(ta, hi);
+          tmem_st32(ta + BKR, lo);
+        } else {
+          tmem_st16(ta, hi);
+          tmem_st16(ta + BKR, lo);
+        }
       }
-      split_tile(base + 2 * WG_A_BYTES, base + 2 * WG_A_BYTES + b_bytes, b_bytes, wtid);
+      if (!(g.diag & 2)) split_tile(base + A_RAW, base + A_RAW + b_bytes, b_bytes, wtid);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_proxy_async();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ready + st);
     }
-    if (do_bias) {
-      // 32-byte-atom swizzle: logical 32 B chunk = physical 32 B chunk ^ (row & 3); the 16 B half inside it is unchanged
-      const int c = ((((wtid & 7) >> 1) ^ ((wtid >> 3) & 3)) << 1) | (wtid & 1);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(sbias + j * 32 + c * 4 + 0, bsum[j].x);
-        atomicAdd(sbias + j * 32 + c * 4 + 1, bsum[j].y);
-        atomicAdd(sbias + j * 32 + c * 4 + 2, bsum[j].z);
-        atomicAdd(sbias + j * 32 + c * 4 + 3, bsum[j].w);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (n0 + wtid < g.n) atomicAdd(g.dbias + n0 + wtid, sbias[wtid]);
-    }
+    if (g.dbias != nullptr && blockIdx.y == 0 && n0 + r < g.n) atomicAdd(g.dbias + n0 + r, bsum);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const int quad = warp & 3;
-    const int row = n0 + quad * 32 + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    for (int c = 0; c < g.kt; c += 16) {
+    const int row = n0 + r;
+    const int width = min(g.kt, g.k_pad - k0);
+    for (int c = 0; c < width; c += 16) {
       float v[16];
-      tmem_ld16(taddr + c, v);
-      if (row < g.n) {
+      tmem_ld16(lane_addr + c, v);
+      if (row < g.n && !(g.diag & 8)) {
         float* cp = g.dW + static_cast<size_t>(row) * g.lddw + k0 + c;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -758,7 +829,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -789,8 +860,9 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;   // 256 B measured no better (wgrad) or worse (forward)
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows %d cols %d ld %d box_rows %d", static_cast<int>(r), rows, cols, ld, box_rows);
   return RR_OK;
 }
@@ -799,42 +871,44 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
 
 
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx) {
-  if (M <= 0 || n < 4 || k < 4 || (n & 3) || (k & 3) || (lddz & 3) || (ldx & 3)) return false;
-  const int tiles = (k + tc::MAX_NT - 1) / tc::MAX_NT;
-  if (tiles == 1) return true;               // one k-tile: columns are padded to a multiple of 16 with TMA zero fill
-  return (k % tiles) == 0 && ((k / tiles) & 15) == 0;
+  return M > 0 && n >= 4 && k >= 4 && !(n & 3) && !(k & 3) && !(lddz & 3) && !(ldx & 3);
 }
 
 int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s) {
   using namespace tc;
   ProfScope prof_scope(KC_GEMM_WGRAD, s);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
   WgArgs g{};
-  const int ktiles = (k + MAX_NT - 1) / MAX_NT;
-  g.kt = ktiles == 1 ? (k + 15) / 16 * 16 : k / ktiles;
+  const char* kt_env = getenv("RR_WG_KT");
+  const int kt_cap = (kt_env && atoi(kt_env) == 160) ? 160 : MAX_NT;
+  const int k_pad = (k + 15) / 16 * 16;                  // columns past k are zero-filled by TMA and never written back
+  const int ktiles = (k_pad + kt_cap - 1) / kt_cap;
+  g.kt = ktiles == 1 ? k_pad : kt_cap;
   g.nb = (g.kt + 31) / 32;
-  const int stage_bytes = 2 * WG_A_BYTES + 2 * g.nb * WG_BOX;
+  g.tm_a = g.kt <= 160 ? 160 : 320;
+  // wide tiles: 16-row stages (4 x 48 KB in flight instead of 2 x 96 KB); narrow tiles fit 3+ stages of 32 rows
+  const char* bkr_env = getenv("RR_WG_BKR");
+  const int bkr = bkr_env ? (atoi(bkr_env) == 16 ? 16 : 32) : (g.kt > 160 ? 16 : 32);
+  const int box = bkr * 128;
+  const int stage_bytes = 4 * box + 2 * g.nb * box;
   int S = (SMEM_LIMIT - 2048) / stage_bytes;
-  if (S > 4) S = 4;
+  if (S > (512 - g.tm_a) / (2 * bkr)) S = (512 - g.tm_a) / (2 * bkr);   // TMEM: accumulator + 2 * bkr columns of A per stage
+  if (S > 6) S = 6;
   RR_REQUIRE(S >= 2, "tc_wgrad: %d columns do not fit two pipeline stages", g.kt);
   g.stages = S;
-  int cols = 32;
-  while (cols < g.kt) cols <<= 1;
-  g.tmem_cols = cols;
-  RR_TRY(make_map(&g.tmA, dZ, M, n, lddz, WG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  RR_TRY(make_map(&g.tmB, X, M, k, ldx, WG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  RR_TRY(make_map(&g.tmA, dZ, M, n, lddz, bkr, CU_TENSOR_MAP_SWIZZLE_NONE));
+  RR_TRY(make_map(&g.tmB, X, M, k, ldx, bkr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   g.M = M;
   g.n = n;
   g.k = k;
+  g.k_pad = k_pad;
   g.dW = dW;
   g.lddw = lddw;
   g.dbias = dbias;
+  const char* diag_env = getenv("RR_TC_DIAG");
+  g.diag = diag_env ? atoi(diag_env) : 0;
+  // one CTA per SM (shared memory and TMEM are both taken whole): never more CTAs than SMs, or the stragglers run as a second wave
   const int ntiles = (n + BM - 1) / BM;
-  int splits = (num_sms() + ntiles * ktiles - 1) / (ntiles * ktiles);
+  int splits = num_sms() / (ntiles * ktiles);
   const int max_splits = (M + 8 * WG_BK - 1) / (8 * WG_BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -842,10 +916,17 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   chunk = (chunk + WG_BK - 1) / WG_BK * WG_BK;
   splits = (M + chunk - 1) / chunk;
   g.m_chunk = chunk;
-  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256 + BM * sizeof(float) + 64;
   dim3 grid(ntiles, ktiles, splits);
-  k_tc_wgrad<<<grid, THREADS, smem, s>>>(g);
-  RR_LAUNCH_CHECK("k_tc_wgrad");
+  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  if (bkr == 32) k_tc_wgrad2<32><<<grid, THREADS, smem, s>>>(g);
+  else k_tc_wgrad2<16><<<grid, THREADS, smem, s>>>(g);
+  RR_LAUNCH_CHECK("k_tc_wgrad2");
   return RR_OK;
 }
 
@@ -860,12 +941,18 @@ bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2) {
 }
 
 // Y = epi(X1 W1^T + X2 W2^T): W* row-major [n, k*] (K-major B operand)
+// W1lo / W2lo != NULL: W1 / W2 are the TF32-exact hi images of the weights and W*lo the remainders (same shape and stride)
 int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
               const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
-              int kclass, cudaStream_t s) {
+              int kclass, cudaStream_t s, const float* W1lo, const float* W2lo) {
   using namespace tc;
   ProfScope prof_scope(kclass, s);
   static const bool use_v1 = getenv("RR_TC_V1") != nullptr;
+  const char* diag_env = getenv("RR_TC_DIAG");
+  if (getenv("RR_TC_FAKE_PRESPLIT") && !W1lo) {  // timing experiments only (scripts/bench_gemm.py): wrong numerics, same traffic as pre-split weights
+    W1lo = W1;
+    W2lo = W2;
+  }
   Args g{};
   const int tiles = (n + MAX_NT - 1) / MAX_NT;
   g.nt = n / tiles;
@@ -881,9 +968,13 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
   RR_TRY(make_map(&g.src[0].tmB, W1, n, k1, ldw1, g.bn));
   g.src[0].K = k1;
+  g.presplit = (!use_v1 && W1lo != nullptr && (!(X2 && k2 > 0) || W2lo != nullptr)) ? 1 : 0;
+  g.diag = diag_env ? atoi(diag_env) : 0;
+  if (g.presplit) RR_TRY(make_map(&g.src[0].tmBlo, W1lo, n, k1, ldw1, g.bn));
   if (X2 && k2 > 0) {
     RR_TRY(make_map(&g.src[1].tmA, X2, M, k2, ldx2, BM));
     RR_TRY(make_map(&g.src[1].tmB, W2, n, k2, ldw2, g.bn));
+    if (g.presplit) RR_TRY(make_map(&g.src[1].tmBlo, W2lo, n, k2, ldw2, g.bn));
     g.src[1].K = k2;
     g.nsrc = 2;
   }
@@ -903,13 +994,17 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   if (!use_v1) {
     static bool attr2_set = false;
     if (!attr2_set) {
-      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
       attr2_set = true;
     }
-    const size_t smem2 = static_cast<size_t>(S2) * STAGE2 + 1024 + 256;
+    const size_t smem2 = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
+    const char* ew_env = getenv("RR_TC_EW");
+    const int ew = (ew_env && atoi(ew_env) == 4) ? 4 : 8;
     const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
     const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-    k_tc_gemm2<<<ctas, THREADS2, smem2, s>>>(g);
+    if (ew == 8) k_tc_gemm2<8><<<ctas, THREADS2_BASE + 256, smem2, s>>>(g);
+    else k_tc_gemm2<4><<<ctas, THREADS2_BASE + 128, smem2, s>>>(g);
     RR_LAUNCH_CHECK("k_tc_gemm2");
     return RR_OK;
   }

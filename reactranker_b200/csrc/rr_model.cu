@@ -12,25 +12,6 @@
 
 namespace rr {
 
-// launchers implemented in the other translation units
-int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream_t);
-int bond_message_bwd(const rr_graph*, const float*, float*, int, cudaStream_t);
-int neighbor_sum_fwd(const rr_graph*, int, const float*, float*, int, int, cudaStream_t);
-int neighbor_sum_bwd(const rr_graph*, int, const float*, float*, int, cudaStream_t);
-int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
-int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
-int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);
-int sub(long long, const float*, const float*, float*, cudaStream_t);
-int linear_fwd(int, int, const float*, int, const float*, int, const float*, int, const float*, int, const float*, const float*, int,
-               float*, int, int, float, uint64_t, uint64_t, cudaStream_t);
-int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
-int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
-
-bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2);
-int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
-              const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
-              int kclass, cudaStream_t s);
-
 static inline int pad16(int x) { return (x + 15) / 16 * 16; }
 int padded(int w) { return pad16(w); }
 
@@ -141,15 +122,24 @@ static PackTable make_table(const rr_model_cfg& c, const PackedLayout& L, const 
 }
 
 // direction 0: packed <- ref (pack);  1: ref <- packed (un-pack gradients)
-__global__ void k_pack(PackTable T, float* __restrict__ packed, int direction) {
+// Packing also writes the TF32 split of every value (hi = nearest TF32, lo = v - hi) into the images hi_off / lo_off floats further on:
+// the tcgen05 GEMMs then TMA-load both halves of the B operand instead of splitting the same weight tile once per row tile.
+__global__ void k_pack(PackTable T, float* __restrict__ packed, int direction, long long hi_off, long long lo_off) {
   const PackEntry e = T.e[blockIdx.y];
   const long long n = static_cast<long long>(e.rows) * e.cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / e.cols), c = static_cast<int>(i - static_cast<long long>(r) * e.cols);
     float* pp = packed + e.packed + (e.transpose ? static_cast<long long>(c) * e.packed_ld + r : static_cast<long long>(r) * e.packed_ld + c);
     float* rp = e.ref + static_cast<long long>(r) * e.ref_ld + e.ref_col0 + c;
-    if (direction == 0) *pp = *rp;
-    else *rp = *pp;
+    if (direction == 0) {
+      const float v = *rp;
+      const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+      *pp = v;
+      pp[hi_off] = hi;
+      pp[lo_off] = v - hi;
+    } else {
+      *rp = *pp;
+    }
   }
 }
 
@@ -198,7 +188,8 @@ struct EncBufs {
 };
 struct Workspace {
   PackedLayout L;
-  float* packed;
+  float* packed;      // raw | TF32 hi image | TF32 lo image, L.total floats each
+  ptrdiff_t hi_off, lo_off;
   float* dpacked;
   EncBufs enc[2];  // 0 = reactants, 1 = products
   float *d, *inp2, *nf, *am2, *hid2, *vec, *zout;
@@ -231,7 +222,9 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
     used += (floats * sizeof(float) + 255) / 256 * 256;
     return ptr;
   };
-  W->packed = take(W->L.total);
+  W->packed = take(3 * W->L.total);
+  W->hi_off = static_cast<ptrdiff_t>(W->L.total);
+  W->lo_off = static_cast<ptrdiff_t>(2 * W->L.total);
   W->dpacked = take(W->L.grad_total);
   for (int s = 0; s < 2; ++s) {
     const size_t B = (s == 0 ? r.n_bonds : p.n_bonds);
@@ -270,9 +263,10 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
 
 // dX[M, k] (+)= dZ[M, n] W[n, k]: tensor cores read the transposed copy Wt[k, n] as a K-major operand, the SIMT path reads W
 static int dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, const float* Wt, int ldwt, float* dX, int lddx,
-                 int accumulate, cudaStream_t s) {
+                 int accumulate, cudaStream_t s, ptrdiff_t hi_off, ptrdiff_t lo_off) {
   if ((g_gemm_mode.load() == 1 || g_gemm_mode.load() == 3) && tc_supported(M, k, n, 0, lddz, 0))
-    return tc_linear(M, k, dZ, lddz, Wt, ldwt, n, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, dX, lddx, 0, accumulate, 0.f, 0, 0, KC_GEMM_DGRAD, s);
+    return tc_linear(M, k, dZ, lddz, Wt + hi_off, ldwt, n, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, dX, lddx, 0, accumulate, 0.f, 0, 0, KC_GEMM_DGRAD, s,
+                     Wt + lo_off, nullptr);
   return linear_dgrad(M, n, k, dZ, lddz, W, ldw, dX, lddx, accumulate, s);
 }
 
@@ -336,9 +330,9 @@ static int check_model_args(const rr_model_cfg* c, const rr_params* w, const rr_
 }
 
 static int pack_params(const rr_model_cfg& c, const Workspace& W, const rr_params& w, cudaStream_t s) {
-  RR_CUDA(cudaMemsetAsync(W.packed, 0, W.L.total * sizeof(float), s));
+  RR_CUDA(cudaMemsetAsync(W.packed, 0, 3 * W.L.total * sizeof(float), s));
   PackTable T = make_table(c, W.L, w, true);
-  k_pack<<<dim3(32, T.n), 256, 0, s>>>(T, W.packed, 0);
+  k_pack<<<dim3(32, T.n), 256, 0, s>>>(T, W.packed, 0, W.hi_off, W.lo_off);
   RR_LAUNCH_CHECK("k_pack");
   return RR_OK;
 }
@@ -363,25 +357,25 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
     const rr_graph* g = gs[k];
     EncBufs& e = W.enc[k];
     RR_TRY(linear_fwd(g->n_bonds, hp, g->f_bonds, RR_FB_LD, P + L.enc_Wi, RR_FB_LD, nullptr, 0, nullptr, 0, P + L.enc_bi, nullptr, 0,
-                      e.inp, hp, 0, 0.f, c->seed, sid++, s));
+                      e.inp, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off));
     const float* src = e.inp;
     int relu_src = 1;
     for (int t = 0; t < T; ++t) {
       RR_TRY(bond_message_fwd(g, src, e.pre[t], hp, relu_src, s));
       RR_TRY(linear_fwd(g->n_bonds, hp, e.pre[t], hp, P + L.enc_Wh, hp, nullptr, 0, nullptr, 0, P + L.enc_bh, e.inp, hp, e.m[t + 1], hp,
-                        act, pdrop, c->seed, sid++, s));
+                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
       src = e.m[t + 1];
       relu_src = 0;
     }
     RR_TRY(neighbor_sum_fwd(g, 0, src, e.am, hp, relu_src, s));
     RR_TRY(linear_fwd(g->n_atoms, hp, g->f_atoms, RR_FA_LD, P + L.enc_Wo_a, RR_FA_LD, e.am, hp, P + L.enc_Wo_m, hp, P + L.enc_bo, nullptr, 0,
-                      e.hid, hp, act, pdrop, c->seed, sid++, s));
+                      e.hid, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
   }
   const int A = p->n_atoms;
   RR_TRY(sub(static_cast<long long>(A) * hp, W.enc[1].hid, W.enc[0].hid, W.d, s));  // base_model.py:168
 
   // mpn.py:170-240 over the product graph
-  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s));
+  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off));
   if (Td > 0) RR_TRY(neighbor_sum_fwd(p, 0, p->f_bonds, W.nf, RR_FB_LD, 0, s));
   {
     const float* src = W.inp2;
@@ -389,13 +383,13 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
     for (int t = 0; t < Td; ++t) {
       RR_TRY(neighbor_sum_fwd(p, 1, src, W.nm[t], hp, relu_src, s));
       RR_TRY(linear_fwd(A, hp, W.nm[t], hp, P + L.dif_Wh_m, hp, W.nf, RR_FB_LD, P + L.dif_Wh_f, RR_FB_LD, P + L.dif_bh, W.inp2, hp, W.m2[t + 1], hp,
-                        act, pdrop, c->seed, sid++, s));
+                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
       src = W.m2[t + 1];
       relu_src = 0;
     }
     RR_TRY(neighbor_sum_fwd(p, 1, src, W.am2, hp, relu_src, s));
   }
-  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wo_d, hp, W.am2, hp, P + L.dif_Wo_m, hp, P + L.dif_bo, nullptr, 0, W.hid2, hp, act, pdrop, c->seed, sid++, s));
+  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wo_d, hp, W.am2, hp, P + L.dif_Wo_m, hp, P + L.dif_bo, nullptr, 0, W.hid2, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
   RR_TRY(readout_fwd(p, W.hid2, hp, c->hidden, addf, c->add_features, W.vec, vp, pdrop, c->seed, sid++, s));
 
   // base_model.py:40-60
@@ -406,7 +400,7 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
     const bool last = (l == c->ffn_depth - 1);
     float* y = last ? W.zout : W.x[l];
     RR_TRY(linear_fwd(N, L.ffn_out[l], x, ldx, P + L.ffn_W[l], L.ffn_in[l], nullptr, 0, nullptr, 0, P + L.ffn_b[l], nullptr, 0, y, L.ffn_out[l],
-                      last ? 0 : act, pdrop, c->seed, sid++, s));
+                      last ? 0 : act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
     x = y;
     ldx = L.ffn_out[l];
   }
@@ -448,12 +442,12 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       RR_TRY(linear_wgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, x, L.ffn_in[l], G + L.ffn_W[l], L.ffn_in[l], G + L.ffn_b[l], s));
       if (l > 0) {
         float* dx = scratch[l & 1];
-        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], dx, hp, 0, s));
+        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], dx, hp, 0, s, W.hi_off, W.lo_off));
         RR_TRY(relu_bwd(N, hp, dx, W.x[l - 1], keep, 0, dx, nullptr, 0, s));
         g = dx;
         ldg = hp;
       } else {
-        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], W.dvec, vp, 0, s));
+        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], W.dvec, vp, 0, s, W.hi_off, W.lo_off));
       }
     }
   }
@@ -461,8 +455,8 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   RR_TRY(readout_bwd(p, W.dvec, vp, W.vec, W.hid2, W.gA1, hp, pdrop, s));
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.d, hp, G + L.dif_Wo_d, hp, G + L.dif_bo, s));
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.am2, hp, G + L.dif_Wo_m, hp, nullptr, s));
-  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, P + L.dif_Wo_d_T, hp, W.dD, hp, 0, s));
-  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, P + L.dif_Wo_m_T, hp, W.gA2, hp, 0, s));
+  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, P + L.dif_Wo_d_T, hp, W.dD, hp, 0, s, W.hi_off, W.lo_off));
+  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, P + L.dif_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
   RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
   if (Td == 0) {
     RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 1, s));
@@ -471,13 +465,13 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       RR_TRY(relu_bwd(A, hp, W.gA3, W.m2[t], keep, 0, W.gA1, W.dI2, t == Td ? 1 : 2, s));
       RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.nm[t - 1], hp, G + L.dif_Wh_m, hp, G + L.dif_bh, s));
       RR_TRY(linear_wgrad(A, hp, RR_FB_LD, W.gA1, hp, W.nf, RR_FB_LD, G + L.dif_Wh_f, RR_FB_LD, nullptr, s));
-      RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s));
+      RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
       RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
     }
     RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 2, s));
   }
   RR_TRY(linear_wgrad(A, hp, hp, W.dI2, hp, W.d, hp, G + L.dif_Wi, hp, G + L.dif_bi, s));
-  RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s));
+  RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s, W.hi_off, W.lo_off));
 
   // shared encoder: products (+dD) then reactants (-dD); weight gradients accumulate (base_model.py:155-156)
   const rr_graph* gs[2] = {r, p};
@@ -489,7 +483,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
     RR_TRY(relu_bwd(A, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
     RR_TRY(linear_wgrad(A, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
     RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
-    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s));
+    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
     RR_TRY(neighbor_sum_bwd(g, 0, W.gA2, W.gB1, hp, s));
     if (T == 0) {
       RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 1, s));
@@ -497,7 +491,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       for (int t = T; t >= 1; --t) {
         RR_TRY(relu_bwd(B, hp, W.gB1, e.m[t], keep, 0, W.gB1, W.dinp, t == T ? 1 : 2, s));
         RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
-        RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s));
+        RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off));
         RR_TRY(bond_message_bwd(g, W.gB2, W.gB1, hp, s));
       }
       RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 2, s));
@@ -506,7 +500,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   }
 
   PackTable Tb = make_table(*c, L, *grads, false);
-  k_pack<<<dim3(32, Tb.n), 256, 0, s>>>(Tb, G, 1);
+  k_pack<<<dim3(32, Tb.n), 256, 0, s>>>(Tb, G, 1, 0, 0);
   RR_LAUNCH_CHECK("k_pack(grads)");
   return RR_OK;
 }
