@@ -269,7 +269,7 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile=False):
+    def timed(fn, steps, warmup, profile=False, trace=None):
         for i in range(warmup):
             fn(i)
         barrier()
@@ -279,7 +279,10 @@ def ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
+            t0 = time.perf_counter()
             fn(warmup + i)
+            if trace is not None:
+                trace.append((time.perf_counter() - t0) * 1e3)     # host wall per step (the e2e step ends with a D2H read)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -294,8 +297,11 @@ def ours(args):
     with ClockSampler(local) as clocks:
         ms, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
     clk = clocks.summary()
-    e2e_steps = max(3, min(args.steps, 10))
-    ms_e2e, _, _ = timed(step_e2e, e2e_steps, 3)
+    e2e_steps = max(3, args.steps)
+    e2e_trace = []
+    ms_e2e, _, _ = timed(step_e2e, e2e_steps, max(3, args.warmup), trace=e2e_trace)
+    if rank == 0:
+        print("e2e host wall per step (ms): " + " ".join(f"{t:.1f}" for t in e2e_trace), file=sys.stderr)
 
     value = rows * world * args.steps / (ms / 1e3)
     e2e_value = rows * world * e2e_steps / (ms_e2e / 1e3)

@@ -149,6 +149,13 @@ int rr_bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp,
 int rr_neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out, int ld, int relu_src, void* stream);
 /* backward of which=0: dsrc[b] = dout[atom b points into]; of which=1: symmetric gather */
 int rr_neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, void* stream);
+/* The two backward gathers fused with the ReLU / inverted-dropout backward that follows them in MPN / MPNDiff (autograd of
+ * mpn.py:81,95-97,208-213): dz = gather_bwd(...) * [y != 0] * scale  (y_is_preact: [y > 0]), written to dm / dsrc unless skip_out,
+ * and acc = dz (acc_mode 1) or acc += dz (acc_mode 2).  y == NULL: the plain gather backward. */
+int rr_bond_message_bwd_act(const rr_graph* g, const float* dpre, float* dm, int hp, const float* y, float scale, int y_is_preact,
+                            float* acc, int acc_mode, int skip_out, void* stream);
+int rr_neighbor_sum_bwd_act(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, const float* y, float scale,
+                            int y_is_preact, float* acc, int acc_mode, int skip_out, void* stream);
 /* mpn.py:224-238: vec[i] = mean(hid[a_scope[i]])[:hidden] || add_features[i] (zero padded to vp),
  * then the FFN's first dropout (base_model.py:40).  hid is [n_atoms, hp], vec is [n_mols, vp]. */
 int rr_readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const float* add_features, int n_add,

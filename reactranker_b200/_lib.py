@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "librr_sm100.so")
-SOURCES = ["rr_api.cu", "rr_mp.cu", "rr_gemm_simt.cu", "rr_gemm_tc.cu", "rr_assemble.cu", "rr_loss.cu", "rr_model.cu"]
+SOURCES = ["rr_api.cu", "rr_mp.cu", "rr_mp_pipe.cu", "rr_gemm_simt.cu", "rr_gemm_tc.cu", "rr_assemble.cu", "rr_loss.cu", "rr_model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -48,7 +48,7 @@ class RRParams(ctypes.Structure):
 EXPORTS = [
     "rr_version", "rr_last_error", "rr_device_check", "rr_padded",
     "rr_graph_assemble", "rr_bond_message_fwd", "rr_bond_message_bwd", "rr_neighbor_sum_fwd", "rr_neighbor_sum_bwd",
-    "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
+    "rr_bond_message_bwd_act", "rr_neighbor_sum_bwd_act", "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
     "rr_loss_fwdbwd", "rr_loss_max_group",
     "rr_model_workspace_bytes", "rr_model_buffer_offset", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
     "rr_profile_begin", "rr_profile_end", "rr_profile_classes", "rr_set_gemm_mode", "rr_get_gemm_mode",
@@ -105,6 +105,8 @@ def lib() -> ctypes.CDLL:
                 L.rr_bond_message_bwd.argtypes = [vp, vp, vp, i32, vp]
                 L.rr_neighbor_sum_fwd.argtypes = [vp, i32, vp, vp, i32, i32, vp]
                 L.rr_neighbor_sum_bwd.argtypes = [vp, i32, vp, vp, i32, vp]
+                L.rr_bond_message_bwd_act.argtypes = [vp, vp, vp, i32, vp, f32, i32, vp, i32, i32, vp]
+                L.rr_neighbor_sum_bwd_act.argtypes = [vp, i32, vp, vp, i32, vp, f32, i32, vp, i32, i32, vp]
                 L.rr_readout_fwd.argtypes = [vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, u64, vp]
                 L.rr_readout_bwd.argtypes = [vp, vp, i32, vp, vp, vp, i32, f32, vp]
                 L.rr_linear_fwd.argtypes = [i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, u64, u64, vp]

@@ -61,6 +61,15 @@ int rr_neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* 
   RR_REQUIRE(which == 0 || which == 1, "which must be 0 (a2b) or 1 (a2a)");
   return rr::neighbor_sum_bwd(g, which, dout, dsrc, ld, S(stream));
 }
+int rr_bond_message_bwd_act(const rr_graph* g, const float* dpre, float* dm, int hp, const float* y, float scale, int y_is_preact, float* acc, int acc_mode,
+                            int skip_out, void* stream) {
+  return rr::bond_message_bwd_act(g, dpre, dm, hp, y, scale, y_is_preact, acc, acc_mode, skip_out, S(stream));
+}
+int rr_neighbor_sum_bwd_act(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, const float* y, float scale, int y_is_preact, float* acc,
+                            int acc_mode, int skip_out, void* stream) {
+  RR_REQUIRE(which == 0 || which == 1, "which must be 0 (a2b) or 1 (a2a)");
+  return rr::neighbor_sum_bwd_act(g, which, dout, dsrc, ld, y, scale, y_is_preact, acc, acc_mode, skip_out, S(stream));
+}
 int rr_readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const float* add_features, int n_add, float* vec, int vp,
                    float dropout, uint64_t seed, uint64_t stream_id, void* stream) {
   return rr::readout_fwd(g, hid, hp, hidden, add_features, n_add, vec, vp, dropout, seed, stream_id, S(stream));

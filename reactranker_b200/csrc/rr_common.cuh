@@ -156,6 +156,15 @@ int bond_message_fwd(const rr_graph*, const float*, float*, int, int, cudaStream
 int bond_message_bwd(const rr_graph*, const float*, float*, int, cudaStream_t);
 int neighbor_sum_fwd(const rr_graph*, int, const float*, float*, int, int, cudaStream_t);
 int neighbor_sum_bwd(const rr_graph*, int, const float*, float*, int, cudaStream_t);
+// gather backward + the ReLU / dropout backward that follows it (y: activation the mask comes from; acc_mode 0 none, 1 acc = dz, 2 acc += dz)
+int bond_message_bwd_act(const rr_graph*, const float* dpre, float* dm, int hp, const float* y, float scale, int preact, float* acc, int acc_mode,
+                         int skip_out, cudaStream_t);
+int neighbor_sum_bwd_act(const rr_graph*, int which, const float* dout, float* dsrc, int ld, const float* y, float scale, int preact, float* acc,
+                         int acc_mode, int skip_out, cudaStream_t);
+int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float* out, int ld, int relu_src, const float* y, float scale, int preact,
+                   float* acc, int acc_mode, int skip_out, cudaStream_t s);
+int pad_rows_act(float* out, const int* rows, int n_rows, int ld, const float* y, float scale, int preact, float* acc, int acc_mode, int skip_out,
+                 cudaStream_t s);
 int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
 int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
 int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);

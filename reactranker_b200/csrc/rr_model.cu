@@ -457,18 +457,19 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.am2, hp, G + L.dif_Wo_m, hp, nullptr, s));
   RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, P + L.dif_Wo_d_T, hp, W.dD, hp, 0, s, W.hi_off, W.lo_off));
   RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, P + L.dif_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
-  RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
-  if (Td == 0) {
-    RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 1, s));
-  } else {
-    for (int t = Td; t >= 1; --t) {
-      RR_TRY(relu_bwd(A, hp, W.gA3, W.m2[t], keep, 0, W.gA1, W.dI2, t == Td ? 1 : 2, s));
-      RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.nm[t - 1], hp, G + L.dif_Wh_m, hp, G + L.dif_bh, s));
-      RR_TRY(linear_wgrad(A, hp, RR_FB_LD, W.gA1, hp, W.nf, RR_FB_LD, G + L.dif_Wh_f, RR_FB_LD, nullptr, s));
-      RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
-      RR_TRY(neighbor_sum_bwd(p, 1, W.gA2, W.gA3, hp, s));
-    }
-    RR_TRY(relu_bwd(A, hp, W.gA3, W.inp2, 1.f, 1, nullptr, W.dI2, 2, s));
+  // Every gather backward is followed by exactly one ReLU (+ dropout) backward: the mask of the message it produced the gradient of.
+  // Both run as one kernel (rr_mp_pipe.cu): t_next >= 1 -> mask of m2^{t_next}, result kept (gA1) and summed into dI2;
+  // t_next == 0 -> mask [inp2 > 0] of m2^0 = relu(inp2), only the sum into dI2 is wanted.
+  auto diff_nbr_bwd = [&](int t_next) {
+    if (t_next >= 1) return neighbor_sum_bwd_act(p, 1, W.gA2, W.gA1, hp, W.m2[t_next], keep, 0, W.dI2, t_next == Td ? 1 : 2, 0, s);
+    return neighbor_sum_bwd_act(p, 1, W.gA2, W.gA3, hp, W.inp2, 1.f, 1, W.dI2, Td == 0 ? 1 : 2, 1, s);
+  };
+  RR_TRY(diff_nbr_bwd(Td));
+  for (int t = Td; t >= 1; --t) {
+    RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.nm[t - 1], hp, G + L.dif_Wh_m, hp, G + L.dif_bh, s));
+    RR_TRY(linear_wgrad(A, hp, RR_FB_LD, W.gA1, hp, W.nf, RR_FB_LD, G + L.dif_Wh_f, RR_FB_LD, nullptr, s));
+    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
+    RR_TRY(diff_nbr_bwd(t - 1));
   }
   RR_TRY(linear_wgrad(A, hp, hp, W.dI2, hp, W.d, hp, G + L.dif_Wi, hp, G + L.dif_bi, s));
   RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s, W.hi_off, W.lo_off));
@@ -484,17 +485,13 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
     RR_TRY(linear_wgrad(A, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
     RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
     RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
-    RR_TRY(neighbor_sum_bwd(g, 0, W.gA2, W.gB1, hp, s));
-    if (T == 0) {
-      RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 1, s));
-    } else {
-      for (int t = T; t >= 1; --t) {
-        RR_TRY(relu_bwd(B, hp, W.gB1, e.m[t], keep, 0, W.gB1, W.dinp, t == T ? 1 : 2, s));
-        RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
-        RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off));
-        RR_TRY(bond_message_bwd(g, W.gB2, W.gB1, hp, s));
-      }
-      RR_TRY(relu_bwd(B, hp, W.gB1, e.inp, 1.f, 1, nullptr, W.dinp, 2, s));
+    if (T >= 1) RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.m[T], keep, 0, W.dinp, 1, 0, s));
+    else RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 1, 1, s));
+    for (int t = T; t >= 1; --t) {
+      RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
+      RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off));
+      if (t - 1 >= 1) RR_TRY(bond_message_bwd_act(g, W.gB2, W.gB1, hp, e.m[t - 1], keep, 0, W.dinp, 2, 0, s));
+      else RR_TRY(bond_message_bwd_act(g, W.gB2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 2, 1, s));
     }
     RR_TRY(linear_wgrad(B, hp, RR_FB_LD, W.dinp, hp, g->f_bonds, RR_FB_LD, G + L.enc_Wi, RR_FB_LD, G + L.enc_bi, s));
   }

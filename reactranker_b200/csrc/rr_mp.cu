@@ -12,6 +12,8 @@
 // is produced from registers without materialising a_message or the [A, W, h] gather
 // (mpn.py:89-92).  The padding row is gathered with its multiplicity instead of once per
 // padded slot (featurization.py:281-286).
+#include <stdlib.h>
+
 #include "rr_common.cuh"
 
 namespace rr {
@@ -366,10 +368,21 @@ static void atom_launch_dims(int n_atoms, int ld, dim3* grid, dim3* block) {
   *block = dim3(threads);
 }
 
+// second-generation kernels (rr_mp_pipe.cu); RR_MP_V1=1 keeps the first generation for A/B measurements
+enum { PIPE_BOND_FWD = 0, PIPE_BOND_BWD = 1, PIPE_NBR_FWD = 2, PIPE_NBR_BWD_BOND = 3, PIPE_NBR_BWD_ATOM = 4 };
+static bool use_pipe() {
+  const char* e = getenv("RR_MP_V1");
+  return !(e && e[0] == '1');
+}
+
 int bond_message_fwd(const rr_graph* g, const float* m, float* pre, int hp, int relu_src, cudaStream_t s) {
   ProfScope prof_scope(KC_BOND_FWD, s);
   RR_TRY(check_graph(g, hp));
   RR_REQUIRE(m && pre && aligned16(m) && aligned16(pre), "m/pre must be non-NULL and 16-byte aligned");
+  if (use_pipe()) {
+    const int st = rowpipe_launch(PIPE_BOND_FWD, g, 0, m, pre, hp, relu_src, nullptr, 1.f, 0, nullptr, 0, 0, s);
+    if (st != RR_ERR_UNSUPPORTED) return st;
+  }
   dim3 grid, block;
   atom_launch_dims(g->n_atoms, hp, &grid, &block);
   k_bond_fwd<<<grid, block, 0, s>>>(*g, m, pre, hp, relu_src);
@@ -384,23 +397,48 @@ static int zero_rows(float* base, const int* rows, int n, int ld, cudaStream_t s
   return RR_OK;
 }
 
-int bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp, cudaStream_t s) {
-  ProfScope prof_scope(KC_BOND_BWD, s);
+static int check_act(const float* y, float* acc, int acc_mode, int skip_out) {
+  RR_REQUIRE(y != nullptr && aligned16(y), "fused relu backward: y must be non-NULL and 16-byte aligned");
+  RR_REQUIRE(acc_mode >= 0 && acc_mode <= 2 && (acc_mode == 0 || (acc && aligned16(acc))), "fused relu backward: acc_mode %d needs an aligned acc", acc_mode);
+  RR_REQUIRE(!skip_out || acc_mode != 0, "fused relu backward: skip_out without acc discards the result");
+  return RR_OK;
+}
+
+// dm = bond_message_bwd(dpre), then (y != NULL) the ReLU / dropout backward that follows it in the model:
+// dz = dm * mask(y) * scale written to dm (unless skip_out) and stored / added into acc
+int bond_message_bwd_act(const rr_graph* g, const float* dpre, float* dm, int hp, const float* y, float scale, int preact, float* acc, int acc_mode,
+                         int skip_out, cudaStream_t s) {
   RR_TRY(check_graph(g, hp));
   RR_REQUIRE(dpre && dm && aligned16(dpre) && aligned16(dm), "dpre/dm must be non-NULL and 16-byte aligned");
   RR_REQUIRE(g->pad_bonds && g->n_segments > 0, "graph needs pad_bonds/n_segments");
-  RR_TRY(zero_rows(dm, g->pad_bonds, g->n_segments, hp, s));
-  dim3 grid, block;
-  atom_launch_dims(g->n_atoms, hp, &grid, &block);
-  k_bond_bwd<<<grid, block, 0, s>>>(*g, dpre, dm, hp);
-  RR_LAUNCH_CHECK("k_bond_bwd");
-  return RR_OK;
+  if (y) RR_TRY(check_act(y, acc, acc_mode, skip_out));
+  {
+    ProfScope prof_scope(KC_BOND_BWD, s);
+    RR_TRY(zero_rows(dm, g->pad_bonds, g->n_segments, hp, s));
+    int st = RR_ERR_UNSUPPORTED;
+    if (use_pipe()) st = rowpipe_launch(PIPE_BOND_BWD, g, 0, dpre, dm, hp, 0, y, scale, preact, acc, acc_mode, skip_out, s);
+    if (st == RR_OK) return y ? pad_rows_act(dm, g->pad_bonds, g->n_segments, hp, y, scale, preact, acc, acc_mode, skip_out, s) : RR_OK;
+    if (st != RR_ERR_UNSUPPORTED) return st;
+    dim3 grid, block;
+    atom_launch_dims(g->n_atoms, hp, &grid, &block);
+    k_bond_bwd<<<grid, block, 0, s>>>(*g, dpre, dm, hp);
+    RR_LAUNCH_CHECK("k_bond_bwd");
+  }
+  return y ? relu_bwd(g->n_bonds, hp, dm, y, scale, preact, skip_out ? nullptr : dm, acc, acc_mode, s) : RR_OK;
+}
+
+int bond_message_bwd(const rr_graph* g, const float* dpre, float* dm, int hp, cudaStream_t s) {
+  return bond_message_bwd_act(g, dpre, dm, hp, nullptr, 1.f, 0, nullptr, 0, 0, s);
 }
 
 int neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out, int ld, int relu_src, cudaStream_t s) {
   ProfScope prof_scope(KC_NBR_FWD, s);
   RR_TRY(check_graph(g, ld));
   RR_REQUIRE(src && out && aligned16(src) && aligned16(out), "src/out must be non-NULL and 16-byte aligned");
+  if (use_pipe()) {
+    const int st = rowpipe_launch(PIPE_NBR_FWD, g, which, src, out, ld, relu_src, nullptr, 1.f, 0, nullptr, 0, 0, s);
+    if (st != RR_ERR_UNSUPPORTED) return st;
+  }
   dim3 grid, block;
   atom_launch_dims(g->n_atoms, ld, &grid, &block);
   k_nbr_sum_fwd<<<grid, block, 0, s>>>(*g, which, src, out, ld, relu_src);
@@ -408,23 +446,35 @@ int neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out,
   return RR_OK;
 }
 
-int neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, cudaStream_t s) {
-  ProfScope prof_scope(KC_NBR_BWD, s);
+int neighbor_sum_bwd_act(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, const float* y, float scale, int preact, float* acc,
+                         int acc_mode, int skip_out, cudaStream_t s) {
   RR_TRY(check_graph(g, ld));
   RR_REQUIRE(dout && dsrc && aligned16(dout) && aligned16(dsrc), "dout/dsrc must be non-NULL and 16-byte aligned");
   RR_REQUIRE(g->pad_bonds && g->pad_atoms && g->n_segments > 0, "graph needs pad rows/n_segments");
-  dim3 grid, block;
-  atom_launch_dims(g->n_atoms, ld, &grid, &block);
-  if (which == 0) {
-    RR_TRY(zero_rows(dsrc, g->pad_bonds, g->n_segments, ld, s));
-    k_nbr_sum_bwd_bond<<<grid, block, 0, s>>>(*g, dout, dsrc, ld);
-    RR_LAUNCH_CHECK("k_nbr_sum_bwd_bond");
-  } else {
-    RR_TRY(zero_rows(dsrc, g->pad_atoms, g->n_segments, ld, s));
-    k_nbr_sum_bwd_atom<<<grid, block, 0, s>>>(*g, dout, dsrc, ld);
-    RR_LAUNCH_CHECK("k_nbr_sum_bwd_atom");
+  if (y) RR_TRY(check_act(y, acc, acc_mode, skip_out));
+  const int* pads = which == 0 ? g->pad_bonds : g->pad_atoms;
+  {
+    ProfScope prof_scope(KC_NBR_BWD, s);
+    RR_TRY(zero_rows(dsrc, pads, g->n_segments, ld, s));
+    int st = RR_ERR_UNSUPPORTED;
+    if (use_pipe()) st = rowpipe_launch(which == 0 ? PIPE_NBR_BWD_BOND : PIPE_NBR_BWD_ATOM, g, which, dout, dsrc, ld, 0, y, scale, preact, acc, acc_mode, skip_out, s);
+    if (st == RR_OK) return y ? pad_rows_act(dsrc, pads, g->n_segments, ld, y, scale, preact, acc, acc_mode, skip_out, s) : RR_OK;
+    if (st != RR_ERR_UNSUPPORTED) return st;
+    dim3 grid, block;
+    atom_launch_dims(g->n_atoms, ld, &grid, &block);
+    if (which == 0) {
+      k_nbr_sum_bwd_bond<<<grid, block, 0, s>>>(*g, dout, dsrc, ld);
+      RR_LAUNCH_CHECK("k_nbr_sum_bwd_bond");
+    } else {
+      k_nbr_sum_bwd_atom<<<grid, block, 0, s>>>(*g, dout, dsrc, ld);
+      RR_LAUNCH_CHECK("k_nbr_sum_bwd_atom");
+    }
   }
-  return RR_OK;
+  return y ? relu_bwd(which == 0 ? g->n_bonds : g->n_atoms, ld, dsrc, y, scale, preact, skip_out ? nullptr : dsrc, acc, acc_mode, s) : RR_OK;
+}
+
+int neighbor_sum_bwd(const rr_graph* g, int which, const float* dout, float* dsrc, int ld, cudaStream_t s) {
+  return neighbor_sum_bwd_act(g, which, dout, dsrc, ld, nullptr, 1.f, 0, nullptr, 0, 0, s);
 }
 
 int readout_fwd(const rr_graph* g, const float* hid, int hp, int hidden, const float* addf, int n_add, float* vec, int vp, float p,

@@ -54,6 +54,30 @@ class FFN(nn.Module):
         raise NotImplementedError("FFN runs fused inside ReactionModel.forward (reactranker_b200/csrc/rr_model.cu)")
 
 
+class _WorkspacePool:
+    """Saved-for-backward workspaces (3-7 GB per step) recycled between steps.  Batch composition changes every step, so
+    the exact size does too: asking the caching allocator for a fresh block per step ends in cudaMalloc / cudaFree
+    round trips (tens of ms).  A forward takes the smallest free buffer that fits (allocating with head-room when none
+    does); the backward gives it back.  A graph that is never back-propagated simply drops its buffer."""
+
+    def __init__(self, headroom: float = 1.125):
+        self.free: List[torch.Tensor] = []
+        self.headroom = headroom
+
+    def take(self, nbytes: int, dev: torch.device) -> torch.Tensor:
+        fits = [t for t in self.free if t.device == dev and t.numel() >= nbytes]
+        if fits:
+            best = min(fits, key=lambda t: t.numel())
+            self.free = [t for t in self.free if t is not best]
+            return best
+        self.free = [t for t in self.free if t.device != dev]      # too small for the batches now arriving: let them go
+        return torch.empty(int(nbytes * self.headroom) + 256, dtype=torch.uint8, device=dev)
+
+    def give(self, t: torch.Tensor) -> None:
+        if len(self.free) < 4:
+            self.free.append(t)
+
+
 class _ReactionFn(torch.autograd.Function):
     """One autograd node for the whole model: rr_model_forward / rr_model_backward."""
 
@@ -66,11 +90,14 @@ class _ReactionFn(torch.autograd.Function):
         if ws_bytes < 0:
             _lib.check(-1)
         dev = params[0].device
-        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)
+        ws = model._ws_pool.take(int(ws_bytes), dev)
         n = pg.n_mols
         scores = torch.empty((n,) if cfg.task_num == 1 else (n, cfg.task_num), dtype=torch.float32, device=dev)
         _lib.check(L.rr_model_forward(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(rg.c), ctypes.byref(pg.c),
-                                      _lib.ptr(addf), scores.data_ptr(), ws.data_ptr(), int(ws_bytes), _lib.stream_ptr()))
+                                      _lib.ptr(addf), scores.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        if not any(ctx.needs_input_grad):        # inference: nothing will come back for the activations
+            model._ws_pool.give(ws)
+            ws = None
         ctx.model, ctx.rg, ctx.pg, ctx.cfg, ctx.ws, ctx.addf = model, rg, pg, cfg, ws, addf
         ctx.save_for_backward(*params)
         return scores
@@ -86,6 +113,7 @@ class _ReactionFn(torch.autograd.Function):
         dscores = dscores.contiguous().float()
         _lib.check(L.rr_model_backward(ctypes.byref(ctx.cfg), ctypes.byref(w), ctypes.byref(ctx.rg.c), ctypes.byref(ctx.pg.c),
                                        dscores.data_ptr(), ctypes.byref(gw), ctx.ws.data_ptr(), ctx.ws.numel(), _lib.stream_ptr()))
+        model._ws_pool.give(ctx.ws)
         ctx.ws = None
         return (None, None, None, None) + tuple(grads)
 
@@ -114,6 +142,7 @@ class ReactionModel(nn.Module):
         self._task_num, self._add, self._dropout = task_num, addtion_react_featrues, float(mpnn_dropout)
         self._head = _HEADS.get(task_type, _lib.HEAD_RAW)     # every other name returns the raw output (base_model.py:105-106)
         self.last_h2d_bytes = 0
+        self._ws_pool = _WorkspacePool()
 
     # ---- plumbing to the C ABI -----------------------------------------------------------
     def _named_slots(self):

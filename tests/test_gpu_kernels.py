@@ -389,3 +389,84 @@ def test_device_assembly_equals_host_packing():
                                 ("mol_start", torch.int32, (nM,)), ("mol_size", torch.int32, (nM,)), ("pad_bonds", torch.int32, (S_,)),
                                 ("pad_atoms", torch.int32, (S_,))):
             assert torch.equal(dev_g.section(name, dt, shape), host_g.section(name, dt, shape)), name
+
+
+# ---- gather backward fused with the ReLU / dropout backward that follows it (rr_mp_pipe.cu) ---------------------------------------
+def _act_reference(d, y, scale, preact, acc0, acc_mode):
+    mask = (y > 0) if preact else (y != 0)
+    dz = d * mask * scale
+    acc = dz if acc_mode == 1 else (acc0 + dz if acc_mode == 2 else None)
+    return dz, acc
+
+
+@pytest.mark.parametrize("acc_mode,skip_out,preact", [(1, 0, 0), (2, 0, 0), (2, 1, 1), (0, 0, 0)])
+@pytest.mark.parametrize("h,star,segments", [(300, None, 1), (40, {1: 9}, 1), (40, {1: 9}, 2)])
+def test_bond_message_bwd_act(h, star, segments, acc_mode, skip_out, preact):
+    L = _lib.lib()
+    ds = synthetic.make_dataset(11, [3, 3], star_leaves_in_group=star)
+    mols = [ds.mols[t] for t in ds.rsmi]
+    batches = [BatchMolGraph(mols)] if segments == 1 else [BatchMolGraph(mols[:3]), BatchMolGraph(mols[3:])]
+    dg = DeviceGraph.from_batches(batches, DEV)
+    hp = L.rr_padded(h)
+    B = sum(b.n_bonds for b in batches)
+    up, y, acc0 = rand(B, hp, h, 2), torch.relu(rand(B, hp, h, 6)), rand(B, hp, h, 7)
+    grads, o = [], 0
+    for b in batches:
+        x = torch.zeros(b.n_bonds, hp, dtype=torch.double, requires_grad=True)
+        (O.gather_sum(x, b.a2b)[b.b2a] - x[b.b2revb]).backward(up[o:o + b.n_bonds].double())
+        grads.append(x.grad)
+        o += b.n_bonds
+    ysrc = (rand(B, hp, h, 6) if preact else y)
+    want_dz, want_acc = _act_reference(torch.cat(grads), ysrc.double(), 0.8, preact, acc0.double(), acc_mode)
+    dm = torch.full((B, hp), float("nan"), device=DEV)
+    acc = acc0.to(DEV).clone()
+    upd, yd = up.to(DEV), ysrc.to(DEV)
+    _lib.check(L.rr_bond_message_bwd_act(ctypes.byref(dg.c), upd.data_ptr(), dm.data_ptr(), hp, yd.data_ptr(), 0.8, preact,
+                                         acc.data_ptr() if acc_mode else None, acc_mode, skip_out, S()))
+    if not skip_out:
+        close(dm, want_dz, 5e-6)
+    if acc_mode:
+        close(acc, want_acc, 5e-6)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("acc_mode,skip_out,preact", [(1, 0, 0), (2, 0, 0), (1, 1, 1), (2, 1, 1)])
+@pytest.mark.parametrize("h,star", [(300, None), (40, {2: 10})])
+def test_neighbor_sum_bwd_act(which, h, star, acc_mode, skip_out, preact):
+    L = _lib.lib()
+    ds, b, dg = graphs(star=star, side="r" if star else "p")
+    hp = L.rr_padded(h)
+    rows = b.n_atoms if which else b.n_bonds
+    table = b.get_a2a() if which else b.a2b
+    src = torch.zeros(rows, hp, dtype=torch.double, requires_grad=True)
+    up = rand(b.n_atoms, hp, h, 5)
+    O.gather_sum(src, table).backward(up.double())
+    ysrc = rand(rows, hp, h, 8) if preact else torch.relu(rand(rows, hp, h, 8))
+    acc0 = rand(rows, hp, h, 9)
+    want_dz, want_acc = _act_reference(src.grad, ysrc.double(), 1.25, preact, acc0.double(), acc_mode)
+    dsrc = torch.full((rows, hp), float("nan"), device=DEV)
+    acc = acc0.to(DEV).clone()
+    upd, yd = up.to(DEV), ysrc.to(DEV)
+    _lib.check(L.rr_neighbor_sum_bwd_act(ctypes.byref(dg.c), which, upd.data_ptr(), dsrc.data_ptr(), hp, yd.data_ptr(), 1.25, preact,
+                                         acc.data_ptr(), acc_mode, skip_out, S()))
+    if not skip_out:
+        close(dsrc, want_dz, 5e-6)
+    close(acc, want_acc, 5e-6)
+
+
+def test_first_generation_gather_kernels_agree(monkeypatch):
+    """RR_MP_V1=1 selects the register-gather kernels of rr_mp.cu; both generations give the same rows (bit-exact for the pure
+    gathers, which add in the same order)."""
+    L = _lib.lib()
+    ds, b, dg = graphs(seed=21, sizes=(6, 5, 7))
+    h, hp = 300, 304
+    m = rand(b.n_bonds, hp, h, 1).to(DEV)
+    outs = {}
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("RR_MP_V1", v1)
+        pre = torch.empty_like(m)
+        am = torch.empty(b.n_atoms, hp, device=DEV)
+        _lib.check(L.rr_bond_message_fwd(ctypes.byref(dg.c), m.data_ptr(), pre.data_ptr(), hp, 1, S()))
+        _lib.check(L.rr_neighbor_sum_fwd(ctypes.byref(dg.c), 0, m.data_ptr(), am.data_ptr(), hp, 0, S()))
+        outs[v1] = (pre.cpu(), am.cpu())
+    assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
