@@ -23,6 +23,8 @@ from __future__ import annotations
 import ctypes
 from typing import List, Optional, Sequence, Tuple
 
+import threading
+
 import numpy as np
 import torch
 
@@ -248,6 +250,7 @@ class MoleculeStore:
         self._d = {}
         self.c = None
         self.h2d_bytes_total = 0
+        self._lock = threading.RLock()      # the prefetch worker registers molecules while the training thread uploads / reads
 
     def __len__(self):
         return len(self.packs)
@@ -259,9 +262,14 @@ class MoleculeStore:
             return sid
         if pack.n_bonds and not np.array_equal(pack.b2revb, np.arange(pack.n_bonds, dtype=np.int32) ^ 1):
             return -1
+        with self._lock:
+            return self._register_locked(pack)
+
+    def _register_locked(self, pack: "_MolPack") -> int:
+        sid = getattr(pack, "sid", None)
+        if sid is not None and getattr(pack, "store", None) is self:
+            return sid
         sid = len(self.packs)
-        self.packs.append(pack)
-        pack.sid, pack.store = sid, self
         if sid >= self.nA.shape[0]:
             cap = max(1024, 2 * self.nA.shape[0])
             for name in ("nA", "nB", "maxdeg", "aoff", "boff"):
@@ -274,6 +282,8 @@ class MoleculeStore:
         self.aoff[sid], self.boff[sid] = self._tot_a, self._tot_b
         self._tot_a += pack.n_atoms
         self._tot_b += pack.n_bonds
+        self.packs.append(pack)              # last: a reader that sees the pack sees its table entries
+        pack.sid, pack.store = sid, self
         return sid
 
     # ---- device mirror -----------------------------------------------------------------
@@ -283,7 +293,10 @@ class MoleculeStore:
 
     def sync(self, device) -> None:
         """Upload molecules registered since the last call (amortised: capacity doubles)."""
-        dev = torch.device(device)
+        with self._lock:
+            self._sync_locked(torch.device(device))
+
+    def _sync_locked(self, dev) -> None:
         if self._dev is not None and self._dev != dev:
             raise RuntimeError(f"MoleculeStore already lives on {self._dev}")
         n = len(self.packs)

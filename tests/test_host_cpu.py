@@ -199,3 +199,64 @@ def test_parsing_features_builds_reference_batches():
     r, p = fz.parsing_reactions(np.stack([ds.rsmi, ds.psmi], 1))
     assert r.n_mols == p.n_mols == 5 and r.n_atoms == p.n_atoms
     assert fz.parsing_reactions(None) == [None, None] and fz.parsing_smiles(None) is None
+
+
+def test_prefetch_batches_order_errors_and_abandon():
+    """data/prefetch.py: items arrive in order, a worker exception surfaces at the consumer, an abandoned generator stops the worker."""
+    import threading
+    import time
+    from reactranker_b200.data.prefetch import prefetch_batches
+    assert list(prefetch_batches(range(20), lambda x: x * x, depth=3)) == [x * x for x in range(20)]
+
+    def boom(x):
+        if x == 3:
+            raise ValueError("bad batch")
+        return x
+    got = []
+    with pytest.raises(ValueError, match="bad batch"):
+        for v in prefetch_batches(range(10), boom):
+            got.append(v)
+    assert got == [0, 1, 2]
+
+    def endless():
+        i = 0
+        while True:
+            yield i
+            i += 1
+    before = threading.active_count()
+    gen = prefetch_batches(endless(), lambda x: x, depth=2)
+    assert [next(gen) for _ in range(5)] == [0, 1, 2, 3, 4]
+    gen.close()
+    for _ in range(50):
+        if threading.active_count() <= before:
+            break
+        time.sleep(0.05)
+    assert threading.active_count() <= before
+
+
+def test_molecule_store_registration_is_thread_safe():
+    """The prefetch worker registers molecules while the training thread reads the store tables."""
+    import threading
+    from reactranker_b200 import synthetic
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(5, [40, 40, 40])
+    fz = Parsing_features()
+    for tok, m in ds.mols.items():
+        fz.add(tok, m)
+    toks = list(ds.psmi)
+    out = {}
+
+    def run(k):
+        out[k] = fz.parsing_smiles(toks[k::4])
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    st = fz.store
+    n = len(st)
+    assert n == len(set(toks)) and len({id(p) for p in st.packs}) == n
+    assert np.array_equal(st.aoff[:n], np.concatenate(([0], np.cumsum(st.nA[:n])[:-1])))
+    for k in range(4):
+        want = BatchMolGraph([ds.mols[t] for t in toks[k::4]])
+        assert out[k].n_atoms == want.n_atoms and torch.equal(out[k].a2b, want.a2b) and torch.equal(out[k].f_bonds, want.f_bonds)
