@@ -175,6 +175,11 @@ int rr_linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int 
  * an on-chip 3xTF32 split (fp32-class accuracy, ~1e-6 relative), TMA-fed, accumulating in TMEM.  Process-wide. */
 int rr_set_gemm_mode(int mode);
 int rr_get_gemm_mode(void);
+/* Operand split of the BACKWARD tensor-core GEMMs (dgrad; gradients never decide a ReLU mask): 1 (default) = 3 x bf16 products
+ * (x = bf16(x) + bf16(x - bf16(x)): 16 significand bits per operand, fp32 accumulation, ~5e-6 relative, half the tensor-pipe time),
+ * 0 = the forward's 3 x tf32 split.  Process-wide; RR_BWD_BF16=0 in the environment selects 0 at load. */
+int rr_set_backward_bf16(int on);
+int rr_get_backward_bf16(void);
 /* dX[M,k] (+)= dZ[M,n] W[n,k]   (accumulate != 0 adds) */
 int rr_linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw,
                     float* dX, int lddx, int accumulate, void* stream);

@@ -189,6 +189,11 @@ bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2);
 int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1, int k1, const float* X2, int ldx2, const float* W2, int ldw2, int k2,
               const float* bias, const float* resid, int ldr, float* Y, int ldy, int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id,
               int kclass, cudaStream_t s, const float* W1lo = nullptr, const float* W2lo = nullptr);
+bool tc_linear_bf16_supported(int M, int n, int k, int ldx, int ldw);
+int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, const uint16_t* Wlo, int ldw, int k, float* Y, int ldy, int accumulate,
+                   int kclass, cudaStream_t s);
+// backward GEMMs: 1 = 3 x bf16 split (default; RR_BWD_BF16=0 or rr_set_backward_bf16(0) keeps 3 x tf32)
+extern std::atomic<int> g_bwd_bf16;
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);
 int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s);
 

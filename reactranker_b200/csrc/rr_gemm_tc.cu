@@ -432,10 +432,54 @@ constexpr int NT2 = 160;                          // output columns per work ite
 constexpr int S2 = 3;                             // pipeline stages (shared memory A/B tiles + TMEM A tiles)
 constexpr int B2_BYTES = NT2 * BK * 4;            // one B box: 160 rows x 128 B
 constexpr int STAGE2 = A_BYTES + 2 * B2_BYTES;    // A raw | B hi | B lo  = 57344 B
-constexpr int TM_A2 = 2 * NT2;                    // TMEM: two accumulators [0,160) [160,320), then 3 x (32 hi + 32 lo) columns of A
+constexpr int TM_A2 = 2 * NT2;                    // TMEM: two accumulators [0,160) [160,320), then the A stages: 3 x (32 hi + 32 lo) columns of A
 
-template <int EW>
+// BF = true: the BACKWARD flavour (dgrad).  Gradients flow linearly through the backward pass and never decide a ReLU mask, so 16
+// significand bits per operand are plenty there (north star: 1e-3 on gradients): x = x1 + x2 with x1 = bf16(x), x2 = bf16(x - x1), and
+//   A*B ~= A2*B1 + A1*B2 + A1*B1      (kind::f16 with bf16 operands, fp32 accumulation; ~5e-6 of a row's maximum)
+// Every MMA covers K = 16 instead of 8, i.e. half the tensor-pipe time of the 3xTF32 split, the weights arrive pre-split as bf16
+// images of half the size (64-byte-swizzled rows: 32 bf16 per k-block), and a stage shrinks from 56 to 36 KB: FIVE stages in flight.
+constexpr int B2_BYTES_BF = NT2 * BK * 2;                  // one bf16 B box: 160 rows x 64 B
+constexpr int STAGE2_BF = A_BYTES + 2 * B2_BYTES_BF;       // A raw fp32 | B hi | B lo = 36864 B
+constexpr int S2_BF = 5;
+
+// K-major, 64-byte swizzle (bf16 k-block of 32): 8-row groups are 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                     // cute::UMMA::LayoutType::SWIZZLE_64B
+  return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// (x0, x1) -> packed bf16 pair (x0 in the low half: the lower k index) and the packed pair of the remainders
+__device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+template <int EW, bool BF>
 __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const __grid_constant__ Args g) {
+  constexpr int S2 = BF ? S2_BF : tc::S2;
+  constexpr int STAGE2 = BF ? STAGE2_BF : tc::STAGE2;
+  constexpr int B2_BYTES = BF ? B2_BYTES_BF : tc::B2_BYTES;
+  constexpr int A_COLS = BF ? 32 : 64;                     // TMEM columns of one A stage (hi | lo)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S2) * STAGE2);
@@ -480,7 +524,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
-      const uint32_t tx = static_cast<uint32_t>(A_BYTES + (g.presplit ? 2 : 1) * B2_BYTES);
+      const uint32_t tx = static_cast<uint32_t>(A_BYTES + ((g.presplit || BF) ? 2 : 1) * B2_BYTES);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
         for (int s = 0; s < g.nsrc; ++s) {
@@ -493,7 +537,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
             mbar_expect_tx(full + st, tx);
             tma_load_2d(&g.src[s].tmA, full + st, base, kb * BK, m0);
             tma_load_2d(&g.src[s].tmB, full + st, base + A_BYTES, kb * BK, n0);   // rows past N are zero-filled
-            if (g.presplit) tma_load_2d(&g.src[s].tmBlo, full + st, base + A_BYTES + B2_BYTES, kb * BK, n0);
+            if (g.presplit || BF) tma_load_2d(&g.src[s].tmBlo, full + st, base + A_BYTES + B2_BYTES, kb * BK, n0);
           }
         }
       }
@@ -505,7 +549,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++w) {
         const int n0 = (tile % n_tiles) * NT2;
         const int width = min(NT2, g.N - n0);
-        const uint32_t idesc = umma_idesc(BM, width);
+        const uint32_t idesc = BF ? umma_idesc_bf16(BM, width) : umma_idesc(BM, width);
         const int buf = w & 1;
         const uint32_t d = tmem_base + buf * NT2;
         mbar_wait(acc_empty + buf, ((w >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator
@@ -517,14 +561,24 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
           tc_fence_after();
           const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * STAGE2);
           const uint32_t b_hi = base + A_BYTES, b_lo = b_hi + B2_BYTES;
-          const uint32_t a_hi = tmem_base + TM_A2 + st * 64, a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_base + TM_A2 + st * A_COLS, a_lo = a_hi + A_COLS / 2;
           if (!(g.diag & 4)) {
+            if constexpr (BF) {
 #pragma unroll
-            for (int k = 0; k < BK / UK; ++k) {
-              const uint32_t ko = k * UK * 4;
-              umma_tf32_ts(d, a_lo + k * UK, umma_desc(b_hi + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_lo + ko), idesc, 1u);
-              umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_hi + ko), idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) {           // UMMA_K = 16 bf16 = 32 bytes of the 64-byte row = 8 TMEM columns of packed pairs
+                const uint32_t ko = k * 32;
+                umma_bf16_ts(d, a_lo + k * 8, umma_desc_sw64(b_hi + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_ts(d, a_hi + k * 8, umma_desc_sw64(b_lo + ko), idesc, 1u);
+                umma_bf16_ts(d, a_hi + k * 8, umma_desc_sw64(b_hi + ko), idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / UK; ++k) {
+                const uint32_t ko = k * UK * 4;
+                umma_tf32_ts(d, a_lo + k * UK, umma_desc(b_hi + ko), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_lo + ko), idesc, 1u);
+                umma_tf32_ts(d, a_hi + k * UK, umma_desc(b_hi + ko), idesc, 1u);
+              }
             }
           }
           umma_commit(empty + st);
@@ -549,28 +603,39 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
         uint8_t* base = smem + static_cast<size_t>(st) * STAGE2;
         // A: this thread's row of 32 floats (128-byte swizzle: chunk c sits at c ^ (row & 7)) -> hi / lo -> TMEM
         if (!(g.diag & 1)) {
-          uint32_t hi[32], lo[32];
           const uint32_t rowp = smem_u32(base) + r * 128;
           float4 av[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) av[c] = lds_f4(rowp + ((c ^ (r & 7)) << 4));
+          if constexpr (BF) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
-              hi[4 * c + j] = h;
-              lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
+            for (int c = 0; c < 8; ++c) {
+              split_bf16_pair(av[c].x, av[c].y, hi[2 * c], lo[2 * c]);
+              split_bf16_pair(av[c].z, av[c].w, hi[2 * c + 1], lo[2 * c + 1]);
             }
+            tmem_st16(lane_addr + TM_A2 + st * A_COLS, hi);
+            tmem_st16(lane_addr + TM_A2 + st * A_COLS + 16, lo);
+          } else {
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
+                hi[4 * c + j] = h;
+                lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
+              }
+            }
+            tmem_st32(lane_addr + TM_A2 + st * A_COLS, hi);
+            tmem_st32(lane_addr + TM_A2 + st * A_COLS + 32, lo);
           }
-          tmem_st32(lane_addr + TM_A2 + st * 64, hi);
-          tmem_st32(lane_addr + TM_A2 + st * 64 + 32, lo);
         }
         // B: elementwise split in shared memory (unless the weights arrived pre-split)
-        if (!g.presplit && !(g.diag & 2)) split_tile(base + A_BYTES, base + A_BYTES + B2_BYTES, b_used, wtid);
+        if (!BF && !g.presplit && !(g.diag & 2)) split_tile(base + A_BYTES, base + A_BYTES + B2_BYTES, b_used, wtid);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (!g.presplit) fence_proxy_async();
+        if (!BF && !g.presplit) fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready + st);
@@ -867,7 +932,59 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
   return RR_OK;
 }
 
+// 2-D bf16 row-major [rows, cols] with row stride ld elements; box = [box_rows x 32 bf16] (64-byte rows, 64-byte swizzle)
+static int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int rows, int cols, int ld, int box_rows) {
+  if (box_rows < 1 || box_rows > 256) return fail(RR_ERR_INVALID, "TMA box of %d rows", box_rows);
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RR_ERR_CUDA, "cuTensorMapEncodeTiled(bf16) failed (%d) rows %d cols %d ld %d box_rows %d", static_cast<int>(r), rows, cols, ld, box_rows);
+  return RR_OK;
+}
+
 }  // namespace tc
+
+// dX[M, n] (+)= dZ[M, k] W^T with the weight given as bf16 (hi, lo) images of Wt[n, k] (row stride ldw elements): the backward flavour of
+// k_tc_gemm2 (3 x bf16 products, five pipeline stages).  Needs n % 16 == 0, k % 8 == 0 (16-byte bf16 rows).
+bool tc_linear_bf16_supported(int M, int n, int k, int ldx, int ldw) {
+  return M > 0 && n >= 16 && !(n & 15) && k > 0 && !(k & 3) && !(ldx & 3) && !(ldw & 7);
+}
+int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, const uint16_t* Wlo, int ldw, int k, float* Y, int ldy, int accumulate,
+                   int kclass, cudaStream_t s) {
+  using namespace tc;
+  ProfScope prof_scope(kclass, s);
+  Args g{};
+  g.nsrc = 1;
+  RR_TRY(make_map(&g.src[0].tmA, X, M, k, ldx, BM));
+  RR_TRY(make_map_bf16(&g.src[0].tmB, Whi, n, k, ldw, NT2));
+  RR_TRY(make_map_bf16(&g.src[0].tmBlo, Wlo, n, k, ldw, NT2));
+  g.src[0].K = k;
+  g.presplit = 1;
+  const char* diag_env = getenv("RR_TC_DIAG");
+  g.diag = diag_env ? atoi(diag_env) : 0;
+  g.M = M;
+  g.N = n;
+  g.C = Y;
+  g.ldc = ldy;
+  g.accumulate = accumulate;
+  g.inv_keep = 1.f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const size_t smem = static_cast<size_t>(S2_BF) * STAGE2_BF + 1024 + 256 + 8 * 4096;
+  const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
+  const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
+  k_tc_gemm2<8, true><<<ctas, THREADS2_BASE + 256, smem, s>>>(g);
+  RR_LAUNCH_CHECK("k_tc_gemm2<bf16>");
+  return RR_OK;
+}
 
 
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx) {
@@ -994,8 +1111,8 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   if (!use_v1) {
     static bool attr2_set = false;
     if (!attr2_set) {
-      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
       attr2_set = true;
     }
     const size_t smem2 = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
@@ -1003,8 +1120,8 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
     const int ew = (ew_env && atoi(ew_env) == 4) ? 4 : 8;
     const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
     const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-    if (ew == 8) k_tc_gemm2<8><<<ctas, THREADS2_BASE + 256, smem2, s>>>(g);
-    else k_tc_gemm2<4><<<ctas, THREADS2_BASE + 128, smem2, s>>>(g);
+    if (ew == 8) k_tc_gemm2<8, false><<<ctas, THREADS2_BASE + 256, smem2, s>>>(g);
+    else k_tc_gemm2<4, false><<<ctas, THREADS2_BASE + 128, smem2, s>>>(g);
     RR_LAUNCH_CHECK("k_tc_gemm2");
     return RR_OK;
   }

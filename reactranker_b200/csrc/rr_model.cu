@@ -124,7 +124,15 @@ static PackTable make_table(const rr_model_cfg& c, const PackedLayout& L, const 
 // direction 0: packed <- ref (pack);  1: ref <- packed (un-pack gradients)
 // Packing also writes the TF32 split of every value (hi = nearest TF32, lo = v - hi) into the images hi_off / lo_off floats further on:
 // the tcgen05 GEMMs then TMA-load both halves of the B operand instead of splitting the same weight tile once per row tile.
-__global__ void k_pack(PackTable T, float* __restrict__ packed, int direction, long long hi_off, long long lo_off) {
+// The same values as bf16 pairs (hi = bf16(v), lo = bf16(v - hi)) go to two uint16 images (bhi / blo, same element offsets) for the
+// backward GEMMs' 3 x bf16 split.
+__device__ __forceinline__ uint16_t bf16_rn(float v) {
+  uint16_t r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return r;
+}
+__global__ void k_pack(PackTable T, float* __restrict__ packed, int direction, long long hi_off, long long lo_off, uint16_t* __restrict__ bhi,
+                       uint16_t* __restrict__ blo) {
   const PackEntry e = T.e[blockIdx.y];
   const long long n = static_cast<long long>(e.rows) * e.cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -137,6 +145,9 @@ __global__ void k_pack(PackTable T, float* __restrict__ packed, int direction, l
       *pp = v;
       pp[hi_off] = hi;
       pp[lo_off] = v - hi;
+      const uint16_t b1 = bf16_rn(v);
+      bhi[pp - packed] = b1;
+      blo[pp - packed] = bf16_rn(v - __uint_as_float(static_cast<uint32_t>(b1) << 16));
     } else {
       *rp = *pp;
     }
@@ -190,6 +201,7 @@ struct Workspace {
   PackedLayout L;
   float* packed;      // raw | TF32 hi image | TF32 lo image, L.total floats each
   ptrdiff_t hi_off, lo_off;
+  uint16_t *bhi, *blo; // bf16 (hi, lo) images, L.total elements each
   float* dpacked;
   EncBufs enc[2];  // 0 = reactants, 1 = products
   float *d, *inp2, *nf, *am2, *hid2, *vec, *zout;
@@ -225,6 +237,8 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   W->packed = take(3 * W->L.total);
   W->hi_off = static_cast<ptrdiff_t>(W->L.total);
   W->lo_off = static_cast<ptrdiff_t>(2 * W->L.total);
+  W->bhi = reinterpret_cast<uint16_t*>(take((W->L.total + 1) / 2));
+  W->blo = reinterpret_cast<uint16_t*>(take((W->L.total + 1) / 2));
   W->dpacked = take(W->L.grad_total);
   for (int s = 0; s < 2; ++s) {
     const size_t B = (s == 0 ? r.n_bonds : p.n_bonds);
@@ -263,8 +277,11 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
 
 // dX[M, k] (+)= dZ[M, n] W[n, k]: tensor cores read the transposed copy Wt[k, n] as a K-major operand, the SIMT path reads W
 static int dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, const float* Wt, int ldwt, float* dX, int lddx,
-                 int accumulate, cudaStream_t s, ptrdiff_t hi_off, ptrdiff_t lo_off) {
-  if ((g_gemm_mode.load() == 1 || g_gemm_mode.load() == 3) && tc_supported(M, k, n, 0, lddz, 0))
+                 int accumulate, cudaStream_t s, ptrdiff_t hi_off, ptrdiff_t lo_off, const float* packed, const uint16_t* bhi, const uint16_t* blo) {
+  const bool tc = g_gemm_mode.load() == 1 || g_gemm_mode.load() == 3;
+  if (tc && g_bwd_bf16.load() && tc_linear_bf16_supported(M, k, n, lddz, ldwt))
+    return tc_linear_bf16(M, k, dZ, lddz, bhi + (Wt - packed), blo + (Wt - packed), ldwt, n, dX, lddx, accumulate, KC_GEMM_DGRAD, s);
+  if (tc && tc_supported(M, k, n, 0, lddz, 0))
     return tc_linear(M, k, dZ, lddz, Wt + hi_off, ldwt, n, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, dX, lddx, 0, accumulate, 0.f, 0, 0, KC_GEMM_DGRAD, s,
                      Wt + lo_off, nullptr);
   return linear_dgrad(M, n, k, dZ, lddz, W, ldw, dX, lddx, accumulate, s);
@@ -331,8 +348,10 @@ static int check_model_args(const rr_model_cfg* c, const rr_params* w, const rr_
 
 static int pack_params(const rr_model_cfg& c, const Workspace& W, const rr_params& w, cudaStream_t s) {
   RR_CUDA(cudaMemsetAsync(W.packed, 0, 3 * W.L.total * sizeof(float), s));
+  RR_CUDA(cudaMemsetAsync(W.bhi, 0, W.L.total * sizeof(uint16_t), s));
+  RR_CUDA(cudaMemsetAsync(W.blo, 0, W.L.total * sizeof(uint16_t), s));
   PackTable T = make_table(c, W.L, w, true);
-  k_pack<<<dim3(32, T.n), 256, 0, s>>>(T, W.packed, 0, W.hi_off, W.lo_off);
+  k_pack<<<dim3(32, T.n), 256, 0, s>>>(T, W.packed, 0, W.hi_off, W.lo_off, W.bhi, W.blo);
   RR_LAUNCH_CHECK("k_pack");
   return RR_OK;
 }
@@ -442,12 +461,12 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
       RR_TRY(linear_wgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, x, L.ffn_in[l], G + L.ffn_W[l], L.ffn_in[l], G + L.ffn_b[l], s));
       if (l > 0) {
         float* dx = scratch[l & 1];
-        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], dx, hp, 0, s, W.hi_off, W.lo_off));
+        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], dx, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
         RR_TRY(relu_bwd(N, hp, dx, W.x[l - 1], keep, 0, dx, nullptr, 0, s));
         g = dx;
         ldg = hp;
       } else {
-        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], W.dvec, vp, 0, s, W.hi_off, W.lo_off));
+        RR_TRY(dgrad(N, L.ffn_out[l], L.ffn_in[l], g, ldg, P + L.ffn_W[l], L.ffn_in[l], P + L.ffn_W_T[l], L.ffn_out[l], W.dvec, vp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
       }
     }
   }
@@ -455,8 +474,8 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   RR_TRY(readout_bwd(p, W.dvec, vp, W.vec, W.hid2, W.gA1, hp, pdrop, s));
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.d, hp, G + L.dif_Wo_d, hp, G + L.dif_bo, s));
   RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.am2, hp, G + L.dif_Wo_m, hp, nullptr, s));
-  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, P + L.dif_Wo_d_T, hp, W.dD, hp, 0, s, W.hi_off, W.lo_off));
-  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, P + L.dif_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
+  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_d, hp, P + L.dif_Wo_d_T, hp, W.dD, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+  RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wo_m, hp, P + L.dif_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
   // Every gather backward is followed by exactly one ReLU (+ dropout) backward: the mask of the message it produced the gradient of.
   // Both run as one kernel (rr_mp_pipe.cu): t_next >= 1 -> mask of m2^{t_next}, result kept (gA1) and summed into dI2;
   // t_next == 0 -> mask [inp2 > 0] of m2^0 = relu(inp2), only the sum into dI2 is wanted.
@@ -468,11 +487,11 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   for (int t = Td; t >= 1; --t) {
     RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, W.nm[t - 1], hp, G + L.dif_Wh_m, hp, G + L.dif_bh, s));
     RR_TRY(linear_wgrad(A, hp, RR_FB_LD, W.gA1, hp, W.nf, RR_FB_LD, G + L.dif_Wh_f, RR_FB_LD, nullptr, s));
-    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
+    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.dif_Wh_m, hp, P + L.dif_Wh_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
     RR_TRY(diff_nbr_bwd(t - 1));
   }
   RR_TRY(linear_wgrad(A, hp, hp, W.dI2, hp, W.d, hp, G + L.dif_Wi, hp, G + L.dif_bi, s));
-  RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s, W.hi_off, W.lo_off));
+  RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
 
   // shared encoder: products (+dD) then reactants (-dD); weight gradients accumulate (base_model.py:155-156)
   const rr_graph* gs[2] = {r, p};
@@ -484,12 +503,12 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
     RR_TRY(relu_bwd(A, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
     RR_TRY(linear_wgrad(A, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
     RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
-    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off));
+    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
     if (T >= 1) RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.m[T], keep, 0, W.dinp, 1, 0, s));
     else RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 1, 1, s));
     for (int t = T; t >= 1; --t) {
       RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
-      RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off));
+      RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
       if (t - 1 >= 1) RR_TRY(bond_message_bwd_act(g, W.gB2, W.gB1, hp, e.m[t - 1], keep, 0, W.dinp, 2, 0, s));
       else RR_TRY(bond_message_bwd_act(g, W.gB2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 2, 1, s));
     }
@@ -497,7 +516,7 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   }
 
   PackTable Tb = make_table(*c, L, *grads, false);
-  k_pack<<<dim3(32, Tb.n), 256, 0, s>>>(Tb, G, 1, 0, 0);
+  k_pack<<<dim3(32, Tb.n), 256, 0, s>>>(Tb, G, 1, 0, 0, nullptr, nullptr);
   RR_LAUNCH_CHECK("k_pack(grads)");
   return RR_OK;
 }
