@@ -898,6 +898,213 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad2(const __grid_constant_
   }
 }
 
+// ================================================================================================
+// wgrad v3: 3 x bf16 split (backward flavour, see k_tc_gemm2<.., true>).
+// dW is a sum over ~10^5 rows whose rounding errors are independent, and it feeds nothing but Adam: 16 significand bits per operand are
+// ample, and they halve both the tensor-pipe time (UMMA_K = 16) and the shared-memory bytes the MMAs read, which is what bounds v2.
+//   raw ring  : TMA lands fp32 tiles  dZ [32 x 128] (unswizzled: column reads)  |  X [32 x kt] in 32-float boxes (128-byte swizzle)
+//   workers   : dZ column n -> registers -> bf16 pairs (hi, lo) -> TMEM (A operand, lane n);  bias gradient = running column sum
+//               X -> bf16 (hi, lo) images in the canonical MN-major 128-byte-swizzle layout (64 columns per 128-byte row, 8-row atoms)
+//   MMA       : kind::f16, A from TMEM, B MN-major from the bf16 ring; the raw slot is free again as soon as the conversion is done
+// ================================================================================================
+constexpr int W3_BKR = 32;                   // rows of the reduction per stage
+constexpr int W3_BOX = W3_BKR * 128;         // bytes of one raw TMA box [32 x 32 floats] == one bf16 MN block [32 x 64 bf16]
+constexpr int W3_A_RAW = 4 * W3_BOX;
+
+__device__ __forceinline__ uint64_t umma_desc_mn_bf16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(W3_BOX >> 4) << 16;        // LBO: next block of 64 columns
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;          // SBO: next 8 rows of the reduction
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+constexpr int W3_WORKERS = 256;   // 8 conversion warps (12 measured no faster): with 4 the fp32 -> bf16 conversion (not the MMAs) paced the kernel
+constexpr int W3_THREADS = 64 + W3_WORKERS;
+
+__global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_constant__ WgArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int S = g.stages;
+  const int nblk = (g.kt + 63) / 64;                     // bf16 MN blocks per image
+  const int raw_bytes = W3_A_RAW + g.nb * W3_BOX;        // dZ | X
+  const int bf_bytes = 2 * nblk * W3_BOX;                // X hi | X lo
+  uint8_t* raw0 = smem;
+  uint8_t* bf0 = smem + static_cast<size_t>(S) * raw_bytes;
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(bf0 + static_cast<size_t>(S) * bf_bytes);
+  uint64_t* raw_empty = raw_full + S;
+  uint64_t* ready = raw_empty + S;
+  uint64_t* mma_done = ready + S;
+  uint64_t* acc_bar = mma_done + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BM, k0 = blockIdx.y * g.kt;
+  const int m_beg = blockIdx.z * g.m_chunk;
+  const int m_end = min(g.M, m_beg + g.m_chunk);
+  const int nst = (m_end - m_beg + W3_BKR - 1) / W3_BKR;
+  const int width = min(g.kt, g.k_pad - k0);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(raw_full + s, 1);
+      mbar_init(raw_empty + s, W3_WORKERS / 32);
+      mbar_init(ready + s, W3_WORKERS / 32);
+      mbar_init(mma_done + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&g.tmA);
+    prefetch_tmap(&g.tmB);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = static_cast<uint32_t>(raw_bytes);
+      for (int it = 0; it < nst; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(raw_empty + st, ph ^ 1);
+        uint8_t* base = raw0 + static_cast<size_t>(st) * raw_bytes;
+        const int m = m_beg + it * W3_BKR;
+        mbar_expect_tx(raw_full + st, tx);
+        for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, raw_full + st, base + j * W3_BOX, n0 + 32 * j, m);
+        for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, raw_full + st, base + W3_A_RAW + j * W3_BOX, k0 + 32 * j, m);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const int n1 = (width <= 256) ? width : 192;     // 192 = three 64-column blocks: the second MMA starts on a block boundary
+      const int n2 = width - n1;
+      const uint32_t mn = (1u << 16);                  // B is MN-major; A comes from TMEM
+      const uint32_t idesc1 = umma_idesc_bf16(BM, n1) | mn;
+      const uint32_t idesc2 = n2 ? (umma_idesc_bf16(BM, n2) | mn) : 0u;
+      for (int it = 0; it < nst; ++it) {
+        const int st = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(ready + st, ph);
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(bf0 + static_cast<size_t>(st) * bf_bytes), b_lo = b_hi + nblk * W3_BOX;
+        const uint32_t a_hi = tmem_base + g.tm_a + st * 32, a_lo = a_hi + 16;
+        if (!(g.diag & 4)) {
+#pragma unroll
+          for (int k = 0; k < W3_BKR / 16; ++k) {
+            const uint32_t ko = k * 2048;              // next 16 rows of the reduction = two 8-row atoms
+            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+            umma_bf16_ts(tmem_base, a_lo + k * 8, umma_desc_mn_bf16(b_hi + ko), idesc1, first);
+            umma_bf16_ts(tmem_base, a_hi + k * 8, umma_desc_mn_bf16(b_lo + ko), idesc1, 1u);
+            umma_bf16_ts(tmem_base, a_hi + k * 8, umma_desc_mn_bf16(b_hi + ko), idesc1, 1u);
+            if (n2) {
+              const uint32_t bo = static_cast<uint32_t>(n1 / 64) * W3_BOX;
+              umma_bf16_ts(tmem_base + n1, a_lo + k * 8, umma_desc_mn_bf16(b_hi + bo + ko), idesc2, first);
+              umma_bf16_ts(tmem_base + n1, a_hi + k * 8, umma_desc_mn_bf16(b_lo + bo + ko), idesc2, 1u);
+              umma_bf16_ts(tmem_base + n1, a_hi + k * 8, umma_desc_mn_bf16(b_hi + bo + ko), idesc2, 1u);
+            }
+          }
+        }
+        umma_commit(mma_done + st);
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    const int wtid = threadIdx.x - 64;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                    // TMEM lane == column n0 + r of dZ
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int G = g.nb * 4;                            // 8-column groups per row of the X tile (whole boxes: the padding converts zeros)
+    const int step_m = W3_WORKERS / G, step_c = W3_WORKERS % G;
+    const bool a_warp = warp < 6;                     // warps 2..5 own the four TMEM lane quadrants: dZ conversion and the final read-out
+    float bsum = 0.f;
+    for (int it = 0; it < nst; ++it) {
+      const int st = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(raw_full + st, ph);
+      mbar_wait(mma_done + st, ph ^ 1);               // the MMAs of the previous lap are done with this bf16 slot and TMEM slot
+      tc_fence_after();
+      const uint32_t raw = smem_u32(raw0 + static_cast<size_t>(st) * raw_bytes);
+      if (a_warp && !(g.diag & 1)) {
+        const uint32_t colp = raw + quad * W3_BOX + lane * 4;
+        float a[W3_BKR];
+#pragma unroll
+        for (int m = 0; m < W3_BKR; ++m) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[m]) : "r"(colp + m * 128));
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          split_bf16_pair(a[2 * m], a[2 * m + 1], hi[m], lo[m]);
+          bsum += a[2 * m] + a[2 * m + 1];
+        }
+        const uint32_t ta = lane_addr + g.tm_a + st * 32;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 16, lo);
+      }
+      if (!(g.diag & 2)) {
+        const uint32_t xraw = raw + W3_A_RAW;
+        const uint32_t xhi = smem_u32(bf0 + static_cast<size_t>(st) * bf_bytes), xlo = xhi + nblk * W3_BOX;
+        int m = wtid / G, cg = wtid - m * G;
+        for (; m < W3_BKR;) {
+          const int jb = cg >> 2, c2 = (cg & 3) << 1, sw = m & 7;
+          const uint32_t rp = xraw + jb * W3_BOX + m * 128;
+          // two 16-byte chunks of 4 floats; boxes of odd index read theirs in the opposite order: 8 consecutive lanes hit 8 distinct bank groups
+          const int first = c2 + (jb & 1), second = c2 + 1 - (jb & 1);
+          const float4 f0 = lds_f4(rp + ((first ^ sw) << 4)), f1 = lds_f4(rp + ((second ^ sw) << 4));
+          const float4 lo4 = (jb & 1) ? f1 : f0, hi4 = (jb & 1) ? f0 : f1;     // columns 8cg..8cg+3 | 8cg+4..8cg+7
+          uint32_t h[4], l[4];
+          split_bf16_pair(lo4.x, lo4.y, h[0], l[0]);
+          split_bf16_pair(lo4.z, lo4.w, h[1], l[1]);
+          split_bf16_pair(hi4.x, hi4.y, h[2], l[2]);
+          split_bf16_pair(hi4.z, hi4.w, h[3], l[3]);
+          const uint32_t off = (cg >> 3) * W3_BOX + m * 128 + (((cg & 7) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xhi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xlo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+          m += step_m;
+          cg += step_c;
+          if (cg >= G) {
+            cg -= G;
+            ++m;
+          }
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(ready + st);
+        mbar_arrive(raw_empty + st);
+      }
+    }
+    if (a_warp && g.dbias != nullptr && blockIdx.y == 0 && n0 + r < g.n) atomicAdd(g.dbias + n0 + r, bsum);
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int row = n0 + r;
+    for (int c = 0; a_warp && c < width; c += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c, v);
+      if (row < g.n && !(g.diag & 8)) {
+        float* cp = g.dW + static_cast<size_t>(row) * g.lddw + k0 + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (k0 + c + 4 * q < g.k) red_add_v4(cp + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1003,6 +1210,46 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   g.nb = (g.kt + 31) / 32;
   g.tm_a = g.kt <= 160 ? 160 : 320;
   // wide tiles: 16-row stages (4 x 48 KB in flight instead of 2 x 96 KB); narrow tiles fit 3+ stages of 32 rows
+  if (g_bwd_bf16.load() && !getenv("RR_WG_TF32")) {
+    // 3 x bf16: raw ring (dZ 16 KB + X boxes) and bf16 ring (hi + lo images), the same number of slots each
+    const int nblk = (g.kt + 63) / 64;
+    const int raw_bytes = W3_A_RAW + g.nb * W3_BOX, bf_bytes = 2 * nblk * W3_BOX;
+    int S3 = (SMEM_LIMIT - 2048) / (raw_bytes + bf_bytes);
+    if (S3 > 4) S3 = 4;
+    if (S3 > (512 - g.tm_a) / 32) S3 = (512 - g.tm_a) / 32;
+    if (S3 >= 2) {
+      g.stages = S3;
+      RR_TRY(make_map(&g.tmA, dZ, M, n, lddz, W3_BKR, CU_TENSOR_MAP_SWIZZLE_NONE));
+      RR_TRY(make_map(&g.tmB, X, M, k, ldx, W3_BKR, CU_TENSOR_MAP_SWIZZLE_128B));
+      g.M = M;
+      g.n = n;
+      g.k = k;
+      g.k_pad = k_pad;
+      g.dW = dW;
+      g.lddw = lddw;
+      g.dbias = dbias;
+      const char* de = getenv("RR_TC_DIAG");
+      g.diag = de ? atoi(de) : 0;
+      const int ntiles3 = (n + BM - 1) / BM;
+      int splits3 = num_sms() / (ntiles3 * ktiles);
+      const int max_splits3 = (M + 8 * W3_BKR - 1) / (8 * W3_BKR);
+      if (splits3 > max_splits3) splits3 = max_splits3;
+      if (splits3 < 1) splits3 = 1;
+      int chunk3 = (M + splits3 - 1) / splits3;
+      chunk3 = (chunk3 + W3_BKR - 1) / W3_BKR * W3_BKR;
+      splits3 = (M + chunk3 - 1) / chunk3;
+      g.m_chunk = chunk3;
+      static bool attr3_set = false;
+      if (!attr3_set) {
+        RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr3_set = true;
+      }
+      const size_t smem3 = static_cast<size_t>(S3) * (raw_bytes + bf_bytes) + 1024 + 512;
+      k_tc_wgrad3<<<dim3(ntiles3, ktiles, splits3), W3_THREADS, smem3, s>>>(g);
+      RR_LAUNCH_CHECK("k_tc_wgrad3");
+      return RR_OK;
+    }
+  }
   const char* bkr_env = getenv("RR_WG_BKR");
   const int bkr = bkr_env ? (atoi(bkr_env) == 16 ? 16 : 32) : (g.kt > 160 ? 16 : 32);
   const int box = bkr * 128;

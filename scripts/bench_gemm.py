@@ -93,16 +93,18 @@ if which in ("all", "fwd"):
 if which in ("all", "wgrad"):
     cases = [("wgrad [B,304]^T[B,304]", wgrad_case(B, 304, 304)), ("wgrad [B,304]^T[B,88]", wgrad_case(B, 304, 88)),
              ("wgrad [A,304]^T[A,304]", wgrad_case(A, 304, 304)), ("wgrad h600 [A,608]^T[A,608]", wgrad_case(A, 608, 608))]
-    for promo in (128, 256):
-        for kt in (320, 160):
-            for bkr in (32, 16):
-                setenv(RR_TMA_PROMO=promo, RR_WG_KT=kt, RR_WG_BKR=bkr, RR_TC_DIAG=0)
-                for name, c in cases:
-                    report(f"promo={promo} kt={kt} bkr={bkr} {name}", c[0], c[1], c[2])
-                for diag in (4, 3, 7, 8):
-                    setenv(RR_TC_DIAG=diag)
-                    report(f"promo={promo} kt={kt} bkr={bkr} diag={diag} {cases[0][0]}", cases[0][1][0], cases[0][1][1], cases[0][1][2])
-    setenv(RR_TC_DIAG=0, RR_TMA_PROMO=128)
+    for tf32 in (1, 0):
+        if tf32:
+            E["RR_WG_TF32"] = "1"
+        else:
+            E.pop("RR_WG_TF32", None)
+        setenv(RR_TC_DIAG=0)
+        for name, c in cases:
+            report(f"{'3xtf32' if tf32 else '3xbf16'} {name}", c[0], c[1], c[2])
+        for diag in (4, 3, 7, 8):
+            setenv(RR_TC_DIAG=diag)
+            report(f"{'3xtf32' if tf32 else '3xbf16'} diag={diag} {cases[0][0]}", cases[0][1][0], cases[0][1][1], cases[0][1][2])
+    setenv(RR_TC_DIAG=0)
 if which == "one":     # one launch of each headline kernel, for ncu
     run, *_ = fwd_case(B, 304, 304)
     run2, *_ = wgrad_case(B, 304, 304)

@@ -349,9 +349,13 @@ def test_tcgen05_and_simt_draw_the_same_dropout_mask(tc_mode):
 
 @pytest.mark.parametrize("M,n,k", [(1000, 304, 304), (4100, 304, 88), (777, 304, 64), (40000, 304, 304), (1000, 608, 608), (300, 16, 304),
                                    (513, 48, 48)])
-def test_tcgen05_wgrad_matches_fp64(tc_mode, M, n, k):
-    """tcgen05 wgrad (MN-major operands, split over the row range, vector reductions into dW) and its fused bias gradient."""
+@pytest.mark.parametrize("bf16", [1, 0])
+def test_tcgen05_wgrad_matches_fp64(tc_mode, M, n, k, bf16):
+    """tcgen05 wgrad (dZ through TMEM, X MN-major, split over the row range, vector reductions into dW) and its fused bias gradient,
+    in both operand splits: 3 x bf16 (default for the backward pass, 16 significand bits per operand: 3e-5) and 3 x tf32 (1e-5)."""
     L = _lib.lib()
+    L.rr_set_backward_bf16(bf16)
+    tol = 3e-5 if bf16 else 1e-5
     g = torch.Generator().manual_seed(M + k)
     dZ, X = torch.randn(M, n, generator=g), torch.randn(M, k, generator=g)
     dZ[0] *= 50.0
@@ -359,10 +363,13 @@ def test_tcgen05_wgrad_matches_fp64(tc_mode, M, n, k):
     dW = torch.zeros(n, k, device=DEV)
     db = torch.zeros(n, device=DEV)
     _lib.check(L.rr_linear_wgrad(M, n, k, dZd.data_ptr(), n, Xd.data_ptr(), k, dW.data_ptr(), k, db.data_ptr(), S()))
-    close(dW, dZ.double().T @ X.double(), 1e-5)
+    L.rr_set_backward_bf16(1)
+    close(dW, dZ.double().T @ X.double(), tol)
     close(db, dZ.double().sum(0), 1e-5)
+    L.rr_set_backward_bf16(bf16)
     _lib.check(L.rr_linear_wgrad(M, n, k, dZd.data_ptr(), n, Xd.data_ptr(), k, dW.data_ptr(), k, None, S()))   # accumulates
-    close(dW, 2 * (dZ.double().T @ X.double()), 1e-5)
+    L.rr_set_backward_bf16(1)
+    close(dW, 2 * (dZ.double().T @ X.double()), tol)
 
 
 def test_device_assembly_equals_host_packing():
