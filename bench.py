@@ -11,7 +11,9 @@ backward, (gradient all-reduce,) Adam, NoamLR.  Prints ONE JSON line (rank 0).
                (``DataProcessor.generate_batch_reactions``), ``Parsing_features.parsing_reactions`` on the warm
                MolGraph cache, the pinned host->device copies (molecule ids, row offsets, extra features, targets),
                on-device batch assembly from the HBM-resident molecule store, forward/loss/backward/Adam, and a
-               device->host read of the loss.
+               device->host read of the loss.  Every step does all of these inside the timed region; the plan / featurise /
+               upload of batch i+1 is issued between enqueuing step i and reading its loss (data/prefetch.py: Lookahead), the
+               way the reference's own loop overlaps them when it does not read the loss back.
 * ``roofline``: the dominant kernel class of the step, timed with CUDA events on the launching
                stream inside the timed region (rr_profile_begin/end of librr_sm100).
 * ``cpu_baseline`` / ``--impl reference``: the CPU restatement of the reference path
@@ -283,21 +285,25 @@ def ours(args):
 
     def featurise(batch):
         reactions, tg, sc, feats = batch
-        return tuple(fz.parsing_reactions(reactions)) + (torch.FloatTensor(tg).squeeze(), sc, feats)   # warm MolGraph cache -> store ids
+        r_b, p_b = fz.parsing_reactions(reactions)                           # warm MolGraph cache -> store ids
+        # pinned H2D of ids / row offsets + on-device assembly from the HBM-resident molecule store, enqueued behind the running step
+        rg, pg = r_b.to_device(dev), p_b.to_device(dev)
+        return rg, pg, torch.FloatTensor(tg).squeeze(), sc, feats, rg.h2d_bytes + pg.h2d_bytes
 
-    from reactranker_b200.data.prefetch import prefetch_batches
-    e2e_feed = prefetch_batches(endless_plan(), featurise, depth=2)           # the same one-batch-ahead worker thread train() uses
+    from reactranker_b200.data.prefetch import Lookahead
+    e2e_feed = Lookahead(endless_plan(), featurise)
 
     def step_e2e(i):
-        r_b, p_b, targets, sc, feats = next(e2e_feed)
-        out = model(r_b, p_b, gpu=local, add_features=feats)                  # H2D (ids, offsets, features) + on-device assembly inside
-        loss = loss_fn(out, sc, targets)
+        rg, pg, targets, sc, feats, graph_bytes = e2e_feed.current
+        out = model(rg, pg, gpu=local, add_features=feats)                    # H2D of the extra features inside
+        loss = loss_fn(out, sc, targets)                                      # H2D of the targets inside
         opt.zero_grad(set_to_none=True)
         loss.backward()
         reduce_grads()
         opt.step()
         sched.step()
-        h2d[0] = model.last_h2d_bytes + targets.numel() * 4
+        h2d[0] = graph_bytes + feats.size * 4 + targets.numel() * 4
+        e2e_feed.advance()                                                    # plan + featurise + upload batch i+1 while step i executes
         return float(loss.detach().cpu().reshape(-1)[0])                     # D2H read of the step's result
 
     def barrier():

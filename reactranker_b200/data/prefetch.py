@@ -1,56 +1,33 @@
-"""Host-side batch prefetch: plan + featurise batch i+1 on a worker thread while the GPU runs step i.
+"""One-batch look-ahead for training loops that read a result back every step.
 
-The reference's training loop (train/train_listwise.py:183-188) plans a batch, featurises it and launches the step strictly in
-sequence.  That is free when nothing waits for the GPU; as soon as the caller reads a step's result (a loss for logging, NaN
-checks, a benchmark's device->host read) the host work of the next step is exposed.  ``prefetch_batches`` keeps ``depth``
-prepared batches ahead.  pandas / numpy release the GIL in their hot loops and ctypes releases it for the kernel launches, so
-the worker overlaps with the launching thread."""
+The reference's loop (train/train_listwise.py:183-188) plans a batch, featurises it and launches the step strictly in
+sequence.  That is free while nothing waits for the GPU: the kernel launches are asynchronous, so the host runs ahead and
+prepares batch i+1 while step i executes.  A loop that reads the loss of every step (logging, NaN checks, a benchmark's
+device->host read) loses that overlap -- unless batch i+1 is prepared BETWEEN enqueuing step i and reading its result:
+
+    feed = Lookahead(plan, featurise)          # featurise: plan item -> whatever the step needs (graphs already on the device)
+    while feed.current is not None:
+        loss = step(feed.current)              # enqueue forward / backward / optimiser: returns immediately
+        feed.advance()                         # host work + H2D of the NEXT batch, overlapping the GPU
+        value = float(loss)                    # only now wait
+
+A worker thread was tried first and was slower: it holds the GIL in 5 ms slices exactly while the launching thread needs it.
+"""
 from __future__ import annotations
 
-import queue
-import threading
-from typing import Callable, Iterable, Iterator
+from typing import Callable, Iterable
 
 
-class _Failure:
-    def __init__(self, exc: BaseException):
-        self.exc = exc
+class Lookahead:
+    def __init__(self, batches: Iterable, prepare: Callable):
+        self._it = iter(batches)
+        self._prepare = prepare
+        self.current = None
+        self.advance()
 
-
-_DONE = object()
-
-
-def prefetch_batches(batches: Iterable, prepare: Callable, depth: int = 2) -> Iterator:
-    """Yield ``prepare(batch)`` for every ``batch`` of ``batches``, computed up to ``depth`` items ahead on a worker thread.
-    Exceptions of the worker are re-raised at the consumer; abandoning the generator stops the worker."""
-    q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
-    stop = threading.Event()
-
-    def work():
+    def advance(self) -> None:
+        """Prepare the next batch (``current`` becomes None when the plan is exhausted)."""
         try:
-            for b in batches:
-                item = prepare(b)
-                while not stop.is_set():
-                    try:
-                        q.put(item, timeout=0.1)
-                        break
-                    except queue.Full:
-                        continue
-                if stop.is_set():
-                    return
-            q.put(_DONE)
-        except BaseException as e:  # noqa: BLE001 - handed to the consumer
-            q.put(_Failure(e))
-
-    t = threading.Thread(target=work, name="rr-batch-prefetch", daemon=True)
-    t.start()
-    try:
-        while True:
-            item = q.get()
-            if item is _DONE:
-                return
-            if isinstance(item, _Failure):
-                raise item.exc
-            yield item
-    finally:
-        stop.set()
+            self.current = self._prepare(next(self._it))
+        except StopIteration:
+            self.current = None

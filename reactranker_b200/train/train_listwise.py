@@ -23,7 +23,6 @@ from tqdm import trange
 
 from .. import _lib
 from ..data.load_reactions import DataProcessor
-from ..data.prefetch import prefetch_batches
 from ..utils import save_checkpoint
 from .eval import calculate_mse, ranking_metrics
 from .loss import GaussDisLoss, ListnetLoss, MLEloss, MSELoss, evidential_ranking
@@ -106,14 +105,11 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
             logger.info('learning rate is: {}'.format(lr))
         model.train()
         loss = torch.zeros(1)
-        plan = train_proc.generate_batch_reactions(smiles_list=smiles_list, target_name='std' + target_name, batch_size=batch_size, seed=epoch,
-                                                   add_features_name=add_features_name)
-
-        def featurise(batch):                      # runs one batch ahead on a worker thread (data/prefetch.py)
-            reactions, targets, scope, add_features = batch
-            return (torch.FloatTensor(targets).squeeze(), scope, add_features) + tuple(smiles2graph_dic.parsing_reactions(reactions))   # train_listwise.py:187-188
-
-        for targets_t, scope, add_features, r_inputs, p_inputs in prefetch_batches(plan, featurise):
+        # nothing below waits for the GPU (the loss is read once per epoch), so the host plans and featurises batch i+1 while step i runs
+        for reactions, targets, scope, add_features in train_proc.generate_batch_reactions(
+                smiles_list=smiles_list, target_name='std' + target_name, batch_size=batch_size, seed=epoch, add_features_name=add_features_name):
+            targets_t = torch.FloatTensor(targets).squeeze()                         # train_listwise.py:187
+            r_inputs, p_inputs = smiles2graph_dic.parsing_reactions(reactions)
             output = model(r_inputs, p_inputs, gpu=dev_idx, add_features=add_features)
             if task_type == 'mle':
                 loss = loss_fn(output, scope, targets_t, dev_idx)

@@ -201,41 +201,27 @@ def test_parsing_features_builds_reference_batches():
     assert fz.parsing_reactions(None) == [None, None] and fz.parsing_smiles(None) is None
 
 
-def test_prefetch_batches_order_errors_and_abandon():
-    """data/prefetch.py: items arrive in order, a worker exception surfaces at the consumer, an abandoned generator stops the worker."""
-    import threading
-    import time
-    from reactranker_b200.data.prefetch import prefetch_batches
-    assert list(prefetch_batches(range(20), lambda x: x * x, depth=3)) == [x * x for x in range(20)]
+def test_lookahead_prepares_one_batch_ahead():
+    """data/prefetch.py: ``current`` is ready at construction, ``advance`` prepares exactly one more item, exhaustion gives None."""
+    from reactranker_b200.data.prefetch import Lookahead
+    seen = []
 
-    def boom(x):
-        if x == 3:
-            raise ValueError("bad batch")
-        return x
-    got = []
-    with pytest.raises(ValueError, match="bad batch"):
-        for v in prefetch_batches(range(10), boom):
-            got.append(v)
-    assert got == [0, 1, 2]
-
-    def endless():
-        i = 0
-        while True:
-            yield i
-            i += 1
-    before = threading.active_count()
-    gen = prefetch_batches(endless(), lambda x: x, depth=2)
-    assert [next(gen) for _ in range(5)] == [0, 1, 2, 3, 4]
-    gen.close()
-    for _ in range(50):
-        if threading.active_count() <= before:
-            break
-        time.sleep(0.05)
-    assert threading.active_count() <= before
+    def prep(x):
+        seen.append(x)
+        return x * 10
+    feed = Lookahead(iter(range(3)), prep)
+    assert feed.current == 0 and seen == [0]
+    feed.advance()
+    assert feed.current == 10 and seen == [0, 1]
+    feed.advance()
+    feed.advance()
+    assert feed.current is None and seen == [0, 1, 2]
+    with pytest.raises(ValueError):
+        Lookahead(iter([1]), lambda x: (_ for _ in ()).throw(ValueError("bad batch")))
 
 
 def test_molecule_store_registration_is_thread_safe():
-    """The prefetch worker registers molecules while the training thread reads the store tables."""
+    """Molecules may be registered from a data-loading thread while the training thread reads the store tables."""
     import threading
     from reactranker_b200 import synthetic
     from reactranker_b200.data.load_reactions import Parsing_features
