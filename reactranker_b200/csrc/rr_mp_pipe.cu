@@ -59,6 +59,8 @@ struct Args {
   float* acc;
   int acc_mode;     // 0 none, 1 acc = dz, 2 acc += dz
   int skip_out;     // do not write dz for ordinary rows (only acc is wanted)
+  int acc_red;      // acc += dz as a fire-and-forget vector reduction (red.global.add.v4.f32) instead of staging the accumulator rows:
+                    // a third fewer bytes per stage, so twice the atoms (and 16 consumer warps) fit the ring
   int apb, stages, n_stage_total;
   int producers, round_stages, consumer_warps;   // active producer warps, stages per producer round
   int n_nbr, n_own; // row sources per neighbour / per atom
@@ -274,7 +276,10 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
       const float4 o = mask_scale(d, yv, A.scale, A.preact);
       if (!A.skip_out) st_f4(out_c + off, o);
       if (A.acc_mode == 1) st_f4(acc_c + off, o);
-      else if (A.acc_mode == 2) st_f4(acc_c + off, f4_add(av, o));
+      else if (A.acc_mode == 2) {
+        if (A.acc_red) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc_c + off), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+        else st_f4(acc_c + off, f4_add(av, o));
+      }
     };
     int st = 0;
     uint32_t ph = 0;
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
             if (k < nf) {
               const size_t off = static_cast<size_t>(wrow[k]) * ld;
               const float4 d = f4_sub(S4, v[k]);
-              if (FUSED) epilogue(d, nbr(k, 1), A.acc_mode == 2 ? nbr(k, 2) : f4_zero(), off);
+              if (FUSED) epilogue(d, nbr(k, 1), (A.acc_mode == 2 && !A.acc_red) ? nbr(k, 2) : f4_zero(), off);
               else st_f4(out_c + off, d);
             }
           if (deg > kFast) {
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
             for (int k = kFast; k < deg; ++k) {
               const size_t off = static_cast<size_t>(__ldg(ib + k)) * ld;
               const float4 d = f4_sub(S4, ld_f4(src_c + static_cast<size_t>(__ldg(rb + k)) * ld));
-              if (FUSED) epilogue(d, ld_f4(y_c + off), A.acc_mode == 2 ? ld_f4(acc_c + off) : f4_zero(), off);
+              if (FUSED) epilogue(d, ld_f4(y_c + off), (A.acc_mode == 2 && !A.acc_red) ? ld_f4(acc_c + off) : f4_zero(), off);
               else st_f4(out_c + off, d);
             }
           }
@@ -391,14 +396,14 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
           for (int k = 0; k < kFast; ++k)
             if (k < nf) {
               const size_t off = static_cast<size_t>(wrow[k]) * ld;
-              if (FUSED) epilogue(d, nbr(k, 0), A.acc_mode == 2 ? nbr(k, 1) : f4_zero(), off);
+              if (FUSED) epilogue(d, nbr(k, 0), (A.acc_mode == 2 && !A.acc_red) ? nbr(k, 1) : f4_zero(), off);
               else st_f4(out_c + off, d);
             }
           if (deg > kFast) {
             const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
             for (int k = kFast; k < deg; ++k) {
               const size_t off = static_cast<size_t>(__ldg(ib + k)) * ld;
-              if (FUSED) epilogue(d, ld_f4(y_c + off), A.acc_mode == 2 ? ld_f4(acc_c + off) : f4_zero(), off);
+              if (FUSED) epilogue(d, ld_f4(y_c + off), (A.acc_mode == 2 && !A.acc_red) ? ld_f4(acc_c + off) : f4_zero(), off);
               else st_f4(out_c + off, d);
             }
           }
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
           }
           if (!is_pad) {
             const size_t off = static_cast<size_t>(a) * ld;
-            if (FUSED) epilogue(acc, lds4(base + own_off_t + own_stride), A.acc_mode == 2 ? lds4(base + own_off_t + 2 * own_stride) : f4_zero(), off);
+            if (FUSED) epilogue(acc, lds4(base + own_off_t + own_stride), (A.acc_mode == 2 && !A.acc_red) ? lds4(base + own_off_t + 2 * own_stride) : f4_zero(), off);
             else st_f4(out_c + off, acc);
           }
           pad_acc = f4_fma(static_cast<float>(pad_count), lds4(base + own_off_t), pad_acc);
@@ -469,12 +474,17 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
   if (cpr < 1 || cpr > 256 || (ld & 3)) return RR_ERR_UNSUPPORTED;
   A.row_bytes = ld * 4;
   const bool fused = y != nullptr;
+  // measured (scripts/bench_mp.py): the bond-row backward gains 30 % (273 -> 190 us) from reducing into acc, the atom-row backward, whose
+  // accumulator rows are one contiguous bulk copy per stage, loses 13 %: every acc element is added to exactly once, so both are deterministic
+  const char* red_env = getenv("RR_MP_ACC_RED");
+  A.acc_red = red_env ? (red_env[0] != '0') : (op == BOND_BWD);
+  const bool stage_acc = fused && A.acc_mode == 2 && !A.acc_red;
   switch (op) {
     case BOND_FWD: A.n_nbr = 1; A.n_own = 0; break;
-    case BOND_BWD: A.n_nbr = fused ? (A.acc_mode == 2 ? 3 : 2) : 1; A.n_own = 0; break;
+    case BOND_BWD: A.n_nbr = fused ? (stage_acc ? 3 : 2) : 1; A.n_own = 0; break;
     case NBR_FWD: A.n_nbr = 1; A.n_own = 0; break;
-    case NBR_BWD_BOND: A.n_nbr = fused ? (A.acc_mode == 2 ? 2 : 1) : 0; A.n_own = 1; break;
-    default: A.n_nbr = 1; A.n_own = fused ? (A.acc_mode == 2 ? 3 : 2) : 1; break;
+    case NBR_BWD_BOND: A.n_nbr = fused ? (stage_acc ? 2 : 1) : 0; A.n_own = 1; break;
+    default: A.n_nbr = 1; A.n_own = fused ? (stage_acc ? 3 : 2) : 1; break;
   }
   const char* cw_env = getenv("RR_MP_CONSUMERS");
   for (int consumers = cw_env ? atoi(cw_env) : MAX_CONSUMERS; consumers >= 256; consumers -= 256) {

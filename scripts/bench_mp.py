@@ -52,7 +52,7 @@ cases = [
      5 * A * row + idx),
     ("relu_bwd [B] alone (dz, acc+=)", lambda: L.rr_relu_bwd(B, hp, mB.data_ptr(), yB.data_ptr(), 1.1, 0, oB.data_ptr(), accB.data_ptr(), 2, S()), 5 * B * row),
 ]
-for v1, cw in (("1", "256"), ("0", "256"), ("0", "512")):
+for v1, cw in (("1", "512"), ("0", "256"), ("0", "512")):
     os.environ["RR_MP_V1"] = v1
     os.environ["RR_MP_CONSUMERS"] = cw
     for name, fn, by in cases:
