@@ -8,18 +8,9 @@
 // so the reference's fp32 results are reproduced to ~1e-6 while the contraction runs on the 5th-gen
 // tensor cores (kind::tf32), accumulating in TMEM.
 //
-// One CTA = one 128-row tile of C across up to 320 output columns (the whole hidden width for h = 300),
-// 6 warps, warp-specialised:
-//   warp 0    : TMA producer   - cp.async.bulk.tensor (128B swizzle) of the A tile [128 x 32] and the B tile
-//                                [nt x 32] per k-block into a 2..4 stage ring (mbarrier complete_tx)
-//   warps 2-5 : split workers  - turn the landed fp32 tiles into (hi, lo) pairs in shared memory,
-//                                fence.proxy.async, signal the MMA warp; afterwards they are the epilogue:
-//                                tcgen05.ld the accumulator (one row per thread), add bias / residual,
-//                                ReLU, Philox dropout, store (or accumulate for dgrad)
-//   warp 1    : MMA issuer     - one elected lane issues 3 x 4 tcgen05.mma (UMMA_K = 8) per k-block and
-//                                per N-half, commits to the stage's "empty" barrier; owns TMEM alloc/dealloc
-//
-// Two-source K (concat-free [x1 || x2] W^T) walks both sources through the same accumulator.
+// Persistent warp-specialised CTAs (k_tc_gemm2): TMA producer, MMA issuer, four split warps that move the A operand through TENSOR
+// MEMORY, eight epilogue warps; see the comment above the kernel.  The backward GEMMs (dgrad: k_tc_gemm2<.., true>, wgrad:
+// k_tc_wgrad3) use a 3 x bf16 split instead.  Two-source K (concat-free [x1 || x2] W^T) walks both sources through one accumulator.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -49,10 +40,6 @@ struct Args {
   Src src[2];
   int nsrc;
   int M, N;
-  int nt;      // output columns per CTA (multiple of 16, <= MAX_NT)
-  int bn;      // rows per B TMA box (nt or nt/2)
-  int stages;
-  int tmem_cols;
   float* C;
   int ldc;
   const float* bias;
@@ -186,149 +173,6 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_p, uint8_t* lo_p, int byt
     sts_f4(lo + off, l);
   }
 }
-
-__global__ void __launch_bounds__(THREADS, 1) k_tc_gemm(const __grid_constant__ Args g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int nt = g.nt;
-  const int b_bytes = nt * BK * 4;
-  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
-  const int S = g.stages;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
-  uint64_t* ready = full + S;
-  uint64_t* empty = ready + S;
-  uint64_t* acc_bar = empty + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * nt;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(ready + s, 4);
-      mbar_init(empty + s, 1);
-    }
-    mbar_init(acc_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int s = 0; s < g.nsrc; ++s) {
-      prefetch_tmap(&g.src[s].tmA);
-      prefetch_tmap(&g.src[s].tmB);
-    }
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(g.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      int it = 0;
-      const uint32_t tx = static_cast<uint32_t>(A_BYTES + b_bytes);
-      for (int s = 0; s < g.nsrc; ++s) {
-        const int nkb = (g.src[s].K + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(empty + st, ph ^ 1);
-          uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
-          mbar_expect_tx(full + st, tx);
-          tma_load_2d(&g.src[s].tmA, full + st, base, kb * BK, m0);
-          for (int j = 0; j < nt; j += g.bn) tma_load_2d(&g.src[s].tmB, full + st, base + 2 * A_BYTES + j * BK * 4, kb * BK, n0 + j);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      const int n1 = (nt <= 256) ? nt : ((nt / 2 + 15) / 16 * 16);
-      const int n2 = nt - n1;
-      const uint32_t idesc1 = umma_idesc(BM, n1);
-      const uint32_t idesc2 = n2 ? umma_idesc(BM, n2) : 0u;
-      int it = 0;
-      for (int s = 0; s < g.nsrc; ++s) {
-        const int nkb = (g.src[s].K + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(ready + st, ph);
-          tc_fence_after();
-          const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * stage_bytes);
-          const uint32_t a_hi = base, a_lo = base + A_BYTES, b_hi = base + 2 * A_BYTES, b_lo = b_hi + b_bytes;
-#pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint32_t ko = k * UK * 4;
-            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            // column half 1
-            umma_tf32(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc1, first);
-            umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc1, 1u);
-            umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc1, 1u);
-            if (n2) {
-              const uint32_t bo = static_cast<uint32_t>(n1) * BK * 4;
-              umma_tf32(tmem_base + n1, umma_desc(a_lo + ko), umma_desc(b_hi + bo + ko), idesc2, first);
-              umma_tf32(tmem_base + n1, umma_desc(a_hi + ko), umma_desc(b_lo + bo + ko), idesc2, 1u);
-              umma_tf32(tmem_base + n1, umma_desc(a_hi + ko), umma_desc(b_hi + bo + ko), idesc2, 1u);
-            }
-          }
-          umma_commit(empty + st);  // frees the stage once these MMAs have read it
-        }
-      }
-      umma_commit(acc_bar);         // accumulator complete
-    }
-  } else {
-    // ---------------- split workers, then epilogue ----------------
-    const int wtid = threadIdx.x - 64;  // 0..127
-    int it = 0;
-    for (int s = 0; s < g.nsrc; ++s) {
-      const int nkb = (g.src[s].K + BK - 1) / BK;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int st = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(full + st, ph);
-        uint8_t* base = smem + static_cast<size_t>(st) * stage_bytes;
-        split_tile(base, base + A_BYTES, A_BYTES, wtid);
-        split_tile(base + 2 * A_BYTES, base + 2 * A_BYTES + b_bytes, b_bytes, wtid);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ready + st);
-      }
-    }
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int row = m0 + quad * 32 + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    for (int c = 0; c < nt; c += 16) {
-      float v[16];
-      tmem_ld16(taddr + c, v);                 // warp-collective: executed by every lane, rows >= M included
-      if (row < g.M) {
-        const int col = n0 + c;
-        float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (g.bias) o = f4_add(o, ld_f4(g.bias + col + 4 * q));
-          if (g.resid) o = f4_add(o, ld_f4(g.resid + static_cast<size_t>(row) * g.ldr + col + 4 * q));
-          if (g.relu) o = f4_relu(o);
-          if (g.p > 0.f) o = dropout4(o, g.p, g.inv_keep, g.seed, g.stream_id, (static_cast<uint64_t>(row) * g.ldc + col + 4 * q) >> 2);
-          if (g.accumulate) o = f4_add(o, *reinterpret_cast<const float4*>(cp + 4 * q));
-          st_f4(cp + 4 * q, o);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
-  }
-}
-
 
 // ================================================================================================
 // v2 forward / dgrad kernel: persistent, A operand through TENSOR MEMORY (tcgen05.mma "TS" form).
@@ -1296,12 +1140,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
 
 // Can this problem run on the tcgen05 kernel?  (everything the model produces can; odd C-ABI calls fall back to SIMT)
 bool tc_supported(int M, int n, int k1, int k2, int ldx1, int ldx2) {
-  if (M <= 0 || n < 16 || (n & 15)) return false;
-  if ((k1 & 3) || (k2 & 3) || (ldx1 & 3) || (ldx2 & 3) || k1 <= 0) return false;
-  const int tiles = (n + tc::MAX_NT - 1) / tc::MAX_NT;
-  if (n % tiles) return false;
-  const int nt = n / tiles;
-  return (nt & 15) == 0 && nt >= 16;
+  return M > 0 && n >= 16 && !(n & 15) && k1 > 0 && !(k1 & 3) && !(k2 & 3) && !(ldx1 & 3) && !(ldx2 & 3);
 }
 
 // Y = epi(X1 W1^T + X2 W2^T): W* row-major [n, k*] (K-major B operand)
@@ -1311,36 +1150,25 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
               int kclass, cudaStream_t s, const float* W1lo, const float* W2lo) {
   using namespace tc;
   ProfScope prof_scope(kclass, s);
-  static const bool use_v1 = getenv("RR_TC_V1") != nullptr;
   const char* diag_env = getenv("RR_TC_DIAG");
   if (getenv("RR_TC_FAKE_PRESPLIT") && !W1lo) {  // timing experiments only (scripts/bench_gemm.py): wrong numerics, same traffic as pre-split weights
     W1lo = W1;
     W2lo = W2;
   }
   Args g{};
-  const int tiles = (n + MAX_NT - 1) / MAX_NT;
-  g.nt = n / tiles;
-  g.bn = use_v1 ? (g.nt <= 256 ? g.nt : g.nt / 2) : NT2;
-  const int stage_bytes = 2 * A_BYTES + 2 * g.nt * BK * 4;
-  int S = (SMEM_LIMIT - 2048) / stage_bytes;
-  if (S > 4) S = 4;
-  g.stages = S;
-  int cols = 32;
-  while (cols < g.nt) cols <<= 1;
-  g.tmem_cols = cols;
-  g.nsrc = 1;
-  RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
-  RR_TRY(make_map(&g.src[0].tmB, W1, n, k1, ldw1, g.bn));
-  g.src[0].K = k1;
-  g.presplit = (!use_v1 && W1lo != nullptr && (!(X2 && k2 > 0) || W2lo != nullptr)) ? 1 : 0;
+  const bool two = X2 && k2 > 0;
+  g.nsrc = two ? 2 : 1;
+  g.presplit = (W1lo != nullptr && (!two || W2lo != nullptr)) ? 1 : 0;
   g.diag = diag_env ? atoi(diag_env) : 0;
-  if (g.presplit) RR_TRY(make_map(&g.src[0].tmBlo, W1lo, n, k1, ldw1, g.bn));
-  if (X2 && k2 > 0) {
+  RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
+  RR_TRY(make_map(&g.src[0].tmB, W1, n, k1, ldw1, NT2));
+  if (g.presplit) RR_TRY(make_map(&g.src[0].tmBlo, W1lo, n, k1, ldw1, NT2));
+  g.src[0].K = k1;
+  if (two) {
     RR_TRY(make_map(&g.src[1].tmA, X2, M, k2, ldx2, BM));
-    RR_TRY(make_map(&g.src[1].tmB, W2, n, k2, ldw2, g.bn));
-    if (g.presplit) RR_TRY(make_map(&g.src[1].tmBlo, W2lo, n, k2, ldw2, g.bn));
+    RR_TRY(make_map(&g.src[1].tmB, W2, n, k2, ldw2, NT2));
+    if (g.presplit) RR_TRY(make_map(&g.src[1].tmBlo, W2lo, n, k2, ldw2, NT2));
     g.src[1].K = k2;
-    g.nsrc = 2;
   }
   g.M = M;
   g.N = n;
@@ -1355,34 +1183,20 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   g.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   g.seed = seed;
   g.stream_id = stream_id;
-  if (!use_v1) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      attr2_set = true;
-    }
-    const size_t smem2 = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
-    const char* ew_env = getenv("RR_TC_EW");
-    const int ew = (ew_env && atoi(ew_env) == 4) ? 4 : 8;
-    const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
-    const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-    if (ew == 8) k_tc_gemm2<8, false><<<ctas, THREADS2_BASE + 256, smem2, s>>>(g);
-    else k_tc_gemm2<4, false><<<ctas, THREADS2_BASE + 128, smem2, s>>>(g);
-    RR_LAUNCH_CHECK("k_tc_gemm2");
-    return RR_OK;
-  }
   static bool attr_set = false;
   if (!attr_set) {
-    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  RR_REQUIRE(g.nt % g.bn == 0 && (g.bn % 8) == 0, "tc_linear: tile %d box %d", g.nt, g.bn);
-  RR_REQUIRE(S >= 2, "tc_linear: tile of %d columns does not fit two pipeline stages", g.nt);
-  const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256;
-  dim3 grid((M + BM - 1) / BM, tiles);
-  k_tc_gemm<<<grid, THREADS, smem, s>>>(g);
-  RR_LAUNCH_CHECK("k_tc_gemm");
+  const size_t smem = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
+  const char* ew_env = getenv("RR_TC_EW");
+  const int ew = (ew_env && atoi(ew_env) == 4) ? 4 : 8;
+  const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
+  const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
+  if (ew == 8) k_tc_gemm2<8, false><<<ctas, THREADS2_BASE + 256, smem, s>>>(g);
+  else k_tc_gemm2<4, false><<<ctas, THREADS2_BASE + 128, smem, s>>>(g);
+  RR_LAUNCH_CHECK("k_tc_gemm2");
   return RR_OK;
 }
 
