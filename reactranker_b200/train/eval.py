@@ -89,7 +89,6 @@ def evaluate_top_scores(model, gpu, data_processor, smiles2graph_dic, ratio=0.25
     (eval.py:76-177).  Groups come from ``generate_batch_querys`` (real ``add_features_name`` column); in the reference
     ``batch_size`` groups share one BatchMolGraph and therefore one ``max_num_bonds`` -- reproduced by packing each
     ``batch_size`` chunk as one segment."""
-    dev = torch.device("cuda", gpu) if isinstance(gpu, int) else torch.device(gpu)
     score, overlap, top1_in = [], [], []
     with torch.no_grad():
         for X, targets, scope, feats in data_processor.generate_batch_querys(smiles_list=smiles_list, target_name=target_name,
@@ -113,6 +112,67 @@ def evaluate_top_scores(model, gpu, data_processor, smiles2graph_dic, ratio=0.25
     return sum(score) / len(score), sum(overlap) / len(overlap), sum(top1_in) / len(top1_in)
 
 
+def calculate_ndcg(model, gpu, data_processor, smiles2graph_dic, batch_size=2, NDCG_cut=0.5, show_info=False, smiles_list=None,
+                   target_name: str = 'ea', logger=None, is_order=True, means=None, stds=None, add_features_name=None):
+    """Rank-based NDCG@cut, KL(softmax(targets) || softmax(scores)), the per-item order table and the re-ordered SMILES of the
+    test report (eval.py:329-457).  ``batch_size`` groups share one forward (one BatchMolGraph, one ``max_num_bonds``) as in the
+    reference; everything after the forward is the reference's host arithmetic in fp32:
+      * ``means/stds`` de-normalise scores (and scale the variance column by ``stds**2``) first (eval.py:379-387);
+      * per group: items sorted by target (descending); ``pred_order`` = rank of each item's score among the group (1 = best);
+        gains are ``n + 1 - order`` and NDCG uses the first ``ceil(n * NDCG_cut)`` positions with a log2 discount (eval.py:309-326, 426-430);
+      * rows of ``total_order``: [target, score, (uncertainty,) true_order, pred_order]; ``smiles_and_idx``: [iteration, rsmi, psmi].
+    ``is_order=False`` only collects [target, score...] rows and SMILES pairs and returns ``None`` for both means."""
+    import math
+    ndcg_list, kl_list, total_order, smiles_and_idx = [], [], [], []
+    it = 0
+    with torch.no_grad():
+        for X, targets, scope, add_features in data_processor.generate_batch_querys(smiles_list=smiles_list, target_name=target_name,
+                                                                                     batch_size=batch_size, shuffle_query=False, shuffle_batch=False,
+                                                                                     add_features_name=add_features_name):
+            rsmi, psmi = [s[0] for s in X], [s[1] for s in X]
+            preds_ini = model(smiles2graph_dic.parsing_smiles(rsmi), smiles2graph_dic.parsing_smiles(psmi), gpu=gpu, add_features=add_features)
+            it += 1
+            preds_ini = preds_ini.detach().float().cpu()
+            if means is not None:
+                if preds_ini.dim() > 1:
+                    preds_ini = torch.stack((preds_ini[:, 0] * stds + means, preds_ini[:, 1] * (stds ** 2)), dim=1)
+                else:
+                    preds_ini = preds_ini * stds + means
+            with_unc = preds_ini.dim() > 1
+            preds = preds_ini[:, 0] if with_unc else preds_ini
+            unc = preds_ini[:, 1] if with_unc else None
+            t_all = torch.FloatTensor(np.squeeze(targets).tolist())
+            if not is_order:
+                rows = preds_ini.numpy().tolist()
+                total_order.extend([[t] + r for t, r in zip(t_all.tolist(), rows)] if with_unc else [[t, r] for t, r in zip(t_all.tolist(), rows)])
+                smiles_and_idx.extend([[a, b] for a, b in zip(rsmi, psmi)])
+                continue
+            o = 0
+            for n in scope:
+                bt, bp = t_all[o:o + n], preds[o:o + n]
+                P, Q = torch.softmax(bt, 0), torch.softmax(bp, 0)
+                # eval.py:400-402 writes exp(x)/sum(exp(x)) without a max shift; identical in exact arithmetic, and fp32-identical to ~1e-7
+                P = torch.exp(bt) / torch.sum(torch.exp(bt))
+                Q = torch.exp(bp) / torch.sum(torch.exp(bp))
+                kl_list.append(float(torch.sum(P * torch.log(P / Q))))
+                st, idx = torch.sort(bt, descending=True)
+                sp = bp[idx]
+                pred_order = torch.argsort(torch.argsort(sp, descending=True)) + 1
+                true_order = torch.arange(n, dtype=torch.float32) + 1
+                cols = [st, sp] + ([unc[o:o + n][idx]] if with_unc else []) + [true_order, pred_order.float()]
+                total_order.extend(torch.stack(cols, dim=1).tolist())
+                k = math.ceil(n * NDCG_cut)
+                disc = torch.log2(torch.arange(min(k, n), dtype=torch.float32) + 2)
+                pred_gain, true_gain = (n + 1 - pred_order).float()[:k], (n + 1 - true_order)[:k]
+                ndcg_list.append(float(torch.sum(pred_gain / disc) / torch.sum(true_gain / disc)))
+                order = idx.tolist()
+                smiles_and_idx.extend([[it, rsmi[o + i], psmi[o + i]] for i in order])
+                o += n
+    if not is_order:
+        return None, None, total_order, smiles_and_idx
+    return np.mean(np.array(ndcg_list), axis=0), np.mean(np.array(kl_list)), total_order, smiles_and_idx
+
+
 def _not_built(name):
     def f(*a, **k):
         raise NotImplementedError(f"{name} is an inference-side metric outside the hot path (SURVEY.md §2 row 8)")
@@ -120,7 +180,6 @@ def _not_built(name):
     return f
 
 
-calculate_ndcg = _not_built("calculate_ndcg")
 calculate_mse = _not_built("calculate_mse")
 pairwise_acc = _not_built("pairwise_acc")
 pairwise_baseline_acc = _not_built("pairwise_baseline_acc")

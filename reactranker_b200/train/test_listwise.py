@@ -5,7 +5,7 @@ from typing import Union
 from .. import _lib
 from ..data.load_reactions import DataProcessor
 from ..utils import load_checkpoint
-from .eval import evaluate_top_scores
+from .eval import calculate_ndcg, evaluate_top_scores
 
 
 def test(model, test_data, path_checkpoints, batch_size, smiles2graph_dic, gpu: Union[int, str], logger: Logger = None, smiles_list=None,
@@ -33,6 +33,16 @@ def test(model, test_data, path_checkpoints, batch_size, smiles2graph_dic, gpu: 
     print('   Note：For average target top1 in pred 0.25 is:{}'.format(average_top1_in_pred))
     if logger is not None:
         logger.info('\n  Note：For test set average score is: {:.4f}\n'.format(average_score))
-    # cal_ngcd (NDCG / KL on the test set) is an inference-side extra outside the hot path; the three scores above are
-    # what main.py collects (main.py:169-173)
+    if cal_ngcd is True:                          # test_listwise.py:58-63
+        scaler = state['data_scaler'] or {}
+        ndcg, kl_div, order, smiles_and_index = calculate_ndcg(
+            model, gpu=gpu, data_processor=proc, smiles2graph_dic=smiles2graph_dic, batch_size=batch_size, NDCG_cut=0.25, smiles_list=smiles_list,
+            target_name='std' + target_name, is_order=is_order, means=scaler.get('means'), stds=scaler.get('stds'), add_features_name=add_features_name)
+        print('   Note：For test set NDCG{} is: {}'.format(0.25, ndcg))
+        print('   Note：For test set KL divergence is: {}'.format(kl_div))
+        if logger is not None:
+            logger.info('\n Note：For test set NDCG{} is: {}'.format(0.25, ndcg))
+            logger.info('\n Note：For test set KL divergence is: {}'.format(kl_div))
+        if return_order is True:
+            return average_score, average_pred_in_targ, average_top1_in_pred, order, smiles_and_index
     return average_score, average_pred_in_targ, average_top1_in_pred

@@ -280,9 +280,78 @@ def golden_steps():
     print("steps.npz losses", losses, "lrs", out["lrs"])
 
 
+class StubScorer(torch.nn.Module):
+    """Deterministic 'model' for the metric goldens: scores depend only on the product token and the extra feature, so the
+    reference's metric code and ours can be fed identical predictions without a GPU (tests/test_host_cpu.py re-creates it)."""
+
+    def __init__(self, two_columns):
+        super().__init__()
+        self.two = two_columns
+
+    @staticmethod
+    def token_value(tok):
+        h = 0
+        for ch in tok:
+            h = (h * 131 + ord(ch)) % 1000003
+        return (h % 2001) / 1000.0 - 1.0
+
+    def forward(self, r_inputs, p_inputs, gpu=None, add_features=None):
+        base = torch.tensor([self.token_value(t) for t in p_inputs.smiles_batch], dtype=torch.float32)
+        if add_features is not None:
+            base = base + 0.25 * torch.tensor(np.asarray(add_features, dtype=np.float32).reshape(-1))
+        if self.two:
+            return torch.stack((base, 0.5 + base.abs()), dim=1)
+        return base
+
+
+def golden_metrics():
+    """evaluate_top_scores / ranking_metrics / calculate_ndcg of the reference (eval.py:76-177, 329-457, 475-555) on a fixed
+    synthetic frame with the stub scorer: return values, the order table and the re-ordered tokens."""
+    lr = ref_loader.ref("data.load_reactions")
+    ev = ref_loader.ref("train.eval")
+    sizes = [6, 3, 9, 4, 7, 2, 5]
+    ds = synthetic.make_dataset(33, sizes, atoms_lo=3, atoms_hi=4)
+    df = ds.to_dataframe()
+
+    class Feat:                                   # duck-typed Parsing_features: only .smiles_batch is read by the stub
+        class B:
+            def __init__(self, toks):
+                self.smiles_batch = list(toks)
+
+        def parsing_smiles(self, toks):
+            return Feat.B(toks)
+
+    cols = ["rsmi_mapped", "psmi_mapped"]
+    out = {"sizes": np.asarray(sizes, np.int64), "seed": np.int64(33)}
+    for two in (False, True):
+        m = StubScorer(two).eval()
+        tag = "two." if two else "one."
+        dp = lr.DataProcessor(df)
+        a, b, c = ev.evaluate_top_scores(m, gpu=None, data_processor=dp, smiles2graph_dic=Feat(), ratio=0.25, batch_size=3, smiles_list=cols,
+                                         target_name="lgk", add_features_name="temp")
+        out[tag + "top_scores"] = np.asarray([a, b, c], np.float64)
+        r = ev.ranking_metrics(m, gpu=None, data_processor=dp, smiles2graph_dic=Feat(), show_info=False, smiles_list=cols, target_name="lgk",
+                               add_features_name="temp")
+        out[tag + "ranking"] = np.asarray([r[0], r[1], r[2]] + list(np.asarray(r[3], np.float64)), np.float64)
+        for means, stds, name in ((None, None, "raw"), (0.7, 1.9, "scaled")):
+            nd, kl, order, smi = ev.calculate_ndcg(m, gpu=None, data_processor=dp, smiles2graph_dic=Feat(), batch_size=3, NDCG_cut=0.25,
+                                                  smiles_list=cols, target_name="lgk", means=means, stds=stds, add_features_name="temp")
+            out[tag + name + ".ndcg_kl"] = np.asarray([nd, kl], np.float64)
+            out[tag + name + ".order"] = np.asarray(order, np.float64)
+            out[tag + name + ".smi_iter"] = np.asarray([x[0] for x in smi], np.int64)
+            out[tag + name + ".smi_p"] = np.asarray([x[2] for x in smi])
+        nd, kl, order, smi = ev.calculate_ndcg(m, gpu=None, data_processor=dp, smiles2graph_dic=Feat(), batch_size=3, NDCG_cut=0.25, smiles_list=cols,
+                                              target_name="lgk", is_order=False, add_features_name="temp")
+        assert nd is None and kl is None
+        out[tag + "unordered.rows"] = np.asarray(order, np.float64)
+        out[tag + "unordered.smi_p"] = np.asarray([x[1] for x in smi])
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print("metrics.npz", len(out))
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     only = sys.argv[1:]
-    for fn in (golden_batching, golden_planner, golden_model, golden_ranknet, golden_steps):
+    for fn in (golden_batching, golden_planner, golden_model, golden_ranknet, golden_steps, golden_metrics):
         if not only or fn.__name__[len("golden_"):] in only:
             fn()

@@ -246,3 +246,61 @@ def test_molecule_store_registration_is_thread_safe():
     for k in range(4):
         want = BatchMolGraph([ds.mols[t] for t in toks[k::4]])
         assert out[k].n_atoms == want.n_atoms and torch.equal(out[k].a2b, want.a2b) and torch.equal(out[k].f_bonds, want.f_bonds)
+
+
+# ---- evaluation metrics vs the reference's own functions (tests/golden/metrics.npz: scripts/make_golden.py golden_metrics) ----------
+class _StubScorer(torch.nn.Module):
+    """Same deterministic scorer the golden was generated with (scores from the product token + the extra feature)."""
+
+    def __init__(self, two):
+        super().__init__()
+        self.two = two
+
+    @staticmethod
+    def token_value(tok):
+        h = 0
+        for ch in tok:
+            h = (h * 131 + ord(ch)) % 1000003
+        return (h % 2001) / 1000.0 - 1.0
+
+    def forward(self, r_inputs, p_inputs, gpu=None, add_features=None):
+        base = torch.tensor([self.token_value(t) for t in p_inputs.smiles_batch], dtype=torch.float32)
+        if add_features is not None:
+            base = base + 0.25 * torch.tensor(np.asarray(add_features, dtype=np.float32).reshape(-1))
+        return torch.stack((base, 0.5 + base.abs()), dim=1) if self.two else base
+
+
+@pytest.mark.parametrize("two", [False, True])
+def test_eval_metrics_match_reference_golden(two, monkeypatch):
+    from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features
+    from reactranker_b200.train import eval as E
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    ds = synthetic.make_dataset(int(g["seed"]), [int(x) for x in g["sizes"]], atoms_lo=3, atoms_hi=4)
+    fz = Parsing_features(ds.mols)
+    dp = DataProcessor(ds.to_dataframe())
+    cols = ["rsmi_mapped", "psmi_mapped"]
+    m = _StubScorer(two).eval()
+    tag = "two." if two else "one."
+    got = E.evaluate_top_scores(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, ratio=0.25, batch_size=3, smiles_list=cols, target_name="lgk",
+                                add_features_name="temp")
+    assert np.allclose(got, g[tag + "top_scores"], rtol=0, atol=1e-12)
+
+    def stub_scores(model, gpu, groups, smiles2graph_dic):      # ranking_metrics batches its forwards through DeviceGraph (GPU): score on the host here
+        out = []
+        for X, feats in groups:
+            p = model(None, smiles2graph_dic.parsing_smiles([s[1] for s in X]), add_features=feats)
+            out.append((p[:, 0] if p.dim() > 1 else p).numpy())
+        return out
+    monkeypatch.setattr(E, "_scores_per_group", stub_scores)
+    r = E.ranking_metrics(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, show_info=False, smiles_list=cols, target_name="lgk", add_features_name="temp")
+    assert np.allclose([r[0], r[1], r[2]] + list(r[3]), g[tag + "ranking"], rtol=1e-6, atol=1e-9)
+    for means, stds, name in ((None, None, "raw"), (0.7, 1.9, "scaled")):
+        nd, kl, order, smi = E.calculate_ndcg(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, batch_size=3, NDCG_cut=0.25, smiles_list=cols,
+                                              target_name="lgk", means=means, stds=stds, add_features_name="temp")
+        assert np.allclose([nd, kl], g[tag + name + ".ndcg_kl"], rtol=1e-6)
+        assert np.allclose(np.asarray(order), g[tag + name + ".order"], rtol=1e-6, atol=1e-6)
+        assert [x[0] for x in smi] == g[tag + name + ".smi_iter"].tolist() and [x[2] for x in smi] == g[tag + name + ".smi_p"].tolist()
+    nd, kl, rows, smi = E.calculate_ndcg(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, batch_size=3, NDCG_cut=0.25, smiles_list=cols,
+                                         target_name="lgk", is_order=False, add_features_name="temp")
+    assert nd is None and kl is None
+    assert np.allclose(np.asarray(rows), g[tag + "unordered.rows"], rtol=1e-6, atol=1e-6) and [x[1] for x in smi] == g[tag + "unordered.smi_p"].tolist()
