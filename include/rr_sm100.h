@@ -202,7 +202,8 @@ typedef enum {
   RR_LOSS_EVIDENTIAL = 2, /* evidential_ranking loss.py:477-556 (scores [N,2])             */
   RR_LOSS_RANKNET = 3,    /* sum_session        train_pairwise.py:98-122,141-147           */
   RR_LOSS_GAUSS = 4,      /* GaussDisLoss       loss.py:144-162 (scores [N,2])             */
-  RR_LOSS_MSE = 5         /* nn.MSELoss         train_listwise.py:166-167                  */
+  RR_LOSS_MSE = 5,        /* nn.MSELoss         train_listwise.py:166-167                  */
+  RR_LOSS_EXPMSE = 6      /* mean((e^t - e^s)^2) train_listwise.py:276-281 ('regression_exploss') */
 } rr_loss_kind;
 /* norm: the divisor the reference applies (G, N or the window's ordered-pair count); sigma: RankNet */
 int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off,

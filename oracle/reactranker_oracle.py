@@ -260,7 +260,7 @@ def ranknet_group_cost(y_pred: torch.Tensor, targets: np.ndarray, sigma: float =
 
 
 def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
-    """Loss dispatch of ``train()`` for the five north-star keys (train_listwise.py:196-285)."""
+    """Loss dispatch of ``train()`` for the five north-star keys and the composite keys built from them (train_listwise.py:196-285)."""
     if task_type == "mle":
         return listmle_loss(output, scope, targets)
     if task_type == "listnet":
@@ -269,6 +269,17 @@ def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
         return evidential_ranking_loss(output, scope, targets)
     if task_type == "gauss_regression":
         return gauss_loss(output[:, 0], output[:, 1], targets)
+    # composite keys: sums of the terms above (train_listwise.py:204-210, 224-227, 263-266, 276-281)
+    if task_type == "mle_gaussian":
+        return listmle_loss(output[:, 0], scope, targets) + gauss_loss(output[:, 0], output[:, 1], targets)
+    if task_type == "listnet_gauss":
+        return listnet_loss(output[:, 0], scope, targets) + gauss_loss(output[:, 0], output[:, 1], targets)
+    if task_type == "mle_regression":
+        return mse_loss(output, targets) + listmle_loss(output, scope, targets)
+    if task_type == "listnet_regression":
+        return listnet_loss(output, scope, targets) + mse_loss(output, targets)
+    if task_type == "regression_exploss":
+        return torch.mean((torch.exp(targets) - torch.exp(output)) ** 2)
     return mse_loss(output, targets)
 
 

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kLossThreads) k_ranknet(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
-// pointwise: GaussDisLoss (loss.py:144-162) and nn.MSELoss (train_listwise.py:166-167)
+// pointwise: GaussDisLoss (loss.py:144-162), nn.MSELoss (train_listwise.py:166-167), the 'regression_exploss' key (276-281)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kLossThreads) k_pointwise(int kind, int N, const float* __restrict__ scores, const float* __restrict__ targets,
                                                             float inv_norm, float* __restrict__ loss, float* __restrict__ dscore) {
@@ -271,6 +271,11 @@ __global__ void __launch_bounds__(kLossThreads) k_pointwise(int kind, int N, con
       part += 0.5f * logf(2.f * 3.14159274101257324f) + 0.5f * logf(v) + d * d / (2.f * v);
       dscore[2 * i] = d / v * inv_norm;
       dscore[2 * i + 1] = (0.5f / v - d * d / (2.f * v * v)) * inv_norm;
+    } else if (kind == RR_LOSS_EXPMSE) {       // mean((exp(t) - exp(s))^2), train_listwise.py:276-281
+      const float e = expf(scores[i]);
+      const float d = e - expf(t);
+      part += d * d;
+      dscore[i] = 2.f * d * e * inv_norm;
     } else {
       const float d = scores[i] - t;
       part += d * d;
@@ -300,7 +305,8 @@ int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* target
       else k_ranknet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
       break;
     case RR_LOSS_GAUSS:
-    case RR_LOSS_MSE: {
+    case RR_LOSS_MSE:
+    case RR_LOSS_EXPMSE: {
       int blocks = (N + kLossThreads - 1) / kLossThreads;
       if (blocks > num_sms() * 4) blocks = num_sms() * 4;
       k_pointwise<<<blocks, kLossThreads, 0, s>>>(kind, N, scores, targets, inv, loss, dscore);

@@ -8,8 +8,9 @@ over groups, ListNet averages over all items of the batch, RankNet divides by th
 pair count of the accumulation window.  ``mle`` and ``evidential_ranking`` return shape [1]
 like the reference, the others a 0-d tensor.
 
-Outside the five north-star keys nothing is built; asking for one of
-the experimental losses raises.
+Besides the five north-star keys, the composite keys that are sums of these terms (``mle_gaussian``, ``listnet_gauss``,
+``mle_regression``, ``listnet_regression``) and ``regression_exploss`` are dispatched by ``train()``; the remaining experimental
+losses of the reference (distribution-valued ListMLE / ListNet, Dirichlet, NIG evidential) raise.
 """
 from __future__ import annotations
 
@@ -165,6 +166,15 @@ class MSELoss(nn.Module):
         dev = _device_of(None, output)
         n = output.shape[0]
         return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_MSE, n, 0, float(n), 1.0, ())
+
+
+class ExpMSELoss(nn.Module):
+    """``mean((exp(targets) - exp(output))**2)``: the 'regression_exploss' key, written inline in the reference (train_listwise.py:276-281)."""
+
+    def forward(self, output, targets):
+        dev = _device_of(None, output)
+        n = output.shape[0]
+        return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_EXPMSE, n, 0, float(n), 1.0, ())
 
 
 def ranknet_window_loss(scores, scope, targets, num_pairs: float, sigma: float = 1.0, gpu: Optional[int] = None):

@@ -25,17 +25,42 @@ from .. import _lib
 from ..data.load_reactions import DataProcessor
 from ..utils import save_checkpoint
 from .eval import calculate_mse, ranking_metrics
-from .loss import GaussDisLoss, ListnetLoss, MLEloss, MSELoss, evidential_ranking
+from .loss import ExpMSELoss, GaussDisLoss, ListnetLoss, MLEloss, MSELoss, evidential_ranking
 
 try:  # only used as the default value of ``writer`` in the reference signature
     from torch.utils.tensorboard import SummaryWriter
 except Exception:  # pragma: no cover
     SummaryWriter = None
 
-BUILT_TASKS = ("mle", "listnet", "evidential_ranking", "gauss_regression")
-UNBUILT_TASKS = ("mle_gaussian", "mledis_gaussian", "mle_regression", "mle_evidential", "mledis_evidential", "listnet_uq", "listnet_evidential",
-                 "listnet_gauss", "listnetdis_gauss", "listnetdis_lognorm", "dirichlet_uq", "listnet_regression", "regression_exploss",
-                 "evidential", "mle_dirichlet")
+BUILT_TASKS = ("mle", "listnet", "evidential_ranking", "gauss_regression",
+               # sums of the terms above, dispatched exactly like train_listwise.py:204-210, 224-227, 263-266, 276-281
+               "mle_gaussian", "listnet_gauss", "mle_regression", "listnet_regression", "regression_exploss")
+UNBUILT_TASKS = ("mledis_gaussian", "mle_evidential", "mledis_evidential", "listnet_uq", "listnet_evidential", "listnetdis_gauss",
+                 "listnetdis_lognorm", "dirichlet_uq", "evidential", "mle_dirichlet")
+
+
+def batch_loss(task_type, output, scope, targets, gpu, max_coeff=0.0001, epoch=0, epochs=1):
+    """The loss dispatch of the reference's step body (train_listwise.py:196-285) for every built key; anything else is the default
+    regression (282-285).  Every term is one segmented / pointwise sm_100a kernel returning loss and dL/dscore; sums are autograd sums."""
+    if task_type == 'mle':
+        return MLEloss()(output, scope, targets, gpu)
+    if task_type == 'listnet':
+        return ListnetLoss()(output, scope, targets, gpu)
+    if task_type == 'evidential_ranking':
+        return evidential_ranking()(output, scope, targets, max_coeff, epoch, epochs, gpu)
+    if task_type == 'gauss_regression':
+        return GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu)
+    if task_type == 'mle_gaussian':
+        return MLEloss()(output[:, 0], scope, targets, gpu) + GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu)
+    if task_type == 'listnet_gauss':
+        return ListnetLoss()(output[:, 0], scope, targets, gpu) + GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu)
+    if task_type == 'mle_regression':
+        return MSELoss()(output, targets) + MLEloss()(output, scope, targets, gpu)
+    if task_type == 'listnet_regression':
+        return ListnetLoss()(output, scope, targets, gpu) + MSELoss()(output, targets)
+    if task_type == 'regression_exploss':
+        return ExpMSELoss()(output, targets)
+    return MSELoss()(output, targets)
 NDCG_METRICS = ['NDCG@1', 'NDCG@2', 'NDCG@25%', 'NDCG@all']
 
 
@@ -85,17 +110,6 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
     print('stds is: ', std)
     print('mean is: ', mean)
 
-    if task_type == 'mle':
-        loss_fn = MLEloss()
-    elif task_type == 'listnet':
-        loss_fn = ListnetLoss()
-    elif task_type == 'evidential_ranking':
-        loss_fn = evidential_ranking()
-    elif task_type == 'gauss_regression':
-        loss_fn = GaussDisLoss()
-    else:                                         # default regression (train_listwise.py:166-167)
-        loss_fn = MSELoss()
-
     train_proc, val_proc = DataProcessor(train_data), DataProcessor(val_data)
     finite = torch.ones((), dtype=torch.bool, device=torch.device("cuda", dev_idx))
     for epoch in trange(epochs):
@@ -111,16 +125,7 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
             targets_t = torch.FloatTensor(targets).squeeze()                         # train_listwise.py:187
             r_inputs, p_inputs = smiles2graph_dic.parsing_reactions(reactions)
             output = model(r_inputs, p_inputs, gpu=dev_idx, add_features=add_features)
-            if task_type == 'mle':
-                loss = loss_fn(output, scope, targets_t, dev_idx)
-            elif task_type == 'listnet':
-                loss = loss_fn(output, scope, targets_t, dev_idx)
-            elif task_type == 'evidential_ranking':
-                loss = loss_fn(output, scope, targets_t, max_coeff, epoch, epochs, dev_idx)
-            elif task_type == 'gauss_regression':
-                loss = loss_fn(output[:, 0], output[:, 1], targets_t, dev_idx)
-            else:
-                loss = loss_fn(output, targets_t)
+            loss = batch_loss(task_type, output, scope, targets_t, dev_idx, max_coeff, epoch, epochs)
             optimizer.zero_grad()
             loss.backward()
             optimizer.step()

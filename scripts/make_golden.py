@@ -44,6 +44,15 @@ TASKS = {
     "gauss_regression": (2, "with_softplus", None),
     "regression": (1, "with_softplus", None),
 }
+# composite keys of train_listwise.py:196-285 whose terms are the losses above (golden_composite)
+COMPOSITE = {
+    "mle_gaussian": (2, "with_softplus", None),
+    "listnet_gauss": (2, "with_softplus", None),
+    "mle_regression": (1, "with_softplus", None),
+    "listnet_regression": (1, "with_softplus", None),
+    "regression_exploss": (1, "with_softplus", None),
+}
+TASKS_ALL = dict(TASKS, **COMPOSITE)
 
 
 def ref_loss(task, out, scope, targets):
@@ -56,6 +65,16 @@ def ref_loss(task, out, scope, targets):
         return L.evidential_ranking()(out, scope, targets, 0.0001, 0, 1, None)
     if task == "gauss_regression":
         return L.GaussDisLoss()(out[:, 0], out[:, 1], targets, None)
+    if task == "mle_gaussian":            # train_listwise.py:204-207
+        return L.MLEloss()(out[:, 0], scope, targets, None) + L.GaussDisLoss()(out[:, 0], out[:, 1], targets, None)
+    if task == "listnet_gauss":           # 208-210
+        return L.ListnetLoss()(out[:, 0], scope, targets, None) + L.GaussDisLoss()(out[:, 0], out[:, 1], targets, None)
+    if task == "mle_regression":          # 263-266
+        return torch.nn.MSELoss()(out, targets) + L.MLEloss()(out, scope, targets, None)
+    if task == "listnet_regression":      # 224-227
+        return L.ListnetLoss()(out, scope, targets, None) + torch.nn.MSELoss()(out, targets)
+    if task == "regression_exploss":      # 276-281
+        return torch.mean((torch.exp(targets) - torch.exp(out)) ** 2)
     return torch.nn.MSELoss()(out, targets)
 
 
@@ -131,7 +150,7 @@ def golden_planner():
 
 def run_case(task, hidden, seed, sizes, star, dtype, depth=3, diff_depth=3):
     ds, fz = dataset_case(seed, sizes, star)
-    tn, last, tt = TASKS[task]
+    tn, last, tt = TASKS_ALL[task]
     model = build_ref_model(hidden, tn, last, tt, seed=seed, depth=depth, diff_depth=diff_depth, dtype=dtype)
     model.train()
     reactions = np.stack([ds.rsmi, ds.psmi], axis=1)
@@ -187,6 +206,30 @@ def golden_model():
         print(name, "loss", out[name + ".f32.loss"], out[name + ".f64.loss"])
     np.savez_compressed(os.path.join(OUT, "model.npz"), **out)
     print("model.npz", len(out))
+
+
+def golden_composite():
+    """The composite task keys (sums of the built losses, train_listwise.py:196-285) at hidden 40: scores, loss, all gradients."""
+    out = {}
+    for task in COMPOSITE:
+        name = f"{task}.h40"
+        for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            ds, model, scores, loss, grads = run_case(task, 40, 41, [5, 3, 6], None, dtype, 3, 3)
+            pre = f"{name}.{tag}."
+            out[pre + "scores"] = scores
+            out[pre + "loss"] = loss
+            for k, v in grads.items():
+                out[pre + "grad." + k] = v
+            if tag == "f32":
+                for k, v in np_sd(model.state_dict()).items():
+                    out[f"{name}.sd.{k}"] = v
+        out[name + ".meta"] = np.asarray([40, 41, 3, 3], np.int64)
+        out[name + ".sizes"] = np.asarray([5, 3, 6], np.int64)
+        out[name + ".star"] = np.zeros((0, 2), np.int64)
+        out[name + ".task"] = np.asarray(task)
+        print(name, "loss", out[name + ".f32.loss"], out[name + ".f64.loss"])
+    np.savez_compressed(os.path.join(OUT, "model_composite.npz"), **out)
+    print("model_composite.npz", len(out))
 
 
 def golden_ranknet():
@@ -352,6 +395,6 @@ def golden_metrics():
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     only = sys.argv[1:]
-    for fn in (golden_batching, golden_planner, golden_model, golden_ranknet, golden_steps, golden_metrics):
+    for fn in (golden_batching, golden_planner, golden_model, golden_ranknet, golden_steps, golden_metrics, golden_composite):
         if not only or fn.__name__[len("golden_"):] in only:
             fn()

@@ -20,19 +20,14 @@ from helpers import dataset_from_golden, sd_from_golden, rel_err, star_dict, gra
 pytestmark = pytest.mark.gpu
 GPU = 0
 TASKS = {"mle": (1, None), "listnet": (1, None), "evidential_ranking": (2, "evidential_ranking"),
-         "gauss_regression": (2, None), "regression": (1, None)}
+         "gauss_regression": (2, None), "regression": (1, None),
+         "mle_gaussian": (2, None), "listnet_gauss": (2, None), "mle_regression": (1, None), "listnet_regression": (1, None),
+         "regression_exploss": (1, None)}
 
 
 def product_loss(task, out, scope, targets, gpu=GPU):
-    if task == "mle":
-        return RL.MLEloss()(out, scope, targets, gpu)
-    if task == "listnet":
-        return RL.ListnetLoss()(out, scope, targets, gpu)
-    if task == "evidential_ranking":
-        return RL.evidential_ranking()(out, scope, targets, 0.0001, 0, 1, gpu)
-    if task == "gauss_regression":
-        return RL.GaussDisLoss()(out[:, 0], out[:, 1], targets, gpu)
-    return RL.MSELoss()(out, targets)
+    from reactranker_b200.train.train_listwise import batch_loss
+    return batch_loss(task, out, scope, targets, gpu)
 
 
 def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_softplus"):
@@ -46,11 +41,12 @@ def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_sof
 
 CASES = ["mle.h40", "listnet.h40", "evidential_ranking.h40", "gauss_regression.h40", "regression.h40", "mle.star.h40",
          "evidential_ranking.h24d5"]
+COMPOSITE = ["mle_gaussian.h40", "listnet_gauss.h40", "mle_regression.h40", "listnet_regression.h40", "regression_exploss.h40"]
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + COMPOSITE)
 def test_scores_loss_grads_vs_reference_golden(golden, name):
-    g = golden("model")
+    g = golden("model_composite" if name in COMPOSITE else "model")
     task = str(g[name + ".task"])
     ds, sizes, hidden, depth, ddepth = dataset_from_golden(g, name)
     model = make_model(hidden, task, depth, ddepth, sd_from_golden(g, name + ".sd"))
