@@ -13,9 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # second step of `--steps 1 --warmup 1`: 29 k_tc_gemm2 / 20 k_tc_wgrad2 launches per step
 ncu --set full --clock-control none -k regex:k_tc_gemm2 --launch-skip 29 -c 4 -o $OUT/${R}_full_gemm \
     python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/${R}_ncu_full_gemm.log 2>&1
-ncu --set full --clock-control none -k regex:k_tc_wgrad2 --launch-skip 31 -c 3 -o $OUT/${R}_full_wgrad \
+ncu --set full --clock-control none -k regex:k_tc_wgrad --launch-skip 31 -c 3 -o $OUT/${R}_full_wgrad \
     python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/${R}_ncu_full_wgrad.log 2>&1
 ncu --set full --clock-control none -k regex:k_rowpipe --launch-skip 24 -c 10 -o $OUT/${R}_full_mp \
     python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/${R}_ncu_full_mp.log 2>&1
-tail -1 $OUT/${R}_ncu_full_gemm.log $OUT/${R}_ncu_full_wgrad.log $OUT/${R}_ncu_full_mp.log
+tail -n 1 $OUT/${R}_ncu_full_gemm.log $OUT/${R}_ncu_full_wgrad.log $OUT/${R}_ncu_full_mp.log
 du -sh $OUT
