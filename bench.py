@@ -43,10 +43,19 @@ WORKLOADS = {
                    group=500, groups=8, desc="ListMLE D-MPNN h300 d3/3/3, 8 groups x 500 candidates = 4000 reactions per GPU per step (configs[4])"),
     "c2": dict(task="listnet", hidden=300, depth=3, diff_depth=3, task_num=1, task_type=None, last="with_softplus", dropout=0.1,
                group=32, groups=128, desc="ListNet@1 D-MPNN h300 d3/3/3, 128 groups x 32 candidates = 4096 reactions per GPU per step (configs[1])"),
+    # configs[2]: RankNet (main_ranknet.py: dropout 0.2, no_softplus), 64 candidates/group, 4096 rows per optimiser step = one accumulation
+    # window of 64 groups, every group its own segment (own padding rows and max_num_bonds) as in the reference's one-forward-per-group loop
+    "c3": dict(task="ranknet", hidden=300, depth=3, diff_depth=3, task_num=1, task_type=None, last="no_softplus", dropout=0.2,
+               group=64, groups=64, desc="RankNet (sum_session) D-MPNN h300 d3/3/3, window of 64 groups x 64 candidates = 4096 reactions, 258k ordered pairs (configs[2])"),
     "c4": dict(task="evidential_ranking", hidden=600, depth=5, diff_depth=5, task_num=2, task_type="evidential_ranking", last="with_softplus",
                dropout=0.1, group=32, groups=128, desc="UC-Listwise D-MPNN h600 d5/5/3, 128 groups x 32 = 4096 reactions per GPU per step (configs[3])"),
 }
-METRIC = "train reactions/sec, D-MPNN+ListMLE"
+METRIC = "train reactions/sec, D-MPNN+ListMLE"                      # BASELINE.json's metric: the default workload (c5)
+LOSS_NAME = {"mle": "ListMLE", "listnet": "ListNet@1", "ranknet": "RankNet", "evidential_ranking": "UC-Listwise"}
+
+
+def metric_of(wl):
+    return METRIC if wl["task"] == "mle" else f"train reactions/sec, D-MPNN+{LOSS_NAME[wl['task']]}"
 UNIT = "reactions/s"
 
 
@@ -195,6 +204,10 @@ def build(wl, dev_index, world):
     elif task == "listnet":
         lm = RL.ListnetLoss(global_norm=N if world > 1 else None)
         loss_fn = lambda out, scope, t: lm(out, scope, t, dev_index)  # noqa: E731
+    elif task == "ranknet":
+        # every group of the synthetic pool has distinct targets: n (n - 1) ordered pairs each; under DP the divisor is the global window's
+        pairs = float(world * wl["groups"] * wl["group"] * (wl["group"] - 1))
+        loss_fn = lambda out, scope, t: RL.ranknet_window_loss(out, scope, t, pairs, sigma=1.0, gpu=dev_index)  # noqa: E731
     else:
         lm = RL.evidential_ranking(global_norm=G if world > 1 else None)
         loss_fn = lambda out, scope, t: lm(out, scope, t, 0.0001, 0, 1, dev_index)  # noqa: E731
@@ -237,11 +250,19 @@ def ours(args):
     frame = pd.concat([ds.to_dataframe().assign(flag=lambda d, i=i: d.flag + i * wl["groups"]) for i, ds in enumerate(pool)], ignore_index=True)
     planner = DataProcessor(frame)
     # device-resident copies for the device-path measurement
+    from reactranker_b200.features.featurization import DeviceGraph
+    per_group = wl["task"] == "ranknet"          # RankNet: one segment per group (train_pairwise.py: each group is its own forward)
+
+    def to_dev(batch_of, tokens):
+        if not per_group:
+            return batch_of(tokens).to_device(dev)
+        g = wl["group"]
+        return DeviceGraph.from_batches([batch_of(tokens[i:i + g]) for i in range(0, len(tokens), g)], dev)
+
     resident = []
     for ds in pool:
-        r_b = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
-        p_b = BatchMolGraph([ds.mols[t] for t in ds.psmi])
-        resident.append((r_b.to_device(dev), p_b.to_device(dev), torch.tensor(ds.temp.reshape(-1, 1), dtype=torch.float32, device=dev),
+        mk = lambda toks, ds=ds: BatchMolGraph([ds.mols[t] for t in toks])  # noqa: E731
+        resident.append((to_dev(mk, list(ds.rsmi)), to_dev(mk, list(ds.psmi)), torch.tensor(ds.temp.reshape(-1, 1), dtype=torch.float32, device=dev),
                          torch.tensor(ds.lgk, dtype=torch.float32, device=dev)))
     torch.cuda.synchronize()
 
@@ -285,9 +306,10 @@ def ours(args):
 
     def featurise(batch):
         reactions, tg, sc, feats = batch
-        r_b, p_b = fz.parsing_reactions(reactions)                           # warm MolGraph cache -> store ids
-        # pinned H2D of ids / row offsets + on-device assembly from the HBM-resident molecule store, enqueued behind the running step
-        rg, pg = r_b.to_device(dev), p_b.to_device(dev)
+        # warm MolGraph cache -> store ids; pinned H2D of ids / row offsets + on-device assembly from the HBM-resident molecule store,
+        # enqueued behind the running step
+        reactions = np.asarray(reactions, dtype=object)
+        rg, pg = to_dev(fz.parsing_smiles, reactions[:, 0].tolist()), to_dev(fz.parsing_smiles, reactions[:, 1].tolist())
         return rg, pg, torch.FloatTensor(tg).squeeze(), sc, feats, rg.h2d_bytes + pg.h2d_bytes
 
     from reactranker_b200.data.prefetch import Lookahead
@@ -384,7 +406,7 @@ def ours(args):
 
     cpu = cpu_baseline(wl, steps=8, warmup=1) if world == 1 and not args.no_cpu else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_of(wl), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (dense layers: tcgen05 kind::tf32 with on-chip 3xTF32 split, fp32 accumulate)" if args.gemm == "tc" else "f32",
         "data": f"synthetic reaction graphs (SURVEY.md 8d generator), pool of {len(pool)} distinct batches per rank cycled; random-init weights",
@@ -426,11 +448,23 @@ def cpu_training_steps(wl, groups, steps, warmup, seed=99):
     for i in range(warmup + steps):
         ds = pool[i % len(pool)]
         t0 = time.perf_counter()
-        r_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi])          # BatchMolGraph build per step (featurization.py:246-290)
-        p_g = O.OracleBatch([ds.mols[t] for t in ds.psmi])
-        out = O.model_forward(full, r_g, p_g, ds.temp.reshape(-1, 1), mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], head=head,
-                              dropout=wl["dropout"], training=True)
-        loss = O.loss_for_task(wl["task"], out, scope, torch.tensor(ds.lgk.astype(np.float32)))
+        if wl["task"] == "ranknet":
+            # train_pairwise.py:81-160: one forward per group, summed pairwise cost / ordered pairs of the window
+            cost, pairs, o = 0.0, 0.0, 0
+            for n in scope:
+                r_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi[o:o + n]])
+                p_g = O.OracleBatch([ds.mols[t] for t in ds.psmi[o:o + n]])
+                y = O.model_forward(full, r_g, p_g, ds.temp[o:o + n].reshape(-1, 1), mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], head=head,
+                                    dropout=wl["dropout"], training=True)
+                c, p = O.ranknet_group_cost(y, ds.lgk[o:o + n])
+                cost, pairs, o = cost + c, pairs + p, o + n
+            loss = cost / pairs
+        else:
+            r_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi])      # BatchMolGraph build per step (featurization.py:246-290)
+            p_g = O.OracleBatch([ds.mols[t] for t in ds.psmi])
+            out = O.model_forward(full, r_g, p_g, ds.temp.reshape(-1, 1), mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], head=head,
+                                  dropout=wl["dropout"], training=True)
+            loss = O.loss_for_task(wl["task"], out, scope, torch.tensor(ds.lgk.astype(np.float32)))
         opt.zero_grad()
         loss.backward()
         opt.step()
@@ -459,7 +493,7 @@ def reference(args):
     cpu = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
            "sample": f"each step = {groups} groups x {wl['group']} = {rows} reactions of the workload on the host CPU"}
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric_of(wl), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic reaction graphs (SURVEY.md 8d generator); random-init weights",
         "config": {"workload": wl["desc"], "name": args.workload, "reactions_per_step_sample": rows},

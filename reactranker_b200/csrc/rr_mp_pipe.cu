@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
   const rr_graph& g = A.g;
   const int S = A.stages, apb = A.apb, ld = A.ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Every CTA takes ONE contiguous run of stages (not a round-robin): with many segments in a launch (RankNet windows, evaluation
+  // batches) a CTA then meets one or two segments, and the atomics into a segment's padding row come from a handful of CTAs instead of all.
+  const int per = A.n_stage_total / gridDim.x, rem = A.n_stage_total - per * gridDim.x;
+  const int first_stage = blockIdx.x * per + min(static_cast<int>(blockIdx.x), rem);
+  const int my_stages = per + (static_cast<int>(blockIdx.x) < rem ? 1 : 0);
   const int nbr_rows_per_atom = kFast * A.n_nbr;
   // stage layout: tasks [apb] | neighbour rows [apb][kFast][n_nbr] | own rows [n_own][apb]
   const int task_bytes = apb * TASK_BYTES;
@@ -163,9 +168,10 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
     const bool atom_tab = (OP == NBR_BWD_ATOM) || (OP == NBR_FWD && A.which);
     constexpr bool need_rev = (OP == BOND_FWD || OP == BOND_BWD);
     auto load = [&](int it_base, Task& t) {
-      const long long sidx = blockIdx.x + static_cast<long long>(it_base + my_r) * gridDim.x;
+      const int my_it = it_base + my_r;
+      const long long sidx = first_stage + my_it;
       const long long a = sidx * apb + my_slot;
-      t.valid = (my_r < R && sidx < A.n_stage_total && a < g.n_atoms) ? 1 : 0;
+      t.valid = (my_r < R && my_it < my_stages && a < g.n_atoms) ? 1 : 0;
       t.atom = static_cast<int>(a);
       t.deg = 0;
       if (!t.valid) return;
@@ -195,14 +201,14 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
     if (pw >= NP) return;
     Task nx;
     load(pw * R, nx);
-    for (int it_base = pw * R; blockIdx.x + static_cast<long long>(it_base) * gridDim.x < A.n_stage_total; it_base += NP * R) {
+    for (int it_base = pw * R; it_base < my_stages; it_base += NP * R) {
       const Task t = nx;
       load(it_base + NP * R, nx);
       const int nfetch = t.valid ? min(t.deg, kFast) : 0;
       for (int rr = 0; rr < R; ++rr) {
         const int it = it_base + rr;
-        const long long sidx = blockIdx.x + static_cast<long long>(it) * gridDim.x;
-        if (sidx >= A.n_stage_total) break;
+        if (it >= my_stages) break;
+        const int sidx = first_stage + it;
         const int st = it % S;
         const uint32_t ph = (it / S) & 1;
         if (lane == 0) mbar_wait(empty + st, ph ^ 1);
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
     };
     int st = 0;
     uint32_t ph = 0;
-    for (int sidx = blockIdx.x; sidx < A.n_stage_total; sidx += gridDim.x) {
+    for (int it = 0; it < my_stages; ++it) {
       mbar_wait(full + st, ph);
       const uint32_t base = stage0_u + static_cast<uint32_t>(st) * A.stage_bytes;
       int4 q0 = make_int4(0, 0, 0, 0);
