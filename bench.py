@@ -231,7 +231,13 @@ def ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # stdout carries exactly one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.dropout is not None:
+        wl["dropout"] = args.dropout
+        wl["desc"] += f", dropout {args.dropout:g}"
+    dedup = wl["dropout"] == 0 and not args.no_dedup       # exact only without dropout (rr_model_cfg.r_atom_map)
+    if dedup:
+        wl["desc"] += ", repeated reactants encoded once"
     _lib.require_device(local)
     _lib.check(_lib.lib().rr_set_gemm_mode(1 if args.gemm == "tc" else 0))
     model, opt, sched, loss_fn = build(wl, local, world)
@@ -253,17 +259,20 @@ def ours(args):
     from reactranker_b200.features.featurization import DeviceGraph
     per_group = wl["task"] == "ranknet"          # RankNet: one segment per group (train_pairwise.py: each group is its own forward)
 
-    def to_dev(batch_of, tokens):
-        if not per_group:
-            return batch_of(tokens).to_device(dev)
-        g = wl["group"]
-        return DeviceGraph.from_batches([batch_of(tokens[i:i + g]) for i in range(0, len(tokens), g)], dev)
+    def split(batch_of, tokens):
+        g = wl["group"] if per_group else len(tokens)
+        return [batch_of(tokens[i:i + g]) for i in range(0, len(tokens), g)]
+
+    def to_dev_pair(batch_of, r_tokens, p_tokens):
+        if dedup:
+            return DeviceGraph.from_batches_dedup(split(fz.parsing_smiles, r_tokens), split(fz.parsing_smiles, p_tokens), dev)
+        return DeviceGraph.from_batches(split(batch_of, r_tokens), dev), DeviceGraph.from_batches(split(batch_of, p_tokens), dev)
 
     resident = []
     for ds in pool:
         mk = lambda toks, ds=ds: BatchMolGraph([ds.mols[t] for t in toks])  # noqa: E731
-        resident.append((to_dev(mk, list(ds.rsmi)), to_dev(mk, list(ds.psmi)), torch.tensor(ds.temp.reshape(-1, 1), dtype=torch.float32, device=dev),
-                         torch.tensor(ds.lgk, dtype=torch.float32, device=dev)))
+        resident.append(to_dev_pair(mk, list(ds.rsmi), list(ds.psmi)) + (torch.tensor(ds.temp.reshape(-1, 1), dtype=torch.float32, device=dev),
+                                                                          torch.tensor(ds.lgk, dtype=torch.float32, device=dev)))
     torch.cuda.synchronize()
 
     def reduce_grads():
@@ -309,7 +318,7 @@ def ours(args):
         # warm MolGraph cache -> store ids; pinned H2D of ids / row offsets + on-device assembly from the HBM-resident molecule store,
         # enqueued behind the running step
         reactions = np.asarray(reactions, dtype=object)
-        rg, pg = to_dev(fz.parsing_smiles, reactions[:, 0].tolist()), to_dev(fz.parsing_smiles, reactions[:, 1].tolist())
+        rg, pg = to_dev_pair(fz.parsing_smiles, reactions[:, 0].tolist(), reactions[:, 1].tolist())
         return rg, pg, torch.FloatTensor(tg).squeeze(), sc, feats, rg.h2d_bytes + pg.h2d_bytes
 
     from reactranker_b200.data.prefetch import Lookahead
@@ -509,6 +518,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches per rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dropout", type=float, default=None, help="override the workload's dropout (the entry scripts' 0.1 / 0.2 by default)")
+    ap.add_argument("--no-dedup", action="store_true", help="at dropout 0: still encode one reactant graph per candidate like the reference")
     ap.add_argument("--gemm", default="tc", choices=["tc", "simt"], help="dense layers: tcgen05 3xTF32 (default) or exact-fp32 SIMT")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 1
+#define RR_ABI_VERSION 2
 #define RR_ATOM_FDIM 61   /* features/featurization.py:63 */
 #define RR_BOND_FDIM 22   /* features/featurization.py:64 */
 #define RR_FBOND_TOTAL 83 /* models/base_model.py:129     */
@@ -106,6 +106,13 @@ typedef struct {
   int32_t training;     /* nn.Module.training: dropout active             */
   float dropout;        /* p of every nn.Dropout                          */
   uint64_t seed;        /* Philox seed of this step's dropout masks       */
+  /* Optional reactant de-duplication (ABI 2).  The reference repeats the reactant MolGraph once per candidate
+   * (load_reactions.py:574-576); without dropout every copy gets the same encoding.  With r_atom_map != NULL the reactant graph holds
+   * each distinct reactant ONCE (per segment) and r_atom_map[a] (device, int32, [p.n_atoms]) names the row of the reactant encoder's
+   * output that product atom row a subtracts (base_model.py:168), padding rows included.  Exact in eval mode and at dropout 0 (the
+   * gradient of the shared rows is the sum over the copies); with dropout > 0 the copies would share their masks, so callers leave
+   * it NULL there.  NULL: one reactant row per product row. */
+  const int32_t* r_atom_map;
 } rr_model_cfg;
 
 /* Parameters in the reference's state_dict layout (row-major [out, in]).

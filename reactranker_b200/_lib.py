@@ -32,7 +32,7 @@ class RRModelCfg(ctypes.Structure):
     _fields_ = [("hidden", ctypes.c_int32), ("depth", ctypes.c_int32), ("diff_depth", ctypes.c_int32),
                 ("ffn_depth", ctypes.c_int32), ("task_num", ctypes.c_int32), ("add_features", ctypes.c_int32),
                 ("head", ctypes.c_int32), ("training", ctypes.c_int32), ("dropout", ctypes.c_float),
-                ("seed", ctypes.c_uint64)]
+                ("seed", ctypes.c_uint64), ("r_atom_map", ctypes.c_void_p)]
 
 
 class RRMolStore(ctypes.Structure):

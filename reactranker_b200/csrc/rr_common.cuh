@@ -171,6 +171,8 @@ int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, floa
 int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
 int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);
 int sub(long long, const float*, const float*, float*, cudaStream_t);
+int sub_gather(long long rows, int ld, const float* a, const float* b, const int* map, float* out, cudaStream_t);
+int scatter_add_rows(long long rows, int ld, const float* src, const int* map, float* dst, cudaStream_t);
 // hi_off / lo_off: float offsets from W1 / W2 to their pre-split TF32 images (0 = split on chip)
 int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
                const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed, uint64_t stream_id,

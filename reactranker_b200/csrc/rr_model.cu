@@ -220,11 +220,14 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   RR_REQUIRE(c.ffn_depth >= 1 && c.ffn_depth <= RR_MAX_FFN, "ffn_depth %d out of range", c.ffn_depth);
   RR_REQUIRE(c.task_num >= 1 && c.task_num <= RR_OUT_LD, "task_num %d out of range", c.task_num);
   RR_REQUIRE(c.add_features >= 0, "add_features < 0");
-  RR_REQUIRE(r.n_atoms == p.n_atoms && r.n_mols == p.n_mols,
+  RR_REQUIRE(c.r_atom_map != nullptr || (r.n_atoms == p.n_atoms && r.n_mols == p.n_mols),
              "reactant and product batches must have identical atom rows (p - r is atom-wise, base_model.py:168): %d vs %d", r.n_atoms, p.n_atoms);
+  RR_REQUIRE(c.r_atom_map == nullptr || !(c.training && c.dropout > 0.f),
+             "r_atom_map (de-duplicated reactants) is exact only without dropout: pass NULL when training with dropout > 0");
   W->L = make_packed(c);
   const size_t hp = W->L.hp, vp = W->L.vp;
-  const size_t A = r.n_atoms, N = p.n_mols;
+  const size_t A = p.n_atoms, N = p.n_mols;
+  const size_t Amax = r.n_atoms > p.n_atoms ? r.n_atoms : p.n_atoms;
   const size_t Bmax = r.n_bonds > p.n_bonds ? r.n_bonds : p.n_bonds;
   const int T = c.depth - 1, Td = c.diff_depth - 1;
   char* cur = static_cast<char*>(base);
@@ -246,8 +249,9 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
     e.inp = take(B * hp);
     for (int t = 0; t < T; ++t) e.pre[t] = take(B * hp);
     for (int t = 1; t <= T; ++t) e.m[t] = take(B * hp);
-    e.am = take(A * hp);
-    e.hid = take(A * hp);
+    const size_t As = (s == 0 ? r.n_atoms : p.n_atoms);
+    e.am = take(As * hp);
+    e.hid = take(As * hp);
   }
   W->d = take(A * hp);
   W->inp2 = take(A * hp);
@@ -262,8 +266,8 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   W->gB1 = take(Bmax * hp);
   W->gB2 = take(Bmax * hp);
   W->dinp = take(Bmax * hp);
-  W->gA1 = take(A * hp);
-  W->gA2 = take(A * hp);
+  W->gA1 = take(Amax * hp);
+  W->gA2 = take(Amax * hp);
   W->gA3 = take(A * hp);
   W->dD = take(A * hp);
   W->dI2 = take(A * hp);
@@ -391,7 +395,8 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
                       e.hid, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
   }
   const int A = p->n_atoms;
-  RR_TRY(sub(static_cast<long long>(A) * hp, W.enc[1].hid, W.enc[0].hid, W.d, s));  // base_model.py:168
+  if (c->r_atom_map) RR_TRY(sub_gather(A, hp, W.enc[1].hid, W.enc[0].hid, c->r_atom_map, W.d, s));
+  else RR_TRY(sub(static_cast<long long>(A) * hp, W.enc[1].hid, W.enc[0].hid, W.d, s));  // base_model.py:168
 
   // mpn.py:170-240 over the product graph
   RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off));
@@ -500,10 +505,17 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
     EncBufs& e = W.enc[k];
     const int B = g->n_bonds;
     const float sign = (k == 1) ? 1.f : -1.f;
-    RR_TRY(relu_bwd(A, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
-    RR_TRY(linear_wgrad(A, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
-    RR_TRY(linear_wgrad(A, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
-    RR_TRY(dgrad(A, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+    const int Ag = g->n_atoms;
+    if (k == 0 && c->r_atom_map) {   // shared reactant rows: sum the gradient over the copies first (gA2 is free until the dgrad below)
+      RR_CUDA(cudaMemsetAsync(W.gA2, 0, static_cast<size_t>(Ag) * hp * sizeof(float), s));
+      RR_TRY(scatter_add_rows(A, hp, W.dD, c->r_atom_map, W.gA2, s));
+      RR_TRY(relu_bwd(Ag, hp, W.gA2, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
+    } else {
+      RR_TRY(relu_bwd(Ag, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
+    }
+    RR_TRY(linear_wgrad(Ag, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
+    RR_TRY(linear_wgrad(Ag, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
+    RR_TRY(dgrad(Ag, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
     if (T >= 1) RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.m[T], keep, 0, W.dinp, 1, 0, s));
     else RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 1, 1, s));
     for (int t = T; t >= 1; --t) {

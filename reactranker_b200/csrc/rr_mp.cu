@@ -340,6 +340,29 @@ __global__ void k_sub(long long n4, const float* __restrict__ a, const float* __
     st_f4(out + i * 4, f4_sub(ld_f4_stream(a + i * 4), ld_f4_stream(b + i * 4)));
 }
 
+// d[a] = hid_p[a] - hid_r[map[a]]: base_model.py:168 with de-duplicated reactants (rr_model_cfg.r_atom_map)
+__global__ void k_sub_gather(long long rows, int cpr, const float* __restrict__ a, const float* __restrict__ b, const int* __restrict__ map,
+                             float* __restrict__ out) {
+  const long long n4 = rows * cpr;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cpr;
+    const int c = static_cast<int>(i - r * cpr);
+    const long long rb = __ldg(map + r);
+    st_f4(out + i * 4, f4_sub(ld_f4_stream(a + i * 4), ld_f4(b + (rb * cpr + c) * 4)));
+  }
+}
+// dst[map[a]] += src[a]: the gradient of a shared reactant row is the sum over its copies (dst zeroed by the caller)
+__global__ void k_scatter_add_rows(long long rows, int cpr, const float* __restrict__ src, const int* __restrict__ map, float* __restrict__ dst) {
+  const long long n4 = rows * cpr;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cpr;
+    const int c = static_cast<int>(i - r * cpr);
+    const float4 v = ld_f4_stream(src + i * 4);
+    float* d = dst + (static_cast<long long>(__ldg(map + r)) * cpr + c) * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
@@ -516,6 +539,30 @@ int relu_bwd(long long rows, int ld, const float* dy, const float* y, float scal
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   k_relu_bwd<<<static_cast<int>(blocks), 256, 0, s>>>(n4, dy, y, scale, preact, dz, acc, acc_mode);
   RR_LAUNCH_CHECK("k_relu_bwd");
+  return RR_OK;
+}
+
+int sub_gather(long long rows, int ld, const float* a, const float* b, const int* map, float* out, cudaStream_t s) {
+  ProfScope prof_scope(KC_ELEMENTWISE, s);
+  RR_REQUIRE((ld & 3) == 0 && a && b && map && out && rows >= 0, "sub_gather: bad argument (ld %d)", ld);
+  const long long n4 = rows * (ld >> 2);
+  if (n4 == 0) return RR_OK;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  k_sub_gather<<<static_cast<int>(blocks), 256, 0, s>>>(rows, ld >> 2, a, b, map, out);
+  RR_LAUNCH_CHECK("k_sub_gather");
+  return RR_OK;
+}
+
+int scatter_add_rows(long long rows, int ld, const float* src, const int* map, float* dst, cudaStream_t s) {
+  ProfScope prof_scope(KC_ELEMENTWISE, s);
+  RR_REQUIRE((ld & 3) == 0 && src && map && dst && rows >= 0, "scatter_add_rows: bad argument (ld %d)", ld);
+  const long long n4 = rows * (ld >> 2);
+  if (n4 == 0) return RR_OK;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  k_scatter_add_rows<<<static_cast<int>(blocks), 256, 0, s>>>(rows, ld >> 2, src, map, dst);
+  RR_LAUNCH_CHECK("k_scatter_add_rows");
   return RR_OK;
 }
 

@@ -649,6 +649,57 @@ class DeviceGraph:
         g._offs = offs
         return g
 
+    # ---- optional reactant de-duplication (rr_model_cfg.r_atom_map) ----------------------------
+    @staticmethod
+    def dedup_plan(r_batches: Sequence[BatchMolGraph], p_batches: Sequence[BatchMolGraph]):
+        """The reference repeats the reactant MolGraph once per candidate (load_reactions.py:574-576).  For store-backed batches this
+        returns (unique reactant batches, their max_num_bonds, atom_map) where every segment keeps each distinct reactant once (in order of
+        first appearance) and ``atom_map[a]`` is the reactant-encoder row that product atom row ``a`` subtracts (segment padding rows map to
+        padding rows), or None when nothing repeats / the batches are not store-backed."""
+        if not r_batches or len(r_batches) != len(p_batches) or any(b._ids is None for b in r_batches):
+            return None
+        uniq, maps, a0_p, a0_u, repeats = [], [], 0, 0, False
+        for rb, pb in zip(r_batches, p_batches):
+            if rb.n_mols != pb.n_mols or not np.array_equal(rb._a_size, pb._a_size):
+                raise ValueError("reactant and product batches must list the same molecules' atom counts (p - r is atom-wise, base_model.py:168)")
+            ids = rb._ids
+            u_sorted, first, inv = np.unique(ids, return_index=True, return_inverse=True)
+            order = np.argsort(first, kind="stable")
+            rank = np.empty_like(order)
+            rank[order] = np.arange(order.shape[0])
+            inv = rank[inv.reshape(-1)]
+            repeats |= u_sorted.shape[0] < ids.shape[0]
+            ub = BatchMolGraph.from_store(rb._store, u_sorted[order], [rb.smiles_batch[i] for i in first[order].tolist()])
+            ub.max_num_bonds = rb.max_num_bonds          # same molecules: same maximum in-degree
+            m = np.empty(pb.n_atoms, np.int32)
+            m[0] = a0_u                                   # the segment's padding atom
+            shift = (ub._a_start[inv].astype(np.int64) + a0_u) - (pb._a_start.astype(np.int64) + a0_p)
+            m[1:] = np.arange(1, pb.n_atoms, dtype=np.int64) + a0_p + np.repeat(shift, pb._a_size)
+            uniq.append(ub)
+            maps.append(m)
+            a0_p += pb.n_atoms
+            a0_u += ub.n_atoms
+        if not repeats:
+            return None
+        return uniq, [b.max_num_bonds for b in r_batches], np.concatenate(maps)
+
+    @staticmethod
+    def from_batches_dedup(r_batches: Sequence[BatchMolGraph], p_batches: Sequence[BatchMolGraph], device):
+        """(reactant DeviceGraph, product DeviceGraph).  When reactants repeat, the reactant graph is de-duplicated and carries
+        ``atom_map`` (device int32) for ``rr_model_cfg.r_atom_map``; exact in eval mode and at dropout 0 only (the model checks)."""
+        dev = torch.device(device)
+        pg = DeviceGraph.from_batches(p_batches, dev)
+        plan = DeviceGraph.dedup_plan(r_batches, p_batches)
+        if plan is None:
+            return DeviceGraph.from_batches(r_batches, dev), pg
+        uniq, w, amap = plan
+        rg = DeviceGraph.from_batches(uniq, dev, w)
+        host = torch.from_numpy(amap).pin_memory()
+        rg.atom_map = host.to(dev, non_blocking=True)
+        rg._atom_map_host = host
+        rg.h2d_bytes += amap.nbytes
+        return rg, pg
+
     def section(self, name: str, dtype: torch.dtype, shape) -> torch.Tensor:
         """Typed view of one section of the device blob (tests / kernels' unit harness)."""
         n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()

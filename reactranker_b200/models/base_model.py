@@ -85,6 +85,11 @@ class _ReactionFn(torch.autograd.Function):
     def forward(ctx, model, rg: DeviceGraph, pg: DeviceGraph, addf, *params):
         L = _lib.lib()
         cfg = model._cfg(training=model.training)
+        amap = getattr(rg, "atom_map", None)
+        if amap is not None:
+            if model.training and model._dropout > 0:
+                raise _lib.RRError("de-duplicated reactants are exact only without dropout (eval mode or dropout = 0)")
+            cfg.r_atom_map = amap.data_ptr()
         w = model._param_struct(params)
         ws_bytes = L.rr_model_workspace_bytes(ctypes.byref(cfg), ctypes.byref(rg.c), ctypes.byref(pg.c))
         if ws_bytes < 0:
@@ -142,6 +147,7 @@ class ReactionModel(nn.Module):
         self._task_num, self._add, self._dropout = task_num, addtion_react_featrues, float(mpnn_dropout)
         self._head = _HEADS.get(task_type, _lib.HEAD_RAW)     # every other name returns the raw output (base_model.py:105-106)
         self.last_h2d_bytes = 0
+        self.dedup_reactants = True      # encode repeated reactants once whenever that is exact (eval mode, dropout 0)
         self._ws_pool = _WorkspacePool()
 
     # ---- plumbing to the C ABI -----------------------------------------------------------
@@ -189,8 +195,14 @@ class ReactionModel(nn.Module):
         params = [p for _, p in self._named_slots()]
         if params[0].device != dev:
             raise _lib.RRError(f"model parameters live on {params[0].device}, expected {dev}: call model.cuda({dev_idx}) first")
-        rg = r_inputs if isinstance(r_inputs, DeviceGraph) else r_inputs.to_device(dev)
-        pg = p_inputs if isinstance(p_inputs, DeviceGraph) else p_inputs.to_device(dev)
+        if (self.dedup_reactants and not (self.training and self._dropout > 0) and isinstance(r_inputs, BatchMolGraph)
+                and isinstance(p_inputs, BatchMolGraph) and r_inputs._ids is not None and p_inputs._ids is not None):
+            # every candidate of a group repeats the reactant graph (load_reactions.py:574-576): without dropout the copies are identical,
+            # so each distinct reactant is encoded once (rr_model_cfg.r_atom_map); with dropout the reference draws a mask per copy
+            rg, pg = DeviceGraph.from_batches_dedup([r_inputs], [p_inputs], dev)
+        else:
+            rg = r_inputs if isinstance(r_inputs, DeviceGraph) else r_inputs.to_device(dev)
+            pg = p_inputs if isinstance(p_inputs, DeviceGraph) else p_inputs.to_device(dev)
         addf = None
         h2d = rg.h2d_bytes + pg.h2d_bytes
         if self._add > 0:

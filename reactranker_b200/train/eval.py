@@ -25,7 +25,11 @@ def _scores_per_group(model, gpu, groups, smiles2graph_dic):
         feats = None
         if chunk[0][1] is not None:
             feats = np.concatenate([np.asarray(f, dtype=np.float64).reshape(len(X), -1) for X, f in chunk], axis=0)
-        preds = model(DeviceGraph.from_batches(r_b, dev), DeviceGraph.from_batches(p_b, dev), gpu=gpu, add_features=feats)
+        if getattr(model, "dedup_reactants", False) and not (model.training and getattr(model, "_dropout", 0) > 0):
+            rg, pg = DeviceGraph.from_batches_dedup(r_b, p_b, dev)       # a group's candidates share one reactant graph
+        else:
+            rg, pg = DeviceGraph.from_batches(r_b, dev), DeviceGraph.from_batches(p_b, dev)
+        preds = model(rg, pg, gpu=gpu, add_features=feats)
         preds = preds[:, 0] if preds.dim() > 1 else preds
         flat = preds.detach().float().cpu().numpy()
         o = 0

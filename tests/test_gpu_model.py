@@ -290,3 +290,69 @@ def test_tcgen05_path_vs_oracle(tc_mode, task, hidden, depth):
             e = got[k] - w
             assert float(np.linalg.norm(e) / np.linalg.norm(w)) < 5e-2, k
             assert float(np.median(np.abs(e))) < 2e-3 * float(np.abs(w).max()), k
+
+
+# ---- optional reactant de-duplication (rr_model_cfg.r_atom_map): exact without dropout ----------------------------------------------
+def _store_batches(ds):
+    from reactranker_b200.data.load_reactions import Parsing_features
+    fz = Parsing_features(ds.mols)
+    return fz, fz.parsing_smiles(list(ds.rsmi)), fz.parsing_smiles(list(ds.psmi))
+
+
+@pytest.mark.parametrize("star", [None, {1: 7}])
+def test_dedup_reactants_eval_scores_identical(star):
+    from reactranker_b200 import synthetic
+    ds = synthetic.make_dataset(51, [6, 4, 5], star_leaves_in_group=star)
+    model = make_model(300, "mle", 3, 3).eval()
+    fz, r_b, p_b = _store_batches(ds)
+    feats = ds.temp.reshape(-1, 1)
+    with torch.no_grad():
+        model.dedup_reactants = False
+        want = model(r_b, p_b, gpu=GPU, add_features=feats)
+        model.dedup_reactants = True
+        got = model(r_b, p_b, gpu=GPU, add_features=feats)
+        assert torch.equal(got, want)                         # same rows, same arithmetic per row
+        # one segment per group (the evaluation path): every segment keeps its own padding rows and max_num_bonds
+        from reactranker_b200.features.featurization import DeviceGraph
+        sizes, o, rs, ps = [6, 4, 5], 0, [], []
+        for n in sizes:
+            rs.append(fz.parsing_smiles(list(ds.rsmi[o:o + n])))
+            ps.append(fz.parsing_smiles(list(ds.psmi[o:o + n])))
+            o += n
+        want_seg = model(DeviceGraph.from_batches(rs, "cuda:0"), DeviceGraph.from_batches(ps, "cuda:0"), gpu=GPU, add_features=feats)
+        rg, pg = DeviceGraph.from_batches_dedup(rs, ps, "cuda:0")
+        assert rg.n_mols == 3 and getattr(rg, "atom_map", None) is not None
+        assert torch.equal(model(rg, pg, gpu=GPU, add_features=feats), want_seg)
+
+
+def test_dedup_reactants_training_gradients_match_at_dropout_zero():
+    from reactranker_b200 import synthetic
+    ds = synthetic.make_dataset(52, [5, 7, 3])
+    sizes = [5, 7, 3]
+    fz, r_b, p_b = _store_batches(ds)
+    feats = ds.temp.reshape(-1, 1)
+    targets = torch.FloatTensor(ds.lgk.reshape(-1, 1)).squeeze()
+    grads = {}
+    for dedup in (False, True):
+        torch.manual_seed(5)
+        model = make_model(64, "mle", 3, 3, dropout=0.0).train()
+        model.dedup_reactants = dedup
+        out = model(r_b, p_b, gpu=GPU, add_features=feats)
+        loss = product_loss("mle", out, sizes, targets)
+        loss.backward()
+        grads[dedup] = ({k: p.grad.double().cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}, out.detach().cpu())
+    assert torch.equal(grads[True][1], grads[False][1])
+    assert not grads_close(grads[True][0], grads[False][0], 2e-5)     # summation order of the shared rows' gradient differs, nothing else
+
+
+def test_dedup_is_refused_with_dropout():
+    from reactranker_b200 import synthetic
+    from reactranker_b200.features.featurization import DeviceGraph
+    ds = synthetic.make_dataset(53, [4, 4])
+    fz, r_b, p_b = _store_batches(ds)
+    model = make_model(40, "mle", 3, 3, dropout=0.2).train()
+    rg, pg = DeviceGraph.from_batches_dedup([r_b], [p_b], "cuda:0")
+    with pytest.raises(Exception, match="dropout"):
+        model(rg, pg, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+    out = model(r_b, p_b, gpu=GPU, add_features=ds.temp.reshape(-1, 1))      # BatchMolGraph inputs: falls back to one row per candidate
+    assert out.shape[0] == 8

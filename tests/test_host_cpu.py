@@ -99,7 +99,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.SO_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.rr_version() == 1
+    assert L.rr_version() == 2
     assert L.rr_padded(300) == 304 and L.rr_padded(600) == 608 and L.rr_padded(40) == 48
     L.rr_loss_max_group.restype = ctypes.c_int
     assert L.rr_loss_max_group() >= 500           # config 5 sweeps groups of 50..500 candidates
@@ -304,3 +304,30 @@ def test_eval_metrics_match_reference_golden(two, monkeypatch):
                                          target_name="lgk", is_order=False, add_features_name="temp")
     assert nd is None and kl is None
     assert np.allclose(np.asarray(rows), g[tag + "unordered.rows"], rtol=1e-6, atol=1e-6) and [x[1] for x in smi] == g[tag + "unordered.smi_p"].tolist()
+
+
+def test_dedup_plan_maps_every_product_atom_to_its_reactant_row():
+    """DeviceGraph.dedup_plan: unique reactants per segment in order of first appearance, padding rows map to padding rows, and every
+    product atom row maps to the row its own (repeated) reactant would have had."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(12, [4, 1, 3])
+    fz = Parsing_features(ds.mols)
+    groups = [(0, 4), (4, 5), (5, 8)]
+    r_b = [fz.parsing_smiles(list(ds.rsmi[a:b])) for a, b in groups]
+    p_b = [fz.parsing_smiles(list(ds.psmi[a:b])) for a, b in groups]
+    uniq, w, amap = DeviceGraph.dedup_plan(r_b, p_b)
+    assert [u.n_mols for u in uniq] == [1, 1, 1] and w == [b.max_num_bonds for b in r_b]
+    assert amap.shape[0] == sum(b.n_atoms for b in p_b)
+    # brute force: features of the mapped reactant row == features of the row in the un-deduplicated reactant batch
+    full = np.concatenate([b.f_atoms.numpy() for b in r_b])
+    dedup = np.concatenate([u.f_atoms.numpy() for u in uniq])
+    assert np.array_equal(dedup[amap], full)
+    a0_p = np.cumsum([0] + [b.n_atoms for b in p_b])[:-1]
+    a0_u = np.cumsum([0] + [u.n_atoms for u in uniq])[:-1]
+    assert np.array_equal(amap[a0_p], a0_u)                       # segment padding atoms
+    # nothing repeats -> no plan; a whole batch with two different reactants keeps both, first appearance first
+    assert DeviceGraph.dedup_plan([fz.parsing_smiles([ds.rsmi[0]])], [fz.parsing_smiles([ds.psmi[0]])]) is None
+    rb, pb = fz.parsing_smiles(list(ds.rsmi)), fz.parsing_smiles(list(ds.psmi))
+    uniq, w, amap = DeviceGraph.dedup_plan([rb], [pb])
+    assert uniq[0].n_mols == 3 and uniq[0].smiles_batch == [ds.rsmi[0], ds.rsmi[4], ds.rsmi[5]]
+    assert np.array_equal(uniq[0].f_atoms.numpy()[amap], rb.f_atoms.numpy())
