@@ -499,6 +499,38 @@ def _align(n: int, a: int = 256) -> int:
     return (n + a - 1) // a * a
 
 
+class _BufferPool:
+    """Device blobs and pinned control buffers of assembled batches, recycled when their DeviceGraph dies.  Batch sizes wander by a
+    per cent from step to step; asking the allocators for a fresh, slightly larger block now and then costs a cudaMalloc / cudaHostAlloc
+    (5-25 ms) in the middle of training.  Buffers are handed out best-fit with 6 % head-room; reuse is stream-ordered (the kernels that
+    read the old contents were enqueued before the assembly that overwrites them)."""
+
+    def __init__(self, keep: int = 8):
+        self.free = {}
+        self.keep = keep
+        self.lock = threading.Lock()
+
+    def take(self, nbytes: int, key, make):
+        with self.lock:
+            lst = self.free.setdefault(key, [])
+            # a pinned staging buffer is reusable only once the asynchronous copy out of it has run (its event has completed)
+            fits = [e for e in lst if e[0].numel() >= nbytes and (e[1] is None or e[1].query())]
+            if fits:
+                best = min(fits, key=lambda e: e[0].numel())
+                lst[:] = [e for e in lst if e is not best]     # identity, not tensor equality
+                return best[0]
+        return make(int(nbytes * 1.0625) + 256)
+
+    def give(self, t, key, event=None):
+        with self.lock:
+            lst = self.free.setdefault(key, [])
+            if len(lst) < self.keep:
+                lst.append((t, event))
+
+
+_POOL = _BufferPool()
+
+
 class DeviceGraph:
     """One or more BatchMolGraphs ("segments") laid out for the kernels and shipped with a
     single host->device copy out of pinned memory."""
@@ -506,10 +538,21 @@ class DeviceGraph:
     def __init__(self):
         self.blob = None
         self.host_blob = None
+        self._pooled = None
         self.c = RRGraph()
         self.h2d_bytes = 0
         self.n_atoms = self.n_bonds = self.n_mols = 0
         self.real_atoms = self.real_bonds = 0
+
+    def __del__(self):
+        p = self._pooled
+        if p is not None:
+            self._pooled = None
+            try:
+                _POOL.give(p[0], p[1])
+                _POOL.give(p[2], "pinned", p[3])
+            except Exception:      # interpreter shutdown
+                pass
 
     @staticmethod
     def _sections(nA, nB, nM, wmax, S):
@@ -551,11 +594,19 @@ class DeviceGraph:
             a0 += b.n_atoms
             b0 += b.n_bonds
             m0 += n
-        host = torch.from_numpy(ctl).pin_memory()
-        d_ctl = host.to(dev, non_blocking=True)
+        # pinned staging + device buffers come from a pool (see _BufferPool); the device control block lives at the end of the blob
+        ctl_bytes = _align(ctl.nbytes)
+        host = _POOL.take(ctl.nbytes, "pinned", lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True))
+        host[:ctl.nbytes].view(torch.int32).numpy()[:] = ctl
+        blob = _POOL.take(total + ctl_bytes, str(dev), lambda n: torch.empty(n, dtype=torch.uint8, device=dev))
+        d_ctl = blob[total:total + ctl.nbytes]
+        d_ctl.copy_(host[:ctl.nbytes], non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record(torch.cuda.current_stream(dev))
         g = DeviceGraph()
         g.host_blob = host
-        g.blob = torch.empty(total, dtype=torch.uint8, device=dev)
+        g.blob = blob
+        g._pooled = (blob, str(dev), host, copied)
         g.h2d_bytes = ctl.nbytes
         base = g.blob.data_ptr()
         c = g.c

@@ -331,3 +331,34 @@ def test_dedup_plan_maps_every_product_atom_to_its_reactant_row():
     uniq, w, amap = DeviceGraph.dedup_plan([rb], [pb])
     assert uniq[0].n_mols == 3 and uniq[0].smiles_batch == [ds.rsmi[0], ds.rsmi[4], ds.rsmi[5]]
     assert np.array_equal(uniq[0].f_atoms.numpy()[amap], rb.f_atoms.numpy())
+
+
+def test_buffer_pool_best_fit_and_event_guard():
+    """features/featurization.py _BufferPool: best-fit reuse by identity, head-room on fresh allocations, pinned buffers held back until
+    their copy event has completed."""
+    from reactranker_b200.features.featurization import _BufferPool
+    pool = _BufferPool()
+    made = []
+
+    def make(n):
+        made.append(n)
+        return torch.empty(n, dtype=torch.uint8)
+    a = pool.take(1000, "k", make)
+    assert a.numel() >= 1000 and made == [a.numel()] and a.numel() <= 1000 * 1.07 + 256
+    b = pool.take(5000, "k", make)
+    pool.give(a, "k")
+    pool.give(b, "k")
+    assert pool.take(900, "k", make) is a and pool.take(900, "k", make) is b and len(made) == 2      # best fit first, then whatever fits
+
+    class Ev:
+        def __init__(self, done):
+            self.done = done
+
+        def query(self):
+            return self.done
+    ev = Ev(False)
+    pool.give(a, "p", ev)
+    c = pool.take(10, "p", make)
+    assert c is not a                      # copy still in flight: a fresh buffer instead
+    ev.done = True
+    assert pool.take(10, "p", make) is a
