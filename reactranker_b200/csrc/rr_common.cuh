@@ -7,6 +7,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "rr_sm100.h"
 
@@ -93,6 +95,30 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// ---- programmatic dependent launch -------------------------------------------------------
+// The big kernels are persistent, one CTA per SM, with a prologue of a few microseconds (barrier init, TMEM allocation, descriptor prefetch).
+// Launched with cudaLaunchAttributeProgrammaticStreamSerialization, the CTAs of kernel N+1 start on every SM that kernel N has left and run
+// their prologue while N's tail still executes; pdl_wait() (griddepcontrol.wait) then holds every thread until kernel N has completed and
+// its writes are visible, BEFORE the first global access of N+1 (reads and writes alike).  RR_NO_PDL=1 falls back to plain launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  static const bool off = getenv("RR_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // ---- float4 helpers ---------------------------------------------------------------------

@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();             // nothing above touches global memory (tensor-map prefetches read kernel parameters)
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -628,6 +630,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad2(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();             // nothing above touches global memory (tensor-map prefetches read kernel parameters)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -811,6 +815,8 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();             // nothing above touches global memory (tensor-map prefetches read kernel parameters)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1032,7 +1038,7 @@ int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, c
   const size_t smem = static_cast<size_t>(S2_BF) * STAGE2_BF + 1024 + 256 + 8 * 4096;
   const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
   const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-  k_tc_gemm2<8, true><<<ctas, THREADS2_BASE + 256, smem, s>>>(g);
+  RR_CUDA(launch_pdl(k_tc_gemm2<8, true>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_gemm2<bf16>");
   return RR_OK;
 }
@@ -1089,7 +1095,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
         attr3_set = true;
       }
       const size_t smem3 = static_cast<size_t>(S3) * (raw_bytes + bf_bytes) + 1024 + 512;
-      k_tc_wgrad3<<<dim3(ntiles3, ktiles, splits3), W3_THREADS, smem3, s>>>(g);
+      RR_CUDA(launch_pdl(k_tc_wgrad3, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       RR_LAUNCH_CHECK("k_tc_wgrad3");
       return RR_OK;
     }
@@ -1132,8 +1138,8 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
     RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  if (bkr == 32) k_tc_wgrad2<32><<<grid, THREADS, smem, s>>>(g);
-  else k_tc_wgrad2<16><<<grid, THREADS, smem, s>>>(g);
+  if (bkr == 32) RR_CUDA(launch_pdl(k_tc_wgrad2<32>, grid, dim3(THREADS), smem, s, g));
+  else RR_CUDA(launch_pdl(k_tc_wgrad2<16>, grid, dim3(THREADS), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_wgrad2");
   return RR_OK;
 }
@@ -1194,8 +1200,8 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   const int ew = (ew_env && atoi(ew_env) == 4) ? 4 : 8;
   const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
   const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-  if (ew == 8) k_tc_gemm2<8, false><<<ctas, THREADS2_BASE + 256, smem, s>>>(g);
-  else k_tc_gemm2<4, false><<<ctas, THREADS2_BASE + 128, smem, s>>>(g);
+  if (ew == 8) RR_CUDA(launch_pdl(k_tc_gemm2<8, false>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
+  else RR_CUDA(launch_pdl(k_tc_gemm2<4, false>, dim3(ctas), dim3(THREADS2_BASE + 128), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_gemm2");
   return RR_OK;
 }

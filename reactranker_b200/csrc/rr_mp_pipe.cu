@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();               // see rr_common.cuh: nothing above reads or writes global memory
 
   if (warp >= A.consumer_warps) {
     // ------------------------------------------------ producer ------------------------------------------------
@@ -519,7 +521,7 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
       RR_CUDA(cudaFuncSetAttribute(k_rowpipe<OPV, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));   \
       attr_set = true;                                                                                                      \
     }                                                                                                                       \
-    k_rowpipe<OPV, F><<<grid, A.consumer_warps * 32 + 32 * PRODUCERS, smem, s>>>(A);                                                                       \
+    RR_CUDA(launch_pdl(k_rowpipe<OPV, F>, dim3(grid), dim3(A.consumer_warps * 32 + 32 * PRODUCERS), smem, s, A));                                                                    \
   } while (0)
   switch (op) {
     case BOND_FWD: RR_PIPE_LAUNCH(BOND_FWD, false); break;
