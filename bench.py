@@ -431,7 +431,7 @@ def ours(args):
     line = {
         "metric": metric_of(wl), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (dense layers: tcgen05 kind::tf32 with on-chip 3xTF32 split, fp32 accumulate)" if args.gemm == "tc" else "f32",
+        "dtype": "f32 (dense layers on tcgen05: forward 3 x TF32 operand split, backward 3 x bf16 split, fp32 accumulation in TMEM)" if args.gemm == "tc" else "f32",
         "data": f"synthetic reaction graphs (SURVEY.md 8d generator), pool of {len(pool)} distinct batches per rank cycled; random-init weights",
         "config": {"workload": wl["desc"], "name": args.workload, "reactions_per_gpu_per_step": rows, "global_batch": rows * world,
                    "parallelism": f"dp{world}" if world > 1 else "single", "optimizer": "Adam(fused)+NoamLR",
