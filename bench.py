@@ -320,7 +320,10 @@ def ours(args):
         # enqueued behind the running step
         reactions = np.asarray(reactions, dtype=object)
         rg, pg = to_dev_pair(fz.parsing_smiles, reactions[:, 0].tolist(), reactions[:, 1].tolist())
-        return rg, pg, torch.FloatTensor(tg).squeeze(), sc, feats, rg.h2d_bytes + pg.h2d_bytes
+        # extra features and targets go up with the graphs (pinned, asynchronous), not between the loss read and the next launch
+        feats_d = torch.as_tensor(np.asarray(feats, dtype=np.float32)).reshape(len(tg), -1).pin_memory().to(dev, non_blocking=True)
+        targets_d = torch.FloatTensor(tg).squeeze().pin_memory().to(dev, non_blocking=True)                 # train_listwise.py:187
+        return rg, pg, targets_d, sc, feats_d, rg.h2d_bytes + pg.h2d_bytes + 4 * (feats_d.numel() + targets_d.numel())
 
     from reactranker_b200.data.prefetch import Lookahead
     e2e_feed = Lookahead(endless_plan(), featurise)
@@ -328,14 +331,14 @@ def ours(args):
 
     def step_e2e(i):
         rg, pg, targets, sc, feats, graph_bytes = e2e_feed.current
-        out = model(rg, pg, gpu=local, add_features=feats)                    # H2D of the extra features inside
-        loss = loss_fn(out, sc, targets)                                      # H2D of the targets inside
+        out = model(rg, pg, gpu=local, add_features=feats)
+        loss = loss_fn(out, sc, targets)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         reduce_grads()
         opt.step()
         sched.step()
-        h2d[0] = graph_bytes + feats.size * 4 + targets.numel() * 4
+        h2d[0] = graph_bytes
         t_adv = time.perf_counter()
         e2e_feed.advance()                                                    # plan + featurise + upload batch i+1 while step i executes
         adv_ms.append((time.perf_counter() - t_adv) * 1e3)
