@@ -477,3 +477,60 @@ def test_first_generation_gather_kernels_agree(monkeypatch):
         _lib.check(L.rr_neighbor_sum_fwd(ctypes.byref(dg.c), 0, m.data_ptr(), am.data_ptr(), hp, 0, S()))
         outs[v1] = (pre.cpu(), am.cpu())
     assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+
+
+@pytest.mark.parametrize("seed,h,sizes,star,segments", [
+    (101, 8, (1, 1, 1), None, 1), (102, 16, (3, 2), {0: 12}, 2), (103, 600, (5, 4, 3), None, 1), (104, 1000, (2, 2), {1: 6}, 1),
+    (105, 300, (9, 1, 7, 2), {2: 5}, 4), (106, 44, (30, 20), None, 2)])
+def test_row_pipeline_matches_first_generation_on_odd_shapes(monkeypatch, seed, h, sizes, star, segments):
+    """Every gather op of the TMA-bulk row pipeline against the register-gather kernels (RR_MP_V1=1) over widths from 8 to 1000 floats,
+    in-degrees above the four staged neighbours, single-molecule groups and multi-segment launches; fused variants against
+    gather + rr_relu_bwd."""
+    L = _lib.lib()
+    ds = synthetic.make_dataset(seed, list(sizes), star_leaves_in_group=star)
+    mols = [ds.mols[t] for t in ds.psmi]
+    if segments == 1:
+        batches = [BatchMolGraph(mols)]
+    else:
+        cuts = np.linspace(0, len(mols), segments + 1).astype(int)
+        batches = [BatchMolGraph(mols[a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    dg = DeviceGraph.from_batches(batches, DEV)
+    hp = L.rr_padded(h)
+    A, B = dg.n_atoms, dg.n_bonds
+    g = ctypes.byref(dg.c)
+    mB, upB, yB, accB0 = (rand(B, hp, h, seed + i).to(DEV) for i in range(4))
+    mA, upA, yA, accA0 = (rand(A, hp, h, seed + 10 + i).to(DEV) for i in range(4))
+    res = {}
+    for v1 in ("1", "0"):
+        monkeypatch.setenv("RR_MP_V1", v1)
+        out = {}
+        t = torch.empty(B, hp, device=DEV)
+        _lib.check(L.rr_bond_message_fwd(g, mB.data_ptr(), t.data_ptr(), hp, 1, S()))
+        out["bond_fwd"] = t
+        t = torch.empty(B, hp, device=DEV)
+        _lib.check(L.rr_bond_message_bwd(g, upB.data_ptr(), t.data_ptr(), hp, S()))
+        out["bond_bwd"] = t
+        for which, src in ((0, mB), (1, mA)):
+            t = torch.empty(A, hp, device=DEV)
+            _lib.check(L.rr_neighbor_sum_fwd(g, which, src.data_ptr(), t.data_ptr(), hp, 0, S()))
+            out[f"nbr_fwd{which}"] = t
+            rows = A if which else B
+            t = torch.empty(rows, hp, device=DEV)
+            _lib.check(L.rr_neighbor_sum_bwd(g, which, upA.data_ptr(), t.data_ptr(), hp, S()))
+            out[f"nbr_bwd{which}"] = t
+            y, acc0 = (yA, accA0) if which else (yB, accB0)
+            for mode, skip in ((1, 0), (2, 0), (2, 1)):
+                dz, acc = torch.zeros(rows, hp, device=DEV), acc0.clone()
+                _lib.check(L.rr_neighbor_sum_bwd_act(g, which, upA.data_ptr(), dz.data_ptr(), hp, y.data_ptr(), 0.9, 0, acc.data_ptr(), mode, skip, S()))
+                out[f"nbr_act{which}.{mode}{skip}"] = acc if skip else torch.cat([dz, acc])
+        for mode, skip, pre in ((1, 0, 0), (2, 0, 0), (2, 1, 1)):
+            dz, acc = torch.zeros(B, hp, device=DEV), accB0.clone()
+            _lib.check(L.rr_bond_message_bwd_act(g, upB.data_ptr(), dz.data_ptr(), hp, yB.data_ptr(), 1.1, pre, acc.data_ptr(), mode, skip, S()))
+            out[f"bond_act.{mode}{skip}"] = acc if skip else torch.cat([dz, acc])
+        res[v1] = {k: v.cpu() for k, v in out.items()}
+    for k in res["0"]:
+        a, b = res["0"][k], res["1"][k]
+        if "act" in k or "bwd" in k:          # padding rows are reduced with atomics (order), fused accumulators may use a reduction
+            close(a, b, 2e-6)
+        else:
+            assert torch.equal(a, b), k
