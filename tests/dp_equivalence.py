@@ -42,9 +42,12 @@ out = model(DeviceGraph.from_batches([rs], dev, [r_g.max_num_bonds]), DeviceGrap
 MLEloss(global_norm=len(sizes))(out, sizes[lo:hi], targets[a:b], local).backward()
 GradSync(model.parameters())()
 got = [p.grad for p in model.parameters() if p.requires_grad]
+# same criterion as tests/helpers.grads_close: per-tensor error <= rtol * max|want_k| + 1e-2 * rtol * (largest gradient entry of the model);
+# the second term absorbs tensors whose true gradient is zero (the last bias under the shift-invariant ListMLE: ~1e-8 of rounding noise)
 gscale = max(float(w.abs().max()) for w in want)
-worst = max(float((g - w).abs().max()) / max(float(w.abs().max()), 1e-3 * gscale) for g, w in zip(got, want))
-assert worst < 2e-4, worst
+rtol = 2e-4
+worst = max(float((g - w).abs().max()) / (float(w.abs().max()) + 1e-2 * gscale) for g, w in zip(got, want))
+assert worst < rtol, worst
 dist.barrier()
 if rank == 0:
     print("DP-EQUIVALENCE-OK worst rel err", worst)
