@@ -210,7 +210,9 @@ typedef enum {
   RR_LOSS_RANKNET = 3,    /* sum_session        train_pairwise.py:98-122,141-147           */
   RR_LOSS_GAUSS = 4,      /* GaussDisLoss       loss.py:144-162 (scores [N,2])             */
   RR_LOSS_MSE = 5,        /* nn.MSELoss         train_listwise.py:166-167                  */
-  RR_LOSS_EXPMSE = 6      /* mean((e^t - e^s)^2) train_listwise.py:276-281 ('regression_exploss') */
+  RR_LOSS_EXPMSE = 6,     /* mean((e^t - e^s)^2) train_listwise.py:276-281 ('regression_exploss') */
+  RR_LOSS_LISTMLE_DIS = 7,/* MLEDisLoss        loss.py:102-141 (scores [N,2] = mean, variance; norm = groups) */
+  RR_LOSS_LISTNET_DIS = 8 /* Listnet_For_Gauss loss.py:233-272 (scores [N,2]; norm = groups, items averaged per group) */
 } rr_loss_kind;
 /* norm: the divisor the reference applies (G, N or the window's ordered-pair count); sigma: RankNet */
 int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off,

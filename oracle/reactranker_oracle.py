@@ -259,6 +259,43 @@ def ranknet_group_cost(y_pred: torch.Tensor, targets: np.ndarray, sigma: float =
     return torch.sum(pos_t * c_pos + neg_t * c_neg), 2.0 * float(npos)
 
 
+def mledis_loss(mean, variance, scope, targets) -> torch.Tensor:
+    """MLEDisLoss (loss.py:102-141), restated as written: per group, items sorted by target descending, the n x n matrix
+    exp(s_i - s_j + (v_i + v_j) / 2) restricted to i >= j, column sums, mean of the logs; mean over groups, shape [1]."""
+    total = torch.zeros(1, dtype=mean.dtype)
+    o = 0
+    for n in scope:
+        t = targets[o:o + n]
+        idx = torch.argsort(t, descending=True)
+        s, v = mean[o:o + n][idx], variance[o:o + n][idx]
+        x1 = -s.repeat(n, 1)
+        x2 = -x1.t()
+        y1 = v.repeat(n, 1)
+        y2 = y1.t()
+        total = total + torch.mean(-torch.log(1 / torch.sum(torch.tril(torch.exp(x1 + x2 + (y1 + y2) / 2)), 0)))
+        o += n
+    return total / len(scope)
+
+
+def listnet_gauss_loss(mean, variance, scope, targets) -> torch.Tensor:
+    """Listnet_For_Gauss (loss.py:233-272), restated as written; mean over groups, shape [1]."""
+    total = torch.zeros(1, dtype=mean.dtype)
+    o = 0
+    for n in scope:
+        m, v, t = mean[o:o + n], variance[o:o + n], targets[o:o + n]
+        x1 = m.repeat(n, 1)
+        x2 = x1.t()
+        y1 = v.repeat(n, 1)
+        y2 = y1.t()
+        pred = 1 / torch.sum(torch.exp(x1 - x2 + (y1 + y2) / 2), dim=1)
+        z1 = t.repeat(n, 1)
+        z2 = z1.t()
+        targ = 1 / torch.sum(torch.exp(z1 - z2), dim=1)
+        total = total + (-torch.mean(targ * torch.log(pred)))
+        o += n
+    return total / len(scope)
+
+
 def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
     """Loss dispatch of ``train()`` for the five north-star keys and the composite keys built from them (train_listwise.py:196-285)."""
     if task_type == "mle":
@@ -280,6 +317,10 @@ def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
         return listnet_loss(output, scope, targets) + mse_loss(output, targets)
     if task_type == "regression_exploss":
         return torch.mean((torch.exp(targets) - torch.exp(output)) ** 2)
+    if task_type == "mledis_gaussian":          # train_listwise.py:196-203
+        return mledis_loss(output[:, 0], torch.exp(output[:, 1]), scope, targets) + gauss_loss(output[:, 0], output[:, 1], targets)
+    if task_type == "listnetdis_gauss":         # train_listwise.py:211-215
+        return listnet_gauss_loss(output[:, 0], output[:, 1], scope, targets) + gauss_loss(output[:, 0], output[:, 1], targets)
     return mse_loss(output, targets)
 
 

@@ -23,7 +23,7 @@ RR_MAX_FFN = 4
 RR_OUT_LD = 16
 FA_LD, FB_LD = 64, 88
 HEAD_RAW, HEAD_EVIDENTIAL_RANKING, HEAD_GAUSS_SOFTPLUS, HEAD_SOFTPLUS = 0, 1, 2, 3
-LOSS_LISTMLE, LOSS_LISTNET, LOSS_EVIDENTIAL, LOSS_RANKNET, LOSS_GAUSS, LOSS_MSE, LOSS_EXPMSE = range(7)
+LOSS_LISTMLE, LOSS_LISTNET, LOSS_EVIDENTIAL, LOSS_RANKNET, LOSS_GAUSS, LOSS_MSE, LOSS_EXPMSE, LOSS_LISTMLE_DIS, LOSS_LISTNET_DIS = range(9)
 
 c_f32p = ctypes.c_void_p   # device pointers travel as plain integers
 

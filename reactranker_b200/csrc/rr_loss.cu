@@ -69,6 +69,9 @@ __device__ void block_scan(float* buf, float* tmp, int n) {
 // ---------------------------------------------------------------------------------------
 // ListMLE  (MLEloss loss.py:64-99, LogCumsumExp loss.py:9-61)
 // ---------------------------------------------------------------------------------------
+// DIS = true: MLEDisLoss (loss.py:102-141) on scores [N,2] = (mean, variance).  Its n x n lower-triangular form reduces to ListMLE of
+// z = mean + variance / 2 plus the group mean of the variance:  mean_j( lcse_j(z) - z_j + v_j ).
+template <bool DIS>
 __global__ void __launch_bounds__(kLossThreads) k_listmle(const float* __restrict__ scores, const float* __restrict__ targets,
                                                           const int* __restrict__ seg, float inv_norm, float* __restrict__ loss,
                                                           float* __restrict__ dscore) {
@@ -106,12 +109,21 @@ __global__ void __launch_bounds__(kLossThreads) k_listmle(const float* __restric
   __syncthreads();
   // x = scores sorted; reuse key[] for x
   float mx = -CUDART_INF_F;
+  float vsum = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float x = scores[o + id[i]];
+    float x;
+    if (DIS) {
+      const float v = scores[2 * (o + id[i]) + 1];
+      x = scores[2 * (o + id[i])] + 0.5f * v;
+      vsum += v;
+    } else {
+      x = scores[o + id[i]];
+    }
     key[i] = x;
     mx = fmaxf(mx, x);
   }
   mx = block_max(mx, red);
+  if (DIS) vsum = block_sum(vsum, red);
   // suffix sums of exp(x - m): scan the reversed array
   for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = expf(key[n - 1 - i] - mx);
   block_scan(a, b, n);  // a[i] = sum_{k >= n-1-i} e_k
@@ -130,44 +142,63 @@ __global__ void __launch_bounds__(kLossThreads) k_listmle(const float* __restric
   const float gscale = inv_norm / static_cast<float>(n);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float e = expf(key[i] - mx);
-    dscore[o + id[i]] = (e * a[i] - 1.f) * gscale;
+    const float gz = (e * a[i] - 1.f) * gscale;
+    if (DIS) {
+      dscore[2 * (o + id[i])] = gz;
+      dscore[2 * (o + id[i]) + 1] = 0.5f * gz + gscale;
+    } else {
+      dscore[o + id[i]] = gz;
+    }
   }
-  if (threadIdx.x == 0) atomicAdd(loss, total * gscale);
+  if (threadIdx.x == 0) atomicAdd(loss, (total + (DIS ? vsum : 0.f)) * gscale);
 }
 
 // ---------------------------------------------------------------------------------------
 // ListNet@1  (ListnetLoss loss.py:317-352): mean over ALL items (norm = N)
 // ---------------------------------------------------------------------------------------
+// DIS = true: Listnet_For_Gauss (loss.py:233-272) on scores [N,2] = (mean, variance): with u = mean + variance / 2 its n x n form is
+// -p_i log pred_i = p_i (lse(u) - u_i + v_i), averaged over the items of the GROUP and then over groups (inv_norm = 1 / G here).
+template <bool DIS>
 __global__ void __launch_bounds__(kLossThreads) k_listnet(const float* __restrict__ scores, const float* __restrict__ targets,
                                                           const int* __restrict__ seg, float inv_norm, float* __restrict__ loss,
                                                           float* __restrict__ dscore) {
   __shared__ float red[32];
   const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
   if (n <= 0) return;
+  auto score = [&](int i) { return DIS ? scores[2 * (o + i)] + 0.5f * scores[2 * (o + i) + 1] : scores[o + i]; };
   float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    ms = fmaxf(ms, scores[o + i]);
+    ms = fmaxf(ms, score(i));
     mt = fmaxf(mt, targets[o + i]);
   }
   ms = block_max(ms, red);
   mt = block_max(mt, red);
   float zs = 0.f, zt = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    zs += expf(scores[o + i] - ms);
+    zs += expf(score(i) - ms);
     zt += expf(targets[o + i] - mt);
   }
   zs = block_sum(zs, red);
   zt = block_sum(zt, red);
   const float lzs = logf(zs), izt = 1.f / zt, izs = 1.f / zs;
+  const float c = DIS ? inv_norm / static_cast<float>(n) : inv_norm;
   float part = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float ds = scores[o + i] - ms;
+    const float ds = score(i) - ms;
     const float p = expf(targets[o + i] - mt) * izt;
-    part -= p * (ds - lzs);
-    dscore[o + i] = (expf(ds) * izs - p) * inv_norm;
+    const float gu = (expf(ds) * izs - p) * c;
+    if (DIS) {
+      const float v = scores[2 * (o + i) + 1];
+      part -= p * (ds - lzs - v);
+      dscore[2 * (o + i)] = gu;
+      dscore[2 * (o + i) + 1] = 0.5f * gu + p * c;
+    } else {
+      part -= p * (ds - lzs);
+      dscore[o + i] = gu;
+    }
   }
   part = block_sum(part, red);
-  if (threadIdx.x == 0) atomicAdd(loss, part * inv_norm);
+  if (threadIdx.x == 0) atomicAdd(loss, part * c);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -298,9 +329,13 @@ int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* target
     case RR_LOSS_LISTNET:
     case RR_LOSS_EVIDENTIAL:
     case RR_LOSS_RANKNET:
+    case RR_LOSS_LISTMLE_DIS:
+    case RR_LOSS_LISTNET_DIS:
       RR_REQUIRE(G > 0 && seg_off, "loss: segmented kinds need seg_off and G > 0");
-      if (kind == RR_LOSS_LISTMLE) k_listmle<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
-      else if (kind == RR_LOSS_LISTNET) k_listnet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      if (kind == RR_LOSS_LISTMLE) k_listmle<false><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      else if (kind == RR_LOSS_LISTMLE_DIS) k_listmle<true><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      else if (kind == RR_LOSS_LISTNET) k_listnet<false><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      else if (kind == RR_LOSS_LISTNET_DIS) k_listnet<true><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_EVIDENTIAL) k_evidential<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else k_ranknet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
       break;

@@ -9,8 +9,9 @@ pair count of the accumulation window.  ``mle`` and ``evidential_ranking`` retur
 like the reference, the others a 0-d tensor.
 
 Besides the five north-star keys, the composite keys that are sums of these terms (``mle_gaussian``, ``listnet_gauss``,
-``mle_regression``, ``listnet_regression``) and ``regression_exploss`` are dispatched by ``train()``; the remaining experimental
-losses of the reference (distribution-valued ListMLE / ListNet, Dirichlet, NIG evidential) raise.
+``mle_regression``, ``listnet_regression``), ``regression_exploss`` and the distribution-valued ``mledis_gaussian`` / ``listnetdis_gauss``
+(``MLEDisLoss``, ``Listnet_For_Gauss``) are dispatched by ``train()``; the remaining experimental losses of the reference (SURVEY.md §2
+row 6: log-normal ListNet, uncertainty-penalised ListNet, Dirichlet, NIG evidential) raise.
 """
 from __future__ import annotations
 
@@ -130,6 +131,32 @@ class evidential_ranking(_DPNorm):
         return _segmented(_lib.LOSS_EVIDENTIAL, possibilities, scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,))
 
 
+def _mean_variance(mean, variance) -> torch.Tensor:
+    """(mean [N] or [N,1], variance [N] or [N,1]) -> contiguous [N,2], the layout of the distribution-valued kernels."""
+    m, v = mean.reshape(-1), variance.reshape(-1)
+    if m.shape != v.shape:
+        raise _lib.RRError(f"mean has {m.numel()} entries, variance {v.numel()}")
+    return torch.stack((m, v), dim=1)
+
+
+class MLEDisLoss(_DPNorm):
+    """ListMLE over Gaussian scores (loss.py:102-141).  The reference builds an n x n lower-triangular matrix per group; it equals
+    ``mean_j(logcumsumexp_tail(z)_j - z_j + v_j)`` with ``z = mean + variance / 2`` in target-descending order, averaged over groups.
+    Returns shape [1]."""
+
+    def forward(self, mean, variance, scope, targets, gpu: int):
+        return _segmented(_lib.LOSS_LISTMLE_DIS, _mean_variance(mean, variance), scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,),
+                          check_max=True)
+
+
+class Listnet_For_Gauss(_DPNorm):
+    """ListNet top-1 over log-normal scores (loss.py:233-272): per group ``mean_i softmax(t)_i (lse(u) - u_i + v_i)`` with
+    ``u = mean + variance / 2``, then the mean over groups.  Returns shape [1]."""
+
+    def forward(self, mean, variance, scope, targets, gpu: int):
+        return _segmented(_lib.LOSS_LISTNET_DIS, _mean_variance(mean, variance), scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,))
+
+
 class _GaussFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mean, var, targets):
@@ -203,10 +230,8 @@ def _unbuilt(name):
     return _Missing
 
 
-MLEDisLoss = _unbuilt("MLEDisLoss")
 Lognorm = _unbuilt("Lognorm")
 Listnet_For_evidential = _unbuilt("Listnet_For_evidential")
-Listnet_For_Gauss = _unbuilt("Listnet_For_Gauss")
 Listnetlognorm = _unbuilt("Listnetlognorm")
 Listnet_with_uq = _unbuilt("Listnet_with_uq")
 evidential_loss_new = _unbuilt("evidential_loss_new")

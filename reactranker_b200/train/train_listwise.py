@@ -25,7 +25,7 @@ from .. import _lib
 from ..data.load_reactions import DataProcessor
 from ..utils import save_checkpoint
 from .eval import calculate_mse, ranking_metrics
-from .loss import ExpMSELoss, GaussDisLoss, ListnetLoss, MLEloss, MSELoss, evidential_ranking
+from .loss import ExpMSELoss, GaussDisLoss, Listnet_For_Gauss, ListnetLoss, MLEDisLoss, MLEloss, MSELoss, evidential_ranking
 
 try:  # only used as the default value of ``writer`` in the reference signature
     from torch.utils.tensorboard import SummaryWriter
@@ -34,9 +34,11 @@ except Exception:  # pragma: no cover
 
 BUILT_TASKS = ("mle", "listnet", "evidential_ranking", "gauss_regression",
                # sums of the terms above, dispatched exactly like train_listwise.py:204-210, 224-227, 263-266, 276-281
-               "mle_gaussian", "listnet_gauss", "mle_regression", "listnet_regression", "regression_exploss")
-UNBUILT_TASKS = ("mledis_gaussian", "mle_evidential", "mledis_evidential", "listnet_uq", "listnet_evidential", "listnetdis_gauss",
-                 "listnetdis_lognorm", "dirichlet_uq", "evidential", "mle_dirichlet")
+               "mle_gaussian", "listnet_gauss", "mle_regression", "listnet_regression", "regression_exploss",
+               # distribution-valued ListMLE / ListNet (loss.py:102-141, 233-272) + the Gaussian NLL (196-203, 211-215)
+               "mledis_gaussian", "listnetdis_gauss")
+UNBUILT_TASKS = ("mle_evidential", "mledis_evidential", "listnet_uq", "listnet_evidential", "listnetdis_lognorm", "dirichlet_uq", "evidential",
+                 "mle_dirichlet")
 
 
 def batch_loss(task_type, output, scope, targets, gpu, max_coeff=0.0001, epoch=0, epochs=1):
@@ -60,6 +62,12 @@ def batch_loss(task_type, output, scope, targets, gpu, max_coeff=0.0001, epoch=0
         return ListnetLoss()(output, scope, targets, gpu) + MSELoss()(output, targets)
     if task_type == 'regression_exploss':
         return ExpMSELoss()(output, targets)
+    if task_type == 'mledis_gaussian':           # the variance column is a log-variance for the ranking term (196-203)
+        return (MLEDisLoss()(output[:, 0::2], torch.exp(output[:, 1::2]), scope, targets, gpu)
+                + GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu))
+    if task_type == 'listnetdis_gauss':          # 211-215
+        return (Listnet_For_Gauss()(output[:, 0::2], output[:, 1::2], scope, targets, gpu)
+                + GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu))
     return MSELoss()(output, targets)
 NDCG_METRICS = ['NDCG@1', 'NDCG@2', 'NDCG@25%', 'NDCG@all']
 

@@ -51,6 +51,8 @@ COMPOSITE = {
     "mle_regression": (1, "with_softplus", None),
     "listnet_regression": (1, "with_softplus", None),
     "regression_exploss": (1, "with_softplus", None),
+    "mledis_gaussian": (2, "with_softplus", None),
+    "listnetdis_gauss": (2, "with_softplus", None),
 }
 TASKS_ALL = dict(TASKS, **COMPOSITE)
 
@@ -75,6 +77,14 @@ def ref_loss(task, out, scope, targets):
         return L.ListnetLoss()(out, scope, targets, None) + torch.nn.MSELoss()(out, targets)
     if task == "regression_exploss":      # 276-281
         return torch.mean((torch.exp(targets) - torch.exp(out)) ** 2)
+    if task == "mledis_gaussian":         # 196-203
+        mu = out[:, [j for j in range(len(out[0])) if j % 2 == 0]]
+        variance = torch.exp(out[:, [j for j in range(len(out[0])) if j % 2 == 1]])
+        return L.MLEDisLoss()(mu, variance, scope, targets, None) + L.GaussDisLoss()(out[:, 0], out[:, 1], targets, None)
+    if task == "listnetdis_gauss":        # 211-215
+        mu = out[:, [j for j in range(len(out[0])) if j % 2 == 0]]
+        variance = out[:, [j for j in range(len(out[0])) if j % 2 == 1]]
+        return L.Listnet_For_Gauss()(mu, variance, scope, targets, None) + L.GaussDisLoss()(out[:, 0], out[:, 1], targets, None)
     return torch.nn.MSELoss()(out, targets)
 
 

@@ -534,3 +534,35 @@ def test_row_pipeline_matches_first_generation_on_odd_shapes(monkeypatch, seed, 
             close(a, b, 2e-6)
         else:
             assert torch.equal(a, b), k
+
+
+@pytest.mark.parametrize("which", ["mledis", "listnet_gauss", "expmse"])
+@pytest.mark.parametrize("scope", [[5, 3, 6], [1, 2, 1], [32] * 8, [50, 100, 200]])
+def test_distribution_valued_losses_match_the_reference_form(which, scope):
+    """RR_LOSS_LISTMLE_DIS / RR_LOSS_LISTNET_DIS against the oracle's literal n x n restatement of MLEDisLoss / Listnet_For_Gauss
+    (loss.py:102-141, 233-272), and RR_LOSS_EXPMSE, on ragged groups, in fp64 on the host."""
+    L = _lib.lib()
+    N, G = sum(scope), len(scope)
+    g = torch.Generator().manual_seed(N + len(which))
+    m = torch.randn(N, generator=g) * 0.7
+    v = torch.nn.functional.softplus(torch.randn(N, generator=g)) * 0.5 + 1e-3
+    t = torch.randn(N, generator=g)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+    if which == "expmse":
+        sx = m.double().requires_grad_(True)
+        want = torch.mean((torch.exp(t.double()) - torch.exp(sx)) ** 2)
+        want.backward()
+        sd, kind, norm, wgrad = m.to(DEV), _lib.LOSS_EXPMSE, float(N), sx.grad
+    else:
+        mx, vx = m.double().requires_grad_(True), v.double().requires_grad_(True)
+        fn = O.mledis_loss if which == "mledis" else O.listnet_gauss_loss
+        want = fn(mx, vx, scope, t.double())
+        want.backward(torch.ones_like(want))
+        sd = torch.stack((m, v), 1).contiguous().to(DEV)
+        kind = _lib.LOSS_LISTMLE_DIS if which == "mledis" else _lib.LOSS_LISTNET_DIS
+        norm, wgrad = float(G), torch.stack((mx.grad, vx.grad), 1)
+    td = t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(sd, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd(kind, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), norm, 1.0, loss.data_ptr(), ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 3e-6)
+    close(ds_, wgrad, 2e-5)

@@ -22,7 +22,7 @@ GPU = 0
 TASKS = {"mle": (1, None), "listnet": (1, None), "evidential_ranking": (2, "evidential_ranking"),
          "gauss_regression": (2, None), "regression": (1, None),
          "mle_gaussian": (2, None), "listnet_gauss": (2, None), "mle_regression": (1, None), "listnet_regression": (1, None),
-         "regression_exploss": (1, None)}
+         "regression_exploss": (1, None), "mledis_gaussian": (2, None), "listnetdis_gauss": (2, None)}
 
 
 def product_loss(task, out, scope, targets, gpu=GPU):
@@ -41,7 +41,8 @@ def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_sof
 
 CASES = ["mle.h40", "listnet.h40", "evidential_ranking.h40", "gauss_regression.h40", "regression.h40", "mle.star.h40",
          "evidential_ranking.h24d5"]
-COMPOSITE = ["mle_gaussian.h40", "listnet_gauss.h40", "mle_regression.h40", "listnet_regression.h40", "regression_exploss.h40"]
+COMPOSITE = ["mle_gaussian.h40", "listnet_gauss.h40", "mle_regression.h40", "listnet_regression.h40", "regression_exploss.h40",
+             "mledis_gaussian.h40", "listnetdis_gauss.h40"]
 
 
 @pytest.mark.parametrize("name", CASES + COMPOSITE)
