@@ -92,7 +92,15 @@ typedef struct {
   const int32_t* b2a;        /* [sum B] source atom of each bond, local             */
 } rr_mol_store;
 
-typedef enum { RR_HEAD_RAW = 0, RR_HEAD_EVIDENTIAL_RANKING = 1, RR_HEAD_GAUSS_SOFTPLUS = 2, RR_HEAD_SOFTPLUS = 3 } rr_head;
+typedef enum {
+  RR_HEAD_RAW = 0,
+  RR_HEAD_EVIDENTIAL_RANKING = 1, /* base_model.py:91-98   (score, softplus + 1e-6) interleaved      */
+  RR_HEAD_GAUSS_SOFTPLUS = 2,     /* base_model.py:71-82   (mu, softplus)                            */
+  RR_HEAD_SOFTPLUS = 3,           /* base_model.py:99-100                                            */
+  RR_HEAD_LOGNORM = 4,            /* base_model.py:83-90   (softplus + 1e-6, softplus + 1e-6)        */
+  RR_HEAD_SOFTPLUS_P1 = 5,        /* base_model.py:101-104 softplus + 1                              */
+  RR_HEAD_NIG = 6                 /* base_model.py:61-70   (mu, sp + 1e-6, sp + 1 + 1e-6, sp + 1e-6), task_num % 4 == 0 */
+} rr_head;
 
 /* build_model(...) (models/base_model.py:235-297) */
 typedef struct {
@@ -212,7 +220,13 @@ typedef enum {
   RR_LOSS_MSE = 5,        /* nn.MSELoss         train_listwise.py:166-167                  */
   RR_LOSS_EXPMSE = 6,     /* mean((e^t - e^s)^2) train_listwise.py:276-281 ('regression_exploss') */
   RR_LOSS_LISTMLE_DIS = 7,/* MLEDisLoss        loss.py:102-141 (scores [N,2] = mean, variance; norm = groups) */
-  RR_LOSS_LISTNET_DIS = 8 /* Listnet_For_Gauss loss.py:233-272 (scores [N,2]; norm = groups, items averaged per group) */
+  RR_LOSS_LISTNET_DIS = 8,/* Listnet_For_Gauss loss.py:233-272 (scores [N,2]; norm = groups, items averaged per group) */
+  RR_LOSS_LISTNET_UQ = 9, /* Listnet_with_uq   loss.py:355-399 (positive scores; `sigma` carries the annealing coefficient) */
+  RR_LOSS_RANKNET_ACC = 10,/* RankNet 'accelerate_grad' train_pairwise.py:123-137: same cost, dscore = the row sums only (half of autograd's) */
+  RR_LOSS_LOGNORM = 11,   /* Lognorm           loss.py:165-184 (scores [N,2] = m, v, both positive; norm = N) */
+  RR_LOSS_DIRICHLET_UQ = 12,/* Dirichlet_uq    loss.py:440-474 (1-D positive concentrations; `sigma` = annealing coefficient; norm = groups) */
+  RR_LOSS_NIG = 13        /* evidential_loss_new loss.py:402-437 as called at train_listwise.py:229-260: scores [N,4] = mu, v, alpha, beta
+                             against EVERY target of the batch (the [N,1] x [N] broadcast); norm = N*N; `sigma` = lam; no seg_off */
 } rr_loss_kind;
 /* norm: the divisor the reference applies (G, N or the window's ordered-pair count); sigma: RankNet */
 int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off,

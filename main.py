@@ -21,6 +21,20 @@ from reactranker.train.train_listwise import train
 from reactranker.train.test_listwise import test
 
 
+# (task_num, build_model task_type, ffn_last_layer) for every key whose loss does not read a single raw / softplus score.  The reference has
+# the user edit main.py:114-123 for these; the rows follow what each branch of train_listwise.py:196-285 indexes.
+_TWO = (2, None, 'with_softplus')            # -> 'gaussian_with_softplus': (mu, softplus)
+_FOUR = (4, None, 'with_softplus')           # -> 'evidential_with_softplus': the NIG head
+_MODEL_FOR_TASK = {
+    'evidential_ranking': (2, 'evidential_ranking', 'with_softplus'),
+    'gauss_regression': _TWO, 'mle_gaussian': _TWO, 'listnet_gauss': _TWO, 'mledis_gaussian': _TWO, 'listnetdis_gauss': _TWO,
+    'listnetdis_lognorm': (2, 'listnetdis_lognorm', 'with_softplus'),
+    'evidential': _FOUR, 'mle_evidential': _FOUR, 'mledis_evidential': _FOUR, 'listnet_evidential': _FOUR,
+    'listnet_uq': (1, 'listnet', 'with_softplus'),               # positive scores
+    'dirichlet_uq': (1, 'listnet', 'with_uncertainty'),          # concentrations > 1
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--path", default="runs/reactranker", help="save path (checkpoints, output.log)")
@@ -93,8 +107,8 @@ def main():
             os.makedirs(p, exist_ok=True)
     # evidential_ranking / gauss_regression need two outputs; main.py's default build (task_num=1, task_type commented out,
     # main.py:114-123) serves mle / listnet / regression
-    task_num = 2 if task_type in ('evidential_ranking', 'gauss_regression') else 1
-    model_task = 'evidential_ranking' if task_type == 'evidential_ranking' else None
+    # The experimental keys need the head their loss reads (base_model.py:252-264 resolves task_num / task_type / ffn_last_layer to it).
+    task_num, model_task, last_layer = _MODEL_FOR_TASK.get(task_type, (1, None, 'with_softplus'))
     for ii in range(k_fold):
         print('**********************************')
         print('**   This is the fold [{}/{}]   **'.format(ii + 1, k_fold))
@@ -115,7 +129,7 @@ def main():
         torch.cuda.manual_seed(seed)
         torch.cuda.manual_seed_all(seed)
         model = build_model(hidden_size=a.hidden_size, mpnn_depth=a.depth, mpnn_diff_depth=a.depth, ffn_depth=3, use_bias=True, dropout=a.dropout,
-                            task_num=task_num, ffn_last_layer='with_softplus', task_type=model_task, add_features_dim=add_features_dim)
+                            task_num=task_num, ffn_last_layer=last_layer, task_type=model_task, add_features_dim=add_features_dim)
         logger.info('Model Structure')
         logger.info(model)
         torch.cuda.set_device(gpu)

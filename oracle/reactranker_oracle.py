@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -173,6 +175,14 @@ def ffn_forward(sd, x, head: str, ffn_depth: int = 3, dropout: float = 0.0, trai
         return torch.stack((mu, F.softplus(lv)), dim=2).view(out.size())
     if head in ("listnet_with_softplus",):                         # base_model.py:99-100
         return F.softplus(out)
+    if head in ("listnet_with_uncertainty", "evidential"):         # base_model.py:101-104
+        return F.softplus(out) + 1
+    if head == "listnetdis_lognorm_with_softplus":                 # base_model.py:83-90
+        mu, lv = torch.split(out, out.shape[1] // 2, dim=1)
+        return torch.stack((F.softplus(mu) + 1e-6, F.softplus(lv) + 1e-6), dim=2).view(out.size())
+    if head == "evidential_with_softplus":                         # base_model.py:61-70
+        mu, ll, la, lb = torch.split(out, out.shape[1] // 4, dim=1)
+        return torch.stack((mu, F.softplus(ll) + 1e-6, F.softplus(la) + 1e-6 + 1, F.softplus(lb) + 1e-6), dim=2).view(out.size())
     return out                                                     # base_model.py:105-106
 
 
@@ -259,6 +269,29 @@ def ranknet_group_cost(y_pred: torch.Tensor, targets: np.ndarray, sigma: float =
     return torch.sum(pos_t * c_pos + neg_t * c_neg), 2.0 * float(npos)
 
 
+def ranknet_group_lambda(y_pred: torch.Tensor, targets: np.ndarray, sigma: float = 1.0):
+    """One group of ``factorized_training_loop``/'accelerate_grad' (train_pairwise.py:123-137): the cost evaluated without a graph and
+    the hand-written gradient ``back`` [n, 1] the loop later feeds to ``y_pred.backward(back / pairs)`` (line 152).
+    Returns (cost, back, num_pairs) or (None, None, 0) for a skipped group."""
+    Y = np.asarray(targets).reshape(-1, 1)
+    rel = Y - Y.T
+    pos = (rel > 0).astype(np.float32)
+    npos = pos.sum()
+    if npos == 0:
+        return None, None, 0.0
+    neg = (rel < 0).astype(np.float32)
+    if y_pred.dim() > 1:
+        y_pred = y_pred[:, 0]
+    y = y_pred.detach().unsqueeze(1)
+    pos_t = torch.from_numpy(pos).to(y.dtype)
+    neg_t = torch.from_numpy(neg).to(y.dtype)
+    l_pos = 1 + torch.exp(sigma * (y - y.t()))
+    l_neg = 1 + torch.exp(-sigma * (y - y.t()))
+    lam = -sigma * pos_t / l_pos + sigma * neg_t / l_neg
+    cost = torch.sum(torch.log(l_neg) * pos_t + torch.log(l_pos) * neg_t)
+    return cost, torch.sum(lam, dim=1, keepdim=True), 2.0 * float(npos)
+
+
 def mledis_loss(mean, variance, scope, targets) -> torch.Tensor:
     """MLEDisLoss (loss.py:102-141), restated as written: per group, items sorted by target descending, the n x n matrix
     exp(s_i - s_j + (v_i + v_j) / 2) restricted to i >= j, column sums, mean of the logs; mean over groups, shape [1]."""
@@ -296,6 +329,57 @@ def listnet_gauss_loss(mean, variance, scope, targets) -> torch.Tensor:
     return total / len(scope)
 
 
+def listnet_uq_loss(score, scope, targets, max_coeff, epoch, epochs) -> torch.Tensor:
+    """Listnet_with_uq (loss.py:355-399), restated as written (KLDivLoss(reduction='batchmean') of 1-D tensors = sum / n)."""
+    total = torch.zeros(1, dtype=score.dtype)
+    o = 0
+    for n in scope:
+        item, t = score[o:o + n], targets[o:o + n]
+        pred_p = item / torch.sum(item)
+        targ_p = torch.softmax(t, dim=0)
+        real_loss = torch.sum(targ_p * (torch.log(targ_p) - torch.log(pred_p))) / n
+        consist = torch.log(targ_p / pred_p)
+        penalty = torch.abs(consist * (item - torch.ones(n, dtype=score.dtype)))
+        coef = max_coeff * (epoch / (epochs - 1)) ** 3
+        total = total + torch.mean(real_loss + coef * penalty)
+        o += n
+    return total / len(scope)
+
+
+def dirichlet_uq_loss(concentration, scope, targets, max_coeff, epoch, epochs) -> torch.Tensor:
+    """Dirichlet_uq (loss.py:440-474), restated as written for the 1-D concentration a task_num = 1 model emits."""
+    total = torch.zeros(1, dtype=concentration.dtype)
+    o = 0
+    for n in scope:
+        alpha, t = concentration[o:o + n], targets[o:o + n]
+        pred_p = alpha / torch.sum(alpha)
+        targ_p = torch.softmax(t, dim=0)
+        err = (pred_p - targ_p) ** 2
+        var = pred_p * (1 - pred_p) / (torch.sum(alpha) + 1)
+        residue = torch.log(targ_p / pred_p) * (alpha - 1)
+        coef = max_coeff * (epoch / (epochs - 1)) ** 3
+        total = total + torch.mean(err + var + coef * torch.abs(residue))
+        o += n
+    return total / len(scope)
+
+
+def lognorm_loss(scores, std_scores, targets) -> torch.Tensor:
+    """Lognorm (loss.py:165-184)."""
+    mse = 0.5 * math.log(2 * math.pi) + 0.5 * torch.log(std_scores * (scores ** 2)) + torch.pow(torch.log(scores) - targets, 2) / (2 * std_scores)
+    return torch.mean(mse)
+
+
+def nig_loss(mu, v, alpha, beta, targets, lam=1.0, epsilon=1e-4) -> torch.Tensor:
+    """evidential_loss_new (loss.py:402-437), restated as written.  NOTE the shapes of its call sites (train_listwise.py:229-260):
+    the four parameters are [N,1] column slices, ``targets`` is [N]; ``targets - mu`` therefore broadcasts to [N,N] and the mean runs
+    over every (reaction, target) pair of the batch.  Nothing here corrects that: pass the same shapes and the same thing happens."""
+    two_b_lambda = 2 * beta * (1 + v)
+    nll = (0.5 * torch.log(math.pi / v) - alpha * torch.log(two_b_lambda) + (alpha + 0.5) * torch.log(v * (targets - mu) ** 2 + two_b_lambda)
+           + torch.lgamma(alpha) - torch.lgamma(alpha + 0.5))
+    reg = torch.abs(targets - mu) * (2 * v + alpha)
+    return torch.mean(nll + lam * (reg - epsilon))
+
+
 def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
     """Loss dispatch of ``train()`` for the five north-star keys and the composite keys built from them (train_listwise.py:196-285)."""
     if task_type == "mle":
@@ -319,6 +403,21 @@ def loss_for_task(task_type: str, output, scope, targets) -> torch.Tensor:
         return torch.mean((torch.exp(targets) - torch.exp(output)) ** 2)
     if task_type == "mledis_gaussian":          # train_listwise.py:196-203
         return mledis_loss(output[:, 0], torch.exp(output[:, 1]), scope, targets) + gauss_loss(output[:, 0], output[:, 1], targets)
+    if task_type == "listnet_uq":               # train_listwise.py:228-229 with the golden's (max_coeff, epoch, epochs) = (0.05, 3, 5)
+        return listnet_uq_loss(output, scope, targets, 0.05, 3, 5)
+    if task_type == "listnetdis_lognorm":       # train_listwise.py:215-219
+        return lognorm_loss(output[:, 0], output[:, 1], targets)
+    if task_type == "dirichlet_uq":             # train_listwise.py:269-270, same schedule point as listnet_uq
+        return dirichlet_uq_loss(output, scope, targets, 0.05, 3, 5)
+    if task_type in ("evidential", "mle_evidential", "mledis_evidential", "listnet_evidential"):   # train_listwise.py:229-260
+        mu, lambdas, alphas, betas = (output[:, k::4] for k in range(4))         # [N,1] each
+        if task_type == "evidential":
+            return nig_loss(mu, lambdas, alphas, betas, targets, lam=0.1)
+        if task_type == "mle_evidential":
+            return listmle_loss(output[:, 0], scope, targets) + nig_loss(mu, lambdas, alphas, betas, targets, lam=0.2)
+        variance = betas / (lambdas * (alphas - 1))
+        rank = mledis_loss if task_type == "mledis_evidential" else listnet_gauss_loss
+        return rank(mu[:, 0], variance[:, 0], scope, targets) + nig_loss(mu, lambdas, alphas, betas, targets, lam=0.1)
     if task_type == "listnetdis_gauss":         # train_listwise.py:211-215
         return listnet_gauss_loss(output[:, 0], output[:, 1], scope, targets) + gauss_loss(output[:, 0], output[:, 1], targets)
     return mse_loss(output, targets)

@@ -22,8 +22,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 RR_MAX_FFN = 4
 RR_OUT_LD = 16
 FA_LD, FB_LD = 64, 88
-HEAD_RAW, HEAD_EVIDENTIAL_RANKING, HEAD_GAUSS_SOFTPLUS, HEAD_SOFTPLUS = 0, 1, 2, 3
-LOSS_LISTMLE, LOSS_LISTNET, LOSS_EVIDENTIAL, LOSS_RANKNET, LOSS_GAUSS, LOSS_MSE, LOSS_EXPMSE, LOSS_LISTMLE_DIS, LOSS_LISTNET_DIS = range(9)
+HEAD_RAW, HEAD_EVIDENTIAL_RANKING, HEAD_GAUSS_SOFTPLUS, HEAD_SOFTPLUS, HEAD_LOGNORM, HEAD_SOFTPLUS_P1, HEAD_NIG = range(7)
+LOSS_LISTMLE, LOSS_LISTNET, LOSS_EVIDENTIAL, LOSS_RANKNET, LOSS_GAUSS, LOSS_MSE, LOSS_EXPMSE, LOSS_LISTMLE_DIS, LOSS_LISTNET_DIS, LOSS_LISTNET_UQ, LOSS_RANKNET_ACC, LOSS_LOGNORM, LOSS_DIRICHLET_UQ, LOSS_NIG = range(14)
 
 c_f32p = ctypes.c_void_p   # device pointers travel as plain integers
 

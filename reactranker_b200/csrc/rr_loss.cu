@@ -248,13 +248,171 @@ __global__ void __launch_bounds__(kLossThreads) k_evidential(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------
+// Listnet_with_uq (loss.py:355-399): positive scores s (softplus head), pred = s / sum(s), p = softmax(t), c_i = log(p_i / pred_i);
+//   group loss = (1/n) sum_i p_i c_i  +  coef * mean_i |c_i (s_i - 1)|        (KLDivLoss 'batchmean' of a 1-D input divides by n)
+// coef = max_coeff * (epoch / (epochs - 1))^3 is computed by the caller.  Mean over groups.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) k_listnet_uq(const float* __restrict__ scores, const float* __restrict__ targets,
+                                                             const int* __restrict__ seg, float inv_norm, float coef, float* __restrict__ loss,
+                                                             float* __restrict__ dscore) {
+  __shared__ float red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  if (n <= 0) return;
+  float mt = -CUDART_INF_F, ssum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    mt = fmaxf(mt, targets[o + i]);
+    ssum += scores[o + i];
+  }
+  mt = block_max(mt, red);
+  ssum = block_sum(ssum, red);
+  float zt = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) zt += expf(targets[o + i] - mt);
+  zt = block_sum(zt, red);
+  const float lzt = logf(zt), lS = logf(ssum);
+  float kl = 0.f, pen = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float s = scores[o + i], logp = targets[o + i] - mt - lzt;
+    const float c = logp - logf(s) + lS;
+    const float res = c * (s - 1.f);
+    kl += expf(logp) * c;
+    pen += fabsf(res);
+    sg += (res > 0.f ? 1.f : (res < 0.f ? -1.f : 0.f)) * (s - 1.f);
+  }
+  kl = block_sum(kl, red);
+  pen = block_sum(pen, red);
+  sg = block_sum(sg, red);
+  const float gscale = inv_norm / static_cast<float>(n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float s = scores[o + i], logp = targets[o + i] - mt - lzt;
+    const float c = logp - logf(s) + lS;
+    const float res = c * (s - 1.f);
+    const float sgn = res > 0.f ? 1.f : (res < 0.f ? -1.f : 0.f);
+    const float dkl = 1.f / ssum - expf(logp) / s;                          // d/ds_k of sum_i p_i c_i
+    const float dpen = sg / ssum + sgn * (c - (s - 1.f) / s);               // d/ds_k of sum_i |c_i (s_i - 1)|
+    dscore[o + i] = (dkl + coef * dpen) * gscale;
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, (kl + coef * pen) * gscale);
+}
+
+// ---------------------------------------------------------------------------------------
+// Dirichlet_uq (loss.py:440-474) on 1-D positive concentrations a: pred = a / S, p = softmax(t),
+//   group loss = mean_i( (pred_i - p_i)^2 + pred_i (1 - pred_i) / (S + 1) + coef |log(p_i / pred_i) (a_i - 1)| ),  mean over groups.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) k_dirichlet_uq(const float* __restrict__ scores, const float* __restrict__ targets,
+                                                               const int* __restrict__ seg, float inv_norm, float coef,
+                                                               float* __restrict__ loss, float* __restrict__ dscore) {
+  __shared__ float red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  if (n <= 0) return;
+  float mt = -CUDART_INF_F, S = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    mt = fmaxf(mt, targets[o + i]);
+    S += scores[o + i];
+  }
+  mt = block_max(mt, red);
+  S = block_sum(S, red);
+  float zt = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) zt += expf(targets[o + i] - mt);
+  zt = block_sum(zt, red);
+  const float lzt = logf(zt), lS = logf(S);
+  float part = 0.f, s_ep = 0.f, s_vp = 0.f, s_v = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = scores[o + i], logp = targets[o + i] - mt - lzt, p = expf(logp);
+    const float pr = a / S;
+    const float res = (logp - logf(a) + lS) * (a - 1.f);
+    part += (pr - p) * (pr - p) + pr * (1.f - pr) / (S + 1.f) + coef * fabsf(res);
+    s_ep += (pr - p) * pr;
+    s_vp += (1.f - 2.f * pr) * pr;
+    s_v += pr * (1.f - pr);
+    sg += (res > 0.f ? 1.f : (res < 0.f ? -1.f : 0.f)) * (a - 1.f);
+  }
+  part = block_sum(part, red);
+  s_ep = block_sum(s_ep, red);
+  s_vp = block_sum(s_vp, red);
+  s_v = block_sum(s_v, red);
+  sg = block_sum(sg, red);
+  const float gscale = inv_norm / static_cast<float>(n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = scores[o + i], logp = targets[o + i] - mt - lzt, p = expf(logp);
+    const float pr = a / S;
+    const float c = logp - logf(a) + lS;
+    const float res = c * (a - 1.f);
+    const float sgn = res > 0.f ? 1.f : (res < 0.f ? -1.f : 0.f);
+    const float derr = 2.f / S * ((pr - p) - s_ep);
+    const float dvar = ((1.f - 2.f * pr) - s_vp) / (S * (S + 1.f)) - s_v / ((S + 1.f) * (S + 1.f));
+    const float dpen = sg / S + sgn * (c - (a - 1.f) / a);
+    dscore[o + i] = (derr + dvar + coef * dpen) * gscale;
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, part * gscale);
+}
+
+// ---------------------------------------------------------------------------------------
+// evidential_loss_new (loss.py:402-437) AS THE TRAINING LOOP CALLS IT (train_listwise.py:229-260): mu, v, alpha, beta are [N,1] column
+// slices of the [N,4] head while targets is [N], so every term broadcasts to an N x N matrix and the reference's loss is
+//   mean over (i, j) of  NLL(mu_i, v_i, alpha_i, beta_i; t_j) + lam (|t_j - mu_i| (2 v_i + alpha_i) - 1e-4),
+// every reaction's NIG scored against every target of the batch.  Reproduced as is: thread per row i, j tiled across blockIdx.y.
+// ---------------------------------------------------------------------------------------
+__device__ double digamma_d(double x) {      // x > 0: recurrence up to x >= 6, then the asymptotic series
+  double r = 0.0;
+  while (x < 6.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  const double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+}
+constexpr int kNigRows = 128;
+constexpr int kNigCols = 512;
+__global__ void __launch_bounds__(kNigRows) k_nig_allpairs(int N, const float* __restrict__ scores, const float* __restrict__ targets,
+                                                           float inv_norm, float lam, float* __restrict__ loss, float* __restrict__ dscore) {
+  __shared__ float ts[kNigCols];
+  __shared__ float red[32];
+  const int i = blockIdx.x * kNigRows + threadIdx.x;
+  const int j0 = blockIdx.y * kNigCols, nj = min(kNigCols, N - j0);
+  for (int j = threadIdx.x; j < nj; j += kNigRows) ts[j] = targets[j0 + j];
+  __syncthreads();
+  float part = 0.f;
+  if (i < N) {
+    const float4 q = *reinterpret_cast<const float4*>(scores + 4 * static_cast<size_t>(i));
+    const float mu = q.x, v = q.y, al = q.z, be = q.w;
+    const float om = 2.f * be * (1.f + v), ah = al + 0.5f, w = 2.f * v + al;
+    float s_log = 0.f, s_abs = 0.f, g_mu = 0.f, s_inv = 0.f, s_d2inv = 0.f;
+    for (int j = 0; j < nj; ++j) {
+      const float d = ts[j] - mu;
+      const float A = v * d * d + om, rA = 1.f / A;
+      s_log += logf(A);
+      s_abs += fabsf(d);
+      s_inv += rA;
+      s_d2inv += d * d * rA;
+      g_mu += -2.f * ah * v * d * rA - lam * (d > 0.f ? w : (d < 0.f ? -w : 0.f));
+    }
+    const float fj = static_cast<float>(nj);
+    // row-only terms, once per (row, column tile) with the tile's share of the N columns
+    const float lg = static_cast<float>(lgamma(static_cast<double>(al)) - lgamma(static_cast<double>(al) + 0.5));
+    const float row = 0.5f * logf(3.14159274101257324f / v) - al * logf(om) + lg - lam * 1e-4f;
+    part = fj * row + ah * s_log + lam * w * s_abs;
+    const float dpsi = static_cast<float>(digamma_d(static_cast<double>(al)) - digamma_d(static_cast<double>(al) + 0.5));
+    const float g_v = fj * (-0.5f / v - al * 2.f * be / om) + ah * (s_d2inv + 2.f * be * s_inv) + 2.f * lam * s_abs;
+    const float g_al = fj * (-logf(om) + dpsi) + s_log + lam * s_abs;
+    const float g_be = -fj * al / be + ah * 2.f * (1.f + v) * s_inv;
+    float* dr = dscore + 4 * static_cast<size_t>(i);
+    atomicAdd(dr + 0, g_mu * inv_norm);
+    atomicAdd(dr + 1, g_v * inv_norm);
+    atomicAdd(dr + 2, g_al * inv_norm);
+    atomicAdd(dr + 3, g_be * inv_norm);
+  }
+  part = block_sum(part, red);
+  if (threadIdx.x == 0) atomicAdd(loss, part * inv_norm);
+}
+
+// ---------------------------------------------------------------------------------------
 // RankNet 'sum_session'  (train_pairwise.py:98-122): all ordered intra-group pairs
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(kLossThreads) k_ranknet(const float* __restrict__ scores, const float* __restrict__ targets,
-                                                          const int* __restrict__ seg, float inv_norm, float sigma,
+                                                          const int* __restrict__ seg, float inv_norm, float sigma, float gfac,
                                                           float* __restrict__ loss, float* __restrict__ dscore) {
   __shared__ float ss[kMaxGroup];
   __shared__ float ts[kMaxGroup];
@@ -281,7 +439,7 @@ __global__ void __launch_bounds__(kLossThreads) k_ranknet(const float* __restric
         g += sigmoid_f(d);
       }
     }
-    dscore[o + i] = 2.f * sigma * g * inv_norm;
+    dscore[o + i] = gfac * sigma * g * inv_norm;
   }
   part = block_sum(part, red);
   if (threadIdx.x == 0) atomicAdd(loss, part * inv_norm);
@@ -301,6 +459,12 @@ __global__ void __launch_bounds__(kLossThreads) k_pointwise(int kind, int N, con
       const float d = mu - t;
       part += 0.5f * logf(2.f * 3.14159274101257324f) + 0.5f * logf(v) + d * d / (2.f * v);
       dscore[2 * i] = d / v * inv_norm;
+      dscore[2 * i + 1] = (0.5f / v - d * d / (2.f * v * v)) * inv_norm;
+    } else if (kind == RR_LOSS_LOGNORM) {      // Lognorm, loss.py:165-184: scores = (m, v), both positive
+      const float m = scores[2 * i], v = scores[2 * i + 1];
+      const float d = logf(m) - t;
+      part += 0.5f * logf(2.f * 3.14159274101257324f) + 0.5f * logf(v * (m * m)) + d * d / (2.f * v);
+      dscore[2 * i] = (1.f / m + d / (v * m)) * inv_norm;
       dscore[2 * i + 1] = (0.5f / v - d * d / (2.f * v * v)) * inv_norm;
     } else if (kind == RR_LOSS_EXPMSE) {       // mean((exp(t) - exp(s))^2), train_listwise.py:276-281
       const float e = expf(scores[i]);
@@ -331,16 +495,29 @@ int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* target
     case RR_LOSS_RANKNET:
     case RR_LOSS_LISTMLE_DIS:
     case RR_LOSS_LISTNET_DIS:
+    case RR_LOSS_LISTNET_UQ:
+    case RR_LOSS_RANKNET_ACC:
+    case RR_LOSS_DIRICHLET_UQ:
       RR_REQUIRE(G > 0 && seg_off, "loss: segmented kinds need seg_off and G > 0");
       if (kind == RR_LOSS_LISTMLE) k_listmle<false><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_LISTMLE_DIS) k_listmle<true><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_LISTNET) k_listnet<false><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_LISTNET_DIS) k_listnet<true><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_EVIDENTIAL) k_evidential<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
-      else k_ranknet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
+      else if (kind == RR_LOSS_DIRICHLET_UQ) k_dirichlet_uq<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
+      else if (kind == RR_LOSS_LISTNET_UQ) k_listnet_uq<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
+      else k_ranknet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, kind == RR_LOSS_RANKNET_ACC ? 1.f : 2.f, loss, dscore);
       break;
+    case RR_LOSS_NIG: {            // norm = N * N (the reference's mean over the broadcast matrix); `sigma` carries lam
+      RR_REQUIRE((reinterpret_cast<uintptr_t>(scores) & 15) == 0, "loss: NIG scores must be 16-byte aligned");
+      RR_CUDA(cudaMemsetAsync(dscore, 0, sizeof(float) * 4 * static_cast<size_t>(N), s));
+      dim3 grid((N + kNigRows - 1) / kNigRows, (N + kNigCols - 1) / kNigCols);
+      k_nig_allpairs<<<grid, kNigRows, 0, s>>>(N, scores, targets, inv, sigma, loss, dscore);
+      break;
+    }
     case RR_LOSS_GAUSS:
     case RR_LOSS_MSE:
+    case RR_LOSS_LOGNORM:
     case RR_LOSS_EXPMSE: {
       int blocks = (N + kLossThreads - 1) / kLossThreads;
       if (blocks > num_sms() * 4) blocks = num_sms() * 4;

@@ -164,10 +164,15 @@ __global__ void k_head_fwd(int N, int task, int head, const float* __restrict__ 
     float v;
     if (head == RR_HEAD_RAW) v = zr[c];
     else if (head == RR_HEAD_SOFTPLUS) v = softplus_t(zr[c]);
-    else {  // stack((first half, f(second half)), dim=2).view(...)  -> interleaved columns
+    else if (head == RR_HEAD_SOFTPLUS_P1) v = softplus_t(zr[c]) + 1.f;
+    else if (head == RR_HEAD_NIG) {  // stack((mu, lambda, alpha, beta), dim=2).view(...): column c = 4 j + k reads quarter k, entry j
+      const int j = c >> 2, k = c & 3, quarter = task >> 2;
+      const float zc = zr[k * quarter + j];
+      v = k == 0 ? zc : (k == 2 ? softplus_t(zc) + 1e-6f + 1.f : softplus_t(zc) + 1e-6f);
+    } else {  // stack((first half, f(second half)), dim=2).view(...)  -> interleaved columns
       const int j = c >> 1;
-      if ((c & 1) == 0) v = zr[j];
-      else v = softplus_t(zr[half + j]) + (head == RR_HEAD_EVIDENTIAL_RANKING ? 1e-6f : 0.f);
+      if ((c & 1) == 0) v = head == RR_HEAD_LOGNORM ? softplus_t(zr[j]) + 1e-6f : zr[j];
+      else v = softplus_t(zr[half + j]) + (head == RR_HEAD_GAUSS_SOFTPLUS ? 0.f : 1e-6f);
     }
     out[i] = v;
   }
@@ -182,8 +187,11 @@ __global__ void k_head_bwd(int N, int task, int head, const float* __restrict__ 
       const float sg = zc > 20.f ? 1.f : 1.f / (1.f + expf(-zc));
       const float* dr = dout + static_cast<size_t>(r) * task;
       if (head == RR_HEAD_RAW) v = dr[c];
-      else if (head == RR_HEAD_SOFTPLUS) v = dr[c] * sg;
-      else v = (c < half) ? dr[2 * c] : dr[2 * (c - half) + 1] * sg;
+      else if (head == RR_HEAD_SOFTPLUS || head == RR_HEAD_SOFTPLUS_P1) v = dr[c] * sg;
+      else if (head == RR_HEAD_NIG) {
+        const int quarter = task >> 2, k = c / quarter, j = c - k * quarter;
+        v = dr[4 * j + k] * (k == 0 ? 1.f : sg);
+      } else v = (c < half) ? dr[2 * c] * (head == RR_HEAD_LOGNORM ? sg : 1.f) : dr[2 * (c - half) + 1] * sg;
     }
     dz[i] = v;
   }
@@ -346,7 +354,10 @@ static int check_model_args(const rr_model_cfg* c, const rr_params* w, const rr_
   for (int l = 0; l < c->ffn_depth; ++l) RR_REQUIRE(w->ffn_W[l], "model: ffn weight %d missing", l);
   RR_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f, "dropout must be in [0,1)");
   RR_REQUIRE(r->f_bonds && r->f_atoms && p->f_bonds && p->f_atoms, "model: graph features missing");
-  if (c->head != RR_HEAD_RAW && c->head != RR_HEAD_SOFTPLUS) RR_REQUIRE((c->task_num & 1) == 0, "two-parameter heads need an even task_num");
+  RR_REQUIRE(c->head >= RR_HEAD_RAW && c->head <= RR_HEAD_NIG, "unknown head %d", c->head);
+  if (c->head == RR_HEAD_NIG) RR_REQUIRE((c->task_num & 3) == 0, "the NIG head needs task_num % 4 == 0");
+  else if (c->head != RR_HEAD_RAW && c->head != RR_HEAD_SOFTPLUS && c->head != RR_HEAD_SOFTPLUS_P1)
+    RR_REQUIRE((c->task_num & 1) == 0, "two-parameter heads need an even task_num");
   return RR_OK;
 }
 

@@ -22,8 +22,12 @@ _HEADS = {
     "gauss_regression_with_softplus": _lib.HEAD_GAUSS_SOFTPLUS,
     "gaussian_with_softplus": _lib.HEAD_GAUSS_SOFTPLUS,
     "listnet_with_softplus": _lib.HEAD_SOFTPLUS,
+    "listnetdis_lognorm_with_softplus": _lib.HEAD_LOGNORM,     # base_model.py:83-90 (without its debugging print of the whole output)
+    "listnet_with_uncertainty": _lib.HEAD_SOFTPLUS_P1,         # base_model.py:101-102
+    "evidential": _lib.HEAD_SOFTPLUS_P1,                       # base_model.py:103-104
+    "evidential_with_softplus": _lib.HEAD_NIG,                 # base_model.py:61-70
 }
-_UNBUILT_HEADS = ("evidential_with_softplus", "listnetdis_lognorm_with_softplus", "listnet_with_uncertainty", "evidential")
+_UNBUILT_HEADS = ()
 
 
 class FFN(nn.Module):

@@ -10,7 +10,7 @@ like the reference, the others a 0-d tensor.
 
 Besides the five north-star keys, the composite keys that are sums of these terms (``mle_gaussian``, ``listnet_gauss``,
 ``mle_regression``, ``listnet_regression``), ``regression_exploss`` and the distribution-valued ``mledis_gaussian`` / ``listnetdis_gauss``
-(``MLEDisLoss``, ``Listnet_For_Gauss``) are dispatched by ``train()``; the remaining experimental losses of the reference (SURVEY.md §2
+(``MLEDisLoss``, ``Listnet_For_Gauss``) and ``listnet_uq`` (``Listnet_with_uq``) are dispatched by ``train()``; the remaining experimental losses of the reference (SURVEY.md §2
 row 6: log-normal ListNet, uncertainty-penalised ListNet, Dirichlet, NIG evidential) raise.
 """
 from __future__ import annotations
@@ -157,6 +157,56 @@ class Listnet_For_Gauss(_DPNorm):
         return _segmented(_lib.LOSS_LISTNET_DIS, _mean_variance(mean, variance), scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,))
 
 
+class Listnet_with_uq(_DPNorm):
+    """ListNet on normalised positive scores with an uncertainty penalty (loss.py:355-399): ``pred = s / sum(s)``, ``p = softmax(t)``,
+    per group ``KL(p || pred) / n + coef * mean_i |log(p_i / pred_i) (s_i - 1)|`` with the reference's annealing
+    ``coef = max_coeff * (epoch / (epochs - 1)) ** 3`` (a ZeroDivisionError at ``epochs == 1``, as there).  Returns shape [1]."""
+
+    def forward(self, score, scope, targets, max_coeff, epoch, epochs, gpu: int):
+        coef = max_coeff * (epoch / (epochs - 1)) ** 3
+        return _segmented(_lib.LOSS_LISTNET_UQ, score, scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,), sigma=coef)
+
+
+class Dirichlet_uq(_DPNorm):
+    """Dirichlet mean / variance loss on 1-D positive concentrations (loss.py:440-474): per group
+    ``mean_i((pred_i - p_i)^2 + pred_i (1 - pred_i) / (S + 1) + coef |log(p_i / pred_i) (a_i - 1)|)``, ``pred = a / S``.  Returns shape [1]."""
+
+    def forward(self, concentration, scope, targets, max_coeff, epoch, epochs, gpu: int):
+        if concentration.dim() != 1:
+            raise _lib.RRError("Dirichlet_uq is built for the 1-D output of a task_num = 1 model (the only shape train_listwise.py:269-270 passes)")
+        coef = max_coeff * (epoch / (epochs - 1)) ** 3
+        return _segmented(_lib.LOSS_DIRICHLET_UQ, concentration, scope, targets, gpu, norm=self._norm(len(scope)), out_shape=(1,), sigma=coef)
+
+
+def evidential_loss_new(mu, v, alpha, beta, targets, gpu, lam=1, epsilon=1e-4):
+    """Deep-evidential-regression loss (loss.py:402-437) with the shapes its four call sites pass (train_listwise.py:229-260):
+    ``mu, v, alpha, beta`` are ``[N, 1]`` column slices and ``targets`` is ``[N]``, so ``targets - mu`` broadcasts to ``[N, N]`` and
+    the value is the mean over ALL (reaction i, target j) pairs of the batch.  That is what the reference trains on, so that is what
+    one all-pairs launch computes here; 1-D / mismatched shapes (element-wise in torch) are rejected rather than guessed."""
+    if epsilon != 1e-4:
+        raise _lib.RRError("evidential_loss_new: epsilon is fixed at the reference default 1e-4")
+    cols = [mu, v, alpha, beta]
+    n = mu.shape[0]
+    if any(c.dim() != 2 or c.shape != (n, 1) for c in cols):
+        raise _lib.RRError("evidential_loss_new expects the [N, 1] column slices of a task_num = 4 model (train_listwise.py:230-233)")
+    dev = _device_of(gpu, mu)
+    t = _to_dev(targets, dev).reshape(-1)
+    if t.numel() != n:
+        raise _lib.RRError(f"{t.numel()} targets for {n} rows")
+    scores = torch.cat(cols, dim=1).float()
+    return _LossFn.apply(scores, t, None, _lib.LOSS_NIG, n, 0, float(n) * float(n), float(lam), ())
+
+
+class Lognorm(nn.Module):
+    """Log-normal NLL (loss.py:165-184): ``mean(0.5 log 2pi + 0.5 log(v m^2) + (log m - t)^2 / (2 v))`` (without its ``print``)."""
+
+    def forward(self, scores, std_scores, targets, gpu: int):
+        dev = _device_of(gpu, scores)
+        both = _mean_variance(scores, std_scores).float()
+        n = both.shape[0]
+        return _LossFn.apply(both, _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_LOGNORM, n, 0, float(n), 1.0, ())
+
+
 class _GaussFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mean, var, targets):
@@ -204,13 +254,20 @@ class ExpMSELoss(nn.Module):
         return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_EXPMSE, n, 0, float(n), 1.0, ())
 
 
-def ranknet_window_loss(scores, scope, targets, num_pairs: float, sigma: float = 1.0, gpu: Optional[int] = None):
-    """'sum_session' RankNet cost of one accumulation window (train_pairwise.py:98-122, 141-147):
+def ranknet_window_loss(scores, scope, targets, num_pairs: float, sigma: float = 1.0, gpu: Optional[int] = None,
+                        training_algo: str = 'sum_session'):
+    """RankNet cost of one accumulation window (train_pairwise.py:98-137, 141-152):
     ``sum over groups and ordered pairs of the pairwise logistic cost / num_pairs``; groups of the
-    window are evaluated by one launch.  ``num_pairs`` is the window's ordered-pair count."""
+    window are evaluated by one launch.  ``num_pairs`` is the window's ordered-pair count.
+    'accelerate_grad' reports the same cost but back-propagates the hand-written lambda of lines 125-133,
+    ``sum_j (-sigma pos_ij / (1 + e^{sigma (s_i - s_j)}) + sigma neg_ij / (1 + e^{-sigma (s_i - s_j)})) / pairs``: the row sums only,
+    i.e. exactly half of what autograd gives 'sum_session' (the column sums are equal by symmetry)."""
+    if training_algo not in ('sum_session', 'accelerate_grad'):
+        raise ValueError("training algo {} not implemented".format(training_algo))
     if scores.dim() > 1:
         scores = scores[:, 0]                        # train_pairwise.py:115-116
-    return _segmented(_lib.LOSS_RANKNET, scores, scope, targets, gpu, norm=float(num_pairs), out_shape=(), sigma=sigma, check_max=True)
+    kind = _lib.LOSS_RANKNET if training_algo == 'sum_session' else _lib.LOSS_RANKNET_ACC
+    return _segmented(kind, scores, scope, targets, gpu, norm=float(num_pairs), out_shape=(), sigma=sigma, check_max=True)
 
 
 def count_ordered_pairs(targets: np.ndarray) -> float:
@@ -230,9 +287,6 @@ def _unbuilt(name):
     return _Missing
 
 
-Lognorm = _unbuilt("Lognorm")
+# constructed by no task key (Listnetlognorm's only call is commented out at train_listwise.py:219; Listnet_For_evidential is imported only)
 Listnet_For_evidential = _unbuilt("Listnet_For_evidential")
 Listnetlognorm = _unbuilt("Listnetlognorm")
-Listnet_with_uq = _unbuilt("Listnet_with_uq")
-evidential_loss_new = _unbuilt("evidential_loss_new")
-Dirichlet_uq = _unbuilt("Dirichlet_uq")

@@ -25,7 +25,8 @@ from .. import _lib
 from ..data.load_reactions import DataProcessor
 from ..utils import save_checkpoint
 from .eval import calculate_mse, ranking_metrics
-from .loss import ExpMSELoss, GaussDisLoss, Listnet_For_Gauss, ListnetLoss, MLEDisLoss, MLEloss, MSELoss, evidential_ranking
+from .loss import (Dirichlet_uq, ExpMSELoss, GaussDisLoss, Listnet_For_Gauss, Listnet_with_uq, ListnetLoss, Lognorm, MLEDisLoss, MLEloss,
+                   MSELoss, evidential_loss_new, evidential_ranking)
 
 try:  # only used as the default value of ``writer`` in the reference signature
     from torch.utils.tensorboard import SummaryWriter
@@ -36,9 +37,12 @@ BUILT_TASKS = ("mle", "listnet", "evidential_ranking", "gauss_regression",
                # sums of the terms above, dispatched exactly like train_listwise.py:204-210, 224-227, 263-266, 276-281
                "mle_gaussian", "listnet_gauss", "mle_regression", "listnet_regression", "regression_exploss",
                # distribution-valued ListMLE / ListNet (loss.py:102-141, 233-272) + the Gaussian NLL (196-203, 211-215)
-               "mledis_gaussian", "listnetdis_gauss")
-UNBUILT_TASKS = ("mle_evidential", "mledis_evidential", "listnet_uq", "listnet_evidential", "listnetdis_lognorm", "dirichlet_uq", "evidential",
-                 "mle_dirichlet")
+               "mledis_gaussian", "listnetdis_gauss", "listnet_uq",
+               # the remaining experimental keys (215-219, 229-260, 269-270)
+               "listnetdis_lognorm", "dirichlet_uq", "evidential", "mle_evidential", "mledis_evidential", "listnet_evidential")
+# 'mle_dirichlet' cannot run in the reference either: no branch of train_listwise.py:128-167 constructs ``dirichlet_loss`` for it and the
+# call at 267-268 passes four arguments to a seven-argument forward.
+UNBUILT_TASKS = ("mle_dirichlet",)
 
 
 def batch_loss(task_type, output, scope, targets, gpu, max_coeff=0.0001, epoch=0, epochs=1):
@@ -65,10 +69,27 @@ def batch_loss(task_type, output, scope, targets, gpu, max_coeff=0.0001, epoch=0
     if task_type == 'mledis_gaussian':           # the variance column is a log-variance for the ranking term (196-203)
         return (MLEDisLoss()(output[:, 0::2], torch.exp(output[:, 1::2]), scope, targets, gpu)
                 + GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu))
+    if task_type == 'listnet_uq':                # 228-229; needs positive scores (task_type='listnet' -> softplus head)
+        return Listnet_with_uq()(output, scope, targets, max_coeff, epoch, epochs, gpu)
     if task_type == 'listnetdis_gauss':          # 211-215
         return (Listnet_For_Gauss()(output[:, 0::2], output[:, 1::2], scope, targets, gpu)
                 + GaussDisLoss()(output[:, 0], output[:, 1], targets, gpu))
+    if task_type == 'listnetdis_lognorm':        # 215-219: the ListNet term is commented out there, the log-normal NLL is the loss
+        return Lognorm()(output[:, 0], output[:, 1], targets, gpu)
+    if task_type == 'dirichlet_uq':              # 269-270
+        return Dirichlet_uq()(output, scope, targets, max_coeff, epoch, epochs, gpu)
+    if task_type in ('evidential', 'mle_evidential', 'mledis_evidential', 'listnet_evidential'):    # 229-260
+        mu, lambdas, alphas, betas = (output[:, k::4] for k in range(4))
+        if task_type == 'evidential':
+            return evidential_loss_new(mu, lambdas, alphas, betas, targets, gpu, lam=0.1)
+        if task_type == 'mle_evidential':
+            return MLEloss()(output[:, 0], scope, targets, gpu) + evidential_loss_new(mu, lambdas, alphas, betas, targets, gpu, lam=0.2)
+        variance = betas / (lambdas * (alphas - 1))
+        rank = MLEDisLoss() if task_type == 'mledis_evidential' else Listnet_For_Gauss()
+        return rank(mu, variance, scope, targets, gpu) + evidential_loss_new(mu, lambdas, alphas, betas, targets, gpu, lam=0.1)
     return MSELoss()(output, targets)
+
+
 NDCG_METRICS = ['NDCG@1', 'NDCG@2', 'NDCG@25%', 'NDCG@all']
 
 

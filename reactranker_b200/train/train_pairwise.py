@@ -1,4 +1,4 @@
-"""RankNet training loop ``factorized_training_loop`` / 'sum_session' (train/train_pairwise.py:81-173).
+"""RankNet training loop ``factorized_training_loop``, 'sum_session' and 'accelerate_grad' (train/train_pairwise.py:81-173).
 
 The reference evaluates one reactant group per forward, keeps every group's autograd graph alive until the accumulated
 candidate count reaches ``batch_size``, then divides the summed pairwise cost by the window's ordered-pair count and
@@ -17,7 +17,7 @@ from ..features.featurization import DeviceGraph
 from .loss import count_ordered_pairs, ranknet_window_loss
 
 
-def _run_window(model, window, pairs, optimizer, gpu, sigma):
+def _run_window(model, window, pairs, optimizer, gpu, sigma, training_algo='sum_session'):
     dev = torch.device("cuda", gpu)
     rg = DeviceGraph.from_batches([w[0] for w in window], dev)
     pg = DeviceGraph.from_batches([w[1] for w in window], dev)
@@ -27,7 +27,7 @@ def _run_window(model, window, pairs, optimizer, gpu, sigma):
         feats = np.concatenate([np.asarray(w[3], dtype=np.float64).reshape(len(w[2]), -1) for w in window], axis=0)
     scope = [len(w[2]) for w in window]
     y = model(rg, pg, gpu=gpu, add_features=feats)
-    loss = ranknet_window_loss(y, scope, targets, pairs, sigma=sigma, gpu=gpu)
+    loss = ranknet_window_loss(y, scope, targets, pairs, sigma=sigma, gpu=gpu, training_algo=training_algo)
     loss.backward()
     optimizer.step()
     model.zero_grad()
@@ -36,9 +36,7 @@ def _run_window(model, window, pairs, optimizer, gpu, sigma):
 
 def factorized_training_loop(epoch, model, loss_func, optimizer, scheduler, smiles2graph_dic, train_data_processor, batch_size=2, sigma=1.0,
                              training_algo='sum_session', gpu=None, smiles_list=None, target_name: str = 'ea', add_features_name=None):
-    if training_algo != 'sum_session':
-        if training_algo == 'accelerate_grad':
-            raise NotImplementedError("'accelerate_grad' is not reachable from main_ranknet.py's defaults (SURVEY.md §2 row 9)")
+    if training_algo not in ('sum_session', 'accelerate_grad'):
         raise ValueError("training algo {} not implemented".format(training_algo))
     gpu = _lib.require_device(gpu)
     minibatch_loss = []
@@ -55,13 +53,13 @@ def factorized_training_loop(epoch, model, loss_func, optimizer, scheduler, smil
         pairs += n_pairs
         count += len(Y)
         if count >= batch_size:                         # train_pairwise.py:146-160
-            loss = _run_window(model, window, pairs, optimizer, gpu, sigma)
+            loss = _run_window(model, window, pairs, optimizer, gpu, sigma, training_algo)
             scheduler.step()
             minibatch_loss.append(loss)
             window, pairs, count = [], 0.0, 0
     if pairs:                                           # tail flush, no scheduler.step() (train_pairwise.py:162-171)
         print('+' * 10, "End of batch, remaining pairs {}".format(pairs))
-        minibatch_loss.append(_run_window(model, window, pairs, optimizer, gpu, sigma))
+        minibatch_loss.append(_run_window(model, window, pairs, optimizer, gpu, sigma, training_algo))
     return float(np.mean([float(l.detach()) for l in minibatch_loss])) if minibatch_loss else float('nan')
 
 

@@ -53,6 +53,13 @@ COMPOSITE = {
     "regression_exploss": (1, "with_softplus", None),
     "mledis_gaussian": (2, "with_softplus", None),
     "listnetdis_gauss": (2, "with_softplus", None),
+    "listnet_uq": (1, "with_softplus", "listnet"),          # positive scores: build_model -> 'listnet_with_softplus' head
+    "listnetdis_lognorm": (2, "with_softplus", "listnetdis_lognorm"),
+    "dirichlet_uq": (1, "with_uncertainty", "listnet"),     # -> 'listnet_with_uncertainty' head: softplus + 1
+    "evidential": (4, "with_softplus", None),               # -> 'evidential_with_softplus': the NIG head
+    "mle_evidential": (4, "with_softplus", None),
+    "mledis_evidential": (4, "with_softplus", None),
+    "listnet_evidential": (4, "with_softplus", None),
 }
 TASKS_ALL = dict(TASKS, **COMPOSITE)
 
@@ -81,6 +88,24 @@ def ref_loss(task, out, scope, targets):
         mu = out[:, [j for j in range(len(out[0])) if j % 2 == 0]]
         variance = torch.exp(out[:, [j for j in range(len(out[0])) if j % 2 == 1]])
         return L.MLEDisLoss()(mu, variance, scope, targets, None) + L.GaussDisLoss()(out[:, 0], out[:, 1], targets, None)
+    if task == "listnet_uq":              # 228-229, in the middle of the annealing schedule
+        return L.Listnet_with_uq()(out, scope, targets, 0.05, 3, 5, None)
+    if task == "listnetdis_lognorm":      # 215-219 (Lognorm prints its value; silenced by the caller)
+        return L.Lognorm()(out[:, 0], out[:, 1], targets, None)
+    if task == "dirichlet_uq":            # 269-270
+        return L.Dirichlet_uq()(out, scope, targets, 0.05, 3, 5, None)
+    if task in ("evidential", "mle_evidential", "mledis_evidential", "listnet_evidential"):     # 229-260, slices exactly as written there
+        mu = out[:, [j for j in range(len(out[0])) if j % 4 == 0]]
+        lambdas = out[:, [j for j in range(len(out[0])) if j % 4 == 1]]
+        alphas = out[:, [j for j in range(len(out[0])) if j % 4 == 2]]
+        betas = out[:, [j for j in range(len(out[0])) if j % 4 == 3]]
+        if task == "evidential":
+            return L.evidential_loss_new(mu, lambdas, alphas, betas, targets, None, lam=0.1)
+        if task == "mle_evidential":
+            return L.MLEloss()(out[:, 0], scope, targets, None) + L.evidential_loss_new(mu, lambdas, alphas, betas, targets, None, lam=0.2)
+        variance = betas / (lambdas * (alphas - 1))
+        rank = L.MLEDisLoss() if task == "mledis_evidential" else L.Listnet_For_Gauss()     # 138-139, 144-145
+        return rank(mu, variance, scope, targets, None) + L.evidential_loss_new(mu, lambdas, alphas, betas, targets, None, lam=0.1)
     if task == "listnetdis_gauss":        # 211-215
         mu = out[:, [j for j in range(len(out[0])) if j % 2 == 0]]
         variance = out[:, [j for j in range(len(out[0])) if j % 2 == 1]]
@@ -172,13 +197,17 @@ def run_case(task, hidden, seed, sizes, star, dtype, depth=3, diff_depth=3):
         # mpn.py:183 casts add_features with FloatTensor (fp32); lift the result to fp64
         orig = torch.FloatTensor
         torch.FloatTensor = lambda x: torch.tensor(np.asarray(x, np.float32), dtype=torch.float64)  # type: ignore
+    import contextlib
+    import io
     try:
-        out = model(r_g, p_g, gpu=None, add_features=feats)
+        with contextlib.redirect_stdout(io.StringIO()):            # base_model.py:90 prints the whole output of the lognorm head
+            out = model(r_g, p_g, gpu=None, add_features=feats)
     finally:
         if dtype == torch.float64:
             torch.FloatTensor = orig  # type: ignore
     targets = torch.tensor(ds.lgk.astype(np.float32)).to(dtype)     # train_listwise.py:187 FloatTensor(...).squeeze()
-    loss = ref_loss(task, out, list(sizes), targets)
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss = ref_loss(task, out, list(sizes), targets)
     model.zero_grad()
     loss.backward()
     grads = {k: p.grad.detach().numpy() for k, p in model.named_parameters() if p.grad is not None}
@@ -256,6 +285,7 @@ def golden_ranknet():
         model.train()
         start, loss, pairs = 0, 0, 0
         scores = []
+        acc_loss, grad_batch, y_pred_batch = 0, [], []       # 'accelerate_grad' state of the same window (train_pairwise.py:86, 123-137)
         for n in sizes:
             rows = slice(start, start + n)
             start += n
@@ -280,6 +310,20 @@ def golden_ranknet():
             C = pos * torch.log(1 + torch.exp(-(y - y.t()))) + neg * torch.log(1 + torch.exp(y - y.t()))
             loss = loss + torch.sum(C, (0, 1))
             pairs += 2 * float(pos.sum())
+            y_pred_batch.append(y)
+            with torch.no_grad():                     # lines 125-137 with sigma = 1
+                l_pos = 1 + torch.exp(y - y.t())
+                l_neg = 1 + torch.exp(-(y - y.t()))
+                lam = -pos / l_pos + neg / l_neg
+                acc_loss = acc_loss + torch.sum(torch.log(l_neg) * pos + torch.log(l_pos) * neg, (0, 1))
+                grad_batch.append(torch.sum(lam, dim=1, keepdim=True))
+        model.zero_grad()
+        for grad, y_pred in zip(grad_batch, y_pred_batch):   # line 151-152
+            y_pred.backward(grad / pairs, retain_graph=True)
+        out[f"acc.{tag}.loss"] = (acc_loss / pairs).numpy()
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                out[f"acc.{tag}.grad.{k}"] = p.grad.numpy().copy()
         loss = loss / pairs
         model.zero_grad()
         loss.backward()

@@ -33,7 +33,7 @@ def rand(rows, hp, h, seed):
 
 
 def close(got, want, tol=2e-6):
-    got, want = got.double().cpu(), want.double().cpu()
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
     scale = max(float(want.abs().max()), 1e-30)
     err = float((got - want).abs().max()) / scale
     assert err < tol, err
@@ -566,3 +566,117 @@ def test_distribution_valued_losses_match_the_reference_form(which, scope):
     _lib.check(L.rr_loss_fwdbwd(kind, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), norm, 1.0, loss.data_ptr(), ds_.data_ptr(), S()))
     close(loss, want.detach().reshape(1), 3e-6)
     close(ds_, wgrad, 2e-5)
+
+
+@pytest.mark.parametrize("coef", [0.0, 0.0216, 0.5])
+@pytest.mark.parametrize("scope", [[5, 3, 6], [1, 2, 1], [32] * 8, [50, 100, 200]])
+def test_listnet_uq_matches_the_reference_form(coef, scope):
+    """RR_LOSS_LISTNET_UQ (annealing coefficient through `sigma`) against the oracle's restatement of Listnet_with_uq (loss.py:355-399),
+    scores on both sides of 1 so that the |.| penalty changes sign inside a group."""
+    L = _lib.lib()
+    N, G = sum(scope), len(scope)
+    g = torch.Generator().manual_seed(N)
+    s = torch.nn.functional.softplus(torch.randn(N, generator=g) * 1.5) + 1e-2
+    t = torch.randn(N, generator=g)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+    sx = s.double().requires_grad_(True)
+    want = O.listnet_uq_loss(sx, scope, t.double(), coef, 1, 2)          # (epoch / (epochs - 1)) ** 3 = 1
+    want.backward(torch.ones_like(want))
+    sd, td = s.to(DEV), t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(sd, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_LISTNET_UQ, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), float(G), coef, loss.data_ptr(),
+                                ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 3e-6)
+    close(ds_, sx.grad, 2e-5)
+
+
+@pytest.mark.parametrize("coef", [0.0, 0.0216])
+@pytest.mark.parametrize("scope", [[5, 3, 6], [1, 2, 1], [32] * 8, [50, 100, 200]])
+def test_dirichlet_uq_matches_the_reference_form(coef, scope):
+    """RR_LOSS_DIRICHLET_UQ against the oracle's restatement of Dirichlet_uq (loss.py:440-474), concentrations on both sides of 1."""
+    L = _lib.lib()
+    N, G = sum(scope), len(scope)
+    g = torch.Generator().manual_seed(N + 1)
+    a = torch.nn.functional.softplus(torch.randn(N, generator=g) * 1.5) + 1e-2
+    t = torch.randn(N, generator=g)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+    ax = a.double().requires_grad_(True)
+    want = O.dirichlet_uq_loss(ax, scope, t.double(), coef, 1, 2)
+    want.backward(torch.ones_like(want))
+    ad, td = a.to(DEV), t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(ad, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_DIRICHLET_UQ, N, G, ad.data_ptr(), td.data_ptr(), seg.data_ptr(), float(G), coef, loss.data_ptr(),
+                                ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 3e-6)
+    close(ds_, ax.grad, 2e-5)
+
+
+@pytest.mark.parametrize("N", [1, 14, 128, 513, 1500])
+@pytest.mark.parametrize("lam", [0.1, 0.2])
+def test_nig_all_pairs_matches_the_reference_broadcast(N, lam):
+    """RR_LOSS_NIG against evidential_loss_new evaluated with the shapes of its call sites ([N,1] parameters, [N] targets -> [N,N]),
+    across row-block and column-tile boundaries (128 / 512)."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(N)
+    sp = torch.nn.functional.softplus
+    mu = torch.randn(N, 1, generator=g)
+    v = sp(torch.randn(N, 1, generator=g)) + 1e-6
+    al = sp(torch.randn(N, 1, generator=g) * 2) + 1 + 1e-6
+    be = sp(torch.randn(N, 1, generator=g)) + 1e-6
+    t = torch.randn(N, generator=g)
+    xs = [x.double().requires_grad_(True) for x in (mu, v, al, be)]
+    want = O.nig_loss(*xs, t.double(), lam=lam)
+    want.backward()
+    sd = torch.cat((mu, v, al, be), 1).contiguous().to(DEV)
+    td = t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(sd, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_NIG, N, 0, sd.data_ptr(), td.data_ptr(), None, float(N) * float(N), lam, loss.data_ptr(),
+                                ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 5e-6)
+    close(ds_, torch.cat([x.grad for x in xs], 1), 2e-5)
+
+
+@pytest.mark.parametrize("N", [1, 14, 5000])
+def test_lognorm_matches_the_reference_form(N):
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(N)
+    sp = torch.nn.functional.softplus
+    m, v, t = sp(torch.randn(N, generator=g)) + 1e-6, sp(torch.randn(N, generator=g)) + 1e-6, torch.randn(N, generator=g)
+    mx, vx = m.double().requires_grad_(True), v.double().requires_grad_(True)
+    want = O.lognorm_loss(mx, vx, t.double())
+    want.backward()
+    sd, td = torch.stack((m, v), 1).contiguous().to(DEV), t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(sd, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_LOGNORM, N, 0, sd.data_ptr(), td.data_ptr(), None, float(N), 1.0, loss.data_ptr(), ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 3e-6)
+    close(ds_, torch.stack((mx.grad, vx.grad), 1), 2e-5)
+
+
+@pytest.mark.parametrize("task_type,last,task", [("listnetdis_lognorm", "with_softplus", 2), ("listnetdis_lognorm", "with_softplus", 6),
+                                                 ("listnet", "with_uncertainty", 1), ("evidential", "with_softplus", 4),
+                                                 ("evidential", "with_softplus", 8)])
+def test_new_heads_against_the_oracle(task_type, last, task):
+    """The FFN heads of base_model.py:61-70, 83-90, 101-104 through the whole model, also on wider-than-minimal task_num
+    (the stack(..., dim=2).view interleave), forward and backward with a random upstream gradient."""
+    from helpers import grads_close
+    from reactranker_b200.models.base_model import build_model
+    ds = synthetic.make_dataset(5, [4, 3])
+    torch.manual_seed(task)
+    model = build_model(hidden_size=24, mpnn_depth=2, mpnn_diff_depth=2, ffn_depth=2, use_bias=True, dropout=0.0, task_num=task,
+                        ffn_last_layer=last, task_type=task_type, add_features_dim=1).cuda(0)
+    sd64 = {k: v.double().cpu() for k, v in model.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if "cached_zero" not in k}
+    full = dict(sd64)
+    full.update(params)
+    r_g, p_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi]), O.OracleBatch([ds.mols[t] for t in ds.psmi])
+    want = O.model_forward(full, r_g, p_g, ds.temp.reshape(-1, 1), mpnn_depth=2, mpnn_diff_depth=2, ffn_depth=2,
+                           head=O.resolve_task_type(task, last, task_type))
+    got = model(BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi]), gpu=0,
+                add_features=ds.temp.reshape(-1, 1))
+    assert tuple(got.shape) == tuple(want.shape)
+    close(got, want.detach(), 2e-5)
+    w = torch.randn(got.shape, generator=torch.Generator().manual_seed(1))
+    (want * w.double()).sum().backward()
+    (got * w.to(got.device)).sum().backward()
+    got_g = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+    assert not grads_close(got_g, {k: params[k].grad.numpy() for k in got_g}, 2e-4)

@@ -22,16 +22,21 @@ GPU = 0
 TASKS = {"mle": (1, None), "listnet": (1, None), "evidential_ranking": (2, "evidential_ranking"),
          "gauss_regression": (2, None), "regression": (1, None),
          "mle_gaussian": (2, None), "listnet_gauss": (2, None), "mle_regression": (1, None), "listnet_regression": (1, None),
-         "regression_exploss": (1, None), "mledis_gaussian": (2, None), "listnetdis_gauss": (2, None)}
+         "regression_exploss": (1, None), "mledis_gaussian": (2, None), "listnetdis_gauss": (2, None),
+        "listnet_uq": (1, "listnet"), "listnetdis_lognorm": (2, "listnetdis_lognorm"), "dirichlet_uq": (1, "listnet", "with_uncertainty"),
+        "evidential": (4, None), "mle_evidential": (4, None), "mledis_evidential": (4, None), "listnet_evidential": (4, None)}
 
 
 def product_loss(task, out, scope, targets, gpu=GPU):
     from reactranker_b200.train.train_listwise import batch_loss
+    if task in ("listnet_uq", "dirichlet_uq"):   # the golden's point on the annealing schedule (scripts/make_golden.py)
+        return batch_loss(task, out, scope, targets, gpu, 0.05, 3, 5)
     return batch_loss(task, out, scope, targets, gpu)
 
 
 def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_softplus"):
-    tn, tt = TASKS[task]
+    tn, tt, *ll = TASKS[task]
+    last = ll[0] if ll else last
     m = build_model(hidden_size=hidden, mpnn_depth=depth, mpnn_diff_depth=ddepth, ffn_depth=3, use_bias=True, dropout=dropout,
                     task_num=tn, ffn_last_layer=last, task_type=tt, add_features_dim=1)
     if sd is not None:
@@ -42,7 +47,8 @@ def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_sof
 CASES = ["mle.h40", "listnet.h40", "evidential_ranking.h40", "gauss_regression.h40", "regression.h40", "mle.star.h40",
          "evidential_ranking.h24d5"]
 COMPOSITE = ["mle_gaussian.h40", "listnet_gauss.h40", "mle_regression.h40", "listnet_regression.h40", "regression_exploss.h40",
-             "mledis_gaussian.h40", "listnetdis_gauss.h40"]
+             "mledis_gaussian.h40", "listnetdis_gauss.h40", "listnet_uq.h40", "listnetdis_lognorm.h40", "dirichlet_uq.h40", "evidential.h40",
+             "mle_evidential.h40", "mledis_evidential.h40", "listnet_evidential.h40"]
 
 
 @pytest.mark.parametrize("name", CASES + COMPOSITE)
@@ -98,8 +104,9 @@ def test_h300_against_reference_golden(golden):
             assert abs(got[1] - s[1]) <= 2e-4 * s[1] and abs(got[2] - s[2]) <= 4e-4 * s[2], k
 
 
-def test_ranknet_window_vs_reference_golden(golden):
-    """One accumulation window of factorized_training_loop (train_pairwise.py:81-160): every group keeps its
+@pytest.mark.parametrize("algo,pre", [("sum_session", ""), ("accelerate_grad", "acc.")])
+def test_ranknet_window_vs_reference_golden(golden, algo, pre):
+    """One accumulation window of factorized_training_loop (train_pairwise.py:81-160), both training_algo values: every group keeps its
     OWN max_num_bonds (one reference forward per group) but all groups share one launch here."""
     g = golden("ranknet")
     sizes = [int(x) for x in g["sizes"]]
@@ -118,12 +125,12 @@ def test_ranknet_window_vs_reference_golden(golden):
     y = model(rg, pg, gpu=GPU, add_features=ds.lgk.reshape(-1, 1))       # the target-column leak (load_reactions.py:264-267)
     pairs = sum(RL.count_ordered_pairs(ds.lgk[a:a + n]) for a, n in zip(np.cumsum([0] + sizes[:-1]), sizes))
     assert pairs == float(g["f64.pairs"])
-    loss = RL.ranknet_window_loss(y, sizes, ds.lgk.astype(np.float32), pairs, sigma=1.0, gpu=GPU)
+    loss = RL.ranknet_window_loss(y, sizes, ds.lgk.astype(np.float32), pairs, sigma=1.0, gpu=GPU, training_algo=algo)
     loss.backward()
     assert rel_err(y.detach().cpu().numpy(), g["f64.scores"]) < 2e-5
-    assert rel_err(loss.detach().cpu().numpy(), g["f64.loss"]) < 2e-5
+    assert rel_err(loss.detach().cpu().numpy(), g[pre + "f64.loss"]) < 2e-5
     got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
-    assert not grads_close(got, {k: g[f"f64.grad.{k}"] for k in got}, 2e-4)
+    assert not grads_close(got, {k: g[f"{pre}f64.grad.{k}"] for k in got}, 2e-4)
 
 
 def test_three_optimizer_steps_vs_reference_golden(golden):

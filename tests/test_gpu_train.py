@@ -18,7 +18,8 @@ def run(cmd, timeout=600):
     return res.stdout
 
 
-@pytest.mark.parametrize("task", ["mle", "listnet", "evidential_ranking", "gauss_regression", "regression"])
+@pytest.mark.parametrize("task", ["mle", "listnet", "evidential_ranking", "gauss_regression", "regression",
+                                  "mledis_gaussian", "listnet_uq", "dirichlet_uq", "listnetdis_lognorm", "evidential", "mledis_evidential"])
 def test_main_trains_every_task_key(tmp_path, task):
     out = run(["main.py", "--synthetic", "40,10", "--path", str(tmp_path), "--gpu", "0", "--task_type", task, "--batch_size", "100",
                "--total_epochs", "3", "--hidden_size", "64", "--max_lr", "3e-3"])
