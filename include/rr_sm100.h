@@ -234,6 +234,17 @@ int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* tar
 /* largest group the segmented kernels accept */
 int rr_loss_max_group(void);
 
+/* Per-group ranking metrics of the validation pass, replacing the host loops of eval.py:475-555 (ranking_metrics) and 76-177
+   (evaluate_top_scores): scores stay on the device, RR_METRIC_COLS doubles per group come back.
+     scores  [N * score_ld] fp32, the ranking score of item i at scores[i * score_ld] (score_ld = task_num picks column 0 of a [N, task] output)
+     targets [N] fp64 (the DataFrame column as is, so ties and order are the reference's), seg_off [G + 1], max_group <= 8192
+     ratio   the top fraction (0.25 everywhere in the reference): K = max(1, round-half-even(n * ratio)), Python's round()
+   out [G, 8]: 0 predicted top-1 == true top-1 | 1 |pred top-K n true top-K| / K | 2 predicted top-1 in true top-K | 3 true top-1 in predicted
+   top-K | 4 NDCG@1 | 5 NDCG@2 as eval.py:544 computes it | 6 NDCG@K | 7 NDCG@all.  Stable descending order (ties keep the earlier item). */
+#define RR_METRIC_COLS 8
+int rr_rank_metrics(int N, int G, const float* scores, int score_ld, const double* targets, const int32_t* seg_off, int max_group,
+                    double ratio, double* out, void* stream);
+
 /* ---- whole model (models/base_model.py:150-171) ---------------------------------------- */
 /* bytes of workspace rr_model_forward/backward need for these sizes */
 int64_t rr_model_workspace_bytes(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p);

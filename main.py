@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--max_lr", type=float, default=1e-3)
     ap.add_argument("--final_lr", type=float, default=1e-4)
     ap.add_argument("--save_metric", default="all")
+    ap.add_argument("--resume", action="store_true", help="write <path>/<fold>.state.pt after every epoch and continue from it if present")
+    ap.add_argument("--stop_after", type=int, default=None, help="stop after this many epochs (the schedule still spans --total_epochs)")
     ap.add_argument("--hidden_size", type=int, default=300)
     ap.add_argument("--depth", type=int, default=3)
     ap.add_argument("--dropout", type=float, default=0.1)
@@ -137,9 +139,10 @@ def main():
         optimizer = build_optimizer(model)
         scheduler = build_lr_scheduler(optimizer, warmup_epochs=2, total_epochs=total_epochs, train_data_size=train_len, batch_size=batch_size,
                                        init_lr=init_lr, max_lr=max_lr, final_lr=final_lr)
-        train(model, scheduler, train_data, val_data, path_checkpoints, optimizer, total_epochs, smiles2graph_dic, batch_size=batch_size, seed=seed,
-              gpu=gpu, task_type=task_type, writer=writer, logger=logger, target_name=target_name, smiles_list=smiles_list,
-              save_metric=save_metric, add_features_name=add_features_name)
+        resume_path = os.path.join(a.path, str(ii) + '.state.pt') if a.resume else None
+        train(model, scheduler, train_data, val_data, path_checkpoints, optimizer, a.stop_after or total_epochs, smiles2graph_dic,
+              batch_size=batch_size, seed=seed, gpu=gpu, task_type=task_type, writer=writer, logger=logger, target_name=target_name,
+              smiles_list=smiles_list, save_metric=save_metric, add_features_name=add_features_name, resume_path=resume_path)
         print(path_checkpoints)
         test_path = path_checkpoints[0] if save_metric == 'all' else path_checkpoints
         score, average_pred_in_targ, score3 = test(model, test_data, test_path, batch_size, smiles2graph_dic, gpu=gpu, smiles_list=smiles_list,

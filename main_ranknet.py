@@ -33,6 +33,8 @@ def parse():
     ap.add_argument("--max_lr", type=float, default=1e-3)
     ap.add_argument("--final_lr", type=float, default=1e-4)
     ap.add_argument("--save_metric", default="all")
+    ap.add_argument("--train_strategy", default="sum_session", choices=["sum_session", "accelerate_grad"])
+    ap.add_argument("--resume", action="store_true", help="write <path>/<fold>.state.pt after every epoch and continue from it if present")
     return ap.parse_args()
 
 
@@ -57,7 +59,7 @@ def main():
     data.filter_bacth(filter_szie=a.filter_size)
     k_fold, gpu = a.k_fold, a.gpu
     test_score = []
-    train_strategy = 'sum_session'
+    train_strategy = a.train_strategy          # main_ranknet.py:62 hard-codes 'sum_session'
     batch_size, total_epochs = a.batch_size, a.total_epochs
     target_name = a.target_name
     smiles_list = ['rsmi_mapped', 'psmi_mapped']
@@ -88,7 +90,8 @@ def main():
                                        init_lr=init_lr, max_lr=max_lr, final_lr=final_lr)
         run_train(model, scheduler, train_data, val_data, path_checkpoints, optimizer, total_epochs, smiles2graph_dic, batch_size=batch_size,
                   seed=seed, gpu=gpu, train_strategy=train_strategy, task_type='baseline', writer=None, logger=logger, smiles_list=smiles_list,
-                  target_name=target_name, save_metric=save_metric, add_features_name=add_features_name)
+                  target_name=target_name, save_metric=save_metric, add_features_name=add_features_name,
+                  resume_path=os.path.join(a.path, str(ii) + '.state.pt') if a.resume else None)
         test_path = path_checkpoints[0] if save_metric == 'all' else path_checkpoints
         score, score3, average_pred_in_targ = test(model, test_data, test_path, smiles2graph_dic, batch_size, gpu=gpu, logger=logger,
                                                    smiles_list=smiles_list, add_features_name=add_features_name, target_name=target_name,

@@ -535,3 +535,38 @@ def init_state_dict(hidden: int, task_num: int, add_features_dim: int, use_bias:
     lin("ffn.ffn.4", hidden, hidden, use_bias)
     lin("ffn.ffn.7", hidden, task_num, use_bias)
     return sd
+
+
+# ----------------------------------------------------------------------------------------
+# validation metrics  (train/eval.py)
+# ----------------------------------------------------------------------------------------
+def _desc_order(x):
+    """``sorted(enumerate(x), key=lambda t: t[1], reverse=True)`` indices (eval.py:500-503): stable, ties keep the earlier item."""
+    return np.argsort(-np.asarray(x, dtype=np.float64), kind="stable")
+
+
+def _ndcg(truth, pred):
+    """compute_NDCG (eval.py:460-472)."""
+    truth, pred = np.asarray(truth, dtype=np.float64), np.asarray(pred, dtype=np.float64)
+    disc = np.log2(np.arange(2, len(truth) + 2))
+    return float(np.sum(np.exp(pred) / disc) / np.sum(np.exp(truth) / disc))
+
+
+def group_metrics(pred, targ, ratio: float = 0.25) -> np.ndarray:
+    """The eight per-group numbers behind ``ranking_metrics`` (eval.py:497-553) and ``evaluate_top_scores`` (eval.py:112-165), host
+    restatement with Python's ``round`` and stable sorts; column order of include/rr_sm100.h ``rr_rank_metrics``."""
+    pred, targ = np.asarray(pred, dtype=np.float64), np.asarray(targ, dtype=np.float64)
+    n = len(targ)
+    p_idx, t_idx = _desc_order(pred), _desc_order(targ)
+    k = max(1, round(n * ratio))
+    p_k, t_k = p_idx[:k].tolist(), set(t_idx[:k].tolist())
+    t_sorted, by_pred = targ[t_idx], targ[p_idx]
+    return np.asarray([
+        float(p_idx[0] == t_idx[0]),
+        sum(int(i in t_k) for i in p_k) / k,
+        float(p_idx[0] in t_k),
+        float(int(np.argmax(targ)) in set(p_k)),
+        _ndcg(t_sorted[:1], by_pred[:1]),
+        float(np.sum(np.exp(by_pred[:2])) / np.sum(np.exp(t_sorted[:2]))),     # eval.py:544 wraps both items in one list position
+        _ndcg(t_sorted[:k], by_pred[:k]),
+        _ndcg(t_sorted, by_pred)], dtype=np.float64)

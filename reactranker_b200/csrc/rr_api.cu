@@ -99,6 +99,10 @@ int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* tar
   return rr::loss_fwdbwd(kind, N, G, scores, targets, seg_off, norm, sigma, loss, dscore, S(stream));
 }
 int rr_loss_max_group(void) { return rr::loss_max_group(); }
+int rr_rank_metrics(int N, int G, const float* scores, int score_ld, const double* targets, const int32_t* seg_off, int max_group, double ratio,
+                    double* out, void* stream) {
+  return rr::rank_metrics(N, G, scores, score_ld, targets, seg_off, max_group, ratio, out, S(stream));
+}
 
 int64_t rr_model_workspace_bytes(const rr_model_cfg* cfg, const rr_graph* r, const rr_graph* p) {
   if (!cfg || !r || !p) {

@@ -207,6 +207,7 @@ int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, in
 int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
 int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
 int loss_max_group();
+int rank_metrics(int, int, const float*, int, const double*, const int*, int, double, double*, cudaStream_t);
 int graph_assemble(const rr_mol_store*, int, const int*, const int*, const int*, const int*, const int*, const int*, int, const int*, const int*,
                    const int*, const rr_graph*, cudaStream_t);
 long long model_workspace_bytes(const rr_model_cfg*, const rr_graph*, const rr_graph*);

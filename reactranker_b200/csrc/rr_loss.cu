@@ -10,6 +10,7 @@ namespace rr {
 
 constexpr int kLossThreads = 256;
 constexpr int kMaxGroup = 2048;
+constexpr int kMaxMetricGroup = 8192;   // 128 KB of shared doubles
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -532,5 +533,112 @@ int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* target
 }
 
 int loss_max_group() { return kMaxGroup; }
+
+// ---------------------------------------------------------------------------------------
+// Per-group ranking metrics of the validation pass (eval.py:475-555 ranking_metrics, 76-177 evaluate_top_scores), one CTA per group:
+// the reference pulls every group's scores to the host and sorts them in Python; here the scores never leave the device, only
+// RR_METRIC_COLS doubles per group do.  Orders are the reference's stable descending sorts (ties keep the earlier item), expressed
+// as ranks:  rank(i) = #{j : x_j > x_i} + #{j < i : x_j == x_i}.  With K = max(1, round_half_even(n * ratio)):
+//   [0] predicted top-1 is the true top-1                    [1] |pred top-K  n  true top-K| / K
+//   [2] predicted top-1 is inside the true top-K              [3] true top-1 is inside the predicted top-K
+//   [4] NDCG@1   [5] the reference's NDCG@2 (both gains at one position, eval.py:544)   [6] NDCG@K   [7] NDCG@all
+// NDCG = sum_k exp(target of the item predicted at k) / log2(k + 2)  over the ideal ordering's same sum (eval.py:460-472).
+// ---------------------------------------------------------------------------------------
+__device__ double block_sum_d(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(kLossThreads) k_rank_metrics(const float* __restrict__ scores, int score_ld, const double* __restrict__ targets,
+                                                               const int* __restrict__ seg, double ratio, double* __restrict__ out) {
+  extern __shared__ double sm_d[];
+  __shared__ double red[32];
+  const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
+  double* res = out + static_cast<size_t>(blockIdx.x) * RR_METRIC_COLS;
+  if (n <= 0) {
+    if (threadIdx.x < RR_METRIC_COLS) res[threadIdx.x] = 0.0;
+    return;
+  }
+  double* sc = sm_d;
+  double* tg = sm_d + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sc[i] = static_cast<double>(scores[static_cast<size_t>(o + i) * score_ld]);
+    tg[i] = targets[o + i];
+  }
+  __syncthreads();
+  const int K = max(1, static_cast<int>(rint(static_cast<double>(n) * ratio)));     // Python's round(): half to even
+  double a[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) a[q] = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double si = sc[i], ti = tg[i];
+    int pr = 0, tr = 0;
+    for (int j = 0; j < n; ++j) {
+      const double sj = sc[j], tj = tg[j];
+      pr += (sj > si) || (sj == si && j < i);
+      tr += (tj > ti) || (tj == ti && j < i);
+    }
+    const double e = exp(ti);
+    if (pr == 0) {
+      a[0] += tr == 0;
+      a[2] += tr < K;
+      a[4] += e;                                    // gain at predicted position 0
+    }
+    if (tr == 0) {
+      a[3] += pr < K;
+      a[5] += e;                                    // ideal gain at position 0
+    }
+    a[1] += (pr < K && tr < K);
+    if (pr < 2) a[6] += e;
+    if (tr < 2) a[7] += e;
+    const double dp = e / log2(static_cast<double>(pr) + 2.0), dt = e / log2(static_cast<double>(tr) + 2.0);
+    if (pr < K) a[8] += dp;
+    if (tr < K) a[9] += dt;
+    a[10] += dp;
+    a[11] += dt;
+  }
+#pragma unroll
+  for (int q = 0; q < 12; ++q) a[q] = block_sum_d(a[q], red);
+  if (threadIdx.x == 0) {
+    res[0] = a[0];
+    res[1] = a[1] / static_cast<double>(K);
+    res[2] = a[2];
+    res[3] = a[3];
+    res[4] = a[4] / a[5];
+    res[5] = a[6] / a[7];
+    res[6] = a[8] / a[9];
+    res[7] = a[10] / a[11];
+  }
+}
+
+int rank_metrics(int N, int G, const float* scores, int score_ld, const double* targets, const int* seg_off, int max_group, double ratio,
+                 double* out, cudaStream_t s) {
+  ProfScope prof_scope(KC_LOSS, s);
+  RR_REQUIRE(N > 0 && G > 0 && scores && targets && seg_off && out, "rank_metrics: NULL argument or empty input");
+  RR_REQUIRE(score_ld >= 1, "rank_metrics: score_ld must be >= 1");
+  RR_REQUIRE(ratio > 0.0 && ratio <= 1.0, "rank_metrics: ratio must lie in (0, 1] (got %g)", ratio);
+  RR_REQUIRE(max_group >= 1 && max_group <= kMaxMetricGroup, "rank_metrics: largest group %d outside [1, %d]", max_group, kMaxMetricGroup);
+  const size_t smem = 2 * sizeof(double) * static_cast<size_t>(max_group);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(cudaFuncSetAttribute(k_rank_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(double) * kMaxMetricGroup));
+    attr_set = true;
+  }
+  k_rank_metrics<<<G, kLossThreads, smem, s>>>(scores, score_ld, targets, seg_off, ratio, out);
+  RR_LAUNCH_CHECK("rank_metrics kernel");
+  return RR_OK;
+}
 
 }  // namespace rr

@@ -9,82 +9,89 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import _lib
 from ..features.featurization import DeviceGraph
+from .loss import segment_offsets
 
 GROUPS_PER_LAUNCH = 256
 
 
-def _scores_per_group(model, gpu, groups, smiles2graph_dic):
-    """groups: list of (smiles [n,2], add_features | None).  Returns a list of 1-D numpy score arrays."""
-    out = []
+def _forward_chunks(model, gpu, chunks, smiles2graph_dic):
+    """chunks: list of (smiles [n,2], add_features | None); every chunk becomes ONE segment of the DeviceGraph (its own padding rows and
+    ``max_num_bonds``, exactly as if it had been the reference's whole BatchMolGraph).  Yields ``(lo, hi, preds)`` with the scores of
+    chunks[lo:hi] on the device, rows in chunk order."""
     dev = torch.device("cuda", gpu) if isinstance(gpu, int) else torch.device(gpu)
-    for lo in range(0, len(groups), GROUPS_PER_LAUNCH):
-        chunk = groups[lo:lo + GROUPS_PER_LAUNCH]
-        r_b = [smiles2graph_dic.parsing_smiles([s[0] for s in X]) for X, _ in chunk]
-        p_b = [smiles2graph_dic.parsing_smiles([s[1] for s in X]) for X, _ in chunk]
+    for lo in range(0, len(chunks), GROUPS_PER_LAUNCH):
+        part = chunks[lo:lo + GROUPS_PER_LAUNCH]
+        r_b = [smiles2graph_dic.parsing_smiles([s[0] for s in X]) for X, _ in part]
+        p_b = [smiles2graph_dic.parsing_smiles([s[1] for s in X]) for X, _ in part]
         feats = None
-        if chunk[0][1] is not None:
-            feats = np.concatenate([np.asarray(f, dtype=np.float64).reshape(len(X), -1) for X, f in chunk], axis=0)
+        if part[0][1] is not None:
+            feats = np.concatenate([np.asarray(f, dtype=np.float64).reshape(len(X), -1) for X, f in part], axis=0)
         if getattr(model, "dedup_reactants", False) and not (model.training and getattr(model, "_dropout", 0) > 0):
             rg, pg = DeviceGraph.from_batches_dedup(r_b, p_b, dev)       # a group's candidates share one reactant graph
         else:
             rg, pg = DeviceGraph.from_batches(r_b, dev), DeviceGraph.from_batches(p_b, dev)
-        preds = model(rg, pg, gpu=gpu, add_features=feats)
-        preds = preds[:, 0] if preds.dim() > 1 else preds
-        flat = preds.detach().float().cpu().numpy()
-        o = 0
-        for X, _ in chunk:
-            out.append(flat[o:o + len(X)])
-            o += len(X)
-    return out
-
-
-def _desc_order(x):
-    """``sorted(enumerate(x), key=lambda t: t[1], reverse=True)`` indices (stable for ties)."""
-    x = np.asarray(x, dtype=np.float64)
-    return np.argsort(-x, kind="stable")
+        yield lo, lo + len(part), model(rg, pg, gpu=gpu, add_features=feats)
 
 
 def compute_NDCG(truth, pred):
-    """eval.py:460-472 (exponential gain, log2 discount)."""
+    """eval.py:460-472 (exponential gain, log2 discount) for two already-ordered host lists; kept for API parity, the validation
+    pass itself uses ``group_metrics``."""
     truth, pred = np.asarray(truth, dtype=np.float64), np.asarray(pred, dtype=np.float64)
-    length = len(truth)
-    disc = np.log2(np.arange(2, length + 2))
+    disc = np.log2(np.arange(2, len(truth) + 2))
     return float(np.sum(np.exp(pred) / disc) / np.sum(np.exp(truth) / disc))
+
+
+def group_metrics(preds: torch.Tensor, scope, targets, ratio: float = 0.25) -> torch.Tensor:
+    """Per-group ranking metrics ON THE DEVICE (``rr_rank_metrics``): ``preds`` [N] or [N, k] (column 0 ranks), ``scope`` the group sizes,
+    ``targets`` the fp64 target column.  Returns a device tensor [G, 8]; columns as in include/rr_sm100.h.  Replaces the per-group host
+    sorts of eval.py:497-553 / 112-165; nothing but 8 doubles per group ever crosses PCIe."""
+    if not preds.is_cuda:
+        raise _lib.RRError("group_metrics: scores must be on the GPU (no CPU fallback)")
+    sc = preds.detach()
+    if sc.dtype != torch.float32:
+        sc = sc.float()
+    if sc.dim() > 2 or (sc.dim() == 2 and sc.stride(1) != 1) or (sc.dim() == 1 and sc.stride(0) != 1):
+        sc = sc.contiguous()
+    ld = sc.stride(0) if sc.dim() == 2 else 1
+    scope = [int(n) for n in scope]
+    N, G = sum(scope), len(scope)
+    if N != sc.shape[0]:
+        raise _lib.RRError(f"sum(scope)={N} does not match the {sc.shape[0]} scores")
+    t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64).reshape(-1))
+    if t.shape[0] != N:
+        raise _lib.RRError(f"{t.shape[0]} targets for {N} scores")
+    t_d = torch.from_numpy(t).pin_memory().to(sc.device, non_blocking=True)
+    seg = segment_offsets(scope, sc.device)
+    out = torch.empty(G, 8, dtype=torch.float64, device=sc.device)
+    with torch.cuda.device(sc.device):
+        _lib.check(_lib.lib().rr_rank_metrics(N, G, sc.data_ptr(), ld, t_d.data_ptr(), seg.data_ptr(), max(scope), float(ratio), out.data_ptr(),
+                                              _lib.stream_ptr()))
+    return out
 
 
 def ranking_metrics(model, gpu, data_processor, smiles2graph_dic, show_info=True, smiles_list=None, target_name: str = 'ea',
                     logger=None, add_features_name=None):
     """top-1 hit, recall@25 %, top-25 % hit, [NDCG@1, NDCG@2, NDCG@25 %, NDCG@all] (eval.py:475-555).  As in the
-    reference the groups come from ``generate_batch_per_query`` (so the extra feature is the target column, load_reactions.py:264)."""
+    reference the groups come from ``generate_batch_per_query`` (so the extra feature is the target column, load_reactions.py:264).
+    Up to GROUPS_PER_LAUNCH groups share a forward, the per-group metrics are computed on the device, and the host waits once."""
     was_training = model.training
     model.eval()
     groups, targets = [], []
     for X, t, feats in data_processor.generate_batch_per_query(smiles_list=smiles_list, target_name=target_name, shuffle_query=False,
                                                                 shuffle_batch=False, add_features_name=add_features_name):
         groups.append((X, feats))
-        targets.append(np.asarray(t, dtype=np.float64))
+        targets.append(np.asarray(t, dtype=np.float64).reshape(-1))
+    parts = []
     with torch.no_grad():
-        scores = _scores_per_group(model, gpu, groups, smiles2graph_dic)
-    top1 = top25 = 0
-    recall, ndcgs = [], []
-    for pred, targ in zip(scores, targets):
-        n = len(targ)
-        p_idx, t_idx = _desc_order(pred), _desc_order(targ)
-        t_sorted = targ[t_idx]
-        top1 += int(p_idx[0] == t_idx[0])
-        len25 = max(1, round(n * 0.25))
-        p25, t25 = p_idx[:len25], set(t_idx[:len25].tolist())
-        top25 += int(p25[0] in t25)
-        recall.append(sum(int(i in t25) for i in p25.tolist()) / len25)
-        by_pred = targ[p_idx]
-        # NDCG@2 in the reference wraps its two-item slices in a list (eval.py:544): one position, both gains summed
-        ndcg2 = float(np.sum(np.exp(by_pred[:2])) / np.sum(np.exp(t_sorted[:2])))
-        ndcgs.append([compute_NDCG(t_sorted[:1], by_pred[:1]), ndcg2, compute_NDCG(t_sorted[:len25], by_pred[:len25]),
-                      compute_NDCG(t_sorted, by_pred)])
+        for lo, hi, preds in _forward_chunks(model, gpu, groups, smiles2graph_dic):
+            parts.append(group_metrics(preds, [len(t) for t in targets[lo:hi]], np.concatenate(targets[lo:hi]), 0.25))
     model.train(was_training)
-    k = max(len(scores), 1)
-    return top1 / k, float(np.mean(recall)), top25 / k, np.mean(ndcgs, axis=0)
+    if not parts:
+        return 0.0, float('nan'), 0.0, np.full(4, np.nan)
+    m = torch.cat(parts).cpu().numpy()
+    return float(m[:, 0].mean()), float(m[:, 1].mean()), float(m[:, 2].mean()), m[:, 4:8].mean(axis=0)
 
 
 def evaluate_top_scores(model, gpu, data_processor, smiles2graph_dic, ratio=0.25, batch_size=2, show_info=False, smiles_list=None,
@@ -92,28 +99,19 @@ def evaluate_top_scores(model, gpu, data_processor, smiles2graph_dic, ratio=0.25
     """top-1 accuracy, mean overlap of predicted/true top-``ratio`` sets, true top-1 inside predicted top-``ratio``
     (eval.py:76-177).  Groups come from ``generate_batch_querys`` (real ``add_features_name`` column); in the reference
     ``batch_size`` groups share one BatchMolGraph and therefore one ``max_num_bonds`` -- reproduced by packing each
-    ``batch_size`` chunk as one segment."""
-    score, overlap, top1_in = [], [], []
+    ``batch_size`` chunk as one segment; many chunks share a launch and the metrics are computed on the device."""
+    chunks, scopes, targets = [], [], []
+    for X, t, scope, feats in data_processor.generate_batch_querys(smiles_list=smiles_list, target_name=target_name, batch_size=batch_size,
+                                                                   shuffle_query=False, shuffle_batch=False, add_features_name=add_features_name):
+        chunks.append((X, feats))
+        scopes.append([int(n) for n in scope])
+        targets.append(np.asarray(t, dtype=np.float64).reshape(-1))
+    parts = []
     with torch.no_grad():
-        for X, targets, scope, feats in data_processor.generate_batch_querys(smiles_list=smiles_list, target_name=target_name,
-                                                                              batch_size=batch_size, shuffle_query=False, shuffle_batch=False,
-                                                                              add_features_name=add_features_name):
-            r_b = smiles2graph_dic.parsing_smiles([s[0] for s in X])
-            p_b = smiles2graph_dic.parsing_smiles([s[1] for s in X])
-            preds = model(r_b, p_b, gpu=gpu, add_features=feats)
-            preds = (preds[:, 0] if preds.dim() > 1 else preds).detach().float().cpu().numpy()
-            targets = np.asarray(targets, dtype=np.float64).reshape(-1)
-            o = 0
-            for n in scope:
-                t, p = targets[o:o + n], preds[o:o + n]
-                o += n
-                t_idx, p_idx = _desc_order(t), _desc_order(p)
-                score.append(int(int(np.argmax(t)) == int(np.argmax(p))))
-                length = max(1, round(n * ratio))
-                tset = set(t_idx[:length].tolist())
-                overlap.append(sum(int(i in tset) for i in p_idx[:length].tolist()) / length)
-                top1_in.append(int(int(np.argmax(t)) in set(p_idx[:length].tolist())))
-    return sum(score) / len(score), sum(overlap) / len(overlap), sum(top1_in) / len(top1_in)
+        for lo, hi, preds in _forward_chunks(model, gpu, chunks, smiles2graph_dic):
+            parts.append(group_metrics(preds, [n for sc in scopes[lo:hi] for n in sc], np.concatenate(targets[lo:hi]), ratio))
+    m = torch.cat(parts).cpu().numpy()
+    return float(m[:, 0].mean()), float(m[:, 1].mean()), float(m[:, 3].mean())
 
 
 def calculate_ndcg(model, gpu, data_processor, smiles2graph_dic, batch_size=2, NDCG_cut=0.5, show_info=False, smiles_list=None,

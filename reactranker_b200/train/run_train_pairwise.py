@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import copy
+import os
 from logging import Logger
 
 import torch
@@ -13,7 +14,7 @@ from tqdm import trange
 
 from .. import _lib
 from ..data.load_reactions import DataProcessor
-from ..utils import save_checkpoint
+from ..utils import load_train_state, save_checkpoint, save_train_state
 from .eval import evaluate_top_scores
 from .train_pairwise import factorized_training_loop
 
@@ -25,9 +26,11 @@ except Exception:  # pragma: no cover
 
 def run_train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, val_data_ini: DataFrame, path_checkpoints: str, optimizer,
               epochs: int, smiles2graph_dic, batch_size: int, seed: int, gpu: int, train_strategy: str = 'baseline', task_type: str = 'baseline',
-              writer=SummaryWriter, logger: Logger = None, smiles_list=None, target_name: str = 'ea', save_metric=None, add_features_name=None):
-    if train_strategy not in ('sum_session',) or task_type != 'baseline':
-        raise NotImplementedError("only train_strategy='sum_session', task_type='baseline' (main_ranknet.py's defaults) is built")
+              writer=SummaryWriter, logger: Logger = None, smiles_list=None, target_name: str = 'ea', save_metric=None, add_features_name=None,
+              resume_path=None):
+    """``run_train`` of run_train_pairwise.py:20-110; ``resume_path`` as in train_listwise.train (None = the reference's behaviour)."""
+    if train_strategy not in ('sum_session', 'accelerate_grad') or task_type != 'baseline':
+        raise NotImplementedError("train_strategy 'sum_session' / 'accelerate_grad' with task_type='baseline' (main_ranknet.py's model) is built")
     gpu = _lib.require_device(gpu)
     torch.cuda.set_device(gpu)
     train_data, val_data = copy.deepcopy(train_data_ini), copy.deepcopy(val_data_ini)
@@ -39,7 +42,12 @@ def run_train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFra
     print('mean is: ', mean)
     train_proc, val_proc = DataProcessor(train_data), DataProcessor(val_data)
     score_old = [0, 0, 0] if save_metric == 'all' else float(0)
-    for epoch in trange(epochs):
+    first_epoch = 0
+    if resume_path is not None and os.path.exists(resume_path):
+        first_epoch, best, _ = load_train_state(resume_path, model, optimizer, scheduler)
+        score_old = best if best is not None else score_old
+        print('Note: resuming after epoch {} from {}'.format(first_epoch, resume_path))
+    for epoch in trange(first_epoch, epochs):
         lr = optimizer.state_dict()['param_groups'][0]['lr']
         print('learning rate: ', lr)
         if logger is not None:
@@ -71,3 +79,5 @@ def run_train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFra
         print('Epoch [{}/{}], average_pred_in_targ_top25%: {:.4f}'.format(epoch + 1, epochs, average_pred_in_targ))
         print('Epoch [{}/{}], average_targtop1_in_predtop25%: {:.4f}'.format(epoch + 1, epochs, average_top1_in_pred))
         print('Epoch [{}/{}], train loss: {:.4f}'.format(epoch + 1, epochs, epoch_loss))
+        if resume_path is not None:
+            save_train_state(resume_path, model, optimizer, scheduler, epoch, mean, std, best=score_old)

@@ -11,6 +11,7 @@ Differences, all on purpose:
 from __future__ import annotations
 
 import copy
+import os
 from logging import Logger
 from typing import Union
 
@@ -23,7 +24,7 @@ from tqdm import trange
 
 from .. import _lib
 from ..data.load_reactions import DataProcessor
-from ..utils import save_checkpoint
+from ..utils import load_train_state, save_checkpoint, save_train_state
 from .eval import calculate_mse, ranking_metrics
 from .loss import (Dirichlet_uq, ExpMSELoss, GaussDisLoss, Listnet_For_Gauss, Listnet_with_uq, ListnetLoss, Lognorm, MLEDisLoss, MLEloss,
                    MSELoss, evidential_loss_new, evidential_ranking)
@@ -116,7 +117,9 @@ def normalized_targets(train_col, val_col, target_name, normalize_target):
 def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, val_data_ini: DataFrame, path_checkpoints: str, optimizer,
           epochs: int, smiles2graph_dic, batch_size: int, seed: int, gpu: Union[int, str], task_type: str = 'mle_gaussian',
           writer=SummaryWriter, logger: Logger = None, target_name: str = 'ea', smiles_list: list = None, save_metric=None,
-          show_info=False, max_coeff=0.0001, normalize_target=True, add_features_name=None):
+          show_info=False, max_coeff=0.0001, normalize_target=True, add_features_name=None, resume_path=None):
+    """``train`` of train_listwise.py:21-372 with one addition: ``resume_path`` (default None = the reference's behaviour).  When given,
+    the full training state is written there after every epoch and, if the file already exists, training continues after its epoch."""
     if task_type in UNBUILT_TASKS:
         raise NotImplementedError(f"task_type '{task_type}' is one of the reference's experimental keys; built: {BUILT_TASKS} and 'regression'")
     dev_idx = _lib.require_device(gpu)
@@ -141,7 +144,12 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
 
     train_proc, val_proc = DataProcessor(train_data), DataProcessor(val_data)
     finite = torch.ones((), dtype=torch.bool, device=torch.device("cuda", dev_idx))
-    for epoch in trange(epochs):
+    first_epoch = 0
+    if resume_path is not None and os.path.exists(resume_path):
+        first_epoch, best, _ = load_train_state(resume_path, model, optimizer, scheduler)
+        score_old = best if best is not None else score_old
+        print('Note: resuming after epoch {} from {}'.format(first_epoch, resume_path))
+    for epoch in trange(first_epoch, epochs):
         lr = optimizer.state_dict()['param_groups'][0]['lr']
         print('learning rate: ', lr)
         if logger is not None:
@@ -219,3 +227,5 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
         print('Epoch [{}/{}], train loss: {:.4f}'.format(epoch + 1, epochs, loss_value))
         if save_metric in NDCG_METRICS:
             print('Epoch [{}/{}], NDCG: {}'.format(epoch + 1, epochs, NDCG_))
+        if resume_path is not None:
+            save_train_state(resume_path, model, optimizer, scheduler, epoch, mean, std, best=score_old)

@@ -680,3 +680,26 @@ def test_new_heads_against_the_oracle(task_type, last, task):
     (got * w.to(got.device)).sum().backward()
     got_g = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
     assert not grads_close(got_g, {k: params[k].grad.numpy() for k in got_g}, 2e-4)
+
+
+@pytest.mark.parametrize("ratio", [0.25, 0.5])
+@pytest.mark.parametrize("scope,ld", [([1, 2, 3, 6, 10, 14], 1), ([7, 1, 64, 300], 2), ([5000, 9], 1), ([33] * 200, 4)])
+def test_rank_metrics_kernel_matches_the_host_restatement(scope, ld, ratio):
+    """rr_rank_metrics against oracle.group_metrics (pinned to the reference's ranking_metrics / evaluate_top_scores goldens on the host):
+    group sizes where n * ratio is exactly half way (2, 6, 10, 14: Python rounds half to even), tied scores AND tied targets (stable
+    order), a group beyond the loss kernels' 2048 limit, strided score columns.  Hits are exact, NDCGs to 1e-12."""
+    from reactranker_b200.train.eval import group_metrics
+    N = sum(scope)
+    g = torch.Generator().manual_seed(N + ld)
+    s = torch.randn(N, ld, generator=g)
+    s[:, 0] = torch.round(s[:, 0] * 4) / 4                      # plenty of exact ties
+    t = np.round(torch.randn(N, generator=g).double().numpy() * 3) / 3
+    got = group_metrics(s.to(DEV) if ld > 1 else s[:, 0].to(DEV), scope, t, ratio).cpu().numpy()
+    want, o = [], 0
+    for n in scope:
+        want.append(O.group_metrics(s[o:o + n, 0].numpy(), t[o:o + n], ratio))
+        o += n
+    want = np.asarray(want)
+    assert np.array_equal(got[:, [0, 2, 3]], want[:, [0, 2, 3]])
+    assert np.allclose(got[:, 1], want[:, 1], rtol=0, atol=1e-15)
+    assert np.allclose(got[:, 4:], want[:, 4:], rtol=1e-12, atol=0)

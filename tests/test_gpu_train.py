@@ -29,8 +29,29 @@ def test_main_trains_every_task_key(tmp_path, task):
     assert "test score for k_fold vailidation" in out
 
 
-def test_main_ranknet_trains(tmp_path):
-    out = run(["main_ranknet.py", "--synthetic", "40,8", "--path", str(tmp_path), "--gpu", "0", "--batch_size", "64", "--total_epochs", "3"])
+def test_resume_continues_the_interrupted_run(tmp_path):
+    """two epochs, stop, resume for two more == four epochs in one go (same batches, Adam moments, Noam position).
+    Rounding order differs between runs only through the kernels' float atomics, so the late losses agree to 1e-3, not bit for bit."""
+    args = ["main.py", "--synthetic", "40,10", "--gpu", "0", "--task_type", "mle", "--batch_size", "100", "--total_epochs", "4",
+            "--hidden_size", "64", "--max_lr", "3e-3", "--dropout", "0.0"]
+    whole = run(args + ["--path", str(tmp_path / "a")])
+    run(args + ["--path", str(tmp_path / "b"), "--resume", "--stop_after", "2"])
+    assert os.path.exists(str(tmp_path / "b" / "0.state.pt"))
+    rest = run(args + ["--path", str(tmp_path / "b"), "--resume"])
+    assert "resuming after epoch 2" in rest
+    want = [float(l.rsplit(":", 1)[1]) for l in whole.splitlines() if "train loss" in l]
+    got = [float(l.rsplit(":", 1)[1]) for l in rest.splitlines() if "train loss" in l]
+    assert len(want) == 4 and len(got) == 2
+    assert np.allclose(got, want[2:], rtol=1e-3), (got, want)
+    # and a weights-only checkpoint cannot be resumed from
+    from reactranker_b200.utils import load_checkpoint
+    assert "optimizer" in load_checkpoint(str(tmp_path / "b" / "0.state.pt"))
+
+
+@pytest.mark.parametrize("algo", ["sum_session", "accelerate_grad"])
+def test_main_ranknet_trains(tmp_path, algo):
+    out = run(["main_ranknet.py", "--synthetic", "40,8", "--path", str(tmp_path), "--gpu", "0", "--batch_size", "64", "--total_epochs", "3",
+               "--train_strategy", algo])
     losses = [float(l.rsplit(":", 1)[1]) for l in out.splitlines() if "train loss" in l]
     assert len(losses) == 3 and all(np.isfinite(losses)) and 0.3 < losses[0] < 1.5      # ~log 2 per pair at initialisation
     assert "test score for k_fold vailidation" in out
@@ -75,3 +96,32 @@ def test_two_gpu_step_equals_one_gpu_step(tmp_path):
     out = run(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29611",
                "tests/dp_equivalence.py"])
     assert "DP-EQUIVALENCE-OK" in out
+
+
+@pytest.mark.parametrize("two", [False, True])
+def test_validation_metrics_on_device_match_reference_golden(two, monkeypatch):
+    """ranking_metrics / evaluate_top_scores as the product runs them (scores on the device, rr_rank_metrics, one host wait) return what
+    the reference's functions returned for the same stub scorer (tests/golden/metrics.npz, scripts/make_golden.py golden_metrics)."""
+    from test_host_cpu import _StubScorer
+    from reactranker_b200 import synthetic
+    from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features
+    from reactranker_b200.train import eval as E
+    g = np.load(os.path.join(ROOT, "tests", "golden", "metrics.npz"))
+    ds = synthetic.make_dataset(int(g["seed"]), [int(x) for x in g["sizes"]], atoms_lo=3, atoms_hi=4)
+    fz = Parsing_features(ds.mols)
+    dp = DataProcessor(ds.to_dataframe())
+    cols = ["rsmi_mapped", "psmi_mapped"]
+    m = _StubScorer(two).eval()
+    tag = "two." if two else "one."
+
+    def stub_chunks(model, gpu, chunks, smiles2graph_dic):       # the stub scores tokens, not graphs: same chunking, scores put on the device
+        for lo in range(0, len(chunks), 2):
+            part = chunks[lo:lo + 2]
+            preds = [model(None, smiles2graph_dic.parsing_smiles([s[1] for s in X]), add_features=f) for X, f in part]
+            yield lo, lo + len(part), torch.cat(preds).cuda(0)
+    monkeypatch.setattr(E, "_forward_chunks", stub_chunks)
+    got = E.evaluate_top_scores(m, gpu=0, data_processor=dp, smiles2graph_dic=fz, ratio=0.25, batch_size=3, smiles_list=cols, target_name="lgk",
+                                add_features_name="temp")
+    assert np.allclose(got, g[tag + "top_scores"], rtol=0, atol=1e-12)
+    r = E.ranking_metrics(m, gpu=0, data_processor=dp, smiles2graph_dic=fz, show_info=False, smiles_list=cols, target_name="lgk", add_features_name="temp")
+    assert np.allclose([r[0], r[1], r[2]] + list(r[3]), g[tag + "ranking"], rtol=1e-12, atol=1e-12)

@@ -271,7 +271,10 @@ class _StubScorer(torch.nn.Module):
 
 
 @pytest.mark.parametrize("two", [False, True])
-def test_eval_metrics_match_reference_golden(two, monkeypatch):
+def test_eval_metrics_match_reference_golden(two):
+    """The oracle's per-group metric restatement (what the GPU kernel rr_rank_metrics is checked against) reproduces the reference's
+    ranking_metrics / evaluate_top_scores return values, and calculate_ndcg (host report arithmetic) its tables."""
+    from oracle import reactranker_oracle as O
     from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features
     from reactranker_b200.train import eval as E
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
@@ -281,19 +284,24 @@ def test_eval_metrics_match_reference_golden(two, monkeypatch):
     cols = ["rsmi_mapped", "psmi_mapped"]
     m = _StubScorer(two).eval()
     tag = "two." if two else "one."
-    got = E.evaluate_top_scores(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, ratio=0.25, batch_size=3, smiles_list=cols, target_name="lgk",
-                                add_features_name="temp")
-    assert np.allclose(got, g[tag + "top_scores"], rtol=0, atol=1e-12)
 
-    def stub_scores(model, gpu, groups, smiles2graph_dic):      # ranking_metrics batches its forwards through DeviceGraph (GPU): score on the host here
-        out = []
-        for X, feats in groups:
-            p = model(None, smiles2graph_dic.parsing_smiles([s[1] for s in X]), add_features=feats)
-            out.append((p[:, 0] if p.dim() > 1 else p).numpy())
-        return out
-    monkeypatch.setattr(E, "_scores_per_group", stub_scores)
-    r = E.ranking_metrics(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, show_info=False, smiles_list=cols, target_name="lgk", add_features_name="temp")
-    assert np.allclose([r[0], r[1], r[2]] + list(r[3]), g[tag + "ranking"], rtol=1e-6, atol=1e-9)
+    def score(X, feats):
+        p = m(None, fz.parsing_smiles([s[1] for s in X]), add_features=feats)
+        return (p[:, 0] if p.dim() > 1 else p).numpy()
+    rows = []
+    for X, t, scope, feats in dp.generate_batch_querys(smiles_list=cols, target_name="lgk", batch_size=3, shuffle_query=False, shuffle_batch=False,
+                                                       add_features_name="temp"):
+        p, t, o = score(X, feats), np.asarray(t, np.float64).reshape(-1), 0
+        for n in scope:
+            rows.append(O.group_metrics(p[o:o + n], t[o:o + n], 0.25))
+            o += n
+    rows = np.asarray(rows)
+    assert np.allclose([rows[:, 0].mean(), rows[:, 1].mean(), rows[:, 3].mean()], g[tag + "top_scores"], rtol=0, atol=1e-12)
+    rows = np.asarray([O.group_metrics(score(X, feats), np.asarray(t, np.float64).reshape(-1), 0.25)
+                       for X, t, feats in dp.generate_batch_per_query(smiles_list=cols, target_name="lgk", shuffle_query=False, shuffle_batch=False,
+                                                                      add_features_name="temp")])
+    got = [rows[:, 0].mean(), rows[:, 1].mean(), rows[:, 2].mean()] + list(rows[:, 4:8].mean(axis=0))
+    assert np.allclose(got, g[tag + "ranking"], rtol=1e-12, atol=1e-12)
     for means, stds, name in ((None, None, "raw"), (0.7, 1.9, "scaled")):
         nd, kl, order, smi = E.calculate_ndcg(m, gpu=None, data_processor=dp, smiles2graph_dic=fz, batch_size=3, NDCG_cut=0.25, smiles_list=cols,
                                               target_name="lgk", means=means, stds=stds, add_features_name="temp")
@@ -362,3 +370,45 @@ def test_buffer_pool_best_fit_and_event_guard():
     assert c is not a                      # copy still in flight: a fresh buffer instead
     ev.done = True
     assert pool.take(10, "p", make) is a
+
+
+def test_train_state_round_trip_resumes_adam_and_noam(tmp_path):
+    """save_train_state / load_train_state on a plain torch module: 3 + 3 steps through a saved state are bit-identical
+    to 6 uninterrupted steps, the reference's loader still finds 'state_dict' / 'data_scaler', and weights-only files are refused."""
+    import torch
+    from reactranker_b200 import _lib
+    from reactranker_b200.train.utils import NoamLR
+    from reactranker_b200.utils import load_checkpoint, load_train_state, save_checkpoint, save_train_state
+
+    def fresh():
+        torch.manual_seed(3)
+        m = torch.nn.Linear(5, 3)
+        o = torch.optim.Adam([{"params": list(m.parameters()), "lr": 1e-4, "weight_decay": 0}])
+        return m, o, NoamLR(o, warmup_epochs=1, total_epochs=3, steps_per_epoch=2, init_lr=1e-4, max_lr=1e-2, final_lr=1e-3)
+
+    def steps(m, o, s, lo, hi):
+        for k in range(lo, hi):
+            x = torch.randn(7, 5, generator=torch.Generator().manual_seed(k))
+            o.zero_grad()
+            (m(x) ** 2).mean().backward()
+            o.step()
+            s.step()
+
+    m1, o1, s1 = fresh()
+    steps(m1, o1, s1, 0, 6)
+    m2, o2, s2 = fresh()
+    steps(m2, o2, s2, 0, 3)
+    path = str(tmp_path / "state.pt")
+    save_train_state(path, m2, o2, s2, epoch=0, means=1.5, stds=0.5, best=[0.1, 0.2, 0.3])
+    m3, o3, s3 = fresh()
+    nxt, best, scaler = load_train_state(path, m3, o3, s3)
+    assert nxt == 1 and best == [0.1, 0.2, 0.3] and scaler == {"means": 1.5, "stds": 0.5}
+    assert s3.current_step == s2.current_step and o3.param_groups[0]["lr"] == o2.param_groups[0]["lr"]
+    steps(m3, o3, s3, 3, 6)
+    for a, b in zip(m1.parameters(), m3.parameters()):
+        assert torch.equal(a, b)
+    assert set(load_checkpoint(path)) >= {"state_dict", "data_scaler"}
+    weights_only = str(tmp_path / "w.pt")
+    save_checkpoint(weights_only, m1, 1.0, 2.0)
+    with pytest.raises(_lib.RRError):
+        load_train_state(weights_only, m3, o3, s3)
