@@ -86,16 +86,28 @@ extern std::atomic<int> g_gemm_mode;
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+// cached per device: one process may drive several GPUs through the `gpu` argument of the Python API
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+// cudaFuncSetAttribute is per device (per context): remember where a kernel's dynamic shared-memory limit has been raised
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool need() const { return !done[current_device()]; }
+  void mark() { done[current_device()] = true; }
+};
 
 // ---- programmatic dependent launch -------------------------------------------------------
 // The big kernels are persistent, one CTA per SM, with a prologue of a few microseconds (barrier init, TMEM allocation, descriptor prefetch).

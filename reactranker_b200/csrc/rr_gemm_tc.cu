@@ -1030,10 +1030,10 @@ int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, c
   g.ldc = ldy;
   g.accumulate = accumulate;
   g.inv_keep = 1.f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    attr_set.mark();
   }
   const size_t smem = static_cast<size_t>(S2_BF) * STAGE2_BF + 1024 + 256 + 8 * 4096;
   const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
@@ -1089,10 +1089,10 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       chunk3 = (chunk3 + W3_BKR - 1) / W3_BKR * W3_BKR;
       splits3 = (M + chunk3 - 1) / chunk3;
       g.m_chunk = chunk3;
-      static bool attr3_set = false;
-      if (!attr3_set) {
+      static PerDeviceOnce attr3_set;
+      if (attr3_set.need()) {
         RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr3_set = true;
+        attr3_set.mark();
       }
       const size_t smem3 = static_cast<size_t>(S3) * (raw_bytes + bf_bytes) + 1024 + 512;
       RR_CUDA(launch_pdl(k_tc_wgrad3, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
@@ -1132,11 +1132,11 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   g.m_chunk = chunk;
   dim3 grid(ntiles, ktiles, splits);
   const size_t smem = static_cast<size_t>(S) * stage_bytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    attr_set.mark();
   }
   if (bkr == 32) RR_CUDA(launch_pdl(k_tc_wgrad2<32>, grid, dim3(THREADS), smem, s, g));
   else RR_CUDA(launch_pdl(k_tc_wgrad2<16>, grid, dim3(THREADS), smem, s, g));
@@ -1189,11 +1189,11 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   g.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   g.seed = seed;
   g.stream_id = stream_id;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    attr_set.mark();
   }
   const size_t smem = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
   const char* ew_env = getenv("RR_TC_EW");

@@ -631,10 +631,10 @@ int rank_metrics(int N, int G, const float* scores, int score_ld, const double* 
   RR_REQUIRE(ratio > 0.0 && ratio <= 1.0, "rank_metrics: ratio must lie in (0, 1] (got %g)", ratio);
   RR_REQUIRE(max_group >= 1 && max_group <= kMaxMetricGroup, "rank_metrics: largest group %d outside [1, %d]", max_group, kMaxMetricGroup);
   const size_t smem = 2 * sizeof(double) * static_cast<size_t>(max_group);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_rank_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(double) * kMaxMetricGroup));
-    attr_set = true;
+    attr_set.mark();
   }
   k_rank_metrics<<<G, kLossThreads, smem, s>>>(scores, score_ld, targets, seg_off, ratio, out);
   RR_LAUNCH_CHECK("rank_metrics kernel");

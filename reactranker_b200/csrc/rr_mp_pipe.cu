@@ -516,10 +516,10 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
   const size_t smem = 128 + 256 + static_cast<size_t>(A.stages) * A.stage_bytes;
 #define RR_PIPE_LAUNCH(OPV, F)                                                                                              \
   do {                                                                                                                      \
-    static bool attr_set = false;                                                                                           \
-    if (!attr_set) {                                                                                                        \
+    static PerDeviceOnce attr_set;                                                                                           \
+    if (attr_set.need()) {                                                                                                        \
       RR_CUDA(cudaFuncSetAttribute(k_rowpipe<OPV, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));   \
-      attr_set = true;                                                                                                      \
+      attr_set.mark();                                                                                                      \
     }                                                                                                                       \
     RR_CUDA(launch_pdl(k_rowpipe<OPV, F>, dim3(grid), dim3(A.consumer_warps * 32 + 32 * PRODUCERS), smem, s, A));                                                                    \
   } while (0)

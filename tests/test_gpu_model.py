@@ -428,3 +428,26 @@ def test_config4_model_properties_at_full_size():
     loss.backward()
     assert bool(torch.isfinite(loss).all())
     assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices():
+    """The `gpu` argument may name any device: per-device kernel attributes (dynamic shared memory limits), SM counts, workspaces and the
+    molecule store mirror must not leak from cuda:0 to cuda:1.  Same step on both devices -> same scores, loss and gradients."""
+    ds = synthetic.make_dataset(9, [6, 5, 7])
+    sizes = [6, 5, 7]
+    res = []
+    for dev in (0, 1, 0):
+        torch.manual_seed(5)
+        model = build_model(hidden_size=300, mpnn_depth=3, mpnn_diff_depth=3, ffn_depth=3, use_bias=True, dropout=0.0, task_num=1,
+                            ffn_last_layer="with_softplus", add_features_dim=1).cuda(dev)
+        r_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
+        p_g = BatchMolGraph([ds.mols[t] for t in ds.psmi])
+        out = model(r_g, p_g, gpu=dev, add_features=ds.temp.reshape(-1, 1))
+        loss = RL.MLEloss()(out, sizes, torch.FloatTensor(ds.lgk), dev)
+        loss.backward()
+        assert out.device.index == dev
+        res.append((out.detach().cpu(), loss.detach().cpu(), {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}))
+    for other in res[1:]:
+        assert rel_err(other[0].numpy(), res[0][0].numpy()) < 1e-6 and rel_err(other[1].numpy(), res[0][1].numpy()) < 1e-6
+        assert not grads_close(other[2], res[0][2], 1e-5)
