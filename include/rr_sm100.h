@@ -195,6 +195,11 @@ int rr_get_gemm_mode(void);
  * 0 = the forward's 3 x tf32 split.  Process-wide; RR_BWD_BF16=0 in the environment selects 0 at load. */
 int rr_set_backward_bf16(int on);
 int rr_get_backward_bf16(void);
+/* Operand split of the FORWARD tensor-core GEMMs of rr_model_forward: 0 (default) = 3 x tf32, 1 = the backward's 3 x bf16 split (same
+ * kernel, half the tensor-pipe time and operand bytes; 16 instead of 21 significand bits per operand).  Process-wide; RR_FWD_BF16=1 in
+ * the environment selects 1 at load. */
+int rr_set_forward_bf16(int on);
+int rr_get_forward_bf16(void);
 /* dX[M,k] (+)= dZ[M,n] W[n,k]   (accumulate != 0 adds) */
 int rr_linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw,
                     float* dX, int lddx, int accumulate, void* stream);

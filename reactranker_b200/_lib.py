@@ -52,6 +52,7 @@ EXPORTS = [
     "rr_loss_fwdbwd", "rr_loss_max_group", "rr_rank_metrics",
     "rr_model_workspace_bytes", "rr_model_buffer_offset", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
     "rr_profile_begin", "rr_profile_end", "rr_profile_classes", "rr_set_gemm_mode", "rr_get_gemm_mode", "rr_set_backward_bf16", "rr_get_backward_bf16",
+    "rr_set_forward_bf16", "rr_get_forward_bf16",
 ]
 KERNEL_CLASSES = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "bond_fwd", "bond_bwd", "nbr_fwd", "nbr_bwd", "readout", "elementwise", "loss", "misc"]
 
@@ -127,6 +128,8 @@ def lib() -> ctypes.CDLL:
                 L.rr_set_gemm_mode(int(os.environ.get("RR_GEMM_MODE", "1")))
                 L.rr_set_backward_bf16.argtypes = [i32]
                 L.rr_set_backward_bf16(int(os.environ.get("RR_BWD_BF16", "1")))
+                L.rr_set_forward_bf16.argtypes = [i32]
+                L.rr_set_forward_bf16(int(os.environ.get("RR_FWD_BF16", "0")))
                 _lib = L
     return _lib
 

@@ -9,6 +9,7 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_gemm_mode{0};
 std::atomic<int> g_bwd_bf16{1};
+std::atomic<int> g_fwd_bf16{0};
 ProfState g_prof;
 std::mutex g_prof_mutex;
 void prof_push(int cls, cudaEvent_t a, cudaEvent_t b) {
@@ -137,6 +138,11 @@ int rr_set_backward_bf16(int on) {
   return RR_OK;
 }
 int rr_get_backward_bf16(void) { return rr::g_bwd_bf16.load(); }
+int rr_set_forward_bf16(int on) {
+  rr::g_fwd_bf16.store(on ? 1 : 0);
+  return RR_OK;
+}
+int rr_get_forward_bf16(void) { return rr::g_fwd_bf16.load(); }
 int rr_profile_begin(void) {
   std::lock_guard<std::mutex> lock(rr::g_prof_mutex);
   rr::g_prof.enabled = true;

@@ -212,9 +212,11 @@ int sub(long long, const float*, const float*, float*, cudaStream_t);
 int sub_gather(long long rows, int ld, const float* a, const float* b, const int* map, float* out, cudaStream_t);
 int scatter_add_rows(long long rows, int ld, const float* src, const int* map, float* dst, cudaStream_t);
 // hi_off / lo_off: float offsets from W1 / W2 to their pre-split TF32 images (0 = split on chip)
+// packed / bhi / blo: base of the packed weights and of their bf16 (hi, lo) images (image of W = bhi + (W - packed)); used when g_fwd_bf16
 int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
                const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed, uint64_t stream_id,
-               cudaStream_t s, ptrdiff_t hi_off = 0, ptrdiff_t lo_off = 0);
+               cudaStream_t s, ptrdiff_t hi_off = 0, ptrdiff_t lo_off = 0, const float* packed = nullptr, const uint16_t* bhi = nullptr,
+               const uint16_t* blo = nullptr);
 int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
 int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
 int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
@@ -235,6 +237,11 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
 bool tc_linear_bf16_supported(int M, int n, int k, int ldx, int ldw);
 int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, const uint16_t* Wlo, int ldw, int k, float* Y, int ldy, int accumulate,
                    int kclass, cudaStream_t s);
+int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t* W1hi, const uint16_t* W1lo, int ldw1, int k1, const float* X2, int ldx2,
+                        const uint16_t* W2hi, const uint16_t* W2lo, int ldw2, int k2, const float* bias, const float* resid, int ldr, float* Y, int ldy,
+                        int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id, int kclass, cudaStream_t s);
+// forward GEMMs: 0 = 3 x tf32 split (default), 1 = 3 x bf16 split (RR_FWD_BF16=1 or rr_set_forward_bf16(1))
+extern std::atomic<int> g_fwd_bf16;
 // backward GEMMs: 1 = 3 x bf16 split (default; RR_BWD_BF16=0 or rr_set_backward_bf16(0) keeps 3 x tf32)
 extern std::atomic<int> g_bwd_bf16;
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);

@@ -183,9 +183,16 @@ static int check_mat(const char* what, const void* p, int ld) {
 
 int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2, int k2,
                const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed, uint64_t stream_id,
-               cudaStream_t s, ptrdiff_t hi_off, ptrdiff_t lo_off) {
+               cudaStream_t s, ptrdiff_t hi_off, ptrdiff_t lo_off, const float* packed, const uint16_t* bhi, const uint16_t* blo) {
   // hi_off / lo_off != 0: TF32-exact (hi, remainder) images of W1 / W2 live at W + hi_off / W + lo_off (the model's packed weights)
   const bool pre = hi_off != 0 && lo_off != 0;
+  const bool two = X2 && k2 > 0;
+  if (g_fwd_bf16.load() && packed && bhi && blo && (g_gemm_mode.load() == 1 || g_gemm_mode.load() == 2) && tc_linear_bf16_supported(M, n, k1, ldx1, k1) &&
+      (!two || tc_linear_bf16_supported(M, n, k2, ldx2, k2)) && aligned16(X1) && aligned16(Y) && (!two || aligned16(X2)) &&
+      (!resid || (aligned16(resid) && (ldr & 3) == 0)) && (!bias || aligned16(bias)) && (ldy & 3) == 0 && p >= 0.f && p < 1.f)
+    return tc_linear_bf16_full(M, n, X1, ldx1, bhi + (W1 - packed), blo + (W1 - packed), k1, k1, two ? X2 : nullptr, ldx2,
+                               two ? bhi + (W2 - packed) : nullptr, two ? blo + (W2 - packed) : nullptr, k2, two ? k2 : 0, bias, resid, ldr, Y, ldy,
+                               flags & 1, 0, (flags & 2) ? p : 0.f, seed, stream_id, KC_GEMM_FWD, s);
   if ((g_gemm_mode.load() == 1 || g_gemm_mode.load() == 2) && tc_supported(M, n, k1, X2 ? k2 : 0, ldx1, X2 ? ldx2 : 0) && aligned16(X1) && aligned16(W1) && aligned16(Y) &&
       (!X2 || (aligned16(X2) && aligned16(W2))) && (!resid || (aligned16(resid) && (ldr & 3) == 0)) && (!bias || aligned16(bias)) && (ldy & 3) == 0 &&
       p >= 0.f && p < 1.f)

@@ -1011,16 +1011,25 @@ static int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int rows, int co
 bool tc_linear_bf16_supported(int M, int n, int k, int ldx, int ldw) {
   return M > 0 && n >= 16 && !(n & 15) && k > 0 && !(k & 3) && !(ldx & 3) && !(ldw & 7);
 }
-int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, const uint16_t* Wlo, int ldw, int k, float* Y, int ldy, int accumulate,
-                   int kclass, cudaStream_t s) {
+// Full-featured bf16-split linear: Y = epi(X1 W1^T + X2 W2^T) with every weight given as bf16 (hi, lo) images.
+int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t* W1hi, const uint16_t* W1lo, int ldw1, int k1, const float* X2, int ldx2,
+                        const uint16_t* W2hi, const uint16_t* W2lo, int ldw2, int k2, const float* bias, const float* resid, int ldr, float* Y, int ldy,
+                        int relu, int accumulate, float p, uint64_t seed, uint64_t stream_id, int kclass, cudaStream_t s) {
   using namespace tc;
   ProfScope prof_scope(kclass, s);
   Args g{};
-  g.nsrc = 1;
-  RR_TRY(make_map(&g.src[0].tmA, X, M, k, ldx, BM));
-  RR_TRY(make_map_bf16(&g.src[0].tmB, Whi, n, k, ldw, NT2));
-  RR_TRY(make_map_bf16(&g.src[0].tmBlo, Wlo, n, k, ldw, NT2));
-  g.src[0].K = k;
+  const bool two = X2 && k2 > 0;
+  g.nsrc = two ? 2 : 1;
+  RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
+  RR_TRY(make_map_bf16(&g.src[0].tmB, W1hi, n, k1, ldw1, NT2));
+  RR_TRY(make_map_bf16(&g.src[0].tmBlo, W1lo, n, k1, ldw1, NT2));
+  g.src[0].K = k1;
+  if (two) {
+    RR_TRY(make_map(&g.src[1].tmA, X2, M, k2, ldx2, BM));
+    RR_TRY(make_map_bf16(&g.src[1].tmB, W2hi, n, k2, ldw2, NT2));
+    RR_TRY(make_map_bf16(&g.src[1].tmBlo, W2lo, n, k2, ldw2, NT2));
+    g.src[1].K = k2;
+  }
   g.presplit = 1;
   const char* diag_env = getenv("RR_TC_DIAG");
   g.diag = diag_env ? atoi(diag_env) : 0;
@@ -1028,8 +1037,15 @@ int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, c
   g.N = n;
   g.C = Y;
   g.ldc = ldy;
+  g.bias = bias;
+  g.resid = resid;
+  g.ldr = ldr;
+  g.relu = relu;
   g.accumulate = accumulate;
-  g.inv_keep = 1.f;
+  g.p = p;
+  g.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  g.seed = seed;
+  g.stream_id = stream_id;
   static PerDeviceOnce attr_set;
   if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1041,6 +1057,11 @@ int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, c
   RR_CUDA(launch_pdl(k_tc_gemm2<8, true>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_gemm2<bf16>");
   return RR_OK;
+}
+int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, const uint16_t* Wlo, int ldw, int k, float* Y, int ldy, int accumulate,
+                   int kclass, cudaStream_t s) {
+  return tc_linear_bf16_full(M, n, X, ldx, Whi, Wlo, ldw, k, nullptr, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, Y, ldy, 0, accumulate, 0.f, 0, 0,
+                             kclass, s);
 }
 
 

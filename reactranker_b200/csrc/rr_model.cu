@@ -391,26 +391,26 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
     const rr_graph* g = gs[k];
     EncBufs& e = W.enc[k];
     RR_TRY(linear_fwd(g->n_bonds, hp, g->f_bonds, RR_FB_LD, P + L.enc_Wi, RR_FB_LD, nullptr, 0, nullptr, 0, P + L.enc_bi, nullptr, 0,
-                      e.inp, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off));
+                      e.inp, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
     const float* src = e.inp;
     int relu_src = 1;
     for (int t = 0; t < T; ++t) {
       RR_TRY(bond_message_fwd(g, src, e.pre[t], hp, relu_src, s));
       RR_TRY(linear_fwd(g->n_bonds, hp, e.pre[t], hp, P + L.enc_Wh, hp, nullptr, 0, nullptr, 0, P + L.enc_bh, e.inp, hp, e.m[t + 1], hp,
-                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
+                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
       src = e.m[t + 1];
       relu_src = 0;
     }
     RR_TRY(neighbor_sum_fwd(g, 0, src, e.am, hp, relu_src, s));
     RR_TRY(linear_fwd(g->n_atoms, hp, g->f_atoms, RR_FA_LD, P + L.enc_Wo_a, RR_FA_LD, e.am, hp, P + L.enc_Wo_m, hp, P + L.enc_bo, nullptr, 0,
-                      e.hid, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
+                      e.hid, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
   }
   const int A = p->n_atoms;
   if (c->r_atom_map) RR_TRY(sub_gather(A, hp, W.enc[1].hid, W.enc[0].hid, c->r_atom_map, W.d, s));
   else RR_TRY(sub(static_cast<long long>(A) * hp, W.enc[1].hid, W.enc[0].hid, W.d, s));  // base_model.py:168
 
   // mpn.py:170-240 over the product graph
-  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off));
+  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
   if (Td > 0) RR_TRY(neighbor_sum_fwd(p, 0, p->f_bonds, W.nf, RR_FB_LD, 0, s));
   {
     const float* src = W.inp2;
@@ -418,13 +418,13 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
     for (int t = 0; t < Td; ++t) {
       RR_TRY(neighbor_sum_fwd(p, 1, src, W.nm[t], hp, relu_src, s));
       RR_TRY(linear_fwd(A, hp, W.nm[t], hp, P + L.dif_Wh_m, hp, W.nf, RR_FB_LD, P + L.dif_Wh_f, RR_FB_LD, P + L.dif_bh, W.inp2, hp, W.m2[t + 1], hp,
-                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
+                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
       src = W.m2[t + 1];
       relu_src = 0;
     }
     RR_TRY(neighbor_sum_fwd(p, 1, src, W.am2, hp, relu_src, s));
   }
-  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wo_d, hp, W.am2, hp, P + L.dif_Wo_m, hp, P + L.dif_bo, nullptr, 0, W.hid2, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
+  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wo_d, hp, W.am2, hp, P + L.dif_Wo_m, hp, P + L.dif_bo, nullptr, 0, W.hid2, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
   RR_TRY(readout_fwd(p, W.hid2, hp, c->hidden, addf, c->add_features, W.vec, vp, pdrop, c->seed, sid++, s));
 
   // base_model.py:40-60
@@ -435,7 +435,7 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
     const bool last = (l == c->ffn_depth - 1);
     float* y = last ? W.zout : W.x[l];
     RR_TRY(linear_fwd(N, L.ffn_out[l], x, ldx, P + L.ffn_W[l], L.ffn_in[l], nullptr, 0, nullptr, 0, P + L.ffn_b[l], nullptr, 0, y, L.ffn_out[l],
-                      last ? 0 : act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off));
+                      last ? 0 : act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
     x = y;
     ldx = L.ffn_out[l];
   }

@@ -105,6 +105,18 @@ if which in ("all", "wgrad"):
             setenv(RR_TC_DIAG=diag)
             report(f"{'3xtf32' if tf32 else '3xbf16'} diag={diag} {cases[0][0]}", cases[0][1][0], cases[0][1][1], cases[0][1][2])
     setenv(RR_TC_DIAG=0)
+if which == "diag":    # what bounds the forward kernel: switch its parts off one at a time (pre-split weights as in the model)
+    E["RR_TC_FAKE_PRESPLIT"] = "1"
+    cases = [("W_h fwd bias+resid+relu+dropout", fwd_case(B, 304, 304)), ("W_h fwd bias+resid+relu", fwd_case(B, 304, 304, p=0.0)),
+             ("plain [B,304]x[304,304]", fwd_case(B, 304, 304, epi=False))]
+    names = {0: "full", 1: "no A split", 4: "no MMA", 8: "no epilogue traffic", 5: "no A split, no MMA", 12: "no MMA, no epilogue", 9: "no A split, no epilogue",
+             13: "TMA ring only"}
+    for name, (run, fl, by, _) in cases:
+        for diag, what in names.items():
+            setenv(RR_TC_DIAG=diag)
+            report(f"{name}: {what}", run, fl, by)
+    setenv(RR_TC_DIAG=0)
+    E.pop("RR_TC_FAKE_PRESPLIT", None)
 if which == "one":     # one launch of each headline kernel, for ncu
     run, *_ = fwd_case(B, 304, 304)
     run2, *_ = wgrad_case(B, 304, 304)
