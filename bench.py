@@ -72,11 +72,15 @@ def ncu_traffic(cls):
     pat = _TRAFFIC_KERNELS.get(cls)
     if not files or pat is None:
         return None
-    try:
-        t = json.load(open(files[-1]))
-    except Exception:
-        return None
-    hits = [v for k, v in t.items() if k.startswith(pat)]
+    hits = []
+    for f in reversed(files):                      # the newest capture that holds this kernel (a partial re-capture only lists what changed)
+        try:
+            t = json.load(open(f))
+        except Exception:
+            continue
+        hits = [v for k, v in t.items() if k.startswith(pat)]
+        if hits:
+            break
     if not hits:
         return None
     n = sum(v["launches_captured"] for v in hits)

@@ -184,7 +184,7 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_p, uint8_t* lo_p, int byt
 // separate epilogue warpgroup drains the accumulator while the producer and the split warps already work on the
 // next tile, and the epilogue moves 128-byte row segments (tcgen05.ld x32).
 //   warp 0: TMA producer | warp 1: MMA issuer (+TMEM alloc) | warps 2-5: split (A -> TMEM, B -> smem hi/lo) |
-//   warps 6-9: epilogue
+//   warps 6-21: epilogue (EW = 16; the 8- and 4-warp flavours remain behind RR_TC_EW)
 // TMEM columns: [0, 320) accumulator, [320 + 64 s, ...) A stage s = 32 columns hi + 32 columns lo.
 // ================================================================================================
 constexpr int THREADS2_BASE = 192;   // TMA warp + MMA warp + 4 split warps; the epilogue adds 4 or 8 warps
@@ -212,6 +212,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
                "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -259,6 +264,47 @@ __device__ __forceinline__ void epilogue_block(const Args& g, const float (&v)[3
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + rsub, row = row0 + r;
     float4 o = lds_f4(stage + r * 128 + ((j ^ (r & 7)) << 4));
+    if (row < g.M && col_ok) {
+      float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
+      if (g.bias) o = f4_add(o, bs);
+      if (g.resid) o = f4_add(o, R[i]);
+      if (g.relu) o = f4_relu(o);
+      if (g.p > 0.f) o = dropout4(o, g.p, g.inv_keep, g.seed, g.stream_id, (static_cast<uint64_t>(row) * g.ldc + col) >> 2);
+      if (g.accumulate) o = f4_add(o, g.resid ? *reinterpret_cast<const float4*>(cp) : R[i]);
+      st_f4(cp, o);
+    }
+  }
+  __syncwarp();
+}
+
+// 16-column flavour of the same epilogue for the 16-epilogue-warp kernel (EW = 16): a [32 rows x 16 columns] sub-block per step, a 2 KB
+// staging tile per warp (rows of 64 B; chunk c of row r sits at c ^ ((r >> 1) & 3), conflict-free for both the row-per-lane writes and the
+// 4-lanes-per-row reads), 8 rows x 64 contiguous bytes per global instruction.  Half the registers of the 32-column version, so twice the
+// warps fit: the epilogue is issue-bound (scripts/bench_gemm.py diag), not bandwidth-bound.
+__device__ __forceinline__ void epi_issue_h(const Args& g, float4 (&R)[4], int row0, int col0, int lane) {
+  const float* src = g.resid ? g.resid : (g.accumulate ? g.C : nullptr);
+  if (src == nullptr) return;
+  const int ld = g.resid ? g.ldr : g.ldc;
+  const int col = col0 + 4 * (lane & 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row0 + i * 8 + (lane >> 2);
+    if (row < g.M && col < g.N) R[i] = ld_f4_stream(src + static_cast<size_t>(row) * ld + col);
+  }
+}
+__device__ __forceinline__ void epilogue_block_h(const Args& g, const float (&v)[16], const float4 (&R)[4], uint32_t stage, int row0, int col0, int lane) {
+  const int j = lane & 3, rsub = lane >> 2;
+  const int col = col0 + 4 * j;
+  const bool col_ok = col < g.N;
+  const float4 bs = (g.bias && col_ok) ? ld_f4(g.bias + col) : f4_zero();
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    sts_f4(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + rsub, row = row0 + r;
+    float4 o = lds_f4(stage + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
     if (row < g.M && col_ok) {
       float* cp = g.C + static_cast<size_t>(row) * g.ldc + col;
       if (g.bias) o = f4_add(o, bs);
@@ -450,6 +496,39 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
         // A: this thread's row of 32 floats (128-byte swizzle: chunk c sits at c ^ (row & 7)) -> hi / lo -> TMEM
         if (!(g.diag & 1)) {
           const uint32_t rowp = smem_u32(base) + r * 128;
+          if constexpr (EW == 16) {
+            // 704 threads cap the kernel at 88 registers: two halves of 16 floats each instead of the whole row at once
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              float4 av[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) av[c] = lds_f4(rowp + (((4 * hlf + c) ^ (r & 7)) << 4));
+              if constexpr (BF) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  split_bf16_pair(av[c].x, av[c].y, hi[2 * c], lo[2 * c]);
+                  split_bf16_pair(av[c].z, av[c].w, hi[2 * c + 1], lo[2 * c + 1]);
+                }
+                tmem_st8(lane_addr + TM_A2 + st * A_COLS + 8 * hlf, hi);
+                tmem_st8(lane_addr + TM_A2 + st * A_COLS + 16 + 8 * hlf, lo);
+              } else {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float e[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t h = (__float_as_uint(e[j]) + 0x1000u) & 0xFFFFE000u;
+                    hi[4 * c + j] = h;
+                    lo[4 * c + j] = __float_as_uint(e[j] - __uint_as_float(h));
+                  }
+                }
+                tmem_st16(lane_addr + TM_A2 + st * A_COLS + 16 * hlf, hi);
+                tmem_st16(lane_addr + TM_A2 + st * A_COLS + 32 + 16 * hlf, lo);
+              }
+            }
+          } else {
           float4 av[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) av[c] = lds_f4(rowp + ((c ^ (r & 7)) << 4));
@@ -477,6 +556,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
             tmem_st32(lane_addr + TM_A2 + st * A_COLS, hi);
             tmem_st32(lane_addr + TM_A2 + st * A_COLS + 32, lo);
           }
+          }
         }
         // B: elementwise split in shared memory (unless the weights arrived pre-split)
         if (!BF && !g.presplit && !(g.diag & 2)) split_tile(base + A_BYTES, base + A_BYTES + B2_BYTES, b_used, wtid);
@@ -492,6 +572,44 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
     constexpr int EPQ = EW / 4;
     const int quad = warp & 3;
     const int eidx = (warp - 6) >> 2;
+    if constexpr (EW == 16) {
+      const uint32_t stage = smem_u32(reinterpret_cast<uint8_t*>(full) + 256) + (warp - 6) * 2048;   // warp-private 2 KB staging tile
+      int w = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++w) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
+        const int nblk = (min(NT2, g.N - n0) + 15) >> 4;            // 16-column sub-blocks (tile widths are multiples of 16)
+        const int row0 = m0 + quad * 32;
+        const int buf = w & 1;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * NT2;
+        float4 R[4];
+        int c = (eidx + w) & (EPQ - 1);                              // rotate the start so the 10 sub-blocks of a tile spread evenly over tiles
+        if (c < nblk && !(g.diag & 8)) epi_issue_h(g, R, row0, n0 + 16 * c, lane);
+        mbar_wait(acc_full + buf, (w >> 1) & 1);
+        tc_fence_after();
+        if (c >= nblk) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + buf);
+        }
+        for (; c < nblk; c += EPQ) {
+          float v[16];
+          tmem_ld16(taddr + 16 * c, v);
+          const bool last = c + EPQ >= nblk;
+          if (last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+          }
+          float4 Rn[4];
+          if (!last && !(g.diag & 8)) epi_issue_h(g, Rn, row0, n0 + 16 * (c + EPQ), lane);
+          if (!(g.diag & 8)) epilogue_block_h(g, v, R, stage, row0, n0 + 16 * c, lane);
+          if (!last) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) R[i] = Rn[i];
+          }
+        }
+      }
+    } else {
     const uint32_t stage = smem_u32(reinterpret_cast<uint8_t*>(full) + 256) + (warp - 6) * 4096;   // warp-private staging tile
     int w = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++w) {
@@ -527,6 +645,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
           for (int i = 0; i < 8; ++i) R[i] = Rn[i];
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -1011,6 +1130,14 @@ static int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int rows, int co
 bool tc_linear_bf16_supported(int M, int n, int k, int ldx, int ldw) {
   return M > 0 && n >= 16 && !(n & 15) && k > 0 && !(k & 3) && !(ldx & 3) && !(ldw & 7);
 }
+// epilogue warps of k_tc_gemm2: 16 (16-column sub-blocks, 704 threads at 80 registers) by default; RR_TC_EW=8 / 4 select the earlier
+// 32-column-block flavours (8 warps: -13 % forward GEMM time per step, scripts/bench_gemm.py diag)
+static int epilogue_warps() {
+  const char* e = getenv("RR_TC_EW");
+  const int v = e ? atoi(e) : 16;
+  return (v == 4 || v == 8) ? v : 16;
+}
+
 // Full-featured bf16-split linear: Y = epi(X1 W1^T + X2 W2^T) with every weight given as bf16 (hi, lo) images.
 int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t* W1hi, const uint16_t* W1lo, int ldw1, int k1, const float* X2, int ldx2,
                         const uint16_t* W2hi, const uint16_t* W2lo, int ldw2, int k2, const float* bias, const float* resid, int ldr, float* Y, int ldy,
@@ -1049,12 +1176,14 @@ int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t*
   static PerDeviceOnce attr_set;
   if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set.mark();
   }
   const size_t smem = static_cast<size_t>(S2_BF) * STAGE2_BF + 1024 + 256 + 8 * 4096;
   const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
   const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-  RR_CUDA(launch_pdl(k_tc_gemm2<8, true>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
+  if (epilogue_warps() == 16) RR_CUDA(launch_pdl(k_tc_gemm2<16, true>, dim3(ctas), dim3(THREADS2_BASE + 512), smem, s, g));
+  else RR_CUDA(launch_pdl(k_tc_gemm2<8, true>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_gemm2<bf16>");
   return RR_OK;
 }
@@ -1214,14 +1343,15 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   if (attr_set.need()) {
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set.mark();
   }
   const size_t smem = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
-  const char* ew_env = getenv("RR_TC_EW");
-  const int ew = (ew_env && atoi(ew_env) == 4) ? 4 : 8;
+  const int ew = epilogue_warps();
   const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
   const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-  if (ew == 8) RR_CUDA(launch_pdl(k_tc_gemm2<8, false>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
+  if (ew == 16) RR_CUDA(launch_pdl(k_tc_gemm2<16, false>, dim3(ctas), dim3(THREADS2_BASE + 512), smem, s, g));
+  else if (ew == 8) RR_CUDA(launch_pdl(k_tc_gemm2<8, false>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
   else RR_CUDA(launch_pdl(k_tc_gemm2<4, false>, dim3(ctas), dim3(THREADS2_BASE + 128), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_gemm2");
   return RR_OK;

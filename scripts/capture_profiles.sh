@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round profile capture on the GPU box (run under gpurun): plain bench first (must exit 0), then the ncu launch list of the
 # same command, then --set full captures of the top kernels (a few launches each: every replay pass saves / restores the
-# multi-GB workspace).  Outputs land in gpurun_out/ (keep them under 64 MiB); scripts/summarise_profiles.py turns them into
+# multi-GB workspace).  A second argument `gemm` stops after the GEMM capture.  Outputs land in gpurun_out/ (keep them under 64 MiB); scripts/summarise_profiles.py turns them into
 # profiles/<round>_*.  Usage: scripts/capture_profiles.sh r01
 set -u
 R=${1:-r01}
@@ -13,6 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # second step of `--steps 1 --warmup 1`: 29 k_tc_gemm2 / 20 k_tc_wgrad2 launches per step
 ncu --set full --clock-control none -k regex:k_tc_gemm2 --launch-skip 29 -c 4 -o $OUT/${R}_full_gemm \
     python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/${R}_ncu_full_gemm.log 2>&1
+[ "${2:-all}" = "gemm" ] && { tail -n 1 $OUT/${R}_ncu_full_gemm.log; du -sh $OUT; exit 0; }   # partial re-capture: only the GEMM kernel changed
 ncu --set full --clock-control none -k regex:k_tc_wgrad --launch-skip 31 -c 3 -o $OUT/${R}_full_wgrad \
     python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/${R}_ncu_full_wgrad.log 2>&1
 ncu --set full --clock-control none -k regex:k_rowpipe --launch-skip 24 -c 10 -o $OUT/${R}_full_mp \
