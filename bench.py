@@ -424,9 +424,13 @@ def ours(args):
     roof = {k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
     roof.update(kernel=top, ms_per_step_instrumented=ms_prof / args.steps, traffic=ncu_traffic(top), peak_source=pk["src"], avg_launch_ms=kernels[top]["ms_per_step"] / kernels[top]["launches_per_step"])
     if roof["bound"] == "tensor":
-        # fp32-class accuracy costs three kind::tf32 MMAs per product, and a tf32 MMA runs at half the bf16 rate the peak was measured with:
-        # the ceiling of this path is peak / 6; frac (of the bf16 peak, as the contract asks) and frac_of_3xtf32_ceiling say the same thing twice
-        roof.update(mma_passes_per_product=3, operand_kind="tf32", frac_of_3xtf32_ceiling=roof["frac"] * 6.0,
+        # fp32-class accuracy costs three MMAs per product.  Forward: kind::tf32, which runs at half the bf16 rate the peak was measured with,
+        # so the ceiling of that path is peak / 6; backward (dgrad, wgrad): bf16 operands at the full rate, ceiling peak / 3.  frac (of the bf16
+        # peak, as the contract asks) and frac_of_split_ceiling say the same thing twice.
+        bwd_bf16 = top in ("gemm_dgrad", "gemm_wgrad") and bool(_lib.lib().rr_get_backward_bf16())
+        fwd_bf16 = top == "gemm_fwd" and bool(_lib.lib().rr_get_forward_bf16())
+        bf = bwd_bf16 or fwd_bf16
+        roof.update(mma_passes_per_product=3, operand_kind="bf16" if bf else "tf32", frac_of_split_ceiling=roof["frac"] * (3.0 if bf else 6.0),
                     achieved_tensor_pipe_tflops=roof["achieved"] * 3.0)
     mp = [c for c in ("bond_fwd", "bond_bwd", "nbr_fwd", "nbr_bwd") if c in kernels]
     mp_bytes = sum(work[c][0] for c in mp)
