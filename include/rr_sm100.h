@@ -245,7 +245,8 @@ int rr_loss_max_group(void);
      targets [N] fp64 (the DataFrame column as is, so ties and order are the reference's), seg_off [G + 1], max_group <= 8192
      ratio   the top fraction (0.25 everywhere in the reference): K = max(1, round-half-even(n * ratio)), Python's round()
    out [G, 8]: 0 predicted top-1 == true top-1 | 1 |pred top-K n true top-K| / K | 2 predicted top-1 in true top-K | 3 true top-1 in predicted
-   top-K | 4 NDCG@1 | 5 NDCG@2 as eval.py:544 computes it | 6 NDCG@K | 7 NDCG@all.  Stable descending order (ties keep the earlier item). */
+   top-K | 4 NDCG@1 | 5 NDCG@2 as eval.py:544 computes it | 6 NDCG@K | 7 NDCG@all.  Stable descending order (ties keep the earlier item).
+   An empty group yields zeros; a group larger than max_group yields NaN in all eight columns. */
 #define RR_METRIC_COLS 8
 int rr_rank_metrics(int N, int G, const float* scores, int score_ld, const double* targets, const int32_t* seg_off, int max_group,
                     double ratio, double* out, void* stream);

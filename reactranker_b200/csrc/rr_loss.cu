@@ -562,13 +562,13 @@ __device__ double block_sum_d(double v, double* red) {
   return r;
 }
 __global__ void __launch_bounds__(kLossThreads) k_rank_metrics(const float* __restrict__ scores, int score_ld, const double* __restrict__ targets,
-                                                               const int* __restrict__ seg, double ratio, double* __restrict__ out) {
+                                                               const int* __restrict__ seg, int max_group, double ratio, double* __restrict__ out) {
   extern __shared__ double sm_d[];
   __shared__ double red[32];
   const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
   double* res = out + static_cast<size_t>(blockIdx.x) * RR_METRIC_COLS;
-  if (n <= 0) {
-    if (threadIdx.x < RR_METRIC_COLS) res[threadIdx.x] = 0.0;
+  if (n <= 0 || n > max_group) {     // empty group: zeros; a group larger than the caller declared (shared memory was sized for max_group): NaN, never an overrun
+    if (threadIdx.x < RR_METRIC_COLS) res[threadIdx.x] = n <= 0 ? 0.0 : CUDART_NAN;
     return;
   }
   double* sc = sm_d;
@@ -636,7 +636,7 @@ int rank_metrics(int N, int G, const float* scores, int score_ld, const double* 
     RR_CUDA(cudaFuncSetAttribute(k_rank_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(double) * kMaxMetricGroup));
     attr_set.mark();
   }
-  k_rank_metrics<<<G, kLossThreads, smem, s>>>(scores, score_ld, targets, seg_off, ratio, out);
+  k_rank_metrics<<<G, kLossThreads, smem, s>>>(scores, score_ld, targets, seg_off, max_group, ratio, out);
   RR_LAUNCH_CHECK("rank_metrics kernel");
   return RR_OK;
 }

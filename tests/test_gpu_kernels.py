@@ -707,3 +707,15 @@ def test_rank_metrics_kernel_matches_the_host_restatement(scope, ld, ratio):
     assert np.array_equal(got[:, [0, 2, 3]], want[:, [0, 2, 3]])
     assert np.allclose(got[:, 1], want[:, 1], rtol=0, atol=1e-15)
     assert np.allclose(got[:, 4:], want[:, 4:], rtol=1e-12, atol=0)
+
+
+def test_rank_metrics_refuses_an_understated_max_group():
+    """Shared memory is sized from max_group: a larger group must come back as NaN, not as an overrun."""
+    L = _lib.lib()
+    s = torch.randn(40, device=DEV)
+    t = torch.randn(40, dtype=torch.float64, device=DEV)
+    seg = torch.tensor([0, 8, 40], dtype=torch.int32, device=DEV)
+    out = torch.zeros(2, 8, dtype=torch.float64, device=DEV)
+    _lib.check(L.rr_rank_metrics(40, 2, s.data_ptr(), 1, t.data_ptr(), seg.data_ptr(), 8, 0.25, out.data_ptr(), S()))
+    o = out.cpu()
+    assert bool(torch.isfinite(o[0]).all()) and bool(torch.isnan(o[1]).all())
