@@ -323,7 +323,12 @@ def ours(args):
         # warm MolGraph cache -> store ids; pinned H2D of ids / row offsets + on-device assembly from the HBM-resident molecule store,
         # enqueued behind the running step
         reactions = np.asarray(reactions, dtype=object)
-        rg, pg = to_dev_pair(fz.parsing_smiles, reactions[:, 0].tolist(), reactions[:, 1].tolist())
+        r_tok, p_tok = reactions[:, 0].tolist(), reactions[:, 1].tolist()
+        if per_group or dedup:      # many segments / de-duplicated reactants: the id-vector path of train_pairwise._window_graphs and eval._forward_chunks
+            lens = [wl["group"]] * (len(r_tok) // wl["group"]) if per_group else [len(r_tok)]
+            rg, pg = DeviceGraph.from_id_groups(fz.store, fz.parsing_ids(r_tok), fz.parsing_ids(p_tok), lens, dev, dedup)
+        else:
+            rg, pg = to_dev_pair(fz.parsing_smiles, r_tok, p_tok)
         # extra features and targets go up with the graphs (pinned, asynchronous), not between the loss read and the next launch
         feats_d = torch.as_tensor(np.asarray(feats, dtype=np.float32)).reshape(len(tg), -1).pin_memory().to(dev, non_blocking=True)
         targets_d = torch.FloatTensor(tg).squeeze().pin_memory().to(dev, non_blocking=True)                 # train_listwise.py:187

@@ -286,6 +286,18 @@ class Parsing_features:
             return BatchMolGraph([self.smiles2graph[s] for s in smiles])
         return BatchMolGraph.from_store(self.store, np.asarray(ids, dtype=np.int32), smiles)
 
+    def parsing_ids(self, smiles) -> Optional[np.ndarray]:
+        """Store ids of the molecules (registering new ones), or None when one of them cannot live in the store.  The batched
+        evaluation / RankNet paths hand these to ``DeviceGraph.from_id_groups`` instead of building one BatchMolGraph per group."""
+        sid_of = self._sid
+        try:
+            ids = [sid_of[s] for s in smiles]
+        except KeyError:
+            ids = [sid_of[s] if s in sid_of else self._register(s) for s in smiles]
+        if ids and min(ids) < 0:
+            return None
+        return np.asarray(ids, dtype=np.int32)
+
     def parsing_reactions(self, reactions: list = None):
         if reactions is None:
             return [None, None]

@@ -561,39 +561,66 @@ class DeviceGraph:
                 ("pad_bonds", S * 4), ("pad_atoms", S * 4)]
 
     @staticmethod
+    def control_block(store: MoleculeStore, ids: np.ndarray, lens: np.ndarray, W: Optional[np.ndarray] = None):
+        """The host side of a device-assembled graph, vectorised over any number of segments: molecule ``ids`` (store ids, segments
+        back to back), ``lens`` molecules per segment, optional per-segment ``W`` (max_num_bonds; default max(1, largest in-degree of the
+        segment)).  Returns ``(ctl int32, (nA, nB, nM, wmax, S), (A_s, B_s, W_s))`` where ctl = [ids | a_start | b_start | W | pad_bond |
+        pad_atom] per molecule + [a0 | b0 | W] per segment, exactly what ``rr_graph_assemble`` reads.  Every segment is laid out as the
+        reference lays out a BatchMolGraph of its molecules: one padding row, then the molecules' rows (featurization.py:264-290)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        lens = np.asarray(lens, dtype=np.int64)
+        S, nM = int(lens.shape[0]), int(ids.shape[0])
+        if int(lens.sum()) != nM:
+            raise ValueError(f"segment lengths sum to {int(lens.sum())}, {nM} molecule ids given")
+        seg_of = np.repeat(np.arange(S, dtype=np.int64), lens)
+        nA_m, nB_m = store.nA[ids].astype(np.int64), store.nB[ids].astype(np.int64)
+        A_s = 1 + np.bincount(seg_of, weights=nA_m, minlength=S).astype(np.int64)
+        B_s = 1 + np.bincount(seg_of, weights=nB_m, minlength=S).astype(np.int64)
+        deg_s = np.zeros(S, np.int64)
+        np.maximum.at(deg_s, seg_of, store.maxdeg[ids].astype(np.int64))
+        W_min = np.maximum(1, deg_s)
+        if W is None:
+            W_s = W_min
+        else:
+            W_s = np.asarray(W, dtype=np.int64)
+            bad = np.nonzero(W_s < W_min)[0]
+            if bad.size:
+                raise ValueError(f"max_num_bonds override {int(W_s[bad[0]])} < this batch's in-degree {int(W_min[bad[0]])}")
+        a0_s = np.concatenate(([0], np.cumsum(A_s)[:-1])) if S else np.zeros(0, np.int64)
+        b0_s = np.concatenate(([0], np.cumsum(B_s)[:-1])) if S else np.zeros(0, np.int64)
+        ctl = np.empty(6 * nM + 3 * S, np.int32)
+        m = ctl[:6 * nM].reshape(6, nM)
+        m[0] = ids
+        # rows before a molecule: all earlier molecules' rows + one padding row per segment up to and including its own
+        m[1] = np.cumsum(nA_m) - nA_m + seg_of + 1
+        m[2] = np.cumsum(nB_m) - nB_m + seg_of + 1
+        m[3], m[4], m[5] = W_s[seg_of], b0_s[seg_of], a0_s[seg_of]
+        seg = ctl[6 * nM:].reshape(3, S)
+        seg[0], seg[1], seg[2] = a0_s, b0_s, W_s
+        wmax = max(1, int(deg_s.max())) if S else 1
+        return ctl, (int(A_s.sum()), int(B_s.sum()), nM, wmax, S), (A_s, B_s, W_s)
+
+    @staticmethod
     def assemble(batches: Sequence[BatchMolGraph], dev, w_override=None) -> "DeviceGraph":
         """Build the graph ON THE DEVICE from the molecule store: the host sends ids and row offsets only."""
-        from .. import _lib
         store = batches[0]._store
+        ids = np.concatenate([b._ids for b in batches]) if len(batches) > 1 else batches[0]._ids
+        W = [b.max_num_bonds if not (w_override and w_override[i]) else int(w_override[i]) for i, b in enumerate(batches)]
+        return DeviceGraph.assemble_ids(store, ids, [b.n_mols for b in batches], dev, W)
+
+    @staticmethod
+    def assemble_ids(store: MoleculeStore, ids, lens, dev, W=None) -> "DeviceGraph":
+        """``assemble`` without BatchMolGraph objects: store ids of all molecules, segments back to back, and the segment lengths.
+        The evaluation pass and the RankNet window hand over hundreds of groups at once; their per-group host objects were the cost."""
+        from .. import _lib
+        dev = torch.device(dev)
         store.sync(dev)
-        S = len(batches)
-        nA = sum(b.n_atoms for b in batches)
-        nB = sum(b.n_bonds for b in batches)
-        nM = sum(b.n_mols for b in batches)
-        wmax = max(1, max(b._max_deg for b in batches))
+        ctl, (nA, nB, nM, wmax, S), _ = DeviceGraph.control_block(store, ids, lens, W)
         sections = DeviceGraph._sections(nA, nB, nM, wmax, S)
         offs, total = {}, 0
         for name, nbytes in sections:
             offs[name] = total
             total += _align(max(nbytes, 4))
-        # one small pinned buffer: [ids | a_start | b_start | W | pad_bond | pad_atom] per molecule + 3 per segment
-        ctl = np.empty(6 * nM + 3 * S, np.int32)
-        ids, a_st, b_st, mW, mpb, mpa = (ctl[i * nM:(i + 1) * nM] for i in range(6))
-        seg = ctl[6 * nM:].reshape(3, S)
-        a0 = b0 = m0 = 0
-        for s_i, b in enumerate(batches):
-            W = b.max_num_bonds if not (w_override and w_override[s_i]) else int(w_override[s_i])
-            if W < b.max_num_bonds:
-                raise ValueError(f"max_num_bonds override {W} < this batch's in-degree {b.max_num_bonds}")
-            n = b.n_mols
-            ids[m0:m0 + n] = b._ids
-            a_st[m0:m0 + n] = b._a_start + a0
-            b_st[m0:m0 + n] = b._b_start + b0
-            mW[m0:m0 + n], mpb[m0:m0 + n], mpa[m0:m0 + n] = W, b0, a0
-            seg[0, s_i], seg[1, s_i], seg[2, s_i] = a0, b0, W
-            a0 += b.n_atoms
-            b0 += b.n_bonds
-            m0 += n
         # pinned staging + device buffers come from a pool (see _BufferPool); the device control block lives at the end of the blob
         ctl_bytes = _align(ctl.nbytes)
         host = _POOL.take(ctl.nbytes, "pinned", lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True))
@@ -745,6 +772,61 @@ class DeviceGraph:
             return DeviceGraph.from_batches(r_batches, dev), pg
         uniq, w, amap = plan
         rg = DeviceGraph.from_batches(uniq, dev, w)
+        host = torch.from_numpy(amap).pin_memory()
+        rg.atom_map = host.to(dev, non_blocking=True)
+        rg._atom_map_host = host
+        rg.h2d_bytes += amap.nbytes
+        return rg, pg
+
+    @staticmethod
+    def dedup_ids(store: MoleculeStore, r_ids, p_ids, lens):
+        """``dedup_plan`` on store ids, vectorised over all segments: returns ``(unique reactant ids, their segment lengths, atom_map)`` or
+        None when no reactant repeats inside a segment.  Unique reactants keep the order of first appearance inside their segment."""
+        r_ids, p_ids = np.asarray(r_ids, dtype=np.int64), np.asarray(p_ids, dtype=np.int64)
+        lens = np.asarray(lens, dtype=np.int64)
+        S, nM = lens.shape[0], r_ids.shape[0]
+        if nM == 0 or p_ids.shape[0] != nM:
+            return None
+        nA_m = store.nA[r_ids].astype(np.int64)
+        if not np.array_equal(nA_m, store.nA[p_ids].astype(np.int64)):
+            raise ValueError("reactant and product batches must list the same molecules' atom counts (p - r is atom-wise, base_model.py:168)")
+        seg_of = np.repeat(np.arange(S, dtype=np.int64), lens)
+        _, first, inv = np.unique(seg_of * (int(r_ids.max()) + 1) + r_ids, return_index=True, return_inverse=True)
+        if first.shape[0] == nM:
+            return None
+        order = np.argsort(first, kind="stable")            # first appearance; segments are contiguous, so this is segment-major too
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.shape[0])
+        inv = rank[inv.reshape(-1)]
+        keep = first[order]
+        u_ids, u_lens = r_ids[keep].astype(np.int32), np.bincount(seg_of[keep], minlength=S)
+        # global first rows: all earlier molecules' rows + one padding row per segment so far
+        u_nA, u_seg = nA_m[keep], seg_of[keep]
+        u_start = np.cumsum(u_nA) - u_nA + u_seg + 1
+        p_start = np.cumsum(nA_m) - nA_m + seg_of + 1
+        A_p = 1 + np.bincount(seg_of, weights=nA_m, minlength=S).astype(np.int64)
+        A_u = 1 + np.bincount(u_seg, weights=u_nA, minlength=S).astype(np.int64)
+        a0_p = np.concatenate(([0], np.cumsum(A_p)[:-1]))
+        a0_u = np.concatenate(([0], np.cumsum(A_u)[:-1]))
+        amap = np.empty(int(A_p.sum()), np.int32)
+        is_pad = np.zeros(amap.shape[0], bool)
+        is_pad[a0_p] = True
+        amap[a0_p] = a0_u                                   # a segment's padding atom maps to its padding atom
+        rows = np.nonzero(~is_pad)[0]                        # molecule rows, in molecule order
+        amap[rows] = rows + np.repeat(u_start[inv] - p_start, nA_m)
+        return u_ids, u_lens, amap
+
+    @staticmethod
+    def from_id_groups(store: MoleculeStore, r_ids, p_ids, lens, device, dedup: bool):
+        """(reactant DeviceGraph, product DeviceGraph) of many segments straight from store ids (``Parsing_features.parsing_ids``): what
+        ``from_batches`` / ``from_batches_dedup`` build from one BatchMolGraph per segment, without creating those objects."""
+        dev = torch.device(device)
+        pg = DeviceGraph.assemble_ids(store, p_ids, lens, dev)
+        plan = DeviceGraph.dedup_ids(store, r_ids, p_ids, lens) if dedup else None
+        if plan is None:
+            return DeviceGraph.assemble_ids(store, r_ids, lens, dev), pg
+        u_ids, u_lens, amap = plan
+        rg = DeviceGraph.assemble_ids(store, u_ids, u_lens, dev)
         host = torch.from_numpy(amap).pin_memory()
         rg.atom_map = host.to(dev, non_blocking=True)
         rg._atom_map_host = host

@@ -21,17 +21,26 @@ def _forward_chunks(model, gpu, chunks, smiles2graph_dic):
     ``max_num_bonds``, exactly as if it had been the reference's whole BatchMolGraph).  Yields ``(lo, hi, preds)`` with the scores of
     chunks[lo:hi] on the device, rows in chunk order."""
     dev = torch.device("cuda", gpu) if isinstance(gpu, int) else torch.device(gpu)
+    dedup = bool(getattr(model, "dedup_reactants", False)) and not (model.training and getattr(model, "_dropout", 0) > 0)
+    fast = hasattr(smiles2graph_dic, "parsing_ids")
     for lo in range(0, len(chunks), GROUPS_PER_LAUNCH):
         part = chunks[lo:lo + GROUPS_PER_LAUNCH]
-        r_b = [smiles2graph_dic.parsing_smiles([s[0] for s in X]) for X, _ in part]
-        p_b = [smiles2graph_dic.parsing_smiles([s[1] for s in X]) for X, _ in part]
         feats = None
         if part[0][1] is not None:
             feats = np.concatenate([np.asarray(f, dtype=np.float64).reshape(len(X), -1) for X, f in part], axis=0)
-        if getattr(model, "dedup_reactants", False) and not (model.training and getattr(model, "_dropout", 0) > 0):
-            rg, pg = DeviceGraph.from_batches_dedup(r_b, p_b, dev)       # a group's candidates share one reactant graph
-        else:
-            rg, pg = DeviceGraph.from_batches(r_b, dev), DeviceGraph.from_batches(p_b, dev)
+        rg = pg = None
+        if fast:                       # store ids of the whole launch at once: no BatchMolGraph per group
+            r_ids = smiles2graph_dic.parsing_ids([s[0] for X, _ in part for s in X])
+            p_ids = smiles2graph_dic.parsing_ids([s[1] for X, _ in part for s in X])
+            if r_ids is not None and p_ids is not None:
+                rg, pg = DeviceGraph.from_id_groups(smiles2graph_dic.store, r_ids, p_ids, [len(X) for X, _ in part], dev, dedup)
+        if rg is None:
+            r_b = [smiles2graph_dic.parsing_smiles([s[0] for s in X]) for X, _ in part]
+            p_b = [smiles2graph_dic.parsing_smiles([s[1] for s in X]) for X, _ in part]
+            if dedup:
+                rg, pg = DeviceGraph.from_batches_dedup(r_b, p_b, dev)       # a group's candidates share one reactant graph
+            else:
+                rg, pg = DeviceGraph.from_batches(r_b, dev), DeviceGraph.from_batches(p_b, dev)
         yield lo, lo + len(part), model(rg, pg, gpu=gpu, add_features=feats)
 
 

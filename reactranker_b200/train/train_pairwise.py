@@ -17,10 +17,21 @@ from ..features.featurization import DeviceGraph
 from .loss import count_ordered_pairs, ranknet_window_loss
 
 
-def _run_window(model, window, pairs, optimizer, gpu, sigma, training_algo='sum_session'):
+def _window_graphs(window, smiles2graph_dic, dev):
+    """Reactant and product DeviceGraphs of a window, one segment per group.  With the package's Parsing_features the whole window goes
+    to the device as two id vectors; any other featuriser (the reference's interface: parsing_smiles only) gets one BatchMolGraph per group."""
+    if hasattr(smiles2graph_dic, "parsing_ids"):
+        r_ids = smiles2graph_dic.parsing_ids([s for w in window for s in w[0]])
+        p_ids = smiles2graph_dic.parsing_ids([s for w in window for s in w[1]])
+        if r_ids is not None and p_ids is not None:
+            return DeviceGraph.from_id_groups(smiles2graph_dic.store, r_ids, p_ids, [len(w[0]) for w in window], dev, dedup=False)
+    return (DeviceGraph.from_batches([smiles2graph_dic.parsing_smiles(w[0]) for w in window], dev),
+            DeviceGraph.from_batches([smiles2graph_dic.parsing_smiles(w[1]) for w in window], dev))
+
+
+def _run_window(model, window, pairs, optimizer, gpu, sigma, training_algo='sum_session', smiles2graph_dic=None):
     dev = torch.device("cuda", gpu)
-    rg = DeviceGraph.from_batches([w[0] for w in window], dev)
-    pg = DeviceGraph.from_batches([w[1] for w in window], dev)
+    rg, pg = _window_graphs(window, smiles2graph_dic, dev)
     targets = np.concatenate([w[2] for w in window]).astype(np.float32)
     feats = None
     if window[0][3] is not None:
@@ -49,17 +60,17 @@ def factorized_training_loop(epoch, model, loss_func, optimizer, scheduler, smil
         n_pairs = count_ordered_pairs(Y)
         if n_pairs == 0:                                # no positive pair: skipped before the forward (train_pairwise.py:103-104)
             continue
-        window.append((smiles2graph_dic.parsing_smiles([s[0] for s in X]), smiles2graph_dic.parsing_smiles([s[1] for s in X]), Y, add_features))
+        window.append(([s[0] for s in X], [s[1] for s in X], Y, add_features))
         pairs += n_pairs
         count += len(Y)
         if count >= batch_size:                         # train_pairwise.py:146-160
-            loss = _run_window(model, window, pairs, optimizer, gpu, sigma, training_algo)
+            loss = _run_window(model, window, pairs, optimizer, gpu, sigma, training_algo, smiles2graph_dic)
             scheduler.step()
             minibatch_loss.append(loss)
             window, pairs, count = [], 0.0, 0
     if pairs:                                           # tail flush, no scheduler.step() (train_pairwise.py:162-171)
         print('+' * 10, "End of batch, remaining pairs {}".format(pairs))
-        minibatch_loss.append(_run_window(model, window, pairs, optimizer, gpu, sigma, training_algo))
+        minibatch_loss.append(_run_window(model, window, pairs, optimizer, gpu, sigma, training_algo, smiles2graph_dic))
     return float(np.mean([float(l.detach()) for l in minibatch_loss])) if minibatch_loss else float('nan')
 
 

@@ -719,3 +719,30 @@ def test_rank_metrics_refuses_an_understated_max_group():
     _lib.check(L.rr_rank_metrics(40, 2, s.data_ptr(), 1, t.data_ptr(), seg.data_ptr(), 8, 0.25, out.data_ptr(), S()))
     o = out.cpu()
     assert bool(torch.isfinite(o[0]).all()) and bool(torch.isnan(o[1]).all())
+
+
+@pytest.mark.parametrize("dedup", [False, True])
+def test_id_vector_assembly_equals_per_group_batches(dedup):
+    """DeviceGraph.from_id_groups (store ids + segment lengths, no BatchMolGraph per group) builds byte-identical device graphs to
+    from_batches / from_batches_dedup: every section of the blob, the sizes and the reactant atom map."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(31, [6, 1, 9, 4], star_leaves_in_group={2: 7})
+    fz = Parsing_features(ds.mols)
+    groups = [(0, 6), (6, 7), (7, 16), (16, 20)]
+    r_b = [fz.parsing_smiles(list(ds.rsmi[a:b])) for a, b in groups]
+    p_b = [fz.parsing_smiles(list(ds.psmi[a:b])) for a, b in groups]
+    if dedup:
+        rg1, pg1 = DeviceGraph.from_batches_dedup(r_b, p_b, DEV)
+    else:
+        rg1, pg1 = DeviceGraph.from_batches(r_b, DEV), DeviceGraph.from_batches(p_b, DEV)
+    rg2, pg2 = DeviceGraph.from_id_groups(fz.store, fz.parsing_ids(list(ds.rsmi)), fz.parsing_ids(list(ds.psmi)), [b - a for a, b in groups], DEV, dedup)
+    torch.cuda.synchronize()
+    for g1, g2 in ((rg1, rg2), (pg1, pg2)):
+        assert (g1.n_atoms, g1.n_bonds, g1.n_mols, g1.c.wmax, g1.c.n_segments) == (g2.n_atoms, g2.n_bonds, g2.n_mols, g2.c.wmax, g2.c.n_segments)
+        assert g1._offs == g2._offs
+        end = max(g1._offs.values())
+        sizes = dict(DeviceGraph._sections(g1.n_atoms, g1.n_bonds, g1.n_mols, g1.c.wmax, g1.c.n_segments))
+        for name, off in g1._offs.items():
+            assert torch.equal(g1.blob[off:off + sizes[name]], g2.blob[off:off + sizes[name]]), name
+    if dedup:
+        assert rg2.n_mols == 4 and torch.equal(rg1.atom_map, rg2.atom_map)

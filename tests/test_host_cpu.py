@@ -412,3 +412,64 @@ def test_train_state_round_trip_resumes_adam_and_noam(tmp_path):
     save_checkpoint(weights_only, m1, 1.0, 2.0)
     with pytest.raises(_lib.RRError):
         load_train_state(weights_only, m3, o3, s3)
+
+
+def test_vectorised_control_block_equals_the_per_batch_layout():
+    """DeviceGraph.control_block (ids + segment lengths, vectorised) against the per-BatchMolGraph bookkeeping it replaced: every segment
+    is a reference-shaped batch (one padding row, running a_start / b_start, its own max_num_bonds), offsets accumulate over segments."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(21, [5, 1, 7, 3], star_leaves_in_group={2: 8})
+    fz = Parsing_features(ds.mols)
+    groups = [(0, 5), (5, 6), (6, 13), (13, 16)]
+    for override in (None, [None, 9, None, 12]):
+        batches = [fz.parsing_smiles(list(ds.rsmi[a:b])) for a, b in groups]     # the star molecule is a reactant
+        nM, S = sum(b.n_mols for b in batches), len(batches)
+        want = np.empty(6 * nM + 3 * S, np.int32)
+        ids, a_st, b_st, mW, mpb, mpa = (want[i * nM:(i + 1) * nM] for i in range(6))
+        seg = want[6 * nM:].reshape(3, S)
+        a0 = b0 = m0 = 0
+        for s_i, b in enumerate(batches):
+            W = b.max_num_bonds if not (override and override[s_i]) else override[s_i]
+            n = b.n_mols
+            ids[m0:m0 + n] = b._ids
+            a_st[m0:m0 + n] = b._a_start + a0
+            b_st[m0:m0 + n] = b._b_start + b0
+            mW[m0:m0 + n], mpb[m0:m0 + n], mpa[m0:m0 + n] = W, b0, a0
+            seg[0, s_i], seg[1, s_i], seg[2, s_i] = a0, b0, W
+            a0 += b.n_atoms
+            b0 += b.n_bonds
+            m0 += n
+        W = None if override is None else [b.max_num_bonds if o is None else o for b, o in zip(batches, override)]
+        got, (nA, nB, nM2, wmax, S2), (A_s, B_s, W_s) = DeviceGraph.control_block(fz.store, np.concatenate([b._ids for b in batches]),
+                                                                                  [b.n_mols for b in batches], W)
+        assert np.array_equal(got, want)
+        assert (nA, nB, nM2, S2) == (a0, b0, nM, S) and wmax == max(1, max(b._max_deg for b in batches))
+        assert A_s.tolist() == [b.n_atoms for b in batches] and B_s.tolist() == [b.n_bonds for b in batches]
+    assert [b.max_num_bonds for b in batches] == [4, 4, 8, 4]    # the star molecule widens its own segment only
+    with pytest.raises(ValueError):
+        DeviceGraph.control_block(fz.store, np.concatenate([b._ids for b in batches]), [b.n_mols for b in batches], [1, 1, 1, 1])
+    # an empty segment is a lone padding row
+    got, (nA, nB, nM2, wmax, S2), (A_s, B_s, W_s) = DeviceGraph.control_block(fz.store, batches[0]._ids, [0, batches[0].n_mols])
+    assert A_s.tolist() == [1, batches[0].n_atoms] and W_s.tolist() == [1, batches[0].max_num_bonds] and got[6 * nM2:].reshape(3, 2)[0].tolist() == [0, 1]
+
+
+def test_dedup_ids_equals_dedup_plan():
+    """The vectorised reactant de-duplication on store ids gives the same unique reactants, segment lengths and atom map as the
+    per-BatchMolGraph dedup_plan, on groups with one reactant each, on a whole batch as one segment and on a group with two reactants."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(12, [4, 1, 3, 6])
+    fz = Parsing_features(ds.mols)
+    layouts = [[(0, 4), (4, 5), (5, 8), (8, 14)], [(0, 14)], [(0, 6), (6, 14)]]       # the last two mix reactants inside a segment
+    for groups in layouts:
+        r_b = [fz.parsing_smiles(list(ds.rsmi[a:b])) for a, b in groups]
+        p_b = [fz.parsing_smiles(list(ds.psmi[a:b])) for a, b in groups]
+        uniq, w, amap = DeviceGraph.dedup_plan(r_b, p_b)
+        r_ids, p_ids = fz.parsing_ids(list(ds.rsmi)), fz.parsing_ids(list(ds.psmi))
+        u_ids, u_lens, amap2 = DeviceGraph.dedup_ids(fz.store, r_ids, p_ids, [b - a for a, b in groups])
+        assert np.array_equal(u_ids, np.concatenate([u._ids for u in uniq])) and u_lens.tolist() == [u.n_mols for u in uniq]
+        assert np.array_equal(amap2, amap)
+        # the widths the unique segments get by default are the widths the full reactant segments had
+        _, _, (_, _, W_s) = DeviceGraph.control_block(fz.store, u_ids, u_lens)
+        assert W_s.tolist() == w
+    # nothing repeats -> None
+    assert DeviceGraph.dedup_ids(fz.store, fz.parsing_ids([ds.rsmi[0]]), fz.parsing_ids([ds.psmi[0]]), [1]) is None
