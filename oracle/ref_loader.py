@@ -5,7 +5,7 @@ is not installed, so stub modules are injected first.  The reference package is
 mounted under the private name ``_rr_reference`` so it never collides with this
 repo's own ``reactranker`` compatibility package.
 
-Only ``tests/`` and ``scripts/make_golden.py`` use this module, and only in the
+Only ``tests/`` and ``tests/golden/make_golden.py`` use this module, and only in the
 build container: ``/root/reference`` does not exist on the GPU box, where
 ``available()`` returns False and everything falls back to the committed golden
 vectors under ``tests/golden/``.

@@ -2,7 +2,7 @@
 """Generate ``tests/golden/*.npz`` by EXECUTING THE REAL REFERENCE (``/root/reference``,
 rdkit stubbed) on synthetic MolGraphs.  Run in the build container only:
 
-    python scripts/make_golden.py
+    python tests/golden/make_golden.py
 
 The GPU box has no ``/root/reference``; the parity tests there read these files.
 Nothing here is product code.
@@ -13,7 +13,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402

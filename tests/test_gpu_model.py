@@ -29,7 +29,7 @@ TASKS = {"mle": (1, None), "listnet": (1, None), "evidential_ranking": (2, "evid
 
 def product_loss(task, out, scope, targets, gpu=GPU):
     from reactranker_b200.train.train_listwise import batch_loss
-    if task in ("listnet_uq", "dirichlet_uq"):   # the golden's point on the annealing schedule (scripts/make_golden.py)
+    if task in ("listnet_uq", "dirichlet_uq"):   # the golden's point on the annealing schedule (tests/golden/make_golden.py)
         return batch_loss(task, out, scope, targets, gpu, 0.05, 3, 5)
     return batch_loss(task, out, scope, targets, gpu)
 

@@ -101,7 +101,7 @@ def test_two_gpu_step_equals_one_gpu_step(tmp_path):
 @pytest.mark.parametrize("two", [False, True])
 def test_validation_metrics_on_device_match_reference_golden(two, monkeypatch):
     """ranking_metrics / evaluate_top_scores as the product runs them (scores on the device, rr_rank_metrics, one host wait) return what
-    the reference's functions returned for the same stub scorer (tests/golden/metrics.npz, scripts/make_golden.py golden_metrics)."""
+    the reference's functions returned for the same stub scorer (tests/golden/metrics.npz, tests/golden/make_golden.py golden_metrics)."""
     from test_host_cpu import _StubScorer
     from reactranker_b200 import synthetic
     from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features

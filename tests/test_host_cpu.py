@@ -248,7 +248,7 @@ def test_molecule_store_registration_is_thread_safe():
         assert out[k].n_atoms == want.n_atoms and torch.equal(out[k].a2b, want.a2b) and torch.equal(out[k].f_bonds, want.f_bonds)
 
 
-# ---- evaluation metrics vs the reference's own functions (tests/golden/metrics.npz: scripts/make_golden.py golden_metrics) ----------
+# ---- evaluation metrics vs the reference's own functions (tests/golden/metrics.npz: tests/golden/make_golden.py golden_metrics) ----------
 class _StubScorer(torch.nn.Module):
     """Same deterministic scorer the golden was generated with (scores from the product token + the extra feature)."""
 

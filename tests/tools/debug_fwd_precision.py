@@ -1,8 +1,9 @@
 """Scores / loss / gradient error of the forward operand splits (3 x tf32, 3 x bf16) against the fp64 oracle, at the two north-star
-model sizes, on a batch large enough for accumulation effects (usage: python scripts/debug_fwd_precision.py)."""
+model sizes, on a batch large enough for accumulation effects (usage: python tests/tools/debug_fwd_precision.py)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import reactranker_oracle as O
 from reactranker_b200 import _lib, synthetic
