@@ -468,11 +468,21 @@ def ours(args):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the oracle port of the reference path -- the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_training_steps(wl, groups, steps, warmup, seed=99):
+def cpu_training_steps(wl, groups, steps, warmup, seed=99, device="cpu"):
+    """Training steps of the oracle port.  ``device="cuda"`` is the informative secondary comparator of SURVEY.md 8(d): the same eager
+    PyTorch code with its tensors on the GPU, as the reference runs with ``gpu=0`` (graphs still built on the host every step)."""
     from oracle import reactranker_oracle as O
     from reactranker_b200 import synthetic
     torch.manual_seed(0)
+    dev = torch.device(device)
     sd = O.init_state_dict(wl["hidden"], wl["task_num"], 1, True, seed=0, mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"])
+    sd = {k: v.to(dev) for k, v in sd.items()}
+
+    def put(g):                                         # featurization tensors follow the model (mpn.py:76-77)
+        if dev.type != "cpu":
+            for name in ("f_atoms", "f_bonds", "a2b", "b2a", "b2revb"):
+                setattr(g, name, getattr(g, name).to(dev))
+        return g
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "cached_zero" not in k}
     full = dict(sd)
     full.update(params)
@@ -483,31 +493,36 @@ def cpu_training_steps(wl, groups, steps, warmup, seed=99):
     for ds in pool:                                     # warm MolGraph cache, as the reference's Parsing_features
         for m in ds.mols.values():
             m._mk_lists()
-    times = []
+    times, model_times = [], []
     for i in range(warmup + steps):
         ds = pool[i % len(pool)]
-        t0 = time.perf_counter()
+        t0 = t1 = time.perf_counter()
         if wl["task"] == "ranknet":
             # train_pairwise.py:81-160: one forward per group, summed pairwise cost / ordered pairs of the window
             cost, pairs, o = 0.0, 0.0, 0
             for n in scope:
-                r_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi[o:o + n]])
-                p_g = O.OracleBatch([ds.mols[t] for t in ds.psmi[o:o + n]])
+                r_g = put(O.OracleBatch([ds.mols[t] for t in ds.rsmi[o:o + n]]))
+                p_g = put(O.OracleBatch([ds.mols[t] for t in ds.psmi[o:o + n]]))
                 y = O.model_forward(full, r_g, p_g, ds.temp[o:o + n].reshape(-1, 1), mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], head=head,
                                     dropout=wl["dropout"], training=True)
                 c, p = O.ranknet_group_cost(y, ds.lgk[o:o + n])
                 cost, pairs, o = cost + c, pairs + p, o + n
             loss = cost / pairs
         else:
-            r_g = O.OracleBatch([ds.mols[t] for t in ds.rsmi])      # BatchMolGraph build per step (featurization.py:246-290)
-            p_g = O.OracleBatch([ds.mols[t] for t in ds.psmi])
+            r_g = put(O.OracleBatch([ds.mols[t] for t in ds.rsmi]))     # BatchMolGraph build per step (featurization.py:246-290)
+            p_g = put(O.OracleBatch([ds.mols[t] for t in ds.psmi]))
+            t1 = time.perf_counter()
             out = O.model_forward(full, r_g, p_g, ds.temp.reshape(-1, 1), mpnn_depth=wl["depth"], mpnn_diff_depth=wl["diff_depth"], head=head,
                                   dropout=wl["dropout"], training=True)
-            loss = O.loss_for_task(wl["task"], out, scope, torch.tensor(ds.lgk.astype(np.float32)))
+            loss = O.loss_for_task(wl["task"], out, scope, torch.tensor(ds.lgk.astype(np.float32)).to(dev))
         opt.zero_grad()
         loss.backward()
         opt.step()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
+        model_times.append(time.perf_counter() - t1)
+    cpu_training_steps.model_only = model_times[warmup:]       # forward + loss + backward + Adam without the per-step graph build
     return times[warmup:], sum(scope)
 
 
@@ -527,6 +542,15 @@ def reference(args):
         return
     wl = WORKLOADS[args.workload]
     groups = max(2, min(wl["groups"], 500 // wl["group"]))
+    if args.ref_device == "cuda":          # informative only, never the reference arm: eager PyTorch on the GPU, full workload batch
+        times, rows = cpu_training_steps(wl, wl["groups"], args.steps, args.warmup, device="cuda")
+        mo = cpu_training_steps.model_only
+        print(json.dumps({"impl": "reference-eager-cuda", "metric": metric_of(wl), "unit": UNIT, "value": rows * len(times) / sum(times),
+                          "value_model_only": rows * len(mo) / sum(mo), "ms_per_step": 1e3 * sum(times) / len(times),
+                          "ms_per_step_model_only": 1e3 * sum(mo) / len(mo), "steps": args.steps, "warmup": args.warmup,
+                          "note": "oracle port of the reference's PyTorch path with tensors on cuda:0 (the reference's gpu=0 mode); graphs are "
+                                  "built on the host every step as the reference does; model_only excludes that build"}))
+        return
     times, rows = cpu_training_steps(wl, groups, args.steps, args.warmup)
     value = rows * len(times) / sum(times)
     cpu = {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
@@ -548,6 +572,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=3, help="distinct synthetic batches per rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cuda = informative extra line, the same eager PyTorch code with its tensors on the GPU")
     ap.add_argument("--dropout", type=float, default=None, help="override the workload's dropout (the entry scripts' 0.1 / 0.2 by default)")
     ap.add_argument("--no-dedup", action="store_true", help="at dropout 0: still encode one reactant graph per candidate like the reference")
     ap.add_argument("--gemm", default="tc", choices=["tc", "simt"], help="dense layers: tcgen05 3xTF32 (default) or exact-fp32 SIMT")

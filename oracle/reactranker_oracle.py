@@ -141,7 +141,7 @@ def mpndiff_forward(sd, diff, g, depth: int, add_features=None, dropout: float =
             vecs.append(hid.narrow(0, start, size).sum(dim=0) / size)
     vecs = torch.stack(vecs, dim=0)
     if add_features is not None:                                   # mpn.py:237-238 (cast mpn.py:183)
-        vecs = torch.cat([vecs, torch.as_tensor(np.asarray(add_features), dtype=torch.float32).to(dt)], dim=1)
+        vecs = torch.cat([vecs, torch.as_tensor(np.asarray(add_features), dtype=torch.float32).to(device=vecs.device, dtype=dt)], dim=1)
     return vecs
 
 
