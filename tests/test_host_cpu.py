@@ -473,3 +473,60 @@ def test_dedup_ids_equals_dedup_plan():
         assert W_s.tolist() == w
     # nothing repeats -> None
     assert DeviceGraph.dedup_ids(fz.store, fz.parsing_ids([ds.rsmi[0]]), fz.parsing_ids([ds.psmi[0]]), [1]) is None
+
+
+def test_control_block_and_dedup_ids_on_random_layouts():
+    """Property check over random segmentations (incl. empty and single-molecule segments, repeated and interleaved reactants): the
+    vectorised host code agrees with a direct per-segment construction of the same quantities."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    ds = synthetic.make_dataset(77, [3, 5, 2, 6, 4])
+    fz = Parsing_features(ds.mols)
+    all_r, all_p = fz.parsing_ids(list(ds.rsmi)), fz.parsing_ids(list(ds.psmi))
+    rng = np.random.default_rng(5)
+    store = fz.store
+    for trial in range(40):
+        n = int(rng.integers(1, 20))
+        pick = rng.integers(0, len(all_r), size=n)
+        r_ids, p_ids = all_r[pick], all_p[pick]
+        cuts = np.sort(rng.integers(0, n + 1, size=int(rng.integers(0, 5))))
+        lens = np.diff(np.concatenate(([0], cuts, [n])))
+        ctl, (nA, nB, nM, wmax, S), (A_s, B_s, W_s) = DeviceGraph.control_block(store, p_ids, lens)
+        m = ctl[:6 * nM].reshape(6, nM)
+        a0 = b0 = o = 0
+        for s_i, ln in enumerate(lens.tolist()):
+            ids = p_ids[o:o + ln]
+            na, nb = store.nA[ids].astype(np.int64), store.nB[ids].astype(np.int64)
+            W = max(1, int(store.maxdeg[ids].max())) if ln else 1
+            assert (A_s[s_i], B_s[s_i], W_s[s_i]) == (1 + na.sum(), 1 + nb.sum(), W)
+            assert m[1, o:o + ln].tolist() == (a0 + 1 + np.cumsum(na) - na).tolist()
+            assert m[2, o:o + ln].tolist() == (b0 + 1 + np.cumsum(nb) - nb).tolist()
+            assert set(m[3, o:o + ln].tolist()) <= {W} and set(m[4, o:o + ln].tolist()) <= {b0} and set(m[5, o:o + ln].tolist()) <= {a0}
+            a0, b0, o = a0 + 1 + int(na.sum()), b0 + 1 + int(nb.sum()), o + ln
+        assert (nA, nB) == (a0, b0)
+        plan = DeviceGraph.dedup_ids(store, r_ids, p_ids, lens)
+        uniq_per_seg, o = [], 0
+        for ln in lens.tolist():
+            seen = []
+            for x in r_ids[o:o + ln].tolist():
+                if x not in seen:
+                    seen.append(x)
+            uniq_per_seg.append(seen)
+            o += ln
+        if sum(len(u) for u in uniq_per_seg) == n:
+            assert plan is None
+            continue
+        u_ids, u_lens, amap = plan
+        assert u_ids.tolist() == [x for u in uniq_per_seg for x in u] and u_lens.tolist() == [len(u) for u in uniq_per_seg]
+        # atom map by brute force: row of atom k of product molecule j -> row of atom k of its reactant inside the de-duplicated graph
+        want, a0_p, a0_u, o = [], 0, 0, 0
+        for ln, useg in zip(lens.tolist(), uniq_per_seg):
+            u_na = store.nA[np.asarray(useg, dtype=np.int64)].astype(np.int64) if useg else np.zeros(0, np.int64)
+            u_start = a0_u + 1 + np.cumsum(u_na) - u_na
+            want.append(a0_u)
+            for x in r_ids[o:o + ln].tolist():
+                st = int(u_start[useg.index(x)])
+                want.extend(range(st, st + int(store.nA[x])))
+            a0_p += 1 + int(store.nA[p_ids[o:o + ln]].sum())
+            a0_u += 1 + int(u_na.sum())
+            o += ln
+        assert amap.tolist() == want
