@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the ReactRanker training hot path (D-MPNN reaction encoder + LTR loss) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c5-500|c2|c3|c4]
 
 One "step" = one training step over one batch of synthetic reaction graphs: forward, loss,
 backward, (gradient all-reduce,) Adam, NoamLR.  Prints ONE JSON line (rank 0).
@@ -20,6 +20,8 @@ backward, (gradient all-reduce,) Adam, NoamLR.  Prints ONE JSON line (rank 0).
 * ``cpu_baseline`` / ``--impl reference``: the CPU restatement of the reference path
                (oracle/reactranker_oracle.py; the reference is Python and /root/reference does not
                travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+               ``--impl reference --ref-device cuda`` prints an extra, informative line instead: the same eager PyTorch code with
+               its tensors on cuda:0 (the reference's gpu=0 mode), full batch, with and without the per-step graph build.
 """
 import argparse
 import json
