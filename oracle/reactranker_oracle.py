@@ -240,7 +240,7 @@ def evidential_ranking_loss(out2, scope, targets) -> torch.Tensor:
 
 def gauss_loss(mu, var, targets) -> torch.Tensor:
     """``GaussDisLoss`` (loss.py:144-162)."""
-    pi = torch.tensor([np.pi], dtype=torch.float32).to(mu.dtype)
+    pi = torch.tensor([np.pi], dtype=torch.float32, device=var.device)         # ``torch.Tensor([np.pi])``: the constant term is evaluated in fp32 even in an fp64 run
     return torch.mean(0.5 * torch.log(2 * pi) + 0.5 * torch.log(var) + (mu - targets) ** 2 / (2 * var))
 
 
@@ -365,7 +365,8 @@ def dirichlet_uq_loss(concentration, scope, targets, max_coeff, epoch, epochs) -
 
 def lognorm_loss(scores, std_scores, targets) -> torch.Tensor:
     """Lognorm (loss.py:165-184)."""
-    mse = 0.5 * math.log(2 * math.pi) + 0.5 * torch.log(std_scores * (scores ** 2)) + torch.pow(torch.log(scores) - targets, 2) / (2 * std_scores)
+    pi = torch.tensor([np.pi], dtype=torch.float32, device=scores.device)     # loss.py:174, as in GaussDisLoss
+    mse = 0.5 * torch.log(2 * pi) + 0.5 * torch.log(std_scores * (scores ** 2)) + torch.pow(torch.log(scores) - targets, 2) / (2 * std_scores)
     return torch.mean(mse)
 
 
