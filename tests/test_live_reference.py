@@ -117,3 +117,125 @@ def test_oracle_equals_live_reference_on_fresh_inputs(task):
     gscale = max(float(np.abs(g).max()) for g in grads.values())
     for k, g in grads.items():
         assert np.abs(params[k].grad.numpy() - g).max() <= 1e-6 * gscale, k
+
+
+@pytest.mark.parametrize("seed,quant", [(401, None), (402, 0.5), (403, 0.25), (404, None)])
+def test_group_metrics_restatement_equals_live_reference(seed, quant):
+    """oracle.group_metrics (the checker of the rr_rank_metrics kernel) against the reference's ranking_metrics and evaluate_top_scores
+    (eval.py:475-555, 76-177) on fresh frames; ``quant`` coarsens the scorer so that groups contain exactly tied scores (stable order)."""
+    import make_golden as MG
+    lr = ref_loader.ref("data.load_reactions")
+    ev = ref_loader.ref("train.eval")
+    rng = np.random.default_rng(seed)
+    sizes = [int(x) for x in rng.integers(1, 24, size=int(rng.integers(4, 12)))]
+    ds = synthetic.make_dataset(seed, sizes, atoms_lo=3, atoms_hi=4)
+    df = ds.to_dataframe()
+
+    class Scorer(MG.StubScorer):
+        def forward(self, r_inputs, p_inputs, gpu=None, add_features=None):
+            s = super().forward(r_inputs, p_inputs, gpu, add_features)
+            return torch.round(s / quant) * quant if quant else s
+
+    class Feat:
+        class B:
+            def __init__(self, toks):
+                self.smiles_batch = list(toks)
+
+        def parsing_smiles(self, toks):
+            return Feat.B(toks)
+
+    m = Scorer(False).eval()
+    dp = lr.DataProcessor(df)
+    with _quiet():
+        a, b, c = ev.evaluate_top_scores(m, gpu=None, data_processor=dp, smiles2graph_dic=Feat(), ratio=0.25, batch_size=3, smiles_list=COLS,
+                                         target_name="lgk", add_features_name="temp")
+        r = ev.ranking_metrics(m, gpu=None, data_processor=dp, smiles2graph_dic=Feat(), show_info=False, smiles_list=COLS, target_name="lgk",
+                               add_features_name="temp")
+
+    def score(X, feats):
+        return m(None, Feat.B([s[1] for s in X]), add_features=feats).numpy()
+    rows = []
+    for X, t, scope, feats in dp.generate_batch_querys(smiles_list=COLS, target_name="lgk", batch_size=3, shuffle_query=False, shuffle_batch=False,
+                                                       add_features_name="temp"):
+        p, t, o = score(X, feats), np.asarray(t, np.float64).reshape(-1), 0
+        for n in scope:
+            rows.append(O.group_metrics(p[o:o + n], t[o:o + n], 0.25))
+            o += n
+    rows = np.asarray(rows)
+    assert np.allclose([rows[:, 0].mean(), rows[:, 1].mean(), rows[:, 3].mean()], [a, b, c], rtol=0, atol=1e-12)
+    rows = np.asarray([O.group_metrics(score(X, feats), np.asarray(t, np.float64).reshape(-1), 0.25)
+                       for X, t, feats in dp.generate_batch_per_query(smiles_list=COLS, target_name="lgk", shuffle_query=False, shuffle_batch=False,
+                                                                      add_features_name="temp")])
+    got = [rows[:, 0].mean(), rows[:, 1].mean(), rows[:, 2].mean()] + list(rows[:, 4:8].mean(axis=0))
+    assert np.allclose(got, [r[0], r[1], r[2]] + list(np.asarray(r[3], np.float64)), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("algo", ["sum_session", "accelerate_grad"])
+def test_oracle_ranknet_window_equals_live_reference_arithmetic(algo):
+    """Both training_algo branches of factorized_training_loop (train_pairwise.py:98-152) on a fresh window: the reference's lines, run with
+    the reference's model class, against the oracle's ranknet_group_cost / ranknet_group_lambda, in fp64."""
+    import make_golden as MG
+    sizes, star, seed = [3, 6, 2, 5], {1: 5}, 505
+    ds, fz = MG.dataset_case(seed, sizes, star)
+    model = MG.build_ref_model(32, 1, "no_softplus", None, seed=seed, depth=3, diff_depth=2, dtype=torch.float64).train()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "cached_zero" not in k}
+    full = dict(sd)
+    full.update(params)
+    orig = torch.FloatTensor
+    torch.FloatTensor = lambda x: torch.tensor(np.asarray(x, np.float32), dtype=torch.float64)  # type: ignore   (mpn.py:183 casts the extra feature)
+    try:
+        start, loss, pairs, ys, grads = 0, 0, 0, [], []
+        for n in sizes:
+            rows = slice(start, start + n)
+            start += n
+            r_g, p_g = fz.parsing_smiles(list(ds.rsmi[rows])), fz.parsing_smiles(list(ds.psmi[rows]))
+            for g in (r_g, p_g):
+                g.f_atoms, g.f_bonds = g.f_atoms.double(), g.f_bonds.double()
+            Y = ds.lgk[rows].reshape(-1, 1)
+            rel = Y - Y.T
+            pos, neg = torch.tensor((rel > 0).astype(np.float64)), torch.tensor((rel < 0).astype(np.float64))
+            y = model(r_g, p_g, gpu=None, add_features=ds.lgk[rows].reshape(-1, 1)).unsqueeze(1)
+            if algo == "sum_session":                           # lines 119-122
+                loss = loss + torch.sum(pos * torch.log(1 + torch.exp(-(y - y.t()))) + neg * torch.log(1 + torch.exp(y - y.t())), (0, 1))
+            else:                                               # lines 123-137
+                ys.append(y)
+                with torch.no_grad():
+                    l_pos, l_neg = 1 + torch.exp(y - y.t()), 1 + torch.exp(-(y - y.t()))
+                    loss = loss + torch.sum(torch.log(l_neg) * pos + torch.log(l_pos) * neg, (0, 1))
+                    grads.append(torch.sum(-pos / l_pos + neg / l_neg, dim=1, keepdim=True))
+            pairs += 2 * float(pos.sum())
+    finally:
+        torch.FloatTensor = orig  # type: ignore
+    model.zero_grad()
+    if algo == "sum_session":
+        (loss / pairs).backward()
+    else:
+        for g, y in zip(grads, ys):
+            y.backward(g / pairs, retain_graph=True)
+    want = {k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None}
+    start, total, opairs, lam, oys = 0, 0, 0.0, [], []
+    for n in sizes:
+        rows = slice(start, start + n)
+        start += n
+        y = O.model_forward(full, O.OracleBatch([ds.mols[t] for t in ds.rsmi[rows]]), O.OracleBatch([ds.mols[t] for t in ds.psmi[rows]]),
+                            ds.lgk[rows].reshape(-1, 1), mpnn_depth=3, mpnn_diff_depth=2, head="no_softplus")
+        if algo == "sum_session":
+            c, npairs = O.ranknet_group_cost(y, ds.lgk[rows])
+        else:
+            c, l, npairs = O.ranknet_group_lambda(y, ds.lgk[rows])
+            lam.append(l)
+            oys.append(y)
+        if c is not None:
+            total, opairs = total + c, opairs + npairs
+    assert opairs == pairs
+    if algo == "sum_session":
+        (total / opairs).backward()
+    else:
+        for l, y in zip(lam, oys):
+            if l is not None:
+                y.reshape(-1, 1).backward(l / opairs, retain_graph=True)
+    assert abs(float((total / opairs).detach()) - float((loss / pairs).detach())) <= 1e-12
+    gscale = max(float(np.abs(g).max()) for g in want.values())
+    for k, g in want.items():
+        assert np.abs(params[k].grad.numpy() - g).max() <= 1e-10 * gscale, k
