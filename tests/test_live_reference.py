@@ -239,3 +239,44 @@ def test_oracle_ranknet_window_equals_live_reference_arithmetic(algo):
     gscale = max(float(np.abs(g).max()) for g in want.values())
     for k, g in want.items():
         assert np.abs(params[k].grad.numpy() - g).max() <= 1e-10 * gscale, k
+
+
+@pytest.mark.parametrize("seed,two", [(601, False), (602, True), (603, True)])
+def test_calculate_ndcg_equals_live_reference(seed, two):
+    """The test-report routine calculate_ndcg (eval.py:329-457; host arithmetic in the product too): NDCG / KL means, the per-item order
+    table and the re-ordered tokens against the reference's function on fresh frames, raw and de-normalised, ordered and unordered."""
+    import make_golden as MG
+    from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features
+    from reactranker_b200.train import eval as E
+    lr = ref_loader.ref("data.load_reactions")
+    ev = ref_loader.ref("train.eval")
+    rng = np.random.default_rng(seed)
+    sizes = [int(x) for x in rng.integers(2, 15, size=int(rng.integers(3, 9)))]
+    ds = synthetic.make_dataset(seed, sizes, atoms_lo=3, atoms_hi=4)
+    df = ds.to_dataframe()
+
+    class Feat:
+        class B:
+            def __init__(self, toks):
+                self.smiles_batch = list(toks)
+
+        def parsing_smiles(self, toks):
+            return Feat.B(toks)
+
+    m = MG.StubScorer(two).eval()
+    fz = Parsing_features(ds.mols)
+    for means, stds, cut in ((None, None, 0.5), (0.3, 2.5, 0.25)):
+        kw = dict(batch_size=int(rng.integers(1, 5)), NDCG_cut=cut, smiles_list=COLS, target_name="lgk", means=means, stds=stds, add_features_name="temp")
+        with _quiet():
+            want = ev.calculate_ndcg(m, gpu=None, data_processor=lr.DataProcessor(df), smiles2graph_dic=Feat(), **kw)
+            got = E.calculate_ndcg(m, gpu=None, data_processor=DataProcessor(df), smiles2graph_dic=fz, **kw)
+        assert np.allclose([got[0], got[1]], [want[0], want[1]], rtol=1e-6)
+        assert np.allclose(np.asarray(got[2], np.float64), np.asarray(want[2], np.float64), rtol=1e-6, atol=1e-6)
+        assert [list(x) for x in got[3]] == [list(x) for x in want[3]]
+    with _quiet():
+        want = ev.calculate_ndcg(m, gpu=None, data_processor=lr.DataProcessor(df), smiles2graph_dic=Feat(), batch_size=2, smiles_list=COLS, target_name="lgk",
+                                 is_order=False, add_features_name="temp")
+        got = E.calculate_ndcg(m, gpu=None, data_processor=DataProcessor(df), smiles2graph_dic=fz, batch_size=2, smiles_list=COLS, target_name="lgk",
+                               is_order=False, add_features_name="temp")
+    assert got[0] is None and got[1] is None and want[0] is None
+    assert np.allclose(np.asarray(got[2], np.float64), np.asarray(want[2], np.float64), rtol=1e-6, atol=1e-6) and [list(x) for x in got[3]] == [list(x) for x in want[3]]
