@@ -280,3 +280,41 @@ def test_calculate_ndcg_equals_live_reference(seed, two):
                                is_order=False, add_features_name="temp")
     assert got[0] is None and got[1] is None and want[0] is None
     assert np.allclose(np.asarray(got[2], np.float64), np.asarray(want[2], np.float64), rtol=1e-6, atol=1e-6) and [list(x) for x in got[3]] == [list(x) for x in want[3]]
+
+
+@pytest.mark.parametrize("target_name", ["lgk", "ea", "lgk_bi"])
+@pytest.mark.parametrize("normalize_target", [True, False, 2.5, "1,7"])
+@pytest.mark.parametrize("save_metric", ["all", "NDCG@2"])
+def test_target_normalisation_equals_live_reference_train(monkeypatch, target_name, normalize_target, save_metric):
+    """The target transform at the top of train() (train_listwise.py:66-124: sign flip for everything but lgk / lgk_bi, z-score / float
+    scale / "lo,hi" range, raw validation targets for the NDCG save metrics) against the reference's own train(), stopped where it hands
+    the two frames to its DataProcessor."""
+    import logging
+    from reactranker_b200.train.train_listwise import NDCG_METRICS, normalized_targets
+    tl = ref_loader.ref("train.train_listwise")
+    ds = synthetic.make_dataset(701, [4, 3, 5, 2], atoms_lo=3, atoms_hi=4)
+    df = ds.to_dataframe()
+    df["ea"] = df["lgk"] * 3.0 + 11.0
+    df["lgk_bi"] = (df["lgk"] > 0).astype(np.float64)
+    train_df, val_df = df.iloc[:9].reset_index(drop=True), df.iloc[9:].reset_index(drop=True)
+    frames = []
+
+    class Stop(Exception):
+        pass
+
+    class Capture:
+        def __init__(self, frame):
+            frames.append(frame.copy())
+            if len(frames) == 2:
+                raise Stop()
+
+    monkeypatch.setattr(tl, "DataProcessor", Capture)
+    with _quiet(), pytest.raises(Stop):
+        tl.train(torch.nn.Linear(1, 1), None, train_df, val_df, "unused", None, 1, None, 4, 0, None, task_type="mle", writer=None,
+                 logger=logging.getLogger("live"), target_name=target_name, smiles_list=COLS, save_metric=save_metric,
+                 normalize_target=normalize_target)
+    t_std, v_std, mean, std = normalized_targets(train_df[target_name], val_df[target_name], target_name, normalize_target)
+    assert np.allclose(np.asarray(t_std, np.float64), frames[0]["std" + target_name].to_numpy(np.float64), rtol=0, atol=1e-15)
+    want_val = val_df[target_name] if save_metric in NDCG_METRICS else v_std
+    assert np.allclose(np.asarray(want_val, np.float64), frames[1]["std" + target_name].to_numpy(np.float64), rtol=0, atol=1e-15)
+    assert mean == train_df[target_name].mean() and std == train_df[target_name].std(ddof=0)
