@@ -318,3 +318,48 @@ def test_target_normalisation_equals_live_reference_train(monkeypatch, target_na
     want_val = val_df[target_name] if save_metric in NDCG_METRICS else v_std
     assert np.allclose(np.asarray(want_val, np.float64), frames[1]["std" + target_name].to_numpy(np.float64), rtol=0, atol=1e-15)
     assert mean == train_df[target_name].mean() and std == train_df[target_name].std(ddof=0)
+
+
+@pytest.mark.parametrize("cfg", [dict(warmup_epochs=2, total_epochs=30, train_data_size=4100, batch_size=410, init_lr=1e-4, max_lr=1e-3, final_lr=1e-4),
+                                 dict(warmup_epochs=1, total_epochs=3, train_data_size=57, batch_size=10, init_lr=3e-5, max_lr=2e-3, final_lr=5e-6),
+                                 dict(warmup_epochs=2.5, total_epochs=8, train_data_size=1000, batch_size=64, init_lr=1e-4, max_lr=1e-3, final_lr=1e-4)])
+def test_noam_schedule_and_optimizer_equal_live_reference(cfg):
+    """build_optimizer / build_lr_scheduler / NoamLR (train/utils.py:7-133): the learning rate written into the optimizer at every step of
+    a whole run, past total_steps too, and Adam's hyper-parameters."""
+    from reactranker_b200.train.utils import build_lr_scheduler, build_optimizer
+    ru = ref_loader.ref("train.utils")
+    m1, m2 = torch.nn.Linear(3, 2), torch.nn.Linear(3, 2)
+    o1, o2 = build_optimizer(m1), ru.build_optimizer(m2)
+    g1, g2 = o1.param_groups[0], o2.param_groups[0]
+    assert (g1["lr"], g1["betas"], g1["eps"], g1["weight_decay"], g1["amsgrad"]) == (g2["lr"], g2["betas"], g2["eps"], g2["weight_decay"], g2["amsgrad"])
+    s1, s2 = build_lr_scheduler(o1, **cfg), ru.build_lr_scheduler(o2, **cfg)
+    steps = int(cfg["total_epochs"] * (cfg["train_data_size"] // cfg["batch_size"])) + 5
+    for _ in range(steps):
+        assert o1.param_groups[0]["lr"] == o2.param_groups[0]["lr"]
+        s1.step()
+        s2.step()
+    assert o1.param_groups[0]["lr"] == o2.param_groups[0]["lr"] == cfg["final_lr"]
+
+
+def test_checkpoints_cross_load_with_the_reference(tmp_path):
+    """save_checkpoint (utils.py:152-173): a file written here is read by the reference's loader lines (test_listwise.py:27-38:
+    ``torch.load(path, map_location=...)`` then ``['state_dict']`` / ``['data_scaler']``), and a file written by the reference's function
+    (numpy-scalar means / stds) is read by load_checkpoint.  A resumable state file reads like a plain checkpoint on the reference's side."""
+    from reactranker_b200.utils import load_checkpoint, save_checkpoint, save_train_state
+    from reactranker_b200.train.utils import build_lr_scheduler, build_optimizer
+    ref_utils = ref_loader.ref("utils")
+    torch.manual_seed(1)
+    model = torch.nn.Linear(4, 3)
+    mean, std = np.float64(1.25), np.float64(0.5)
+    ours, theirs, state = str(tmp_path / "ours.pt"), str(tmp_path / "theirs.pt"), str(tmp_path / "state.pt")
+    save_checkpoint(ours, model, mean, std)
+    ref_utils.save_checkpoint(theirs, model, mean, std)
+    opt = build_optimizer(model)
+    save_train_state(state, model, opt, build_lr_scheduler(opt, 1, 2, 20, 5, 1e-4, 1e-3, 1e-4), epoch=0, means=mean, stds=std, best=0.5)
+    for path in (ours, state):
+        got = torch.load(path, map_location=lambda storage, loc: storage)          # the reference's loader line, torch >= 2.6 defaults
+        assert got["data_scaler"] == {"means": 1.25, "stds": 0.5}
+        assert all(torch.equal(v, model.state_dict()[k]) for k, v in got["state_dict"].items())
+    got = load_checkpoint(theirs)
+    assert float(got["data_scaler"]["means"]) == 1.25 and float(got["data_scaler"]["stds"]) == 0.5
+    assert all(torch.equal(v, model.state_dict()[k]) for k, v in got["state_dict"].items())
