@@ -203,6 +203,13 @@ int rr_get_forward_bf16(void);
 /* dX[M,k] (+)= dZ[M,n] W[n,k]   (accumulate != 0 adds) */
 int rr_linear_dgrad(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw,
                     float* dX, int lddx, int accumulate, void* stream);
+/* The same dX (+)= dZ W on the tcgen05 tensor cores, in the operand split rr_set_backward_bf16 selects (the kernel rr_model_backward uses:
+ * autograd of every nn.Linear of mpn.py / base_model.py).  The model keeps transposed, pre-split images of its weights; a direct caller
+ * provides `scratch` (device, 16-byte aligned, >= rr_linear_dgrad_tc_scratch_bytes(n, k)) for them.  Needs k % 16 == 0 and n % 4 == 0
+ * (RR_ERR_UNSUPPORTED otherwise). */
+int64_t rr_linear_dgrad_tc_scratch_bytes(int n, int k);
+int rr_linear_dgrad_tc(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx,
+                       int accumulate, void* scratch, int64_t scratch_bytes, void* stream);
 /* dW[n,k] += dZ^T X ; dbias[n] += colsum(dZ) when dbias != NULL.  Caller zeroes dW/dbias. */
 int rr_linear_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx,
                     float* dW, int lddw, float* dbias, void* stream);

@@ -48,7 +48,7 @@ class RRParams(ctypes.Structure):
 EXPORTS = [
     "rr_version", "rr_last_error", "rr_device_check", "rr_padded",
     "rr_graph_assemble", "rr_bond_message_fwd", "rr_bond_message_bwd", "rr_neighbor_sum_fwd", "rr_neighbor_sum_bwd",
-    "rr_bond_message_bwd_act", "rr_neighbor_sum_bwd_act", "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
+    "rr_bond_message_bwd_act", "rr_neighbor_sum_bwd_act", "rr_readout_fwd", "rr_readout_bwd", "rr_linear_fwd", "rr_linear_dgrad", "rr_linear_dgrad_tc", "rr_linear_dgrad_tc_scratch_bytes", "rr_linear_wgrad", "rr_relu_bwd", "rr_sub",
     "rr_loss_fwdbwd", "rr_loss_max_group", "rr_rank_metrics",
     "rr_model_workspace_bytes", "rr_model_buffer_offset", "rr_model_forward", "rr_model_backward", "rr_launch_count", "rr_launch_count_reset",
     "rr_profile_begin", "rr_profile_end", "rr_profile_classes", "rr_set_gemm_mode", "rr_get_gemm_mode", "rr_set_backward_bf16", "rr_get_backward_bf16",
@@ -112,6 +112,9 @@ def lib() -> ctypes.CDLL:
                 L.rr_readout_bwd.argtypes = [vp, vp, i32, vp, vp, vp, i32, f32, vp]
                 L.rr_linear_fwd.argtypes = [i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, u64, u64, vp]
                 L.rr_linear_dgrad.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp]
+                L.rr_linear_dgrad_tc.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, i64, vp]
+                L.rr_linear_dgrad_tc_scratch_bytes.argtypes = [i32, i32]
+                L.rr_linear_dgrad_tc_scratch_bytes.restype = ctypes.c_int64
                 L.rr_linear_wgrad.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
                 L.rr_relu_bwd.argtypes = [i64, i32, vp, vp, f32, i32, vp, vp, i32, vp]
                 L.rr_sub.argtypes = [i64, vp, vp, vp, vp]

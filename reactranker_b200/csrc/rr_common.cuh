@@ -244,6 +244,9 @@ int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t*
 extern std::atomic<int> g_fwd_bf16;
 // backward GEMMs: 1 = 3 x bf16 split (default; RR_BWD_BF16=0 or rr_set_backward_bf16(0) keeps 3 x tf32)
 extern std::atomic<int> g_bwd_bf16;
+long long tc_dgrad_scratch_bytes(int n, int k);
+int tc_dgrad_standalone(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx, int accumulate, void* scratch,
+                        long long scratch_bytes, cudaStream_t s);
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);
 int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s);
 

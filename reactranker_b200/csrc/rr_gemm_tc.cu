@@ -1194,6 +1194,60 @@ int tc_linear_bf16(int M, int n, const float* X, int ldx, const uint16_t* Whi, c
 }
 
 
+// ---- stand-alone tensor-core dgrad (C ABI: rr_linear_dgrad_tc) ---------------------------------------------------------------------
+// The model keeps the transposed, pre-split operand images of every weight in its packed workspace (k_pack).  A direct caller of the C ABI
+// hands over W[n, k] only, so the images are made here, into caller-provided scratch: Wt[k, ldt] as TF32 (hi, lo) floats and bf16 (hi, lo).
+__global__ void k_transpose_split(const float* __restrict__ W, int n, int k, int ldw, float* __restrict__ thi, float* __restrict__ tlo,
+                                  uint16_t* __restrict__ bhi, uint16_t* __restrict__ blo, int ldt) {
+  const long long total = static_cast<long long>(n) * k;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / k), c = static_cast<int>(i - static_cast<long long>(r) * k);
+    const float v = W[static_cast<size_t>(r) * ldw + c];
+    const size_t o = static_cast<size_t>(c) * ldt + r;
+    const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    thi[o] = hi;
+    tlo[o] = v - hi;
+    uint16_t b1, b2;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(b1) : "f"(v));
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(b2) : "f"(v - __uint_as_float(static_cast<uint32_t>(b1) << 16)));
+    bhi[o] = b1;
+    blo[o] = b2;
+  }
+}
+static inline int dgrad_ldt(int n) { return (n + 7) / 8 * 8; }
+long long tc_dgrad_scratch_bytes(int n, int k) {
+  const size_t e = static_cast<size_t>(k) * dgrad_ldt(n);
+  return static_cast<long long>((e * 4 + 255) / 256 * 256 * 2 + (e * 2 + 255) / 256 * 256 * 2);
+}
+int tc_dgrad_standalone(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx, int accumulate, void* scratch,
+                        long long scratch_bytes, cudaStream_t s) {
+  RR_REQUIRE(M > 0 && n > 0 && k > 0 && dZ && W && dX && scratch, "linear_dgrad_tc: bad argument");
+  RR_REQUIRE(aligned16(dZ) && aligned16(dX) && aligned16(scratch) && !(lddz & 3) && !(lddx & 3), "linear_dgrad_tc: operands must be 16-byte aligned rows");
+  RR_REQUIRE(scratch_bytes >= tc_dgrad_scratch_bytes(n, k), "linear_dgrad_tc: scratch %lld bytes < required %lld", scratch_bytes, tc_dgrad_scratch_bytes(n, k));
+  const int ldt = dgrad_ldt(n);
+  const size_t e = static_cast<size_t>(k) * ldt;
+  const size_t fb = (e * 4 + 255) / 256 * 256, hb = (e * 2 + 255) / 256 * 256;
+  char* base = static_cast<char*>(scratch);
+  float* thi = reinterpret_cast<float*>(base);
+  float* tlo = reinterpret_cast<float*>(base + fb);
+  uint16_t* bhi = reinterpret_cast<uint16_t*>(base + 2 * fb);
+  uint16_t* blo = reinterpret_cast<uint16_t*>(base + 2 * fb + hb);
+  const bool bf = g_bwd_bf16.load() != 0;
+  if (bf ? !tc_linear_bf16_supported(M, k, n, lddz, ldt) : !tc_supported(M, k, n, 0, lddz, 0))
+    return fail(RR_ERR_UNSUPPORTED, "linear_dgrad_tc: shape M %d n %d k %d does not suit the tensor-core kernel (k %% 16, n %% 4)", M, n, k);
+  RR_CUDA(cudaMemsetAsync(scratch, 0, 2 * fb + 2 * hb, s));
+  {
+    const long long total = static_cast<long long>(n) * k;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    k_transpose_split<<<blocks, 256, 0, s>>>(W, n, k, ldw, thi, tlo, bhi, blo, ldt);
+    RR_LAUNCH_CHECK("k_transpose_split");
+  }
+  if (bf) return tc_linear_bf16(M, k, dZ, lddz, bhi, blo, ldt, n, dX, lddx, accumulate, KC_GEMM_DGRAD, s);
+  return tc_linear(M, k, dZ, lddz, thi, ldt, n, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, dX, lddx, 0, accumulate, 0.f, 0, 0, KC_GEMM_DGRAD, s, tlo,
+                   nullptr);
+}
+
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx) {
   return M > 0 && n >= 4 && k >= 4 && !(n & 3) && !(k & 3) && !(lddz & 3) && !(ldx & 3);
 }

@@ -197,6 +197,79 @@ __global__ void k_head_bwd(int N, int task, int head, const float* __restrict__ 
   }
 }
 
+// ---- padding rows in exact arithmetic -------------------------------------------------------
+// A segment's padding bond / padding atom row is gathered by EVERY padded neighbour slot of the segment (featurization.py:281-286), so in
+// the backward pass it collects the gradient of all of them: at the c5 batch one such row weighs as much as ~10^5 ordinary rows.  Its ReLU
+// masks must therefore be decided as the reference's fp32 run decides them.  The tensor-core forward (3 x TF32, RZ accumulation) leaves
+// 2-5e-6 of relative error on a pre-activation, which flips the mask of an entry that lies that close to zero; on an ordinary row such a
+// flip moves the gradient by one row's share, on a padding row by a macroscopic amount.  After every tensor-core forward GEMM whose output
+// feeds a ReLU, the n_segments padding rows are therefore recomputed here from the unsplit fp32 weights with fp64 accumulation (one
+// rounding, tighter than any fp32 GEMM) and overwritten, epilogue (bias, residual, ReLU, the same Philox dropout mask) included.
+struct PadFix {
+  const int* rows;
+  int n_rows, n;
+  const float *X1, *W1, *X2, *W2, *bias, *resid;
+  int ldx1, k1, ldx2, k2, ldr;
+  float* Y;
+  int ldy, relu;
+  float p, inv_keep;
+  uint64_t seed, stream_id;
+};
+__global__ void k_pad_rows_linear(PadFix a) {
+  const size_t row = static_cast<size_t>(__ldg(a.rows + blockIdx.x));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = blockIdx.y * nwarps + warp; c < a.n; c += gridDim.y * nwarps) {
+    double acc = 0.0;
+    const float* x = a.X1 + row * a.ldx1;
+    const float* w = a.W1 + static_cast<size_t>(c) * a.k1;
+    for (int k = lane; k < a.k1; k += 32) acc += static_cast<double>(x[k]) * static_cast<double>(__ldg(w + k));
+    if (a.X2) {
+      x = a.X2 + row * a.ldx2;
+      w = a.W2 + static_cast<size_t>(c) * a.k2;
+      for (int k = lane; k < a.k2; k += 32) acc += static_cast<double>(x[k]) * static_cast<double>(__ldg(w + k));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (a.bias) acc += static_cast<double>(a.bias[c]);
+      if (a.resid) acc += static_cast<double>(a.resid[row * a.ldr + c]);
+      float o = static_cast<float>(acc);
+      if (a.relu) o = fmaxf(o, 0.f);
+      if (a.p > 0.f) {   // element (c & 3) of the 4-wide Philox draw the GEMM epilogue makes for this chunk (dropout4)
+        const uint4 r = philox4x32(a.seed, a.stream_id, (row * a.ldy + c) >> 2);
+        const uint32_t thr = static_cast<uint32_t>(fminf(a.p, 1.f) * 4294967295.f);
+        const uint32_t rv = (c & 3) == 0 ? r.x : ((c & 3) == 1 ? r.y : ((c & 3) == 2 ? r.z : r.w));
+        o = rv >= thr ? o * a.inv_keep : 0.f;
+      }
+      a.Y[row * a.ldy + c] = o;
+    }
+  }
+}
+// same argument order as linear_fwd; W1 / W2 are the raw (unsplit) packed weights
+static int pad_rows_linear(const int* rows, int n_rows, int n, const float* X1, int ldx1, const float* W1, int k1, const float* X2, int ldx2, const float* W2,
+                           int k2, const float* bias, const float* resid, int ldr, float* Y, int ldy, int flags, float p, uint64_t seed,
+                           uint64_t stream_id, cudaStream_t s) {
+  if (n_rows <= 0 || rows == nullptr) return RR_OK;
+  ProfScope prof_scope(KC_MISC, s);
+  PadFix a{};
+  a.rows = rows;
+  a.n_rows = n_rows;
+  a.n = n;
+  a.X1 = X1; a.ldx1 = ldx1; a.W1 = W1; a.k1 = k1;
+  a.X2 = (X2 && k2 > 0) ? X2 : nullptr; a.ldx2 = ldx2; a.W2 = W2; a.k2 = k2;
+  a.bias = bias; a.resid = resid; a.ldr = ldr;
+  a.Y = Y; a.ldy = ldy;
+  a.relu = flags & 1;
+  a.p = (flags & 2) ? p : 0.f;
+  a.inv_keep = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
+  a.seed = seed;
+  a.stream_id = stream_id;
+  const int by = n_rows >= 64 ? 1 : (n_rows >= 8 ? 2 : 8);
+  k_pad_rows_linear<<<dim3(n_rows, by), 256, 0, s>>>(a);
+  RR_LAUNCH_CHECK("k_pad_rows_linear");
+  return RR_OK;
+}
+
 // ---- workspace layout -----------------------------------------------------------------------
 struct EncBufs {
   float* inp;
@@ -333,6 +406,10 @@ long long model_buffer_offset(const rr_model_cfg* c, const rr_graph* r, const rr
   if (!strcmp(name, "hid2")) return off(W.hid2);
   if (!strcmp(name, "vec")) return off(W.vec);
   if (!strcmp(name, "zout")) return off(W.zout);
+  for (int l = 0; l + 1 < c->ffn_depth; ++l) {
+    snprintf(buf, sizeof(buf), "x%d", l);
+    if (!strcmp(name, buf)) return off(W.x[l]);
+  }
   fail(RR_ERR_INVALID, "unknown buffer name %s", name);
   return -1;
 }
@@ -355,7 +432,7 @@ static int check_model_args(const rr_model_cfg* c, const rr_params* w, const rr_
   RR_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f, "dropout must be in [0,1)");
   RR_REQUIRE(r->f_bonds && r->f_atoms && p->f_bonds && p->f_atoms, "model: graph features missing");
   RR_REQUIRE(c->head >= RR_HEAD_RAW && c->head <= RR_HEAD_NIG, "unknown head %d", c->head);
-  if (c->head == RR_HEAD_NIG) RR_REQUIRE((c->task_num & 3) == 0, "the NIG head needs task_num % 4 == 0");
+  if (c->head == RR_HEAD_NIG) RR_REQUIRE((c->task_num & 3) == 0, "the NIG head needs task_num %% 4 == 0");
   else if (c->head != RR_HEAD_RAW && c->head != RR_HEAD_SOFTPLUS && c->head != RR_HEAD_SOFTPLUS_P1)
     RR_REQUIRE((c->task_num & 1) == 0, "two-parameter heads need an even task_num");
   return RR_OK;
@@ -386,45 +463,55 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
   uint64_t sid = 1;
   RR_TRY(pack_params(*c, W, *w, s));
 
+  // Y = act(X1 W1^T + X2 W2^T + bias + resid), then the segment padding rows once more in exact arithmetic when the GEMM ran on tensor cores
+  const int gmode = g_gemm_mode.load();
+  const bool fix_pads = (gmode == 1 || gmode == 2);
+  auto lin = [&](const int* pad_rows, int n_pad, int M, int n, const float* X1, int ldx1, size_t W1, int k1, const float* X2, int ldx2, size_t W2, int k2,
+                 size_t bias, const float* resid, float* Y, int ldy, int flags) -> int {
+    const uint64_t id = sid++;
+    RR_TRY(linear_fwd(M, n, X1, ldx1, P + W1, k1, X2, ldx2, X2 ? P + W2 : nullptr, k2, P + bias, resid, hp, Y, ldy, flags, pdrop, c->seed, id, s, W.hi_off,
+                      W.lo_off, W.packed, W.bhi, W.blo));
+    if (fix_pads && pad_rows)
+      RR_TRY(pad_rows_linear(pad_rows, n_pad, n, X1, ldx1, P + W1, k1, X2, ldx2, X2 ? P + W2 : nullptr, k2, P + bias, resid, hp, Y, ldy, flags, pdrop, c->seed,
+                             id, s));
+    return RR_OK;
+  };
   const rr_graph* gs[2] = {r, p};
   for (int k = 0; k < 2; ++k) {  // mpn.py:61-108
     const rr_graph* g = gs[k];
     EncBufs& e = W.enc[k];
-    RR_TRY(linear_fwd(g->n_bonds, hp, g->f_bonds, RR_FB_LD, P + L.enc_Wi, RR_FB_LD, nullptr, 0, nullptr, 0, P + L.enc_bi, nullptr, 0,
-                      e.inp, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+    // f_bonds[pad] = 0: the padding rows of W_i's output are the bias exactly, on any GEMM path
+    RR_TRY(lin(nullptr, 0, g->n_bonds, hp, g->f_bonds, RR_FB_LD, L.enc_Wi, RR_FB_LD, nullptr, 0, 0, 0, L.enc_bi, nullptr, e.inp, hp, 0));
     const float* src = e.inp;
     int relu_src = 1;
     for (int t = 0; t < T; ++t) {
       RR_TRY(bond_message_fwd(g, src, e.pre[t], hp, relu_src, s));
-      RR_TRY(linear_fwd(g->n_bonds, hp, e.pre[t], hp, P + L.enc_Wh, hp, nullptr, 0, nullptr, 0, P + L.enc_bh, e.inp, hp, e.m[t + 1], hp,
-                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+      RR_TRY(lin(g->pad_bonds, g->n_segments, g->n_bonds, hp, e.pre[t], hp, L.enc_Wh, hp, nullptr, 0, 0, 0, L.enc_bh, e.inp, e.m[t + 1], hp, act));
       src = e.m[t + 1];
       relu_src = 0;
     }
     RR_TRY(neighbor_sum_fwd(g, 0, src, e.am, hp, relu_src, s));
-    RR_TRY(linear_fwd(g->n_atoms, hp, g->f_atoms, RR_FA_LD, P + L.enc_Wo_a, RR_FA_LD, e.am, hp, P + L.enc_Wo_m, hp, P + L.enc_bo, nullptr, 0,
-                      e.hid, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+    RR_TRY(lin(g->pad_atoms, g->n_segments, g->n_atoms, hp, g->f_atoms, RR_FA_LD, L.enc_Wo_a, RR_FA_LD, e.am, hp, L.enc_Wo_m, hp, L.enc_bo, nullptr, e.hid, hp, act));
   }
   const int A = p->n_atoms;
   if (c->r_atom_map) RR_TRY(sub_gather(A, hp, W.enc[1].hid, W.enc[0].hid, c->r_atom_map, W.d, s));
   else RR_TRY(sub(static_cast<long long>(A) * hp, W.enc[1].hid, W.enc[0].hid, W.d, s));  // base_model.py:168
 
   // mpn.py:170-240 over the product graph
-  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wi, hp, nullptr, 0, nullptr, 0, P + L.dif_bi, nullptr, 0, W.inp2, hp, 0, 0.f, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+  RR_TRY(lin(p->pad_atoms, p->n_segments, A, hp, W.d, hp, L.dif_Wi, hp, nullptr, 0, 0, 0, L.dif_bi, nullptr, W.inp2, hp, 0));
   if (Td > 0) RR_TRY(neighbor_sum_fwd(p, 0, p->f_bonds, W.nf, RR_FB_LD, 0, s));
   {
     const float* src = W.inp2;
     int relu_src = 1;
     for (int t = 0; t < Td; ++t) {
       RR_TRY(neighbor_sum_fwd(p, 1, src, W.nm[t], hp, relu_src, s));
-      RR_TRY(linear_fwd(A, hp, W.nm[t], hp, P + L.dif_Wh_m, hp, W.nf, RR_FB_LD, P + L.dif_Wh_f, RR_FB_LD, P + L.dif_bh, W.inp2, hp, W.m2[t + 1], hp,
-                        act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+      RR_TRY(lin(p->pad_atoms, p->n_segments, A, hp, W.nm[t], hp, L.dif_Wh_m, hp, W.nf, RR_FB_LD, L.dif_Wh_f, RR_FB_LD, L.dif_bh, W.inp2, W.m2[t + 1], hp, act));
       src = W.m2[t + 1];
       relu_src = 0;
     }
     RR_TRY(neighbor_sum_fwd(p, 1, src, W.am2, hp, relu_src, s));
   }
-  RR_TRY(linear_fwd(A, hp, W.d, hp, P + L.dif_Wo_d, hp, W.am2, hp, P + L.dif_Wo_m, hp, P + L.dif_bo, nullptr, 0, W.hid2, hp, act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+  RR_TRY(lin(p->pad_atoms, p->n_segments, A, hp, W.d, hp, L.dif_Wo_d, hp, W.am2, hp, L.dif_Wo_m, hp, L.dif_bo, nullptr, W.hid2, hp, act));
   RR_TRY(readout_fwd(p, W.hid2, hp, c->hidden, addf, c->add_features, W.vec, vp, pdrop, c->seed, sid++, s));
 
   // base_model.py:40-60
@@ -434,8 +521,7 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
   for (int l = 0; l < c->ffn_depth; ++l) {
     const bool last = (l == c->ffn_depth - 1);
     float* y = last ? W.zout : W.x[l];
-    RR_TRY(linear_fwd(N, L.ffn_out[l], x, ldx, P + L.ffn_W[l], L.ffn_in[l], nullptr, 0, nullptr, 0, P + L.ffn_b[l], nullptr, 0, y, L.ffn_out[l],
-                      last ? 0 : act, pdrop, c->seed, sid++, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+    RR_TRY(lin(nullptr, 0, N, L.ffn_out[l], x, ldx, L.ffn_W[l], L.ffn_in[l], nullptr, 0, 0, 0, L.ffn_b[l], nullptr, y, L.ffn_out[l], last ? 0 : act));
     x = y;
     ldx = L.ffn_out[l];
   }

@@ -376,6 +376,37 @@ def test_tcgen05_wgrad_matches_fp64(tc_mode, M, n, k, bf16):
     close(dW, 2 * (dZ.double().T @ X.double()), tol)
 
 
+@pytest.mark.parametrize("M,n,k", [(1000, 304, 304), (4100, 304, 304), (777, 304, 64), (40000, 304, 304), (1000, 608, 608), (300, 304, 16),
+                                   (513, 48, 48), (129, 16, 320)])
+@pytest.mark.parametrize("bf16", [1, 0])
+def test_tcgen05_dgrad_matches_fp64(tc_mode, M, n, k, bf16):
+    """The tensor-core dgrad of rr_model_backward (k_tc_gemm2<16, BF> with the transposed, pre-split weight images; 14 launches of every
+    training step) through its own C-ABI entry point, dX (+)= dZ W, in both operand splits: 3 x bf16 (the default of the backward pass:
+    16 significand bits per operand) and 3 x tf32, overwrite and accumulate."""
+    L = _lib.lib()
+    tol = 3e-5 if bf16 else 1e-5
+    g = torch.Generator().manual_seed(M + n + k)
+    dZ, W = torch.randn(M, n, generator=g), torch.randn(n, k, generator=g) / n ** 0.5
+    dZ[0] *= 50.0                                   # one row two orders of magnitude larger (a padding row's gradient)
+    dZd, Wd = dZ.to(DEV), W.to(DEV)
+    nbytes = int(L.rr_linear_dgrad_tc_scratch_bytes(n, k))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    dX = torch.full((M, k), float("nan"), device=DEV)
+    want = dZ.double() @ W.double()
+    row_scale = want.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
+    try:
+        L.rr_set_backward_bf16(bf16)
+        _lib.check(L.rr_linear_dgrad_tc(M, n, k, dZd.data_ptr(), n, Wd.data_ptr(), k, dX.data_ptr(), k, 0, scratch.data_ptr(), nbytes, S()))
+        torch.cuda.synchronize()
+        assert float(((dX.double().cpu() - want).abs() / row_scale).max()) < tol          # per row: the large row must not hide the others
+        _lib.check(L.rr_linear_dgrad_tc(M, n, k, dZd.data_ptr(), n, Wd.data_ptr(), k, dX.data_ptr(), k, 1, scratch.data_ptr(), nbytes, S()))
+        assert float(((dX.double().cpu() - 2 * want).abs() / (2 * row_scale)).max()) < tol
+        st = L.rr_linear_dgrad_tc(M, n, 20, dZd.data_ptr(), n, Wd.data_ptr(), k, dX.data_ptr(), k, 0, scratch.data_ptr(), nbytes, S())
+        assert st == -4 and b"tensor-core" in L.rr_last_error()                             # RR_ERR_UNSUPPORTED, reported not crashed
+    finally:
+        L.rr_set_backward_bf16(1)
+
+
 def test_device_assembly_equals_host_packing():
     """rr_graph_assemble (molecule store in HBM, ids + offsets from the host) writes exactly the arrays the host packer
     ships, for a single batch, for a multi-segment launch and with a max_num_bonds override."""

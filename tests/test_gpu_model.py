@@ -15,7 +15,8 @@ from reactranker_b200 import _lib, synthetic
 from reactranker_b200.features.featurization import BatchMolGraph, DeviceGraph
 from reactranker_b200.models.base_model import build_model
 from reactranker_b200.train import loss as RL
-from helpers import dataset_from_golden, sd_from_golden, rel_err, star_dict, grads_close
+from helpers import (TOL, check_grads, dataset_from_golden, forced_relu_masks, gpu_relu_masks, grads_close, rel_err, sd_from_golden,
+                     star_dict)
 
 pytestmark = pytest.mark.gpu
 GPU = 0
@@ -44,6 +45,40 @@ def make_model(hidden, task, depth, ddepth, sd=None, dropout=0.0, last="with_sof
     return m.cuda(GPU)
 
 
+def oracle_run(sd, ds, sizes, task, depth, ddepth, masks=None, last="with_softplus", feats=None):
+    """fp64 oracle forward + loss + backward on the data set of a test; with ``masks`` the ReLU decisions are the GPU's
+    (helpers.forced_relu_masks).  Returns (scores, loss, {name: gradient}, mask flips)."""
+    sd64 = {k: v.double().cpu() for k, v in sd.items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if "cached_zero" not in k}
+    full = dict(sd64)
+    full.update(params)
+    tn, tt, *ll = TASKS[task]
+    head = O.resolve_task_type(tn, ll[0] if ll else last, tt)
+    r_o, p_o = O.OracleBatch([ds.mols[t] for t in ds.rsmi]), O.OracleBatch([ds.mols[t] for t in ds.psmi])
+    feats = ds.temp.reshape(-1, 1) if feats is None else feats
+    targets = torch.tensor(ds.lgk.astype(np.float32)).double()
+    flips = 0
+    if masks is None:
+        want = O.model_forward(full, r_o, p_o, feats, mpnn_depth=depth, mpnn_diff_depth=ddepth, head=head)
+    else:
+        with forced_relu_masks(masks) as fm:
+            want = O.model_forward(full, r_o, p_o, feats, mpnn_depth=depth, mpnn_diff_depth=ddepth, head=head)
+        flips = fm.flips
+    wl = O.loss_for_task(task, want, sizes, targets)
+    wl.backward(torch.ones_like(wl))
+    return want.detach().numpy(), wl.detach().numpy(), {k: v.grad.numpy() for k, v in params.items()}, flips
+
+
+def masked_oracle_factory(model, out, r_g, p_g, sd, ds, sizes, task, hidden, depth, ddepth, **kw):
+    """Reads the GPU's ReLU masks NOW (before backward recycles the workspace); the returned callable re-runs the oracle with them."""
+    masks = gpu_relu_masks(model, out, (r_g.n_atoms, r_g.n_bonds), (p_g.n_atoms, p_g.n_bonds), hidden, depth, ddepth)
+
+    def run():
+        _, _, g, flips = oracle_run(sd, ds, sizes, task, depth, ddepth, masks=masks, **kw)
+        return g, flips
+    return run
+
+
 CASES = ["mle.h40", "listnet.h40", "evidential_ranking.h40", "gauss_regression.h40", "regression.h40", "mle.star.h40",
          "evidential_ranking.h24d5"]
 COMPOSITE = ["mle_gaussian.h40", "listnet_gauss.h40", "mle_regression.h40", "listnet_regression.h40", "regression_exploss.h40",
@@ -52,30 +87,34 @@ COMPOSITE = ["mle_gaussian.h40", "listnet_gauss.h40", "mle_regression.h40", "lis
 
 
 @pytest.mark.parametrize("name", CASES + COMPOSITE)
-def test_scores_loss_grads_vs_reference_golden(golden, name):
+def test_scores_loss_grads_vs_reference_golden(golden, name, gemm_mode):
+    """All 21 golden cases of the real reference, on the exact-fp32 SIMT GEMMs and on the product's tcgen05 path."""
     g = golden("model_composite" if name in COMPOSITE else "model")
     task = str(g[name + ".task"])
     ds, sizes, hidden, depth, ddepth = dataset_from_golden(g, name)
-    model = make_model(hidden, task, depth, ddepth, sd_from_golden(g, name + ".sd"))
+    sd = sd_from_golden(g, name + ".sd")
+    model = make_model(hidden, task, depth, ddepth, sd)
     model.train()
     r_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi])
     p_g = BatchMolGraph([ds.mols[t] for t in ds.psmi])
     out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
     targets = torch.FloatTensor(ds.lgk.reshape(-1, 1)).squeeze()          # train_listwise.py:187
     loss = product_loss(task, out, sizes, targets)
+    redo = masked_oracle_factory(model, out, r_g, p_g, sd, ds, sizes, task, hidden, depth, ddepth) if gemm_mode == 1 else None
     model.zero_grad()
     loss.backward()
+    tol = TOL[gemm_mode]
     assert tuple(out.shape) == tuple(g[name + ".f32.scores"].shape)
     assert tuple(loss.shape) == tuple(g[name + ".f32.loss"].shape)       # [1] for mle/evidential, 0-d otherwise
-    assert rel_err(out.detach().cpu().numpy(), g[name + ".f64.scores"]) < 2e-5
-    assert rel_err(loss.detach().cpu().numpy(), g[name + ".f64.loss"]) < 2e-5
+    assert rel_err(out.detach().cpu().numpy(), g[name + ".f64.scores"]) < tol["score"]
+    assert rel_err(loss.detach().cpu().numpy(), g[name + ".f64.loss"]) < tol["loss"]
     got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
     want = {k: g[f"{name}.f64.grad.{k}"] for k in got}
-    assert not grads_close(got, want, 2e-4)
+    check_grads(gemm_mode, got, want, redo)
     assert model.encoder.cached_zero_vector.grad is None
 
 
-def test_h300_against_reference_golden(golden):
+def test_h300_against_reference_golden(golden, gemm_mode):
     """hidden 300 (the north-star width): weights re-created from the torch seed (checked bit-exact on CPU in
     test_host_cpu), outputs/loss/large-gradient checksums from the reference run."""
     g = golden("model")
@@ -88,24 +127,26 @@ def test_h300_against_reference_golden(golden):
     out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
     loss = RL.MLEloss()(out, sizes, torch.FloatTensor(ds.lgk), GPU)
     loss.backward()
-    assert rel_err(out.detach().cpu().numpy(), g[name + ".f64.scores"]) < 2e-5
-    assert rel_err(loss.detach().cpu().numpy(), g[name + ".f64.loss"]) < 2e-5
+    tol = TOL[gemm_mode]
+    assert rel_err(out.detach().cpu().numpy(), g[name + ".f64.scores"]) < tol["score"]
+    assert rel_err(loss.detach().cpu().numpy(), g[name + ".f64.loss"]) < tol["loss"]
     gscale = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith(name + ".f64.grad."))
+    gt = tol["grad"]
     for k, p in model.named_parameters():
         if not p.requires_grad:
             continue
         v = p.grad.double().cpu().numpy()
         if f"{name}.f64.grad.{k}" in g.files:
             w = g[f"{name}.f64.grad.{k}"]
-            assert np.abs(v - w).max() <= 2e-4 * np.abs(w).max() + 1e-4 * gscale, k
+            assert np.abs(v - w).max() <= gt * np.abs(w).max() + 0.5 * gt * gscale, k
         else:
             s = g[f"{name}.f64.gradsum.{k}"]
             got = np.asarray([v.sum(), np.abs(v).sum(), (v ** 2).sum()])
-            assert abs(got[1] - s[1]) <= 2e-4 * s[1] and abs(got[2] - s[2]) <= 4e-4 * s[2], k
+            assert abs(got[1] - s[1]) <= gt * s[1] and abs(got[2] - s[2]) <= 2 * gt * s[2], k
 
 
 @pytest.mark.parametrize("algo,pre", [("sum_session", ""), ("accelerate_grad", "acc.")])
-def test_ranknet_window_vs_reference_golden(golden, algo, pre):
+def test_ranknet_window_vs_reference_golden(golden, algo, pre, gemm_mode):
     """One accumulation window of factorized_training_loop (train_pairwise.py:81-160), both training_algo values: every group keeps its
     OWN max_num_bonds (one reference forward per group) but all groups share one launch here."""
     g = golden("ranknet")
@@ -127,13 +168,14 @@ def test_ranknet_window_vs_reference_golden(golden, algo, pre):
     assert pairs == float(g["f64.pairs"])
     loss = RL.ranknet_window_loss(y, sizes, ds.lgk.astype(np.float32), pairs, sigma=1.0, gpu=GPU, training_algo=algo)
     loss.backward()
-    assert rel_err(y.detach().cpu().numpy(), g["f64.scores"]) < 2e-5
-    assert rel_err(loss.detach().cpu().numpy(), g[pre + "f64.loss"]) < 2e-5
+    tol = TOL[gemm_mode]
+    assert rel_err(y.detach().cpu().numpy(), g["f64.scores"]) < tol["score"]
+    assert rel_err(loss.detach().cpu().numpy(), g[pre + "f64.loss"]) < tol["loss"]
     got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
-    assert not grads_close(got, {k: g[f"{pre}f64.grad.{k}"] for k in got}, 2e-4)
+    assert not grads_close(got, {k: g[f"{pre}f64.grad.{k}"] for k in got}, tol["grad"])
 
 
-def test_three_optimizer_steps_vs_reference_golden(golden):
+def test_three_optimizer_steps_vs_reference_golden(golden, gemm_mode):
     """Forward, ListMLE, backward, Adam, NoamLR for three steps (train_listwise.py:177-290)."""
     from reactranker_b200.train.utils import build_lr_scheduler, build_optimizer
     g = golden("steps")
@@ -167,33 +209,58 @@ def test_three_optimizer_steps_vs_reference_golden(golden):
             assert float(np.median(d)) <= 1e-6, k
 
 
-@pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5)])
-def test_vs_oracle_fresh_inputs(task, hidden, depth):
-    """The two north-star widths on inputs the goldens do not cover, oracle run in fp64 on the host."""
-    ds = synthetic.make_dataset(77, [7, 5, 9, 4])
+@pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5), ("mle", 296, 3)])
+def test_vs_oracle_fresh_inputs(task, hidden, depth, gemm_mode):
+    """The two north-star widths (and one that is not a multiple of 16) on inputs the goldens do not cover, oracle run in fp64 on the
+    host, in both GEMM modes.  Mode 1 (the product default) is held to the north star's 1e-4 on scores / loss and 1e-3 on every
+    gradient tensor; see helpers.check_grads for the one accepted exception (a mask decided by a pre-activation within 2e-5 of zero)."""
     sizes = [7, 5, 9, 4]
+    ds = synthetic.make_dataset(77, sizes)
     torch.manual_seed(3)
     model = make_model(hidden, task, depth, depth)
-    sd64 = {k: v.double().cpu() for k, v in model.state_dict().items()}
-    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if "cached_zero" not in k}
-    full = dict(sd64)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ws, wl, wg, _ = oracle_run(sd, ds, sizes, task, depth, depth)
+    r_g, p_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi])
+    out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+    loss = product_loss(task, out, sizes, torch.tensor(ds.lgk.astype(np.float32)))
+    redo = masked_oracle_factory(model, out, r_g, p_g, sd, ds, sizes, task, hidden, depth, depth) if gemm_mode == 1 else None
+    loss.backward()
+    tol = TOL[gemm_mode]
+    assert rel_err(out.detach().cpu().numpy(), ws) < tol["score"]
+    assert rel_err(loss.detach().cpu().numpy(), wl) < tol["loss"]
+    got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+    check_grads(gemm_mode, got, {k: wg[k] for k in got}, redo)
+
+
+@pytest.mark.parametrize("task,hidden,depth,groups,n", [("mle", 300, 3, 82, 50), ("evidential_ranking", 600, 5, 32, 32)])
+def test_default_mode_at_bench_size_vs_oracle(task, hidden, depth, groups, n):
+    """The benchmarked path at the benchmark's own size: c5 (ListMLE h300 d3, 82 groups x 50 = 4100 reactions, ~82 k atom and ~161 k bond
+    rows per graph) and a c4-shaped batch (UC-Listwise h600 d5, 32 x 32), dropout 0, product-default GEMM mode (tcgen05), against the
+    fp32 CPU oracle (the reference's own arithmetic: PyTorch fp32 on the host).  North-star tolerances, no exceptions: at this size a
+    single ReLU-kink flip weighs 1e-5 of a gradient tensor, so 1e-3 holds outright."""
+    assert _lib.lib().rr_get_gemm_mode() == 1
+    sizes = [n] * groups
+    ds = synthetic.make_dataset(4242, sizes)
+    torch.manual_seed(11)
+    model = make_model(hidden, task, depth, depth)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "cached_zero" not in k}
+    full = dict(sd)
     full.update(params)
-    r_o = O.OracleBatch([ds.mols[t] for t in ds.rsmi])
-    p_o = O.OracleBatch([ds.mols[t] for t in ds.psmi])
     tn, tt = TASKS[task]
-    want = O.model_forward(full, r_o, p_o, ds.temp.reshape(-1, 1), mpnn_depth=depth, mpnn_diff_depth=depth,
-                           head=O.resolve_task_type(tn, "with_softplus", tt))
+    want = O.model_forward(full, O.OracleBatch([ds.mols[t] for t in ds.rsmi]), O.OracleBatch([ds.mols[t] for t in ds.psmi]),
+                           ds.temp.reshape(-1, 1), mpnn_depth=depth, mpnn_diff_depth=depth, head=O.resolve_task_type(tn, "with_softplus", tt))
     targets = torch.tensor(ds.lgk.astype(np.float32))
-    wl = O.loss_for_task(task, want, sizes, targets.double())
+    wl = O.loss_for_task(task, want, sizes, targets)
     wl.backward(torch.ones_like(wl))
     out = model(BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi]), gpu=GPU,
                 add_features=ds.temp.reshape(-1, 1))
     loss = product_loss(task, out, sizes, targets)
     loss.backward()
-    assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < 2e-5
-    assert rel_err(loss.detach().cpu().numpy(), wl.detach().numpy()) < 2e-5
+    assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < 1e-4
+    assert rel_err(loss.detach().cpu().numpy(), wl.detach().numpy()) < 1e-4
     got = {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
-    assert not grads_close(got, {k: params[k].grad.numpy() for k in got}, 2e-4)
+    assert not grads_close(got, {k: params[k].grad.numpy() for k in got}, 1e-3)
 
 
 def test_eval_mode_is_deterministic_and_dropout_is_unbiased():
@@ -248,56 +315,60 @@ def test_full_batch_properties_at_config2_size():
     assert float(loss) > 0
 
 
-@pytest.mark.parametrize("name", ["mle.h40", "evidential_ranking.h24d5", "mle.star.h40", "listnet.h40"])
-def test_tcgen05_path_vs_reference_golden(golden, tc_mode, name):
-    """Same parity bar with the dense layers on tcgen05 (3xTF32 split, fp32-class accuracy)."""
-    test_scores_loss_grads_vs_reference_golden(golden, name)
-
-
-@pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5), ("mle", 296, 3)])
-def test_tcgen05_path_vs_oracle(tc_mode, task, hidden, depth):
-    """Dense layers on tcgen05 (3xTF32 split): activations / scores carry ~5e-6 relative error (the tensor core truncates
-    its fp32 accumulator once per MMA).  Gradients are checked in two parts, because this network is ill-conditioned at
-    the ReLU kinks of its padding rows (one padding row collects the gradient of every padded neighbour slot of the batch):
-    perturbing the WEIGHTS of the fp64 oracle by 5e-6 relative moves some gradient tensors by 3e-2 through a single mask
-    flip.  (1) With the forward masks fixed (exact-fp32 forward, tensor-core dgrad: gemm mode 3) gradients match the fp64
-    oracle to 2e-4 like the SIMT path; (2) with everything on tensor cores the scores/loss match to 5e-5 / 1e-5 and each
-    gradient tensor to 5e-2 in relative L2 with a typical (median) entry error below 2e-3 of the tensor's maximum."""
-    ds = synthetic.make_dataset(77, [7, 5, 9, 4])
+@pytest.mark.parametrize("task,hidden,depth", [("mle", 300, 3), ("evidential_ranking", 600, 5)])
+def test_tcgen05_backward_with_exact_forward(tc_mode, task, hidden, depth):
+    """gemm mode 3 = exact-fp32 forward (the oracle's masks up to fp32 rounding) + tensor-core dgrad / wgrad (3 x bf16): isolates the
+    backward GEMMs' accuracy from the forward's mask decisions.  Held to the SIMT path's 2e-4."""
     sizes = [7, 5, 9, 4]
+    ds = synthetic.make_dataset(77, sizes)
     torch.manual_seed(3)
     model = make_model(hidden, task, depth, depth)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    _, _, wg, _ = oracle_run(sd, ds, sizes, task, depth, depth)
+    _lib.check(_lib.lib().rr_set_gemm_mode(3))
+    out = model(BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi]), gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+    product_loss(task, out, sizes, torch.tensor(ds.lgk.astype(np.float32))).backward()
+    got = {k: p.grad.double().cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
+    gscale = max(float(np.abs(v).max()) for v in wg.values())
+    live = {k: w for k, w in wg.items() if float(np.abs(w).max()) >= 1e-6 * gscale}   # drop structurally-zero gradients
+    assert not grads_close(got, live, 2e-4)
+
+
+def test_padding_rows_are_exact_on_the_tensor_core_path(tc_mode):
+    """After every tensor-core forward GEMM the segment padding rows are recomputed from the unsplit fp32 weights with fp64 accumulation
+    (rr_model.cu: k_pad_rows_linear): one such row collects the gradient of every padded neighbour slot of its segment, so its ReLU masks
+    must be the reference's.  Check: padding rows of every saved activation agree with the fp64 oracle to fp32 rounding (5e-7 of the row's
+    maximum; the tensor-core rows carry 2-5e-6), also with several segments in one launch."""
+    sizes = [6, 4, 5]
+    ds = synthetic.make_dataset(31, sizes, star_leaves_in_group={1: 7})
+    torch.manual_seed(4)
+    model = make_model(300, "mle", 3, 3).eval()
     sd64 = {k: v.double().cpu() for k, v in model.state_dict().items()}
-    params = {k: v.clone().requires_grad_(True) for k, v in sd64.items() if "cached_zero" not in k}
-    full = dict(sd64)
-    full.update(params)
-    tn, tt = TASKS[task]
-    want = O.model_forward(full, O.OracleBatch([ds.mols[t] for t in ds.rsmi]), O.OracleBatch([ds.mols[t] for t in ds.psmi]),
-                           ds.temp.reshape(-1, 1), mpnn_depth=depth, mpnn_diff_depth=depth, head=O.resolve_task_type(tn, "with_softplus", tt))
-    targets = torch.tensor(ds.lgk.astype(np.float32))
-    wl = O.loss_for_task(task, want, sizes, targets.double())
-    wl.backward(torch.ones_like(wl))
-    wg = {k: v.grad.numpy() for k, v in params.items()}
-    r_g, p_g = BatchMolGraph([ds.mols[t] for t in ds.rsmi]), BatchMolGraph([ds.mols[t] for t in ds.psmi])
-    L = _lib.lib()
-    for mode in (3, 1):
-        _lib.check(L.rr_set_gemm_mode(mode))
-        model.zero_grad()
-        out = model(r_g, p_g, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
-        loss = product_loss(task, out, sizes, targets)
-        loss.backward()
-        got = {k: p.grad.double().cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}
-        gscale = max(float(np.abs(v).max()) for v in wg.values())
-        live = {k: w for k, w in wg.items() if float(np.abs(w).max()) >= 1e-6 * gscale}   # drop structurally-zero gradients
-        if mode == 3:
-            assert not grads_close(got, live, 2e-4)
-            continue
-        assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < 5e-5
-        assert rel_err(loss.detach().cpu().numpy(), wl.detach().numpy()) < 1e-5
-        for k, w in live.items():
-            e = got[k] - w
-            assert float(np.linalg.norm(e) / np.linalg.norm(w)) < 5e-2, k
-            assert float(np.median(np.abs(e))) < 2e-3 * float(np.abs(w).max()), k
+    dev = torch.device("cuda", GPU)
+    hp = _lib.lib().rr_padded(300)
+    o, rb, pb = 0, [], []
+    for n in sizes:
+        rb.append(BatchMolGraph([ds.mols[t] for t in ds.rsmi[o:o + n]]))
+        pb.append(BatchMolGraph([ds.mols[t] for t in ds.psmi[o:o + n]]))
+        o += n
+    rg, pg = DeviceGraph.from_batches(rb, dev), DeviceGraph.from_batches(pb, dev)
+    for p_ in model.parameters():
+        p_.requires_grad_(True)
+    out = model(rg, pg, gpu=GPU, add_features=ds.temp.reshape(-1, 1))
+    a0 = b0 = 0
+    for s_, n in enumerate(sizes):              # one oracle forward per segment = the reference's per-group forward
+        lo = sum(sizes[:s_])
+        trace = {}
+        O.model_forward(sd64, O.OracleBatch([ds.mols[t] for t in ds.rsmi[lo:lo + n]]), O.OracleBatch([ds.mols[t] for t in ds.psmi[lo:lo + n]]),
+                        ds.temp[lo:lo + n].reshape(-1, 1), trace=trace)
+        for name, rows, row0, key in (("enc1.m1", pg.n_bonds, b0, "encoder.msg1"), ("enc1.m2", pg.n_bonds, b0, "encoder.msg2"),
+                                      ("enc1.hid", pg.n_atoms, a0, "p_hiddens"), ("hid2", pg.n_atoms, a0, "diff_encoder.atom_hiddens")):
+            got = model.saved_activation(out, name, rows, hp)[row0, :300].double().cpu()
+            want = trace[key][0]
+            err = float((got - want).abs().max()) / max(float(want.abs().max()), 1e-30)
+            assert err <= (1e-6 if name == "hid2" else 5e-7), (s_, name, err)
+        a0 += pb[s_].n_atoms
+        b0 += pb[s_].n_bonds
 
 
 # ---- optional reactant de-duplication (rr_model_cfg.r_atom_map): exact without dropout ----------------------------------------------
