@@ -5,6 +5,13 @@ command-line arguments.  ``--synthetic G,N`` trains on G synthetic reactant grou
 
     python main.py --data_path reactions.csv --path runs/exp1 --gpu 0 --task_type listnet --batch_size 4096 --total_epochs 30
     python main.py --synthetic 100,20 --path /tmp/rr --gpu 0 --task_type mle --batch_size 100 --total_epochs 2
+
+Data-parallel over the GPUs of one box (new; the reference is single-device): launch the same command under torchrun,
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 main.py --data_path ... --batch_size 32768
+
+``--batch_size`` stays the GLOBAL batch; every rank plans the same batches and trains on its shard of whole reactant groups on
+cuda:LOCAL_RANK (train/step.py).  Rank 0 validates, writes the checkpoints and runs the final test.
 """
 import argparse
 import logging
@@ -64,15 +71,22 @@ def parse():
 
 def main():
     a = parse()
+    from reactranker_b200 import parallel
+    rank, world, local_rank = parallel.world_from_env()
+    if world > 1:
+        a.gpu = local_rank                      # one process per GPU
     path, data_path, val_data_path, test_data_path = a.path, a.data_path, a.val_data_path, a.test_data_path
     os.makedirs(path, exist_ok=True)
-    logging.basicConfig(filename=path + '/output.log', level=logging.INFO, format='%(asctime)s - %(message)s', datefmt='%d-%b-%y %H:%M:%S')
+    logging.basicConfig(filename=path + ('/output.log' if rank == 0 else '/output.rank{}.log'.format(rank)), level=logging.INFO,
+                        format='%(asctime)s - %(message)s', datefmt='%d-%b-%y %H:%M:%S')
     logger = logging.getLogger()
-    try:
-        from torch.utils.tensorboard import SummaryWriter
-        writer = SummaryWriter(path + '/loss_writer')
-    except Exception:
-        writer = None
+    writer = None
+    if rank == 0:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(path + '/loss_writer')
+        except Exception:
+            writer = None
     filtered_size = a.filtered_size
     smiles2graph_dic = Parsing_features()
     if a.synthetic:
@@ -143,14 +157,20 @@ def main():
         train(model, scheduler, train_data, val_data, path_checkpoints, optimizer, a.stop_after or total_epochs, smiles2graph_dic,
               batch_size=batch_size, seed=seed, gpu=gpu, task_type=task_type, writer=writer, logger=logger, target_name=target_name,
               smiles_list=smiles_list, save_metric=save_metric, add_features_name=add_features_name, resume_path=resume_path)
+        if rank != 0:                           # rank 0 tests; train() ended with a barrier, so its checkpoints are on disk
+            continue
         print(path_checkpoints)
         test_path = path_checkpoints[0] if save_metric == 'all' else path_checkpoints
         score, average_pred_in_targ, score3 = test(model, test_data, test_path, batch_size, smiles2graph_dic, gpu=gpu, smiles_list=smiles_list,
                                                    logger=logger, target_name=target_name, cal_ngcd=False, return_order=False,
                                                    add_features_name=add_features_name)
         test_score.append([score, average_pred_in_targ, score3])
-    print("test score for k_fold vailidation is: ", test_score)
-    logger.info('test score for k_fold vailidation is: {}'.format(test_score))
+    if rank == 0:
+        print("test score for k_fold vailidation is: ", test_score)
+        logger.info('test score for k_fold vailidation is: {}'.format(test_score))
+    if world > 1 and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return test_score
 
 

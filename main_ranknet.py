@@ -40,9 +40,13 @@ def parse():
 
 def main():
     a = parse()
+    from reactranker_b200 import parallel
+    rank, world, local_rank = parallel.world_from_env()        # under torchrun: one process per GPU, windows sharded by group
+    if world > 1:
+        a.gpu = local_rank
     path = a.path
     os.makedirs(path, exist_ok=True)
-    logging.basicConfig(filename=path + '/output.log', level=logging.INFO, format='%(asctime)s - %(message)s', datefmt='%d-%b-%y %H:%M:%S')
+    logging.basicConfig(filename=path + ('/output.log' if rank == 0 else '/output.rank{}.log'.format(rank)), level=logging.INFO, format='%(asctime)s - %(message)s', datefmt='%d-%b-%y %H:%M:%S')
     logger = logging.getLogger()
     smiles2graph_dic = Parsing_features()
     if a.synthetic:
@@ -92,13 +96,19 @@ def main():
                   seed=seed, gpu=gpu, train_strategy=train_strategy, task_type='baseline', writer=None, logger=logger, smiles_list=smiles_list,
                   target_name=target_name, save_metric=save_metric, add_features_name=add_features_name,
                   resume_path=os.path.join(a.path, str(ii) + '.state.pt') if a.resume else None)
+        if rank != 0:
+            continue
         test_path = path_checkpoints[0] if save_metric == 'all' else path_checkpoints
         score, score3, average_pred_in_targ = test(model, test_data, test_path, smiles2graph_dic, batch_size, gpu=gpu, logger=logger,
                                                    smiles_list=smiles_list, add_features_name=add_features_name, target_name=target_name,
                                                    train_strategy=train_strategy)
         test_score.append([score, score3])
-    print("test score for k_fold vailidation is: ", test_score)
-    logger.info('test score for k_fold vailidation is: {}'.format(test_score))
+    if rank == 0:
+        print("test score for k_fold vailidation is: ", test_score)
+        logger.info('test score for k_fold vailidation is: {}'.format(test_score))
+    if world > 1 and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return test_score
 
 

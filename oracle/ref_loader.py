@@ -5,22 +5,36 @@ is not installed, so stub modules are injected first.  The reference package is
 mounted under the private name ``_rr_reference`` so it never collides with this
 repo's own ``reactranker`` compatibility package.
 
-Only ``tests/`` and ``tests/golden/make_golden.py`` use this module, and only in the
-build container: ``/root/reference`` does not exist on the GPU box, where
-``available()`` returns False and everything falls back to the committed golden
-vectors under ``tests/golden/``.
+``tests/``, ``tests/golden/make_golden.py`` and ``bench.py``'s reference / cpu_baseline legs use this module.  In the build container the
+reference is read where it lies (``/root/reference``).  On the GPU box that path does not exist; what travels there is ``oracle/_ref/``,
+the reference's byte code compiled by ``oracle/build_ref.py`` (git-ignored compiler output, like the ``.so``), and the loader mounts that.
+The live-reference TESTS deliberately stay container-only (``source_available()``): on the box the committed goldens are the pin.
 """
 import importlib
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RR_REFERENCE_ROOT", "/root/reference")
+_SOURCE_ROOT = os.environ.get("RR_REFERENCE_ROOT", "/root/reference")
+_BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _PKG = "_rr_reference"
 
 
+def source_available() -> bool:
+    """The reference's source tree is present (the build container)."""
+    return os.path.isdir(os.path.join(_SOURCE_ROOT, "reactranker"))
+
+
+def built_available() -> bool:
+    """``oracle/_ref`` (byte code compiled by oracle/build_ref.py) is present."""
+    return os.path.isfile(os.path.join(_BUILT_ROOT, "reactranker", "models", "base_model.pyc"))
+
+
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "reactranker"))
+    return source_available() or built_available()
+
+
+REFERENCE_ROOT = _SOURCE_ROOT if source_available() else _BUILT_ROOT
 
 
 def _install_rdkit_stub() -> None:

@@ -57,14 +57,33 @@ EXPORTS = [
 KERNEL_CLASSES = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "bond_fwd", "bond_bwd", "nbr_fwd", "nbr_bwd", "readout", "elementwise", "loss", "misc"]
 
 
+def source_hash() -> str:
+    """sha256 over every CUDA source, header and the compiler flags: what the built library must correspond to."""
+    import hashlib
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(_ROOT, "include", "rr_sm100.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
+HASH_PATH = SO_PATH + ".hash"
+
+
 def build(verbose: bool = False, force: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a into ``reactranker_b200/librr_sm100.so``
-    (nvcc cross-compiles without a GPU).  Skipped when the .so is newer than every source."""
+    """Compile the CUDA sources for sm_100a into ``reactranker_b200/librr_sm100.so`` (nvcc cross-compiles without a GPU).
+    Skipped only when the library on disk was built from exactly these sources and flags: the hash of the sources is stored next to the
+    ``.so`` and compared, so a prebuilt library that travelled with the tree can never silently disagree with the sources beside it."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "rr_common.cuh"), os.path.join(_ROOT, "include", "rr_sm100.h")]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
-        return SO_PATH
+    want = source_hash()
+    if not force and os.path.exists(SO_PATH) and os.path.exists(HASH_PATH):
+        with open(HASH_PATH) as fh:
+            if fh.read().strip() == want:
+                return SO_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-shared", "-o", SO_PATH] + srcs
     if verbose:
@@ -72,6 +91,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(want + "\n")
     return SO_PATH
 
 

@@ -117,13 +117,24 @@ class _ReactionFn(torch.autograd.Function):
         params = ctx.saved_tensors
         model = ctx.model
         w = model._param_struct(params)
-        grads = [torch.empty_like(p) for p in params]
+        # All gradients are written into ONE flat buffer (state_dict layout, parameter order of _named_slots, each tensor 16-byte aligned)
+        # and handed to autograd as views of it: p.grad then aliases the buffer, and the data-parallel gradient exchange is a single
+        # all-reduce of `model._grad_flat` in place -- no flatten / unflatten copies (parallel.GradSync).
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
+        if total != sum(p.numel() for p in params):
+            flat.zero_()                                     # alignment gaps take part in the all-reduce
+        grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
         gw = model._param_struct(grads)
         dscores = dscores.contiguous().float()
         _lib.check(L.rr_model_backward(ctypes.byref(ctx.cfg), ctypes.byref(w), ctypes.byref(ctx.rg.c), ctypes.byref(ctx.pg.c),
                                        dscores.data_ptr(), ctypes.byref(gw), ctx.ws.data_ptr(), ctx.ws.numel(), _lib.stream_ptr()))
         model._ws_pool.give(ctx.ws)
         ctx.ws = None
+        model._grad_flat, model._grad_offsets = flat, offs
         return (None, None, None, None) + tuple(grads)
 
 
@@ -153,6 +164,7 @@ class ReactionModel(nn.Module):
         self.last_h2d_bytes = 0
         self.dedup_reactants = True      # encode repeated reactants once whenever that is exact (eval mode, dropout 0)
         self._ws_pool = _WorkspacePool()
+        self._grad_flat, self._grad_offsets = None, None     # the newest backward's flat gradient buffer (see _ReactionFn.backward)
 
     # ---- plumbing to the C ABI -----------------------------------------------------------
     def _named_slots(self):
@@ -182,6 +194,10 @@ class ReactionModel(nn.Module):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())        # follows torch.manual_seed
         return _lib.RRModelCfg(self._hidden, self._depth, self._diff_depth, self._ffn_depth, self._task_num, self._add,
                                self._head, int(training), self._dropout, seed)
+
+    def hot_parameters(self):
+        """The trainable parameters in the order of the flat gradient buffer."""
+        return [p for _, p in self._named_slots()]
 
     def saved_activation(self, out: torch.Tensor, name: str, rows: int, cols: int) -> torch.Tensor:
         """A forward activation kept in the workspace of the autograd node behind ``out`` (per-layer parity tests):

@@ -11,6 +11,7 @@ single-device step is kept by two rules:
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -48,27 +49,96 @@ def shard_rows(scope: Sequence[int], lo: int, hi: int) -> Tuple[int, int]:
 
 
 class GradSync:
-    """SUM all-reduce of all gradients through one flat bucket (one collective per step)."""
+    """SUM all-reduce of all gradients as ONE collective per step.
 
-    def __init__(self, params, group=None):
+    Fast path: ``ReactionModel`` writes the gradients of a backward pass into one flat buffer and gives autograd views of it, so
+    ``p.grad`` aliases ``model._grad_flat``; the buffer is all-reduced in place (3.16 MB at h = 300, 12.1 MB at h = 600) and nothing
+    is copied.  Whenever that aliasing does not hold (gradients accumulated over several backward passes into older tensors, a
+    hook that replaced ``p.grad``, parameters outside the model) the gradients go through a flat staging bucket instead."""
+
+    def __init__(self, params, group=None, model=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.model = model
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
+        self.fast_path_steps = 0
+        self.copy_path_steps = 0
+
+    def _aliased(self):
+        m = self.model
+        flat = getattr(m, "_grad_flat", None) if m is not None else None
+        if flat is None:
+            return None
+        hot = m.hot_parameters()
+        if len(hot) != len(self.params) or any(a is not b for a, b in zip(hot, self.params)):
+            return None
+        base = flat.data_ptr()
+        for p, off in zip(hot, m._grad_offsets):
+            g = p.grad
+            if g is None or not g.is_contiguous() or g.data_ptr() != base + 4 * off:
+                return None
+        return flat
 
     def __call__(self):
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        flat = self._aliased()
+        if flat is not None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.fast_path_steps += 1
+            return
+        self.copy_path_steps += 1
+        for p in self.params:
+            if p.grad is None:                     # a rank whose shard is empty still takes part in the collective
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
         if self.flat is None or self.flat.device != grads[0].device:
             self.flat = torch.empty(self.numel, dtype=grads[0].dtype, device=grads[0].device)
-        views = list(torch.split(self.flat, [g.numel() for g in grads]))
-        torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+        views = [v.view_as(g) for v, g in zip(torch.split(self.flat, [g.numel() for g in grads]), grads)]
+        torch._foreach_copy_(views, grads)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        torch._foreach_copy_([g.reshape(-1) for g in grads], views)
-        for p, g in zip(self.params, grads):
-            if p.grad is None:
-                p.grad = g
+        torch._foreach_copy_(grads, views)         # copies INTO p.grad whatever its strides are
+
+
+# ---- process-group plumbing for the entry points (train(), run_train(), main.py, main_ranknet.py, bench.py) ------------------------
+def world_from_env() -> Tuple[int, int, int]:
+    """(rank, world size, local rank) as torchrun exports them; (0, 1, 0) in a plain ``python main.py`` run."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_from_env(device=None, backend: str = None) -> Tuple[int, int]:
+    """Join the process group torchrun describes (no-op for world size 1 or when a group already exists).  ``device``: this rank's CUDA
+    device (NCCL) or None (gloo: the CPU tests).  Returns (rank, world)."""
+    rank, world, _ = world_from_env()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if device is not None and torch.cuda.is_available() else "gloo"
+        kw = {"device_id": torch.device(device)} if backend == "nccl" and device is not None else {}
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def current() -> Tuple[int, int]:
+    """(rank, world) of the initialised default group, (0, 1) otherwise."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def plan_shard(scope: Sequence[int], atoms_per_row: Sequence[int], rank: int, world: int) -> Tuple[int, int, int, int]:
+    """This rank's part of a global batch: ``(group_lo, group_hi, row_lo, row_hi)``.  ``scope`` = the batch's group sizes in rows,
+    ``atoms_per_row`` = atoms of every candidate row (balances the shards by work)."""
+    scope = np.asarray(scope, dtype=np.int64)
+    off = np.concatenate(([0], np.cumsum(scope)))
+    atoms = np.asarray(atoms_per_row, dtype=np.float64)
+    csum = np.concatenate(([0.0], np.cumsum(atoms)))
+    group_atoms = csum[off[1:]] - csum[off[:-1]]
+    lo, hi = shard_groups(group_atoms, world)[rank]
+    return lo, hi, int(off[lo]), int(off[hi])
 
 
 def broadcast_parameters(model, src: int = 0, group=None):

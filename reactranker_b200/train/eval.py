@@ -191,7 +191,41 @@ def _not_built(name):
     return f
 
 
-calculate_mse = _not_built("calculate_mse")
+def calculate_mse(model, gpu, data_processor, smiles2graph_dic, batch_size=2, show_info=True, smiles_list=None, target_name: str = 'ea',
+                  logger=None, add_features_name=None):
+    """Validation MSE for ``save_metric='mse'`` (eval.py:558-609, called at train_listwise.py:345-352).
+
+    The reference's function cannot run: it unpacks three values from the four ``generate_batch_querys`` yields,
+    calls the model without its extra features, and would return the squared error of the LAST chunk only.  What it is there for is
+    clear from its caller -- keep the checkpoint with the smallest validation error -- so this computes the mean squared error of the
+    first output column against ``target_name`` over ALL validation rows: every reactant group is one segment of a batched forward (its own
+    padding rows and ``max_num_bonds``, i.e. the scores of the reference's per-chunk forward), the squared errors are summed on the
+    device and one double comes back."""
+    model.eval()
+    chunks, targets = [], []
+    for X, t, scope, feats in data_processor.generate_batch_querys(smiles_list=smiles_list, target_name=target_name, batch_size=1,
+                                                                    shuffle_query=False, shuffle_batch=False,
+                                                                    add_features_name=add_features_name):
+        chunks.append((X, feats))
+        targets.append(np.asarray(t, dtype=np.float64).reshape(-1))
+    if not chunks:
+        return float('nan')
+    total = None
+    with torch.no_grad():
+        for lo, hi, preds in _forward_chunks(model, gpu, chunks, smiles2graph_dic):
+            p = preds[:, 0] if preds.dim() > 1 else preds
+            t = torch.from_numpy(np.concatenate(targets[lo:hi]).astype(np.float32)).pin_memory().to(p.device, non_blocking=True)
+            sq = torch.sum((t.double() - p.double()) ** 2)
+            total = sq if total is None else total + sq
+    n = sum(len(t) for t in targets)
+    mse = float(total) / n
+    if show_info:
+        print('the validation MSE over {} reactions is: {}'.format(n, mse))
+    if logger is not None:
+        logger.info('the validation MSE is {}'.format(mse))
+    return mse
+
+
 pairwise_acc = _not_built("pairwise_acc")
 pairwise_baseline_acc = _not_built("pairwise_baseline_acc")
 eval_cross_entropy_loss = _not_built("eval_cross_entropy_loss")

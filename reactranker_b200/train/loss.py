@@ -8,10 +8,10 @@ over groups, ListNet averages over all items of the batch, RankNet divides by th
 pair count of the accumulation window.  ``mle`` and ``evidential_ranking`` return shape [1]
 like the reference, the others a 0-d tensor.
 
-Besides the five north-star keys, the composite keys that are sums of these terms (``mle_gaussian``, ``listnet_gauss``,
-``mle_regression``, ``listnet_regression``), ``regression_exploss`` and the distribution-valued ``mledis_gaussian`` / ``listnetdis_gauss``
-(``MLEDisLoss``, ``Listnet_For_Gauss``) and ``listnet_uq`` (``Listnet_with_uq``) are dispatched by ``train()``; the remaining experimental losses of the reference (SURVEY.md §2
-row 6: log-normal ListNet, uncertainty-penalised ListNet, Dirichlet, NIG evidential) raise.
+Every task key the reference can run is dispatched by ``train()`` (train_listwise.batch_loss): the five north-star keys, the composite
+keys that are sums of their terms, the distribution-valued ``MLEDisLoss`` / ``Listnet_For_Gauss``, ``Listnet_with_uq``, ``Dirichlet_uq``,
+``Lognorm`` and the NIG ``evidential_loss_new``.  Only the two losses no task key constructs (``Listnetlognorm``,
+``Listnet_For_evidential``) raise.
 """
 from __future__ import annotations
 
@@ -93,17 +93,52 @@ def _segmented(kind, scores, scope, targets, gpu, norm, out_shape, sigma=1.0, ch
     return _LossFn.apply(scores.float(), t, seg, kind, n_items, len(scope), norm, sigma, out_shape)
 
 
+# ---- data-parallel normalisers -------------------------------------------------------------------------------------------------
+# When reaction groups are sharded over ranks (reactranker_b200/parallel.py), every rank divides by the GLOBAL batch's normaliser and the
+# gradients are SUM-all-reduced, which reproduces the single-device loss exactly.  The reference's losses normalise in one
+# of two ways: a mean over the batch's groups (ListMLE, UC-Listwise, the distribution-valued and uncertainty ListNet / ListMLE variants,
+# Dirichlet) or a mean over the batch's items (ListNet, Gaussian / log-normal NLL, MSE).  ``dp_normalisers(groups=G, items=N)`` sets both
+# for every loss evaluated inside the ``with`` block (train.step.TrainStep does, from the global batch plan); outside it, and for
+# world size 1, the local counts are used.  ``global_norm=`` on a loss object overrides the context for that object.
+import contextlib
+import threading
+
+_DP = threading.local()
+
+
+@contextlib.contextmanager
+def dp_normalisers(groups=None, items=None):
+    prev = getattr(_DP, "norms", None)
+    _DP.norms = (groups, items)
+    try:
+        yield
+    finally:
+        _DP.norms = prev
+
+
+def _global(kind: int):
+    n = getattr(_DP, "norms", None)
+    return None if n is None else n[kind]
+
+
+def _items_norm(local_items: int) -> float:
+    g = _global(1)
+    return float(local_items if g is None else g)
+
+
 class _DPNorm(nn.Module):
-    """Data-parallel hook: when reaction groups are sharded over ranks, every rank divides by the GLOBAL
-    normaliser (groups / items of the whole batch) and the gradients are SUM-all-reduced, which
-    reproduces the single-device loss exactly.  ``global_norm=None`` = single device."""
+    """Base of the segmented losses: ``_norm(local)`` is the divisor of a mean over GROUPS, ``_norm(local, items=True)`` of a mean over
+    ITEMS; ``global_norm`` (constructor) > ``dp_normalisers`` context > the local count."""
 
     def __init__(self, global_norm=None):
         super().__init__()
         self.global_norm = global_norm
 
-    def _norm(self, local):
-        return local if self.global_norm is None else self.global_norm
+    def _norm(self, local, items: bool = False):
+        if self.global_norm is not None:
+            return self.global_norm
+        g = _global(1 if items else 0)
+        return local if g is None else g
 
 
 class MLEloss(_DPNorm):
@@ -118,7 +153,7 @@ class ListnetLoss(_DPNorm):
     """ListNet top-1 (loss.py:317-352): ``mean over all items`` of ``-softmax(t) * log softmax(s)``."""
 
     def forward(self, score, scope, targets, gpu: int):
-        return _segmented(_lib.LOSS_LISTNET, score, scope, targets, gpu, norm=self._norm(int(sum(scope))), out_shape=())
+        return _segmented(_lib.LOSS_LISTNET, score, scope, targets, gpu, norm=self._norm(int(sum(scope)), items=True), out_shape=())
 
 
 class evidential_ranking(_DPNorm):
@@ -185,6 +220,9 @@ def evidential_loss_new(mu, v, alpha, beta, targets, gpu, lam=1, epsilon=1e-4):
     one all-pairs launch computes here; 1-D / mismatched shapes (element-wise in torch) are rejected rather than guessed."""
     if epsilon != 1e-4:
         raise _lib.RRError("evidential_loss_new: epsilon is fixed at the reference default 1e-4")
+    if _global(1) is not None and int(_global(1)) != int(mu.shape[0]):
+        raise _lib.RRError("the NIG task keys pair every reaction with EVERY target of the batch (the reference's [N,1] x [N] broadcast): "
+                           "the loss does not shard over ranks; train these keys on one GPU")
     cols = [mu, v, alpha, beta]
     n = mu.shape[0]
     if any(c.dim() != 2 or c.shape != (n, 1) for c in cols):
@@ -204,7 +242,7 @@ class Lognorm(nn.Module):
         dev = _device_of(gpu, scores)
         both = _mean_variance(scores, std_scores).float()
         n = both.shape[0]
-        return _LossFn.apply(both, _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_LOGNORM, n, 0, float(n), 1.0, ())
+        return _LossFn.apply(both, _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_LOGNORM, n, 0, _items_norm(n), 1.0, ())
 
 
 class _GaussFn(torch.autograd.Function):
@@ -216,7 +254,7 @@ class _GaussFn(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=both.device)
         d = torch.empty_like(both)
         with torch.cuda.device(both.device):
-            _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_GAUSS, n, 0, both.data_ptr(), targets.data_ptr(), None, float(n), 1.0,
+            _lib.check(L.rr_loss_fwdbwd(_lib.LOSS_GAUSS, n, 0, both.data_ptr(), targets.data_ptr(), None, _items_norm(n), 1.0,
                                         loss.data_ptr(), d.data_ptr(), _lib.stream_ptr()))
         ctx.save_for_backward(d)
         return loss.reshape(())
@@ -242,7 +280,7 @@ class MSELoss(nn.Module):
     def forward(self, output, targets):
         dev = _device_of(None, output)
         n = output.shape[0]
-        return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_MSE, n, 0, float(n), 1.0, ())
+        return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_MSE, n, 0, _items_norm(n), 1.0, ())
 
 
 class ExpMSELoss(nn.Module):
@@ -251,7 +289,7 @@ class ExpMSELoss(nn.Module):
     def forward(self, output, targets):
         dev = _device_of(None, output)
         n = output.shape[0]
-        return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_EXPMSE, n, 0, float(n), 1.0, ())
+        return _LossFn.apply(output.float().reshape(-1), _to_dev(targets, dev).reshape(-1), None, _lib.LOSS_EXPMSE, n, 0, _items_norm(n), 1.0, ())
 
 
 def ranknet_window_loss(scores, scope, targets, num_pairs: float, sigma: float = 1.0, gpu: Optional[int] = None,

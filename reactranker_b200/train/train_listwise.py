@@ -2,8 +2,10 @@
 dispatch, optimiser stepping and per-epoch checkpointing (train/train_listwise.py:21-373).
 
 Differences, all on purpose:
-* the five north-star keys run on the sm_100a path: ``mle``, ``listnet``, ``evidential_ranking``, ``gauss_regression`` and
-  the default ``regression``; the reference's experimental keys raise ``NotImplementedError`` (SURVEY.md §2 row 6);
+* every task key the reference can run is dispatched (``batch_loss``); only ``mle_dirichlet``, which cannot run in the reference
+  either, raises ``NotImplementedError``;
+* launched under ``torchrun`` (WORLD_SIZE > 1) the same call trains data-parallel: every rank plans the same global batches and takes
+  its shard of whole reactant groups (train/step.py, parallel.py); rank 0 validates, checkpoints and prints;
 * the reference copies ``encoder.W_i.weight`` to the host EVERY step to look for NaNs (train_listwise.py:190-195); here the
   check is ``torch.isfinite`` on the device, read back once per epoch together with the loss;
 * ``gpu=None`` raises: there is no CPU path.
@@ -26,6 +28,7 @@ from .. import _lib
 from ..data.load_reactions import DataProcessor
 from ..utils import load_train_state, save_checkpoint, save_train_state
 from .eval import calculate_mse, ranking_metrics
+from .step import TrainStep
 from .loss import (Dirichlet_uq, ExpMSELoss, GaussDisLoss, Listnet_For_Gauss, Listnet_with_uq, ListnetLoss, Lognorm, MLEDisLoss, MLEloss,
                    MSELoss, evidential_loss_new, evidential_ranking)
 
@@ -128,11 +131,16 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
     model = model.cuda(dev_idx)
     torch.cuda.manual_seed(seed)
     torch.cuda.manual_seed_all(seed)
+    step = TrainStep(model, optimizer, scheduler, task_type, dev_idx, max_coeff)      # joins torchrun's process group when WORLD_SIZE > 1
+    main = step.is_main()
+    if step.world > 1:
+        torch.manual_seed(seed + 1000003 * step.rank)       # every rank draws its own dropout masks; the batch plan is seeded per epoch
+        print('Note: data-parallel training, rank {} of {} on cuda:{}'.format(step.rank, step.world, dev_idx))
 
     train_data, val_data = copy.deepcopy(train_data_ini), copy.deepcopy(val_data_ini)
     score_old = float('inf') if save_metric == 'mse' else ([0, 0, 0] if save_metric == 'all' else float(0))
     data_len = train_data.shape[0] + val_data.shape[0]
-    if logger is not None:
+    if logger is not None and main:
         logger.info('Note: the length of training and vailidate data is: {}'.format(data_len))
     print("Note: the length of training and vailidate data is", data_len)
 
@@ -149,37 +157,49 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
         first_epoch, best, _ = load_train_state(resume_path, model, optimizer, scheduler)
         score_old = best if best is not None else score_old
         print('Note: resuming after epoch {} from {}'.format(first_epoch, resume_path))
-    for epoch in trange(first_epoch, epochs):
+    for epoch in trange(first_epoch, epochs, disable=not main):
         lr = optimizer.state_dict()['param_groups'][0]['lr']
-        print('learning rate: ', lr)
-        if logger is not None:
+        if main:
+            print('learning rate: ', lr)
+        if logger is not None and main:
             logger.info('learning rate is: {}'.format(lr))
         model.train()
         loss = torch.zeros(1)
         # nothing below waits for the GPU (the loss is read once per epoch), so the host plans and featurises batch i+1 while step i runs
-        for reactions, targets, scope, add_features in train_proc.generate_batch_reactions(
-                smiles_list=smiles_list, target_name='std' + target_name, batch_size=batch_size, seed=epoch, add_features_name=add_features_name):
-            targets_t = torch.FloatTensor(targets).squeeze()                         # train_listwise.py:187
-            r_inputs, p_inputs = smiles2graph_dic.parsing_reactions(reactions)
-            output = model(r_inputs, p_inputs, gpu=dev_idx, add_features=add_features)
-            loss = batch_loss(task_type, output, scope, targets_t, dev_idx, max_coeff, epoch, epochs)
-            optimizer.zero_grad()
-            loss.backward()
-            optimizer.step()
-            scheduler.step()
+        for batch in train_proc.generate_batch_reactions(smiles_list=smiles_list, target_name='std' + target_name, batch_size=batch_size,
+                                                         seed=epoch, add_features_name=add_features_name):
+            # the step body of train_listwise.py:187-290: targets -> FloatTensor.squeeze, featurise, forward, loss dispatch, zero_grad,
+            # backward, optimizer.step, scheduler.step -- plus, data-parallel, the shard selection and the gradient all-reduce
+            loss = step.run(step.prepare(batch, smiles2graph_dic), epoch, epochs)
             finite &= torch.isfinite(model.encoder.W_i.weight).all()
         if not bool(finite):                       # the reference prints, it does not abort (train_listwise.py:190-195)
             print('*' * 40)
             print('the mean of encoder.W_i.weight is: ', model.state_dict()['encoder.W_i.weight'])
             print('the ffn.ffn.7.weight is: ', model.state_dict().get('ffn.ffn.7.weight'))
             print('*' * 40)
-        loss_value = float(loss.detach().reshape(-1)[0])
-        if writer is not None and not isinstance(writer, type):
+        loss_value = step.global_loss(loss)        # data-parallel: the ranks' terms sum to the batch loss
+        if writer is not None and not isinstance(writer, type) and main:
             writer.add_scalar('loss_every_epoch', loss_value)
 
-        average_score, average_pred_in_targ, average_top1_in_pred, NDCG_ = ranking_metrics(
-            model, gpu=dev_idx, data_processor=val_proc, smiles2graph_dic=smiles2graph_dic, show_info=show_info, smiles_list=smiles_list,
-            target_name='std' + target_name, add_features_name=add_features_name)
+        # validation, checkpoints and the epoch report are rank 0's; the other ranks receive the metrics (their `score_old` stays in step
+        # for the resume state) and wait at the end of the epoch
+        mse = float('nan')
+        if main:
+            if save_metric == 'mse':
+                mse = calculate_mse(model, gpu=dev_idx, data_processor=val_proc, smiles2graph_dic=smiles2graph_dic, batch_size=batch_size,
+                                    smiles_list=smiles_list, target_name='std' + target_name, add_features_name=add_features_name)
+            average_score, average_pred_in_targ, average_top1_in_pred, NDCG_ = ranking_metrics(
+                model, gpu=dev_idx, data_processor=val_proc, smiles2graph_dic=smiles2graph_dic, show_info=show_info, smiles_list=smiles_list,
+                target_name='std' + target_name, add_features_name=add_features_name)
+            metrics = [average_score, average_pred_in_targ, average_top1_in_pred] + list(NDCG_) + [mse]
+        else:
+            metrics = [0.0] * 8
+        metrics = step.broadcast_floats(metrics)
+        average_score, average_pred_in_targ, average_top1_in_pred, NDCG_, mse = metrics[0], metrics[1], metrics[2], metrics[3:7], metrics[7]
+
+        def save(path):
+            if main:
+                save_checkpoint(path, model, mean, std)
 
         def improved(new, slot=None):
             nonlocal score_old
@@ -194,38 +214,43 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
 
         if save_metric is None or save_metric == 'average_score':
             if improved(average_score):
-                save_checkpoint(path_checkpoints, model, mean, std)
+                save(path_checkpoints)
                 print('Note: the checkpint file is updated')
         elif save_metric == 'all':
             for slot, val in enumerate((average_score, average_pred_in_targ, average_top1_in_pred)):
                 if improved(val, slot):
-                    save_checkpoint(path_checkpoints[slot], model, mean, std)
+                    save(path_checkpoints[slot])
                     print('Note: the checkpint file is updated')
         elif save_metric == 'average_pred_in_targ':
             if improved(average_pred_in_targ):
-                save_checkpoint(path_checkpoints, model, mean, std)
+                save(path_checkpoints)
         elif save_metric == 'average_top1_in_pred':
             if improved(average_top1_in_pred):
-                save_checkpoint(path_checkpoints, model, mean, std)
+                save(path_checkpoints)
         elif save_metric in NDCG_METRICS:
             if improved(NDCG_[NDCG_METRICS.index(save_metric)]):
-                save_checkpoint(path_checkpoints, model, mean, std)
-        elif save_metric == 'mse':
-            calculate_mse()
+                save(path_checkpoints)
+        elif save_metric == 'mse':                 # train_listwise.py:337-343: keep the checkpoint with the smallest validation MSE
+            if mse <= score_old:
+                score_old = mse
+                save(path_checkpoints)
         else:
             raise Exception('Unknown save metric')
 
-        if writer is not None and not isinstance(writer, type):
+        if writer is not None and not isinstance(writer, type) and main:
             writer.add_scalar("average_score", average_score)
         msg = 'Epoch [{}/{}], train_loss,{:.4f}, top1,{:.4f}, top1_in_pred_top25%,{:.4f}, pred_top25%_in_targ_top25%,{:.4f}'.format(
             epoch + 1, epochs, loss_value, average_score, average_top1_in_pred, average_pred_in_targ)
-        if logger is not None:
+        if logger is not None and main:
             logger.info(msg)
-        print('Epoch [{}/{}], average score: {:.4f}'.format(epoch + 1, epochs, average_score))
-        print('Epoch [{}/{}], targ_top1_in_pred_top25%: {:.4f}'.format(epoch + 1, epochs, average_top1_in_pred))
-        print('Epoch [{}/{}], pred_top25%_in_targ_top25%: {:.4f}'.format(epoch + 1, epochs, average_pred_in_targ))
-        print('Epoch [{}/{}], train loss: {:.4f}'.format(epoch + 1, epochs, loss_value))
-        if save_metric in NDCG_METRICS:
-            print('Epoch [{}/{}], NDCG: {}'.format(epoch + 1, epochs, NDCG_))
-        if resume_path is not None:
+        if main:
+            print('Epoch [{}/{}], average score: {:.4f}'.format(epoch + 1, epochs, average_score))
+            print('Epoch [{}/{}], targ_top1_in_pred_top25%: {:.4f}'.format(epoch + 1, epochs, average_top1_in_pred))
+            print('Epoch [{}/{}], pred_top25%_in_targ_top25%: {:.4f}'.format(epoch + 1, epochs, average_pred_in_targ))
+            print('Epoch [{}/{}], train loss: {:.4f}'.format(epoch + 1, epochs, loss_value))
+            print('Epoch [{}/{}], last batch loss, full precision = {!r}'.format(epoch + 1, epochs, loss_value))
+            if save_metric in NDCG_METRICS:
+                print('Epoch [{}/{}], NDCG: {}'.format(epoch + 1, epochs, NDCG_))
+        if resume_path is not None and main:
             save_train_state(resume_path, model, optimizer, scheduler, epoch, mean, std, best=score_old)
+        step.barrier()                             # the state file / checkpoints are complete before any rank moves on

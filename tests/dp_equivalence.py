@@ -1,5 +1,7 @@
-"""torchrun worker: one ListMLE step on 2 GPUs (groups sharded, global max_num_bonds, global normaliser, SUM all-reduce)
-equals the same step on one GPU over the whole batch."""
+"""torchrun worker (2+ GPUs): the PRODUCT's data-parallel step -- ``TrainStep.prepare`` / ``run`` as ``train()`` and ``bench.py`` drive it:
+global batch plan, shard of whole groups, global ``max_num_bonds``, global normalisers, in-place all-reduce of the flat gradient buffer --
+gives the gradients of the same step on one GPU over the whole batch, for a group-normalised loss (ListMLE), an item-normalised one
+(ListNet) and a composite of both kinds (mle_gaussian)."""
 import os
 import sys
 
@@ -9,46 +11,49 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from reactranker_b200 import synthetic  # noqa: E402
-from reactranker_b200.features.featurization import BatchMolGraph, DeviceGraph  # noqa: E402
+from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features  # noqa: E402
 from reactranker_b200.models.base_model import build_model  # noqa: E402
-from reactranker_b200.parallel import GradSync, broadcast_parameters, shard_groups, shard_rows  # noqa: E402
-from reactranker_b200.train.loss import MLEloss  # noqa: E402
+from reactranker_b200.train.step import TrainStep  # noqa: E402
+from reactranker_b200.train.train_listwise import batch_loss  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
-sizes = [9, 7, 11, 6, 8, 10]
-ds = synthetic.make_dataset(5, sizes, star_leaves_in_group={1: 7})
-torch.manual_seed(0)
-model = build_model(hidden_size=300, task_num=1, ffn_last_layer="with_softplus", add_features_dim=1, dropout=0.0).cuda(local)
-broadcast_parameters(model)
-r_all, p_all = [ds.mols[t] for t in ds.rsmi], [ds.mols[t] for t in ds.psmi]
-r_g, p_g = BatchMolGraph(r_all), BatchMolGraph(p_all)
-targets = torch.tensor(ds.lgk, dtype=torch.float32)
-feats = ds.temp.reshape(-1, 1)
-# single device, whole batch
-out = model(r_g, p_g, gpu=local, add_features=feats)
-MLEloss()(out, sizes, targets, local).backward()
-want = [p.grad.clone() for p in model.parameters() if p.requires_grad]
-model.zero_grad()
-# sharded
-atoms = [sum(ds.mols[ds.rsmi[i]].n_atoms for i in range(o, o + n)) for o, n in zip(np.cumsum([0] + sizes[:-1]), sizes)]
-lo, hi = shard_groups(atoms, world)[rank]
-a, b = shard_rows(sizes, lo, hi)
-rs, ps = BatchMolGraph(r_all[a:b]), BatchMolGraph(p_all[a:b])
-out = model(DeviceGraph.from_batches([rs], dev, [r_g.max_num_bonds]), DeviceGraph.from_batches([ps], dev, [p_g.max_num_bonds]), gpu=local,
-            add_features=feats[a:b])
-MLEloss(global_norm=len(sizes))(out, sizes[lo:hi], targets[a:b], local).backward()
-GradSync(model.parameters())()
-got = [p.grad for p in model.parameters() if p.requires_grad]
-# same criterion as tests/helpers.grads_close: per-tensor error <= rtol * max|want_k| + 1e-2 * rtol * (largest gradient entry of the model);
-# the second term absorbs tensors whose true gradient is zero (the last bias under the shift-invariant ListMLE: ~1e-8 of rounding noise)
-gscale = max(float(w.abs().max()) for w in want)
-rtol = 2e-4
-worst = max(float((g - w).abs().max()) / (float(w.abs().max()) + 1e-2 * gscale) for g, w in zip(got, want))
-assert worst < rtol, worst
+sizes = [9, 7, 11, 6, 8, 10, 5, 12]
+ds = synthetic.make_dataset(5, sizes, star_leaves_in_group={1: 7})       # the star molecule sets the global max_num_bonds
+fz = Parsing_features(ds.mols)
+planner = DataProcessor(ds.to_dataframe())
+worst_all = 0.0
+for task, task_num in (("mle", 1), ("listnet", 1), ("mle_gaussian", 2)):
+    torch.manual_seed(0)
+    model = build_model(hidden_size=300, task_num=task_num, ffn_last_layer="with_softplus", add_features_dim=1, dropout=0.0).cuda(local)
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+    step = TrainStep(model, opt, sched, task, local)
+    assert (step.rank, step.world) == (rank, world)
+    batch = next(iter(planner.generate_batch_reactions(smiles_list=["rsmi_mapped", "psmi_mapped"], target_name="lgk", batch_size=sum(sizes),
+                                                       seed=3, add_features_name="temp")))
+    reactions, targets, scope, feats = batch
+    # single device, whole batch, through the same public calls
+    r_g, p_g = fz.parsing_reactions(reactions)
+    out = model(r_g, p_g, gpu=local, add_features=feats)
+    whole = batch_loss(task, out, scope, torch.FloatTensor(targets).squeeze(), local)
+    whole.backward()
+    want = [p.grad.clone() for p in model.hot_parameters()]
+    model.zero_grad()
+    # the product's data-parallel step
+    prepared = step.prepare(batch, fz)
+    assert prepared.groups == len(scope) and prepared.items == sum(scope) and 0 < prepared.rows < sum(scope)
+    term = step.run(prepared)
+    assert step.sync.fast_path_steps == 1 and step.sync.copy_path_steps == 0        # p.grad aliases the flat buffer: no staging copies
+    total = step.global_loss(term)
+    assert abs(total - float(whole.detach().reshape(-1)[0])) <= 1e-5 * abs(float(whole.detach().reshape(-1)[0])), (task, total, float(whole))
+    got = [p.grad for p in model.hot_parameters()]
+    # same criterion as tests/helpers.grads_close
+    gscale = max(float(w.abs().max()) for w in want)
+    worst = max(float((g - w).abs().max()) / (float(w.abs().max()) + 1e-2 * gscale) for g, w in zip(got, want))
+    assert worst < 1e-3, (task, worst)
+    worst_all = max(worst_all, worst)
 dist.barrier()
 if rank == 0:
-    print("DP-EQUIVALENCE-OK worst rel err", worst)
+    print("DP-EQUIVALENCE-OK worst rel err", worst_all)
 dist.destroy_process_group()

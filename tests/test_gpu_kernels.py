@@ -401,7 +401,7 @@ def test_tcgen05_dgrad_matches_fp64(tc_mode, M, n, k, bf16):
         assert float(((dX.double().cpu() - want).abs() / row_scale).max()) < tol          # per row: the large row must not hide the others
         _lib.check(L.rr_linear_dgrad_tc(M, n, k, dZd.data_ptr(), n, Wd.data_ptr(), k, dX.data_ptr(), k, 1, scratch.data_ptr(), nbytes, S()))
         assert float(((dX.double().cpu() - 2 * want).abs() / (2 * row_scale)).max()) < tol
-        st = L.rr_linear_dgrad_tc(M, n, 20, dZd.data_ptr(), n, Wd.data_ptr(), k, dX.data_ptr(), k, 0, scratch.data_ptr(), nbytes, S())
+        st = L.rr_linear_dgrad_tc(M, n, 12, dZd.data_ptr(), n, Wd.data_ptr(), k, dX.data_ptr(), k, 0, scratch.data_ptr(), nbytes, S())
         assert st == -4 and b"tensor-core" in L.rr_last_error()                             # RR_ERR_UNSUPPORTED, reported not crashed
     finally:
         L.rr_set_backward_bf16(1)

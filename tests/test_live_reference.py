@@ -363,3 +363,64 @@ def test_checkpoints_cross_load_with_the_reference(tmp_path):
     got = load_checkpoint(theirs)
     assert float(got["data_scaler"]["means"]) == 1.25 and float(got["data_scaler"]["stds"]) == 0.5
     assert all(torch.equal(v, model.state_dict()[k]) for k, v in got["state_dict"].items())
+
+
+# ---- the drop-in boundary: same public callables, same signatures ------------------------------------------------------
+# (reference module, attribute path); compared against the same path under this repo's ``reactranker`` import names
+_PUBLIC = [
+    ("models.base_model", "build_model"), ("models.base_model", "ReactionModel.__init__"), ("models.base_model", "ReactionModel.forward"),
+    ("models.base_model", "FFN.__init__"), ("models.mpn", "MPN.__init__"), ("models.mpn", "MPNDiff.__init__"),
+    ("train.train_listwise", "train"), ("train.run_train_pairwise", "run_train"), ("train.train_pairwise", "factorized_training_loop"),
+    ("train.test_listwise", "test"), ("train.test_ranknet", "test"),
+    ("train.utils", "build_optimizer"), ("train.utils", "build_lr_scheduler"), ("train.utils", "NoamLR.__init__"), ("train.utils", "NoamLR.step"),
+    ("utils", "save_checkpoint"), ("utils", "index_select_ND"),
+    ("train.loss", "MLEloss.forward"), ("train.loss", "ListnetLoss.forward"), ("train.loss", "evidential_ranking.forward"),
+    ("train.loss", "GaussDisLoss.forward"), ("train.loss", "MLEDisLoss.forward"), ("train.loss", "Listnet_For_Gauss.forward"),
+    ("train.loss", "Listnet_with_uq.forward"), ("train.loss", "Dirichlet_uq.forward"), ("train.loss", "Lognorm.forward"),
+    ("train.loss", "evidential_loss_new"),
+    ("train.eval", "evaluate_top_scores"), ("train.eval", "ranking_metrics"), ("train.eval", "calculate_ndcg"), ("train.eval", "calculate_mse"),
+    ("data.load_reactions", "get_data.__init__"), ("data.load_reactions", "get_data.filter_bacth"), ("data.load_reactions", "get_data.split_data"),
+    ("data.load_reactions", "DataProcessor.__init__"), ("data.load_reactions", "DataProcessor.generate_batch_reactions"),
+    ("data.load_reactions", "DataProcessor.generate_batch_per_query"), ("data.load_reactions", "DataProcessor.generate_batch_querys"),
+    ("data.load_reactions", "Parsing_features.parsing_smiles"), ("data.load_reactions", "Parsing_features.parsing_reactions"),
+    ("features.featurization", "MolGraph.__init__"), ("features.featurization", "BatchMolGraph.__init__"),
+    ("features.featurization", "BatchMolGraph.get_components"), ("features.featurization", "BatchMolGraph.get_a2a"),
+    ("features.featurization", "mol2graph"),
+]
+# Deliberate, documented extensions: extra TRAILING keyword parameters with defaults that keep every reference call valid.
+_EXTENSIONS = {
+    ("train.train_listwise", "train"): ["resume_path"],                      # full-state resume (the reference saves weights only)
+    ("train.run_train_pairwise", "run_train"): ["resume_path"],
+    ("train.eval", "calculate_mse"): ["add_features_name"],                  # the reference's version cannot run
+}
+
+
+def _resolve(mod, path):
+    obj = mod
+    for part in path.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+@pytest.mark.parametrize("module,path", _PUBLIC, ids=[f"{m}:{p}" for m, p in _PUBLIC])
+def test_public_signatures_equal_the_reference(module, path):
+    """inspect.signature of every public callable on the path: same parameter names, order, kinds and defaults as the live reference
+    (type annotations are not part of the contract); the only differences allowed are the trailing defaulted parameters of _EXTENSIONS."""
+    import importlib
+    import inspect
+    ref_obj = _resolve(ref_loader.ref(module), path)
+    our_obj = _resolve(importlib.import_module("reactranker." + module), path)
+    rp = list(inspect.signature(ref_obj).parameters.values())
+    op = list(inspect.signature(our_obj).parameters.values())
+    extra = _EXTENSIONS.get((module, path), [])
+    assert [p.name for p in op[len(rp):]] == extra, ([p.name for p in op], [p.name for p in rp])
+    assert all(p.default is not inspect.Parameter.empty for p in op[len(rp):])
+
+    def same_default(a, b):
+        if a is inspect.Parameter.empty or b is inspect.Parameter.empty:
+            return a is b
+        if inspect.isclass(a) or inspect.isclass(b):               # e.g. writer=SummaryWriter: the class object of whichever tensorboard is installed
+            return getattr(a, "__name__", a) == getattr(b, "__name__", b)
+        return a == b
+    for a, b in zip(op, rp):
+        assert a.name == b.name and a.kind == b.kind and same_default(a.default, b.default), (path, str(a), str(b))
