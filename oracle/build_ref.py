@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- recipe that builds ``oracle/_ref/`` from the reference where it lies under ``/root/reference``.
 
 The reference is pure Python, so its "binary" is byte code: every module of ``/root/reference/reactranker`` is compiled with
-``py_compile`` straight from its source file into ``oracle/_ref/reactranker/<same relative path>.pyc`` (sourceless import layout).
+``py_compile`` straight from its source file into ``oracle/_ref/reactranker/<same relative path>.rrc`` (CPython byte code; the neutral extension keeps file-sync filters that drop
+``*.pyc`` from leaving it behind; oracle/ref_loader.py imports these files with importlib's SourcelessFileLoader).
 No reference source enters this repository: ``oracle/_ref/`` is git-ignored and holds compiler OUTPUT only -- like the ``.so`` the CUDA
 sources compile to it is not gpurun-ignored, so it travels to the GPU box, where ``/root/reference`` does not exist and
 ``bench.py --impl reference`` / ``cpu_baseline`` then time the reference's own modules (``kind: "reference"``) instead of the oracle port.
@@ -35,7 +36,7 @@ def build(verbose: bool = False) -> int:
                 continue
             dst_dir = os.path.join(out_pkg, rel) if rel != "." else out_pkg
             os.makedirs(dst_dir, exist_ok=True)
-            py_compile.compile(os.path.join(root, f), cfile=os.path.join(dst_dir, f + "c"), dfile=os.path.join("reactranker", rel, f),
+            py_compile.compile(os.path.join(root, f), cfile=os.path.join(dst_dir, f[:-3] + ".rrc"), dfile=os.path.join("reactranker", rel, f),
                                doraise=True, optimize=0)
             n += 1
     with open(os.path.join(DST, "BUILT_FROM"), "w") as fh:

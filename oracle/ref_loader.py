@@ -27,7 +27,7 @@ def source_available() -> bool:
 
 def built_available() -> bool:
     """``oracle/_ref`` (byte code compiled by oracle/build_ref.py) is present."""
-    return os.path.isfile(os.path.join(_BUILT_ROOT, "reactranker", "models", "base_model.pyc"))
+    return os.path.isfile(os.path.join(_BUILT_ROOT, "reactranker", "models", "base_model.rrc"))
 
 
 def available() -> bool:
@@ -90,10 +90,27 @@ def _install_rdkit_stub() -> None:
     rdkit.DataStructs = sys.modules["rdkit.DataStructs"]
 
 
+class _BuiltFinder:
+    """Meta-path finder for the byte code under oracle/_ref: ``_rr_reference.a.b`` -> ``oracle/_ref/reactranker/a/b.rrc``."""
+
+    @staticmethod
+    def find_spec(fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if not fullname.startswith(_PKG + "."):
+            return None
+        f = os.path.join(_BUILT_ROOT, "reactranker", *fullname[len(_PKG) + 1:].split(".")) + ".rrc"
+        if not os.path.isfile(f):
+            return None
+        return importlib.util.spec_from_file_location(fullname, f, loader=importlib.machinery.SourcelessFileLoader(fullname, f))
+
+
 def _mount() -> None:
     if _PKG in sys.modules:
         return
     _install_rdkit_stub()
+    if not source_available():
+        sys.meta_path.insert(0, _BuiltFinder)
     root = os.path.join(REFERENCE_ROOT, "reactranker")
     pkg = types.ModuleType(_PKG)
     pkg.__path__ = [root]  # namespace-style package

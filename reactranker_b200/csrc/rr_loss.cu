@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(kLossThreads) k_listmle(const float* __restric
   __shared__ float red[32];
   const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
   if (n <= 0) return;
+  if (n > kMaxGroup) {   // the static shared arrays hold kMaxGroup candidates: a larger group poisons the result instead of overrunning them
+    for (int i = threadIdx.x; i < n * (DIS ? 2 : 1); i += blockDim.x) dscore[static_cast<size_t>(o) * (DIS ? 2 : 1) + i] = CUDART_NAN_F;
+    if (threadIdx.x == 0) atomicAdd(loss, CUDART_NAN_F);
+    return;
+  }
   int P = 1;
   while (P < n) P <<= 1;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
@@ -420,6 +425,11 @@ __global__ void __launch_bounds__(kLossThreads) k_ranknet(const float* __restric
   __shared__ float red[32];
   const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
   if (n <= 0) return;
+  if (n > kMaxGroup) {   // as in k_listmle: NaN, never a shared-memory overrun (direct C-ABI callers bypass the Python-side check)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dscore[o + i] = CUDART_NAN_F;
+    if (threadIdx.x == 0) atomicAdd(loss, CUDART_NAN_F);
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     ss[i] = scores[o + i];
     ts[i] = targets[o + i];

@@ -270,6 +270,41 @@ static int pad_rows_linear(const int* rows, int n_rows, int n, const float* X1, 
   return RR_OK;
 }
 
+// ---- joint graph ------------------------------------------------------------------------------
+// Index tables of the concatenation [reactant batch | product batch] in joint row space: the reactant part is copied, the product part
+// is shifted by the reactant batch's row counts (valid slots only: an unused slot stays 0 and is never read, its multiplicity lives in
+// rr_atom_meta).  Every segment keeps its own padding rows and max_num_bonds, so the joint launch computes exactly what two launches did.
+__global__ void k_join_tables(rr_graph r, rr_graph p, rr_graph J) {
+  const int A_r = r.n_atoms, B_r = r.n_bonds;
+  int4* meta = reinterpret_cast<int4*>(const_cast<rr_atom_meta*>(J.a_meta));
+  int* a2b = const_cast<int*>(J.a2b);
+  int* a2r = const_cast<int*>(J.a2b_rev);
+  int* a2a = const_cast<int*>(J.a2a);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < J.n_atoms; a += gridDim.x * blockDim.x) {
+    const bool second = a >= A_r;
+    const rr_graph& g = second ? p : r;
+    const int la = second ? a - A_r : a, ob = second ? B_r : 0, oa = second ? A_r : 0;
+    int4 m = __ldg(reinterpret_cast<const int4*>(g.a_meta) + la);
+    const int deg = m.x & 0xff;
+    m.z += ob;
+    m.w += oa;
+    meta[a] = m;
+    const size_t src = static_cast<size_t>(la) * g.wmax, dst = static_cast<size_t>(a) * J.wmax;
+    for (int k = 0; k < J.wmax; ++k) {
+      const bool v = k < deg;
+      a2b[dst + k] = v ? __ldg(g.a2b + src + k) + ob : 0;
+      a2r[dst + k] = v ? __ldg(g.a2b_rev + src + k) + ob : 0;
+      a2a[dst + k] = v ? __ldg(g.a2a + src + k) + oa : 0;
+    }
+  }
+  for (int sgm = blockIdx.x * blockDim.x + threadIdx.x; sgm < J.n_segments; sgm += gridDim.x * blockDim.x) {
+    const bool second = sgm >= r.n_segments;
+    const int ls = second ? sgm - r.n_segments : sgm;
+    const_cast<int*>(J.pad_bonds)[sgm] = second ? __ldg(p.pad_bonds + ls) + B_r : __ldg(r.pad_bonds + ls);
+    const_cast<int*>(J.pad_atoms)[sgm] = second ? __ldg(p.pad_atoms + ls) + A_r : __ldg(r.pad_atoms + ls);
+  }
+}
+
 // ---- workspace layout -----------------------------------------------------------------------
 struct EncBufs {
   float* inp;
@@ -284,7 +319,13 @@ struct Workspace {
   ptrdiff_t hi_off, lo_off;
   uint16_t *bhi, *blo; // bf16 (hi, lo) images, L.total elements each
   float* dpacked;
-  EncBufs enc[2];  // 0 = reactants, 1 = products
+  // The shared-weight encoder runs ONCE over the reactant and product batches together (mpn.py:61-108 is row-wise apart from the gathers,
+  // and those stay inside a segment): every encoder buffer holds the reactant rows followed by the product rows.
+  EncBufs enc[2];     // views: 0 = reactant rows, 1 = product rows of the joint buffers below
+  EncBufs j;          // joint buffers [r rows | p rows]
+  rr_graph J;         // the joint graph: index tables in joint row space (built by k_join_tables), features contiguous [r | p]
+  bool copy_feats;    // r / p feature arrays are not adjacent in memory: copied into j_fa / j_fb once per forward
+  float *j_fa, *j_fb;
   float *d, *inp2, *nf, *am2, *hid2, *vec, *zout;
   float* nm[kMaxDepth];
   float* m2[kMaxDepth + 1];
@@ -308,8 +349,6 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   W->L = make_packed(c);
   const size_t hp = W->L.hp, vp = W->L.vp;
   const size_t A = p.n_atoms, N = p.n_mols;
-  const size_t Amax = r.n_atoms > p.n_atoms ? r.n_atoms : p.n_atoms;
-  const size_t Bmax = r.n_bonds > p.n_bonds ? r.n_bonds : p.n_bonds;
   const int T = c.depth - 1, Td = c.diff_depth - 1;
   char* cur = static_cast<char*>(base);
   size_t used = 0;
@@ -324,15 +363,42 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   W->bhi = reinterpret_cast<uint16_t*>(take((W->L.total + 1) / 2));
   W->blo = reinterpret_cast<uint16_t*>(take((W->L.total + 1) / 2));
   W->dpacked = take(W->L.grad_total);
-  for (int s = 0; s < 2; ++s) {
-    const size_t B = (s == 0 ? r.n_bonds : p.n_bonds);
-    EncBufs& e = W->enc[s];
-    e.inp = take(B * hp);
-    for (int t = 0; t < T; ++t) e.pre[t] = take(B * hp);
-    for (int t = 1; t <= T; ++t) e.m[t] = take(B * hp);
-    const size_t As = (s == 0 ? r.n_atoms : p.n_atoms);
-    e.am = take(As * hp);
-    e.hid = take(As * hp);
+  const size_t A_r = r.n_atoms, B_r = r.n_bonds, A_J = A_r + p.n_atoms, B_J = B_r + p.n_bonds;
+  {
+    EncBufs& e = W->j;
+    e.inp = take(B_J * hp);
+    for (int t = 0; t < T; ++t) e.pre[t] = take(B_J * hp);
+    for (int t = 1; t <= T; ++t) e.m[t] = take(B_J * hp);
+    e.am = take(A_J * hp);
+    e.hid = take(A_J * hp);
+    auto part = [&](float* q, size_t rows) { return q ? q + rows * hp : nullptr; };
+    W->enc[0] = e;
+    EncBufs& q = W->enc[1];
+    q.inp = part(e.inp, B_r);
+    for (int t = 0; t < T; ++t) q.pre[t] = part(e.pre[t], B_r);
+    for (int t = 1; t <= T; ++t) q.m[t] = part(e.m[t], B_r);
+    q.am = part(e.am, A_r);
+    q.hid = part(e.hid, A_r);
+  }
+  {   // joint graph tables (int32) and, when the two batches' features are not adjacent in memory, a contiguous copy of them
+    rr_graph& J = W->J;
+    J = rr_graph{};
+    J.n_atoms = static_cast<int>(A_J);
+    J.n_bonds = static_cast<int>(B_J);
+    J.n_mols = r.n_mols + p.n_mols;
+    J.wmax = r.wmax > p.wmax ? r.wmax : p.wmax;
+    J.n_segments = r.n_segments + p.n_segments;
+    J.a_meta = reinterpret_cast<const rr_atom_meta*>(take(A_J * 4));
+    J.a2b = reinterpret_cast<const int*>(take(A_J * J.wmax));
+    J.a2b_rev = reinterpret_cast<const int*>(take(A_J * J.wmax));
+    J.a2a = reinterpret_cast<const int*>(take(A_J * J.wmax));
+    J.pad_bonds = reinterpret_cast<const int*>(take(J.n_segments));
+    J.pad_atoms = reinterpret_cast<const int*>(take(J.n_segments));
+    W->copy_feats = !(p.f_atoms == r.f_atoms + A_r * RR_FA_LD && p.f_bonds == r.f_bonds + B_r * RR_FB_LD);
+    W->j_fa = W->copy_feats ? take(A_J * RR_FA_LD) : nullptr;
+    W->j_fb = W->copy_feats ? take(B_J * RR_FB_LD) : nullptr;
+    J.f_atoms = W->copy_feats ? W->j_fa : r.f_atoms;
+    J.f_bonds = W->copy_feats ? W->j_fb : r.f_bonds;
   }
   W->d = take(A * hp);
   W->inp2 = take(A * hp);
@@ -344,11 +410,11 @@ static int carve(const rr_model_cfg& c, const rr_graph& r, const rr_graph& p, vo
   W->vec = take(N * vp);
   for (int l = 0; l + 1 < c.ffn_depth; ++l) W->x[l] = take(N * hp);
   W->zout = take(N * RR_OUT_LD);
-  W->gB1 = take(Bmax * hp);
-  W->gB2 = take(Bmax * hp);
-  W->dinp = take(Bmax * hp);
-  W->gA1 = take(Amax * hp);
-  W->gA2 = take(Amax * hp);
+  W->gB1 = take(B_J * hp);
+  W->gB2 = take(B_J * hp);
+  W->dinp = take(B_J * hp);
+  W->gA1 = take(A_J * hp);
+  W->gA2 = take(A_J * hp);
   W->gA3 = take(A * hp);
   W->dD = take(A * hp);
   W->dI2 = take(A * hp);
@@ -448,6 +514,25 @@ static int pack_params(const rr_model_cfg& c, const Workspace& W, const rr_param
   return RR_OK;
 }
 
+// Fill the joint graph of this call's workspace: write the index tables; the features are copied only when the two batches
+// do not already sit next to each other in memory (DeviceGraph.assemble_pair lays them out adjacent, so the product path copies nothing).
+static int build_joint(const Workspace& W, const rr_graph& r, const rr_graph& p, cudaStream_t s) {
+  ProfScope prof_scope(KC_MISC, s);
+  const int n = W.J.n_atoms;
+  int blocks = (n + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  if (blocks < 1) blocks = 1;
+  k_join_tables<<<blocks, 256, 0, s>>>(r, p, W.J);
+  RR_LAUNCH_CHECK("k_join_tables");
+  if (W.copy_feats) {
+    RR_CUDA(cudaMemcpyAsync(W.j_fa, r.f_atoms, static_cast<size_t>(r.n_atoms) * RR_FA_LD * 4, cudaMemcpyDeviceToDevice, s));
+    RR_CUDA(cudaMemcpyAsync(W.j_fa + static_cast<size_t>(r.n_atoms) * RR_FA_LD, p.f_atoms, static_cast<size_t>(p.n_atoms) * RR_FA_LD * 4, cudaMemcpyDeviceToDevice, s));
+    RR_CUDA(cudaMemcpyAsync(W.j_fb, r.f_bonds, static_cast<size_t>(r.n_bonds) * RR_FB_LD * 4, cudaMemcpyDeviceToDevice, s));
+    RR_CUDA(cudaMemcpyAsync(W.j_fb + static_cast<size_t>(r.n_bonds) * RR_FB_LD, p.f_bonds, static_cast<size_t>(p.n_bonds) * RR_FB_LD * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return RR_OK;
+}
+
 int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, const rr_graph* p, const float* addf, float* scores,
                   void* ws, long long ws_bytes, cudaStream_t s) {
   Workspace W;
@@ -476,10 +561,10 @@ int model_forward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r, 
                              id, s));
     return RR_OK;
   };
-  const rr_graph* gs[2] = {r, p};
-  for (int k = 0; k < 2; ++k) {  // mpn.py:61-108
-    const rr_graph* g = gs[k];
-    EncBufs& e = W.enc[k];
+  RR_TRY(build_joint(W, *r, *p, s));
+  {  // mpn.py:61-108, once over [reactant rows | product rows]: the weights are shared (base_model.py:155-156)
+    const rr_graph* g = &W.J;
+    EncBufs& e = W.j;
     // f_bonds[pad] = 0: the padding rows of W_i's output are the bias exactly, on any GEMM path
     RR_TRY(lin(nullptr, 0, g->n_bonds, hp, g->f_bonds, RR_FB_LD, L.enc_Wi, RR_FB_LD, nullptr, 0, 0, 0, L.enc_bi, nullptr, e.inp, hp, 0));
     const float* src = e.inp;
@@ -595,33 +680,34 @@ int model_backward(const rr_model_cfg* c, const rr_params* w, const rr_graph* r,
   RR_TRY(linear_wgrad(A, hp, hp, W.dI2, hp, W.d, hp, G + L.dif_Wi, hp, G + L.dif_bi, s));
   RR_TRY(dgrad(A, hp, hp, W.dI2, hp, P + L.dif_Wi, hp, P + L.dif_Wi_T, hp, W.dD, hp, 1, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
 
-  // shared encoder: products (+dD) then reactants (-dD); weight gradients accumulate (base_model.py:155-156)
-  const rr_graph* gs[2] = {r, p};
-  for (int k = 1; k >= 0; --k) {
-    const rr_graph* g = gs[k];
-    EncBufs& e = W.enc[k];
-    const int B = g->n_bonds;
-    const float sign = (k == 1) ? 1.f : -1.f;
-    const int Ag = g->n_atoms;
-    if (k == 0 && c->r_atom_map) {   // shared reactant rows: sum the gradient over the copies first (gA2 is free until the dgrad below)
-      RR_CUDA(cudaMemsetAsync(W.gA2, 0, static_cast<size_t>(Ag) * hp * sizeof(float), s));
+  // shared encoder, once over [reactant rows | product rows]: d(hid_p) = +dD, d(hid_r) = -dD (base_model.py:168), each through the
+  // ReLU / dropout mask of its own rows; the weight gradients of both halves come out of one launch per layer (base_model.py:155-156)
+  {
+    // (the joint graph's tables, and its feature copy if one was needed, are in the workspace since the forward)
+    const rr_graph* g = &W.J;
+    EncBufs& e = W.j;
+    const int A_r = r->n_atoms, A_J = g->n_atoms, B_J = g->n_bonds;
+    float* gA1_p = W.gA1 + static_cast<size_t>(A_r) * hp;
+    RR_TRY(relu_bwd(A, hp, W.dD, W.enc[1].hid, keep, 0, gA1_p, nullptr, 0, s));
+    if (c->r_atom_map) {   // shared reactant rows: sum the gradient over the copies first (gA2 is free until the dgrad below)
+      RR_CUDA(cudaMemsetAsync(W.gA2, 0, static_cast<size_t>(A_r) * hp * sizeof(float), s));
       RR_TRY(scatter_add_rows(A, hp, W.dD, c->r_atom_map, W.gA2, s));
-      RR_TRY(relu_bwd(Ag, hp, W.gA2, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
+      RR_TRY(relu_bwd(A_r, hp, W.gA2, W.enc[0].hid, -keep, 0, W.gA1, nullptr, 0, s));
     } else {
-      RR_TRY(relu_bwd(Ag, hp, W.dD, e.hid, sign * keep, 0, W.gA1, nullptr, 0, s));
+      RR_TRY(relu_bwd(A_r, hp, W.dD, W.enc[0].hid, -keep, 0, W.gA1, nullptr, 0, s));
     }
-    RR_TRY(linear_wgrad(Ag, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
-    RR_TRY(linear_wgrad(Ag, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
-    RR_TRY(dgrad(Ag, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+    RR_TRY(linear_wgrad(A_J, hp, RR_FA_LD, W.gA1, hp, g->f_atoms, RR_FA_LD, G + L.enc_Wo_a, RR_FA_LD, G + L.enc_bo, s));
+    RR_TRY(linear_wgrad(A_J, hp, hp, W.gA1, hp, e.am, hp, G + L.enc_Wo_m, hp, nullptr, s));
+    RR_TRY(dgrad(A_J, hp, hp, W.gA1, hp, P + L.enc_Wo_m, hp, P + L.enc_Wo_m_T, hp, W.gA2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
     if (T >= 1) RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.m[T], keep, 0, W.dinp, 1, 0, s));
     else RR_TRY(neighbor_sum_bwd_act(g, 0, W.gA2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 1, 1, s));
     for (int t = T; t >= 1; --t) {
-      RR_TRY(linear_wgrad(B, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
-      RR_TRY(dgrad(B, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
+      RR_TRY(linear_wgrad(B_J, hp, hp, W.gB1, hp, e.pre[t - 1], hp, G + L.enc_Wh, hp, G + L.enc_bh, s));
+      RR_TRY(dgrad(B_J, hp, hp, W.gB1, hp, P + L.enc_Wh, hp, P + L.enc_Wh_T, hp, W.gB2, hp, 0, s, W.hi_off, W.lo_off, W.packed, W.bhi, W.blo));
       if (t - 1 >= 1) RR_TRY(bond_message_bwd_act(g, W.gB2, W.gB1, hp, e.m[t - 1], keep, 0, W.dinp, 2, 0, s));
       else RR_TRY(bond_message_bwd_act(g, W.gB2, W.gB1, hp, e.inp, 1.f, 1, W.dinp, 2, 1, s));
     }
-    RR_TRY(linear_wgrad(B, hp, RR_FB_LD, W.dinp, hp, g->f_bonds, RR_FB_LD, G + L.enc_Wi, RR_FB_LD, G + L.enc_bi, s));
+    RR_TRY(linear_wgrad(B_J, hp, RR_FB_LD, W.dinp, hp, g->f_bonds, RR_FB_LD, G + L.enc_Wi, RR_FB_LD, G + L.enc_bi, s));
   }
 
   PackTable Tb = make_table(*c, L, *grads, false);

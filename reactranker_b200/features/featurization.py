@@ -531,6 +531,22 @@ class _BufferPool:
 _POOL = _BufferPool()
 
 
+class _SharedBlob:
+    """Pooled device blob + pinned control buffer shared by the two DeviceGraphs of a pair: returned to the pool when both are gone."""
+
+    def __init__(self, blob, key, host, event):
+        self.p = (blob, key, host, event)
+
+    def __del__(self):
+        p, self.p = self.p, None
+        if p is not None:
+            try:
+                _POOL.give(p[0], p[1])
+                _POOL.give(p[2], "pinned", p[3])
+            except Exception:      # interpreter shutdown
+                pass
+
+
 class DeviceGraph:
     """One or more BatchMolGraphs ("segments") laid out for the kernels and shipped with a
     single host->device copy out of pinned memory."""
@@ -652,6 +668,77 @@ class DeviceGraph:
         return g
 
     @staticmethod
+    def assemble_pair_ids(store: MoleculeStore, r_ids, r_lens, p_ids, p_lens, dev, r_W=None, p_W=None):
+        """(reactant DeviceGraph, product DeviceGraph) assembled on the device into ONE blob whose feature arrays are adjacent --
+        ``[f_atoms(r) | f_atoms(p)]`` and ``[f_bonds(r) | f_bonds(p)]`` -- so that the model can run its shared-weight encoder once over
+        both batches (rr_model.cu: joint graph) without copying a feature row.  Otherwise identical to two ``assemble_ids`` calls."""
+        from .. import _lib
+        dev = torch.device(dev)
+        store.sync(dev)
+        blocks = [DeviceGraph.control_block(store, r_ids, r_lens, r_W), DeviceGraph.control_block(store, p_ids, p_lens, p_W)]
+        dims = [b[1] for b in blocks]
+        offs, total = [{}, {}], 0
+        for name, ld in (("f_atoms", FA_LD), ("f_bonds", FB_LD)):          # the two feature pairs first, each pair contiguous
+            for k in (0, 1):
+                offs[k][name] = total
+                total += dims[k][0 if name == "f_atoms" else 1] * ld * 4
+            total = _align(total)
+        for k in (0, 1):
+            nA, nB, nM, wmax, S = dims[k]
+            for name, nbytes in DeviceGraph._sections(nA, nB, nM, wmax, S)[2:]:
+                offs[k][name] = total
+                total += _align(max(nbytes, 4))
+        ctl_off = [total, total + _align(blocks[0][0].nbytes)]
+        total_all = ctl_off[1] + _align(blocks[1][0].nbytes)
+        ctl_bytes = blocks[0][0].nbytes + blocks[1][0].nbytes
+        host = _POOL.take(_align(blocks[0][0].nbytes) + blocks[1][0].nbytes, "pinned", lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True))
+        h_off = [0, _align(blocks[0][0].nbytes)]
+        for k in (0, 1):
+            ctl = blocks[k][0]
+            host[h_off[k]:h_off[k] + ctl.nbytes].view(torch.int32).numpy()[:] = ctl
+        blob = _POOL.take(total_all, str(dev), lambda n: torch.empty(n, dtype=torch.uint8, device=dev))
+        n_ctl = h_off[1] + blocks[1][0].nbytes
+        blob[ctl_off[0]:ctl_off[0] + n_ctl].copy_(host[:n_ctl], non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record(torch.cuda.current_stream(dev))
+        shared = _SharedBlob(blob, str(dev), host, copied)
+        out = []
+        base = blob.data_ptr()
+        for k in (0, 1):
+            nA, nB, nM, wmax, S = dims[k]
+            g = DeviceGraph()
+            g.blob, g.host_blob, g._shared = blob, host, shared
+            g.h2d_bytes = blocks[k][0].nbytes
+            c = g.c
+            c.n_atoms, c.n_bonds, c.n_mols, c.wmax, c.n_segments = nA, nB, nM, wmax, S
+            for name, _ in DeviceGraph._sections(nA, nB, nM, wmax, S):
+                setattr(c, name, base + offs[k][name])
+            p0 = base + ctl_off[0] + h_off[k]
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().rr_graph_assemble(ctypes.byref(store.c), nM, p0, p0 + 4 * nM, p0 + 8 * nM, p0 + 12 * nM, p0 + 16 * nM, p0 + 20 * nM,
+                                                        S, p0 + 24 * nM, p0 + 24 * nM + 4 * S, p0 + 24 * nM + 8 * S, ctypes.byref(c),
+                                                        torch.cuda.current_stream().cuda_stream))
+            g.n_atoms, g.n_bonds, g.n_mols = nA, nB, nM
+            g.real_atoms, g.real_bonds = nA - S, nB - S
+            g._offs = offs[k]
+            out.append(g)
+        _ = ctl_bytes
+        return out[0], out[1]
+
+    @staticmethod
+    def pair_from_batches(r_batches: Sequence[BatchMolGraph], p_batches: Sequence[BatchMolGraph], device):
+        """(reactant, product) DeviceGraphs of store-backed batches with adjacent feature arrays (``assemble_pair_ids``); host-packed
+        batches fall back to two independent graphs (the model then makes the contiguous copy itself)."""
+        dev = torch.device(device)
+        every = list(r_batches) + list(p_batches)
+        if dev.type == "cuda" and all(b._ids is not None and b._store is every[0]._store for b in every):
+            cat = lambda bs: np.concatenate([b._ids for b in bs]) if len(bs) > 1 else bs[0]._ids  # noqa: E731
+            return DeviceGraph.assemble_pair_ids(every[0]._store, cat(r_batches), [b.n_mols for b in r_batches], cat(p_batches),
+                                                 [b.n_mols for b in p_batches], dev, [b.max_num_bonds for b in r_batches],
+                                                 [b.max_num_bonds for b in p_batches])
+        return DeviceGraph.from_batches(r_batches, dev), DeviceGraph.from_batches(p_batches, dev)
+
+    @staticmethod
     def from_batches(batches: Sequence[BatchMolGraph], device, w_override: Optional[Sequence[Optional[int]]] = None,
                      non_blocking: bool = True) -> "DeviceGraph":
         dev = torch.device(device)
@@ -766,12 +853,13 @@ class DeviceGraph:
         """(reactant DeviceGraph, product DeviceGraph).  When reactants repeat, the reactant graph is de-duplicated and carries
         ``atom_map`` (device int32) for ``rr_model_cfg.r_atom_map``; exact in eval mode and at dropout 0 only (the model checks)."""
         dev = torch.device(device)
-        pg = DeviceGraph.from_batches(p_batches, dev)
         plan = DeviceGraph.dedup_plan(r_batches, p_batches)
         if plan is None:
-            return DeviceGraph.from_batches(r_batches, dev), pg
+            return DeviceGraph.pair_from_batches(r_batches, p_batches, dev)
         uniq, w, amap = plan
-        rg = DeviceGraph.from_batches(uniq, dev, w)
+        for b, wb in zip(uniq, w):
+            b.max_num_bonds = wb
+        rg, pg = DeviceGraph.pair_from_batches(uniq, p_batches, dev)
         host = torch.from_numpy(amap).pin_memory()
         rg.atom_map = host.to(dev, non_blocking=True)
         rg._atom_map_host = host
@@ -821,12 +909,12 @@ class DeviceGraph:
         """(reactant DeviceGraph, product DeviceGraph) of many segments straight from store ids (``Parsing_features.parsing_ids``): what
         ``from_batches`` / ``from_batches_dedup`` build from one BatchMolGraph per segment, without creating those objects."""
         dev = torch.device(device)
-        pg = DeviceGraph.assemble_ids(store, p_ids, lens, dev)
         plan = DeviceGraph.dedup_ids(store, r_ids, p_ids, lens) if dedup else None
         if plan is None:
-            return DeviceGraph.assemble_ids(store, r_ids, lens, dev), pg
+            return DeviceGraph.assemble_pair_ids(store, r_ids, lens, p_ids, lens, dev)
         u_ids, u_lens, amap = plan
-        rg = DeviceGraph.assemble_ids(store, u_ids, u_lens, dev)
+        # the unique reactants of a segment keep the segment's max_num_bonds (same molecules: same largest in-degree)
+        rg, pg = DeviceGraph.assemble_pair_ids(store, u_ids, u_lens, p_ids, lens, dev)
         host = torch.from_numpy(amap).pin_memory()
         rg.atom_map = host.to(dev, non_blocking=True)
         rg._atom_map_host = host

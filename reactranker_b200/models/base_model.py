@@ -220,6 +220,9 @@ class ReactionModel(nn.Module):
             # every candidate of a group repeats the reactant graph (load_reactions.py:574-576): without dropout the copies are identical,
             # so each distinct reactant is encoded once (rr_model_cfg.r_atom_map); with dropout the reference draws a mask per copy
             rg, pg = DeviceGraph.from_batches_dedup([r_inputs], [p_inputs], dev)
+        elif isinstance(r_inputs, BatchMolGraph) and isinstance(p_inputs, BatchMolGraph):
+            # one blob with adjacent feature arrays: the shared-weight encoder runs once over both batches without copying a feature row
+            rg, pg = DeviceGraph.pair_from_batches([r_inputs], [p_inputs], dev)
         else:
             rg = r_inputs if isinstance(r_inputs, DeviceGraph) else r_inputs.to_device(dev)
             pg = p_inputs if isinstance(p_inputs, DeviceGraph) else p_inputs.to_device(dev)

@@ -88,7 +88,7 @@ class TrainStep:
             if (store_backed and getattr(model, "dedup_reactants", False) and not (model.training and getattr(model, "_dropout", 0) > 0)):
                 r_inputs, p_inputs = DeviceGraph.from_batches_dedup([r_inputs], [p_inputs], self.dev)     # exact without dropout only
             else:
-                r_inputs, p_inputs = r_inputs.to_device(self.dev), p_inputs.to_device(self.dev)
+                r_inputs, p_inputs = DeviceGraph.pair_from_batches([r_inputs], [p_inputs], self.dev)
             h2d = r_inputs.h2d_bytes + p_inputs.h2d_bytes
         if pinned:                                                              # targets / extra features ride up asynchronously with the graphs
             targets_t = targets_t.pin_memory().to(self.dev, non_blocking=True)

@@ -22,8 +22,13 @@ def save_train_state(path, model, optimizer, scheduler, epoch, means=None, stds=
     same batches as an uninterrupted one.  Written to a temporary name and renamed: a crash mid-write cannot destroy the last state."""
     import os
     scaler = {'means': float(means), 'stds': float(stds)} if means is not None and stds is not None else None
+    # plain Python numbers only (no numpy scalars), so that the file loads with torch.load's safe default weights_only=True
+    if isinstance(best, (list, tuple)):
+        best = [float(b) for b in best]
+    elif best is not None:
+        best = float(best)
     state = {'state_dict': model.state_dict(), 'data_scaler': scaler, 'optimizer': optimizer.state_dict(),
-             'scheduler': {k: v for k, v in scheduler.state_dict().items() if not k.startswith('_')} if scheduler is not None else None,
+             'scheduler': {k: _plain(v) for k, v in scheduler.state_dict().items() if not k.startswith('_')} if scheduler is not None else None,
              'epoch': int(epoch), 'best': best, 'rng_state': torch.get_rng_state()}
     tmp = str(path) + '.tmp'
     torch.save(state, tmp)
@@ -45,12 +50,48 @@ def load_train_state(path, model, optimizer, scheduler=None):
     return state['epoch'] + 1, state.get('best'), state['data_scaler']
 
 
-def load_checkpoint(path):
-    """Reads checkpoints written by this package or by the reference (numpy-scalar means/stds)."""
+def _plain(v):
+    """numpy scalars / arrays -> Python numbers / lists (what torch.load(weights_only=True) accepts)."""
+    import numpy as np
+    if isinstance(v, np.generic):
+        return v.item()
+    if isinstance(v, np.ndarray):
+        return v.tolist()
+    if isinstance(v, (list, tuple)):
+        return [_plain(x) for x in v]
+    return v
+
+
+def load_checkpoint(path, allow_unsafe_pickle=None):
+    """Reads checkpoints written by this package or by the reference.
+
+    Always ``torch.load(weights_only=True)``: tensors, Python containers and numbers, plus an allow-list of exactly what the reference's
+    own files add -- numpy scalars for ``data_scaler['means' / 'stds']`` (utils.py:165-173 stores ``np.float64``).  Anything else in the
+    pickle stream is refused; a corrupt or hostile file can therefore not execute code.  Full unpickling is an explicit opt-in
+    (``allow_unsafe_pickle=True`` or ``RR_UNSAFE_CHECKPOINTS=1``) for files from a source you trust."""
+    import os
+    import pickle
+    import numpy as np
+    if allow_unsafe_pickle is None:
+        allow_unsafe_pickle = os.environ.get("RR_UNSAFE_CHECKPOINTS", "0") == "1"
+    loc = lambda storage, _loc: storage  # noqa: E731
+    safe = [np.dtype, np.float64, np.float32, np.int64, np.int32, np.bool_, np.ndarray]
     try:
-        return torch.load(path, map_location=lambda storage, loc: storage)
-    except Exception:
-        return torch.load(path, map_location=lambda storage, loc: storage, weights_only=False)
+        from numpy._core.multiarray import scalar as _np_scalar, _reconstruct as _np_reconstruct
+    except Exception:  # numpy < 2
+        from numpy.core.multiarray import scalar as _np_scalar, _reconstruct as _np_reconstruct
+    safe += [_np_scalar, _np_reconstruct]
+    for name in ("Float64DType", "Float32DType", "Int64DType", "Int32DType", "BoolDType"):
+        t = getattr(getattr(np, "dtypes", None), name, None)
+        if t is not None:
+            safe.append(t)
+    try:
+        with torch.serialization.safe_globals(safe):
+            return torch.load(path, map_location=loc, weights_only=True)
+    except pickle.UnpicklingError:
+        if not allow_unsafe_pickle:
+            raise
+        return torch.load(path, map_location=loc, weights_only=False)
 
 
 def index_select_ND(source: torch.Tensor, index: torch.Tensor) -> torch.Tensor:

@@ -386,6 +386,52 @@ def test_padding_rows_are_exact_on_the_tensor_core_path(tc_mode):
         b0 += pb[s_].n_bonds
 
 
+def test_joint_encoder_paths_agree_bit_for_bit():
+    """The shared-weight encoder runs once over [reactant rows | product rows] (rr_model.cu: joint graph).  Store-backed batches are
+    assembled into one blob with adjacent feature arrays (no copy); host-packed batches, or two independently assembled DeviceGraphs,
+    get their features copied next to each other inside the workspace.  Same kernels, same rows: scores and gradients are identical, with
+    one segment and with several, with and without different max_num_bonds on the two sides (a star molecule among the reactants only)."""
+    from reactranker_b200.data.load_reactions import Parsing_features
+    dev = torch.device("cuda", GPU)
+    for star in (None, {1: 7}):
+        sizes = [6, 4, 5]
+        ds = synthetic.make_dataset(61, sizes, star_leaves_in_group=star)
+        fz = Parsing_features(ds.mols)
+        feats = ds.temp.reshape(-1, 1)
+        torch.manual_seed(2)
+        model = make_model(300, "mle", 3, 3).train()
+        model.dedup_reactants = False
+        res = []
+        for how in ("pair", "separate", "host"):
+            if how == "host":
+                rg = DeviceGraph.from_batches([BatchMolGraph([ds.mols[t] for t in ds.rsmi])], dev)
+                pg = DeviceGraph.from_batches([BatchMolGraph([ds.mols[t] for t in ds.psmi])], dev)
+            else:
+                r_b, p_b = fz.parsing_smiles(list(ds.rsmi)), fz.parsing_smiles(list(ds.psmi))
+                rg, pg = DeviceGraph.pair_from_batches([r_b], [p_b], dev) if how == "pair" else (r_b.to_device(dev), p_b.to_device(dev))
+            adjacent = pg.c.f_atoms == rg.c.f_atoms + rg.n_atoms * 64 * 4 and pg.c.f_bonds == rg.c.f_bonds + rg.n_bonds * 88 * 4
+            assert adjacent == (how == "pair")
+            model.zero_grad()
+            out = model(rg, pg, gpu=GPU, add_features=feats)
+            product_loss("mle", out, sizes, torch.tensor(ds.lgk.astype(np.float32))).backward()
+            res.append((out.detach().clone(), [p.grad.clone() for p in model.hot_parameters()]))
+        for other in res[1:]:
+            assert torch.equal(other[0], res[0][0])
+            # weight gradients are accumulated with float atomics (split-K reductions): equal up to their order
+            for a, b in zip(other[1], res[0][1]):
+                assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
+        # several segments per side (the RankNet window / evaluation layout)
+        o, rs, ps = 0, [], []
+        for n in sizes:
+            rs.append(fz.parsing_smiles(list(ds.rsmi[o:o + n])))
+            ps.append(fz.parsing_smiles(list(ds.psmi[o:o + n])))
+            o += n
+        with torch.no_grad():
+            a = model.eval()(*DeviceGraph.pair_from_batches(rs, ps, dev), gpu=GPU, add_features=feats)
+            b = model(DeviceGraph.from_batches(rs, dev), DeviceGraph.from_batches(ps, dev), gpu=GPU, add_features=feats)
+        assert torch.equal(a, b)
+
+
 # ---- optional reactant de-duplication (rr_model_cfg.r_atom_map): exact without dropout ----------------------------------------------
 def _store_batches(ds):
     from reactranker_b200.data.load_reactions import Parsing_features

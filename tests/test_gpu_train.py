@@ -22,8 +22,8 @@ def test_save_metric_mse_trains_and_checkpoints(tmp_path):
     """save_metric='mse' (train_listwise.py:345-352): the validation MSE is computed every epoch and the best checkpoint kept -- the
     reference's own calculate_mse cannot run; here it does."""
     out = run(["main.py", "--synthetic", "40,10", "--path", str(tmp_path), "--gpu", "0", "--task_type", "regression", "--batch_size", "100",
-               "--total_epochs", "2", "--hidden_size", "64", "--save_metric", "mse"])
-    assert out.count("the validation MSE over") == 2
+               "--total_epochs", "3", "--hidden_size", "64", "--save_metric", "mse"])
+    assert out.count("the validation MSE over") == 3
     assert os.path.exists(os.path.join(str(tmp_path), "0.pt"))
 
 
