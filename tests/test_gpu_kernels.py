@@ -770,10 +770,9 @@ def test_id_vector_assembly_equals_per_group_batches(dedup):
     torch.cuda.synchronize()
     for g1, g2 in ((rg1, rg2), (pg1, pg2)):
         assert (g1.n_atoms, g1.n_bonds, g1.n_mols, g1.c.wmax, g1.c.n_segments) == (g2.n_atoms, g2.n_bonds, g2.n_mols, g2.c.wmax, g2.c.n_segments)
-        assert g1._offs == g2._offs
-        end = max(g1._offs.values())
         sizes = dict(DeviceGraph._sections(g1.n_atoms, g1.n_bonds, g1.n_mols, g1.c.wmax, g1.c.n_segments))
-        for name, off in g1._offs.items():
-            assert torch.equal(g1.blob[off:off + sizes[name]], g2.blob[off:off + sizes[name]]), name
+        for name in sizes:          # same bytes in every section (a pair's blob lays its sections out differently: adjacent feature arrays)
+            o1, o2 = g1._offs[name], g2._offs[name]
+            assert torch.equal(g1.blob[o1:o1 + sizes[name]], g2.blob[o2:o2 + sizes[name]]), name
     if dedup:
         assert rg2.n_mols == 4 and torch.equal(rg1.atom_map, rg2.atom_map)
