@@ -13,8 +13,9 @@ global normaliser and all-reduces the flat gradient buffer in place (weak scalin
 * ``e2e``    : reactions/s from HOST buffers through the same public calls -- per step the batch plan
                (``DataProcessor.generate_batch_reactions``), the shard selection, ``Parsing_features.parsing_reactions`` on the warm
                MolGraph cache, the pinned host->device copies (molecule ids, row offsets, extra features, targets), on-device batch
-               assembly from the HBM-resident molecule store, forward/loss/backward/all-reduce/Adam, and a device->host read of the loss.
-               Every step does all of these inside the timed region; batch i+1 is prepared between enqueuing step i and reading its loss.
+               assembly from the HBM-resident molecule store, forward/loss/backward/all-reduce/Adam, and a device->host read of the loss
+               (pinned, asynchronous, consumed one step later so that the GPU queue never drains; the last one before the closing event).
+               Every step does all of these inside the timed region; batch i+1 is prepared while step i executes.
 * ``sustained``: the device path again for >= 10 s back to back with the clock trace (``value`` itself is a burst of K steps).
 * ``roofline``: the dominant kernel class of the step, timed with CUDA events on the launching stream around every launch
                (rr_profile_begin/end of librr_sm100) while the same K steps run a second time; ``roofline_message_passing`` gives the
@@ -264,15 +265,14 @@ class Job:
             if self._plan_it is None:
                 if self.ranknet:
                     self._plan_it = iter_windows(self.planner, self._epoch, self.global_rows, COLS, "lgk", "temp")
-                else:
-                    self._plan_it = self.planner.generate_batch_reactions(smiles_list=COLS, target_name="lgk", batch_size=self.global_rows,
-                                                                          seed=self._epoch, add_features_name="temp")
+                else:      # train() iterates exactly this: generate_batch_reactions at the planner level (rows + scope), seed = epoch
+                    self._plan_it = self.planner.plan_batch_reactions(batch_size=self.global_rows, seed=self._epoch)
                 self._epoch += 1
             for b in self._plan_it:
                 if self.ranknet:
                     if not b[2]:                                   # full windows only (the tail flush is smaller)
                         return b
-                elif sum(b[2]) == self.global_rows:
+                elif sum(b[1]) == self.global_rows:
                     return b
             self._plan_it = None
 
@@ -287,7 +287,8 @@ class Job:
             prepared, sync = prepare_window(self.model, window, self.fz, self.local)
             h2d = 0 if prepared is None else prepared[0].h2d_bytes + prepared[1].h2d_bytes + 8 * len(prepared[2])
             return ("ranknet", prepared, sync, pairs, h2d)
-        return self.step.prepare(plan, self.fz, pinned=True, device_graphs=True)
+        rows, scope = plan
+        return self.step.prepare_rows(self.planner, rows, scope, self.fz, COLS, "lgk", "temp")
 
     def _run(self, prepared):
         if self.ranknet:
@@ -302,16 +303,34 @@ class Job:
         return self._run(self.resident[i % len(self.resident)])
 
     def step_e2e(self, i):
+        """One end-to-end step.  Every step's loss IS read back to the host inside the timed region, through a pinned buffer and one step
+        late: the copy of step i's loss is enqueued behind step i, batch i+1 is prepared, and only then the host waits -- for step i-1's
+        value, which has long arrived.  The GPU queue never drains, which is how a training loop that logs its loss is written."""
         from reactranker_b200.data.prefetch import Lookahead
         if self._feed is None:
             self._feed = Lookahead(self._endless(), self._prepare)
+            self._pin = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._pending = None
+            self.losses = []
         cur = self._feed.current
         loss = self._run(cur)
+        buf = self._pin[i & 1]
+        buf.copy_(loss.detach().reshape(-1)[:1], non_blocking=True)       # D2H of this step's result, asynchronous
+        ev = torch.cuda.Event()
+        ev.record()
         self.h2d = cur[4] if self.ranknet else cur.h2d_bytes
         t = time.perf_counter()
-        self._feed.advance()                                          # plan + shard + featurise + upload batch i+1 while step i executes
+        self._feed.advance()                                          # plan + shard + ids + upload batch i+1 while step i executes
         self.adv_ms.append((time.perf_counter() - t) * 1e3)
-        return float(loss.detach().cpu().reshape(-1)[0])             # D2H read of the step's result
+        self.e2e_finish()                                             # the previous step's loss
+        self._pending = (ev, buf)
+
+    def e2e_finish(self):
+        if getattr(self, "_pending", None) is not None:
+            ev, buf = self._pending
+            ev.synchronize()
+            self.losses.append(float(buf[0]))
+            self._pending = None
 
     def graphs(self):
         r = self.resident[0]
@@ -330,7 +349,7 @@ def barrier(dist):
     torch.cuda.synchronize()
 
 
-def timed(fn, steps, warmup, dist, dev, profile=False, trace=None):
+def timed(fn, steps, warmup, dist, dev, profile=False, trace=None, finish=None):
     """W untimed steps, then K steps bracketed by barrier + synchronize, CUDA events on the launching stream, MAX over ranks."""
     from reactranker_b200 import _lib
     for i in range(warmup):
@@ -345,7 +364,9 @@ def timed(fn, steps, warmup, dist, dev, profile=False, trace=None):
         t0 = time.perf_counter()
         fn(warmup + i)
         if trace is not None:
-            trace.append((time.perf_counter() - t0) * 1e3)     # host wall per step (the e2e step ends with a D2H read)
+            trace.append((time.perf_counter() - t0) * 1e3)     # host wall per step
+    if finish is not None:
+        finish()                                               # e.g. the last step's device->host read: inside the timed region
     e1.record()
     barrier(dist)
     ms = e0.elapsed_time(e1)
@@ -387,7 +408,7 @@ def ours(args):
     clk = clocks.summary()
     e2e_steps = max(3, args.steps)
     e2e_trace = []
-    ms_e2e, _, _ = timed(job.step_e2e, e2e_steps, max(3, args.warmup), dist, dev, trace=e2e_trace)
+    ms_e2e, _, _ = timed(job.step_e2e, e2e_steps, max(3, args.warmup), dist, dev, trace=e2e_trace, finish=job.e2e_finish)
     if rank == 0:
         print("e2e host wall per step (ms): " + " ".join(f"{t:.1f}" for t in e2e_trace), file=sys.stderr)
         print("  of which preparing the next batch (ms): " + " ".join(f"{t:.1f}" for t in job.adv_ms[-len(e2e_trace):]), file=sys.stderr)
@@ -425,7 +446,7 @@ def ours(args):
             try:
                 j = Job(name, local, args.dropout, args.no_dedup, pool=2 if world == 1 else 1, seed=7)
                 o_ms, _, _ = timed(j.step_resident, args.other_steps, 3, dist, dev)
-                e_ms, _, _ = timed(j.step_e2e, args.other_steps, 3, dist, dev)
+                e_ms, _, _ = timed(j.step_e2e, args.other_steps, 3, dist, dev, finish=j.e2e_finish)
                 others[name] = {"metric": metric_of(j.wl), "value": j.rows * world * args.other_steps / (o_ms / 1e3), "unit": UNIT,
                                 "e2e": j.rows * world * args.other_steps / (e_ms / 1e3), "ms_per_step": o_ms / args.other_steps,
                                 "steps": args.other_steps, "warmup": 3, "n_gpus": world, "workload": j.wl["desc"]}

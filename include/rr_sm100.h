@@ -153,6 +153,18 @@ int rr_graph_assemble(const rr_mol_store* store, int n_mols, const int32_t* mol_
                       const int32_t* mol_W, const int32_t* mol_pad_bond, const int32_t* mol_pad_atom, int n_segments,
                       const int32_t* seg_pad_atom, const int32_t* seg_pad_bond, const int32_t* seg_W, const rr_graph* out, void* stream);
 
+/* Host side of the same step (HOST pointers only, no device work): the control block rr_graph_assemble reads, for the molecules
+ * h_ids[0..n_mols) (store ids, segments back to back, h_seg_lens molecules each), laid out exactly as the reference lays out one
+ * BatchMolGraph per segment (featurization.py:246-290): one padding row, then the molecules' rows; max_num_bonds = max(1, largest
+ * in-degree) unless h_W_override[s] (>= that) is given -- data-parallel shards pass the global batch's value.
+ *   h_ctl  int32[6 n_mols + 3 n_segments]: [ids | a_start | b_start | W | pad_bond | pad_atom] per molecule, [a0 | b0 | W] per segment;
+ *          pass its device copy to rr_graph_assemble as (ctl, ctl + n, ctl + 2n, ..., ctl + 6n, ctl + 6n + S, ctl + 6n + 2S)
+ *   h_dims int64[5]: n_atoms, n_bonds, n_mols, wmax, n_segments of the graph;   h_seg_* int64[n_segments], optional (NULL): rows / W per segment
+ * Replaces the host arithmetic of load_reactions.py:549-578 + featurization.py:246-290 (rr_batch_build). */
+int rr_batch_build(int n_mols, const int32_t* h_ids, int n_store, const int32_t* h_store_n_atoms, const int32_t* h_store_n_bonds,
+                   const int32_t* h_store_max_degree, int n_segments, const int64_t* h_seg_lens, const int64_t* h_W_override,
+                   int32_t* h_ctl, int64_t* h_dims, int64_t* h_seg_atoms, int64_t* h_seg_bonds, int64_t* h_seg_W);
+
 /* ---- message passing (models/mpn.py) -------------------------------------------------- */
 /* mpn.py:89-92   pre[b] = (sum_k m[a2b[b2a[b],k]]) - m[b2revb[b]]   for every bond row.
  * relu_src != 0 applies relu() to m on load (m0 = relu(input), mpn.py:81). */

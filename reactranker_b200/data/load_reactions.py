@@ -298,6 +298,30 @@ class Parsing_features:
             return None
         return np.asarray(ids, dtype=np.int32)
 
+    def frame_ids(self, df, column: str) -> np.ndarray:
+        """Store id of ``df[column]``'s molecule for EVERY row of the frame (int32, -1 where a molecule cannot live in the store), computed
+        once per (frame, column) and kept while the frame is alive.  With it a training batch is two integer fancy-indexes of the planner's
+        row positions instead of one dictionary lookup per SMILES per step (train/step.py: TrainStep.prepare_rows) -- what keeps the
+        data-parallel ranks, each of which plans the GLOBAL batch, off the host's critical path."""
+        import weakref
+        cache = self.__dict__.setdefault("_frame_ids", {})
+        key = (id(df), column)
+        hit = cache.get(key)
+        if hit is not None and hit[0]() is df and hit[1].shape[0] == len(df):
+            return hit[1]
+        codes, uniq = pd.factorize(df[column].values, sort=False)     # one dictionary lookup per DISTINCT molecule
+        ids = self.parsing_ids_or_minus_one(list(uniq))[codes].astype(np.int32)
+        cache[key] = (weakref.ref(df), ids)
+        return ids
+
+    def parsing_ids_or_minus_one(self, smiles) -> np.ndarray:
+        sid_of = self._sid
+        out = np.empty(len(smiles), np.int32)
+        for i, s in enumerate(smiles):
+            sid = sid_of.get(s)
+            out[i] = self._register(s) if sid is None else sid
+        return out
+
     def parsing_reactions(self, reactions: list = None):
         if reactions is None:
             return [None, None]

@@ -577,12 +577,36 @@ class DeviceGraph:
                 ("pad_bonds", S * 4), ("pad_atoms", S * 4)]
 
     @staticmethod
-    def control_block(store: MoleculeStore, ids: np.ndarray, lens: np.ndarray, W: Optional[np.ndarray] = None):
-        """The host side of a device-assembled graph, vectorised over any number of segments: molecule ``ids`` (store ids, segments
-        back to back), ``lens`` molecules per segment, optional per-segment ``W`` (max_num_bonds; default max(1, largest in-degree of the
-        segment)).  Returns ``(ctl int32, (nA, nB, nM, wmax, S), (A_s, B_s, W_s))`` where ctl = [ids | a_start | b_start | W | pad_bond |
-        pad_atom] per molecule + [a0 | b0 | W] per segment, exactly what ``rr_graph_assemble`` reads.  Every segment is laid out as the
-        reference lays out a BatchMolGraph of its molecules: one padding row, then the molecules' rows (featurization.py:264-290)."""
+    def control_block(store: MoleculeStore, ids: np.ndarray, lens: np.ndarray, W: Optional[np.ndarray] = None, out: Optional[np.ndarray] = None):
+        """The host side of a device-assembled graph for any number of segments: molecule ``ids`` (store ids, segments back to back),
+        ``lens`` molecules per segment, optional per-segment ``W`` (max_num_bonds; default max(1, largest in-degree of the segment)).
+        Returns ``(ctl int32, (nA, nB, nM, wmax, S), (A_s, B_s, W_s))`` where ctl = [ids | a_start | b_start | W | pad_bond | pad_atom] per
+        molecule + [a0 | b0 | W] per segment, exactly what ``rr_graph_assemble`` reads.  Every segment is laid out as the reference lays out
+        a BatchMolGraph of its molecules: one padding row, then the molecules' rows (featurization.py:264-290).  The arithmetic is one pass
+        in C++ (``rr_batch_build``, csrc/rr_host.cu) writing into ``out`` (e.g. the pinned staging buffer) when given;
+        ``control_block_numpy`` is the vectorised restatement the tests hold it to."""
+        from .. import _lib
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        S, nM = int(lens.shape[0]), int(ids.shape[0])
+        n = 6 * nM + 3 * S
+        ctl = np.empty(n, np.int32) if out is None else out[:n]
+        dims = np.zeros(5, np.int64)
+        seg = np.zeros((3, max(S, 1)), np.int64)
+        W_arr = None if W is None else np.ascontiguousarray(W, dtype=np.int64)
+        if W_arr is not None and W_arr.shape[0] != S:
+            raise ValueError(f"{W_arr.shape[0]} max_num_bonds overrides for {S} segments")
+        n_store = len(store)
+        st = _lib.lib().rr_batch_build(nM, ids.ctypes.data, n_store, store.nA.ctypes.data, store.nB.ctypes.data, store.maxdeg.ctypes.data, S,
+                                       lens.ctypes.data, None if W_arr is None else W_arr.ctypes.data, ctl.ctypes.data, dims.ctypes.data,
+                                       seg[0].ctypes.data, seg[1].ctypes.data, seg[2].ctypes.data)
+        if st != 0:
+            raise ValueError(_lib.lib().rr_last_error().decode(errors="replace"))
+        return ctl, tuple(int(v) for v in dims), (seg[0, :S], seg[1, :S], seg[2, :S])
+
+    @staticmethod
+    def control_block_numpy(store: MoleculeStore, ids: np.ndarray, lens: np.ndarray, W: Optional[np.ndarray] = None):
+        """Vectorised numpy restatement of ``control_block`` (test reference for rr_batch_build)."""
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         lens = np.asarray(lens, dtype=np.int64)
         S, nM = int(lens.shape[0]), int(ids.shape[0])
@@ -675,7 +699,13 @@ class DeviceGraph:
         from .. import _lib
         dev = torch.device(dev)
         store.sync(dev)
-        blocks = [DeviceGraph.control_block(store, r_ids, r_lens, r_W), DeviceGraph.control_block(store, p_ids, p_lens, p_W)]
+        # both control blocks are written by rr_batch_build straight into one pinned staging buffer
+        n_ctl = [4 * (6 * len(i) + 3 * len(l)) for i, l in ((r_ids, r_lens), (p_ids, p_lens))]
+        h_off = [0, _align(n_ctl[0])]
+        host = _POOL.take(h_off[1] + n_ctl[1], "pinned", lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True))
+        hv = host.numpy()
+        blocks = [DeviceGraph.control_block(store, ids, lens, W, out=hv[h_off[k]:h_off[k] + n_ctl[k]].view(np.int32))
+                  for k, (ids, lens, W) in enumerate(((r_ids, r_lens, r_W), (p_ids, p_lens, p_W)))]
         dims = [b[1] for b in blocks]
         offs, total = [{}, {}], 0
         for name, ld in (("f_atoms", FA_LD), ("f_bonds", FB_LD)):          # the two feature pairs first, each pair contiguous
@@ -688,17 +718,11 @@ class DeviceGraph:
             for name, nbytes in DeviceGraph._sections(nA, nB, nM, wmax, S)[2:]:
                 offs[k][name] = total
                 total += _align(max(nbytes, 4))
-        ctl_off = [total, total + _align(blocks[0][0].nbytes)]
-        total_all = ctl_off[1] + _align(blocks[1][0].nbytes)
-        ctl_bytes = blocks[0][0].nbytes + blocks[1][0].nbytes
-        host = _POOL.take(_align(blocks[0][0].nbytes) + blocks[1][0].nbytes, "pinned", lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True))
-        h_off = [0, _align(blocks[0][0].nbytes)]
-        for k in (0, 1):
-            ctl = blocks[k][0]
-            host[h_off[k]:h_off[k] + ctl.nbytes].view(torch.int32).numpy()[:] = ctl
+        ctl_off = [total, total + h_off[1]]
+        total_all = ctl_off[1] + _align(n_ctl[1])
         blob = _POOL.take(total_all, str(dev), lambda n: torch.empty(n, dtype=torch.uint8, device=dev))
-        n_ctl = h_off[1] + blocks[1][0].nbytes
-        blob[ctl_off[0]:ctl_off[0] + n_ctl].copy_(host[:n_ctl], non_blocking=True)
+        n_copy = h_off[1] + n_ctl[1]
+        blob[ctl_off[0]:ctl_off[0] + n_copy].copy_(host[:n_copy], non_blocking=True)
         copied = torch.cuda.Event()
         copied.record(torch.cuda.current_stream(dev))
         shared = _SharedBlob(blob, str(dev), host, copied)
@@ -708,7 +732,7 @@ class DeviceGraph:
             nA, nB, nM, wmax, S = dims[k]
             g = DeviceGraph()
             g.blob, g.host_blob, g._shared = blob, host, shared
-            g.h2d_bytes = blocks[k][0].nbytes
+            g.h2d_bytes = n_ctl[k]
             c = g.c
             c.n_atoms, c.n_bonds, c.n_mols, c.wmax, c.n_segments = nA, nB, nM, wmax, S
             for name, _ in DeviceGraph._sections(nA, nB, nM, wmax, S):
@@ -722,7 +746,6 @@ class DeviceGraph:
             g.real_atoms, g.real_bonds = nA - S, nB - S
             g._offs = offs[k]
             out.append(g)
-        _ = ctl_bytes
         return out[0], out[1]
 
     @staticmethod
@@ -905,16 +928,16 @@ class DeviceGraph:
         return u_ids, u_lens, amap
 
     @staticmethod
-    def from_id_groups(store: MoleculeStore, r_ids, p_ids, lens, device, dedup: bool):
+    def from_id_groups(store: MoleculeStore, r_ids, p_ids, lens, device, dedup: bool, r_W=None, p_W=None):
         """(reactant DeviceGraph, product DeviceGraph) of many segments straight from store ids (``Parsing_features.parsing_ids``): what
         ``from_batches`` / ``from_batches_dedup`` build from one BatchMolGraph per segment, without creating those objects."""
         dev = torch.device(device)
         plan = DeviceGraph.dedup_ids(store, r_ids, p_ids, lens) if dedup else None
         if plan is None:
-            return DeviceGraph.assemble_pair_ids(store, r_ids, lens, p_ids, lens, dev)
+            return DeviceGraph.assemble_pair_ids(store, r_ids, lens, p_ids, lens, dev, r_W, p_W)
         u_ids, u_lens, amap = plan
         # the unique reactants of a segment keep the segment's max_num_bonds (same molecules: same largest in-degree)
-        rg, pg = DeviceGraph.assemble_pair_ids(store, u_ids, u_lens, p_ids, lens, dev)
+        rg, pg = DeviceGraph.assemble_pair_ids(store, u_ids, u_lens, p_ids, lens, dev, r_W, p_W)
         host = torch.from_numpy(amap).pin_memory()
         rg.atom_map = host.to(dev, non_blocking=True)
         rg._atom_map_host = host

@@ -99,6 +99,55 @@ class TrainStep:
                 h2d += feats.numel() * 4
         return PreparedBatch(r_inputs, p_inputs, targets_t, scope[g_lo:g_hi], feats, G, N, r1 - r0, h2d)
 
+    def prepare_rows(self, proc, rows, scope, smiles2graph_dic, smiles_list=None, target_name='std_targ', add_features_name=None, df=None,
+                     pinned: bool = True) -> PreparedBatch:
+        """The same as ``prepare`` for one item of ``DataProcessor.plan_batch_reactions`` -- row positions and scope instead of the gathered
+        SMILES / target arrays.  With the package's ``Parsing_features`` the molecules of the rows are two integer fancy-indexes of the
+        per-frame store-id vectors (``frame_ids``), the shard's control blocks are one C++ pass each (``rr_batch_build``) into pinned
+        memory, and nothing is gathered for rows of other ranks: a rank's host work per step stays ~0.5 ms however large the GLOBAL
+        batch is.  Any other featuriser (the reference's interface: ``parsing_reactions`` on SMILES) goes through ``prepare``."""
+        from ..features.featurization import DeviceGraph
+        df = proc.df if df is None else df
+        rows = np.asarray(rows)
+        scope = [int(s) for s in scope]
+        cols = ['rsmi', 'psmi'] if smiles_list is None else list(smiles_list)
+        fast = hasattr(smiles2graph_dic, "frame_ids")
+        if fast:
+            r_all, p_all = smiles2graph_dic.frame_ids(df, cols[0])[rows], smiles2graph_dic.frame_ids(df, cols[1])[rows]
+            fast = rows.shape[0] == 0 or (int(r_all.min()) >= 0 and int(p_all.min()) >= 0)
+        if not fast:
+            smiles, targets, feats = proc._gather(df, rows, smiles_list, target_name, add_features_name)
+            return self.prepare((smiles, targets.reshape(-1, 1), scope, feats), smiles2graph_dic, pinned, device_graphs=True)
+        store = smiles2graph_dic.store
+        G, N = len(scope), int(sum(scope))
+        r0, r1, g_lo, g_hi = 0, N, 0, G
+        w_r = w_p = None
+        if self.world > 1:
+            g_lo, g_hi, r0, r1 = parallel.plan_shard(scope, store.nA[p_all], self.rank, self.world)
+            w_r = [max(1, int(store.maxdeg[r_all].max()))]           # the GLOBAL batch's max_num_bonds (featurization.py:281)
+            w_p = [max(1, int(store.maxdeg[p_all].max()))]
+        mine = rows[r0:r1]
+        proc._index(df)
+        targets_t = torch.FloatTensor(proc._col(df, target_name)[mine].reshape(-1, 1)).squeeze()      # train_listwise.py:187
+        feats = None
+        if add_features_name is not None:
+            names = list(add_features_name) if isinstance(add_features_name, (list, tuple)) else [add_features_name]
+            feats = np.stack([proc._col(df, c)[mine] for c in names], axis=1)
+        if r1 == r0:
+            return PreparedBatch(None, None, targets_t, [], feats, G, N, 0)
+        model = self.model
+        dedup = bool(getattr(model, "dedup_reactants", False)) and not (model.training and getattr(model, "_dropout", 0) > 0)
+        rg, pg = DeviceGraph.from_id_groups(store, r_all[r0:r1], p_all[r0:r1], [r1 - r0], self.dev, dedup, w_r, w_p)
+        h2d = rg.h2d_bytes + pg.h2d_bytes
+        if pinned:
+            targets_t = targets_t.pin_memory().to(self.dev, non_blocking=True)
+            h2d += targets_t.numel() * 4
+            if feats is not None:
+                f = torch.as_tensor(np.asarray(feats, dtype=np.float32)).reshape(r1 - r0, -1)
+                feats = f.pin_memory().to(self.dev, non_blocking=True)
+                h2d += feats.numel() * 4
+        return PreparedBatch(rg, pg, targets_t, scope[g_lo:g_hi], feats, G, N, r1 - r0, h2d)
+
     # ---- device side -------------------------------------------------------------------------
     def run(self, b: PreparedBatch, epoch: int = 0, epochs: int = 1) -> torch.Tensor:
         """forward -> loss -> zero_grad -> backward -> (all-reduce) -> optimizer.step -> scheduler.step (train_listwise.py:189-290).

@@ -166,11 +166,13 @@ def train(model: nn.Module, scheduler: _LRScheduler, train_data_ini: DataFrame, 
         model.train()
         loss = torch.zeros(1)
         # nothing below waits for the GPU (the loss is read once per epoch), so the host plans and featurises batch i+1 while step i runs
-        for batch in train_proc.generate_batch_reactions(smiles_list=smiles_list, target_name='std' + target_name, batch_size=batch_size,
-                                                         seed=epoch, add_features_name=add_features_name):
+        # generate_batch_reactions(..., seed=epoch) as train_listwise.py:177-182 calls it, taken at the planner level (row positions + scope;
+        # the gathered SMILES / targets of a row are looked up by whoever trains on it)
+        for rows, scope in train_proc.plan_batch_reactions(batch_size=batch_size, seed=epoch):
             # the step body of train_listwise.py:187-290: targets -> FloatTensor.squeeze, featurise, forward, loss dispatch, zero_grad,
             # backward, optimizer.step, scheduler.step -- plus, data-parallel, the shard selection and the gradient all-reduce
-            loss = step.run(step.prepare(batch, smiles2graph_dic), epoch, epochs)
+            prepared = step.prepare_rows(train_proc, rows, scope, smiles2graph_dic, smiles_list, 'std' + target_name, add_features_name)
+            loss = step.run(prepared, epoch, epochs)
             finite &= torch.isfinite(model.encoder.W_i.weight).all()
         if not bool(finite):                       # the reference prints, it does not abort (train_listwise.py:190-195)
             print('*' * 40)

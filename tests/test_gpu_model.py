@@ -600,4 +600,4 @@ def test_one_process_two_devices():
         res.append((out.detach().cpu(), loss.detach().cpu(), {k: p.grad.cpu().numpy() for k, p in model.named_parameters() if p.requires_grad}))
     for other in res[1:]:
         assert rel_err(other[0].numpy(), res[0][0].numpy()) < 1e-6 and rel_err(other[1].numpy(), res[0][1].numpy()) < 1e-6
-        assert not grads_close(other[2], res[0][2], 1e-5)
+        assert not grads_close(other[2], res[0][2], 1e-4)          # float-atomic order in the split-K weight gradients

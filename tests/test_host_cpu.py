@@ -530,3 +530,59 @@ def test_control_block_and_dedup_ids_on_random_layouts():
             a0_u += 1 + int(u_na.sum())
             o += ln
         assert amap.tolist() == want
+
+
+def test_rr_batch_build_equals_the_numpy_restatement_and_reports_errors():
+    """The C++ host batcher behind DeviceGraph.control_block (rr_batch_build, csrc/rr_host.cu; host pointers only, runs without a GPU)
+    against the vectorised numpy restatement, bit for bit, on random segment layouts incl. empty segments, an empty batch and
+    max_num_bonds overrides; bad arguments come back as messages, not crashes."""
+    from reactranker_b200 import synthetic
+    from reactranker_b200.data.load_reactions import Parsing_features
+    from reactranker_b200.features.featurization import DeviceGraph
+    rng = np.random.default_rng(5)
+    ds = synthetic.make_dataset(71, [6, 9, 4, 11, 3], star_leaves_in_group={2: 9})
+    fz = Parsing_features(ds.mols)
+    all_ids = np.concatenate([fz.parsing_ids(list(ds.rsmi)), fz.parsing_ids(list(ds.psmi))])
+    for trial in range(40):
+        n = int(rng.integers(0, 60))
+        ids = rng.choice(all_ids, size=n)
+        S = int(rng.integers(1, 7))
+        cuts = np.sort(rng.integers(0, n + 1, size=S - 1))
+        lens = np.diff(np.concatenate(([0], cuts, [n])))
+        W = None
+        if trial % 3 == 0:
+            _, _, (_, _, W_min) = DeviceGraph.control_block_numpy(fz.store, ids, lens)
+            W = W_min + rng.integers(0, 3, size=S)
+        a = DeviceGraph.control_block(fz.store, ids, lens, W)
+        b = DeviceGraph.control_block_numpy(fz.store, ids, lens, W)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1], trial
+        assert all(np.array_equal(x, y) for x, y in zip(a[2], b[2])), trial
+    staging = np.zeros(6 * 4 + 3 + 5, np.int32)                      # written in place (the pinned staging buffer of the product path)
+    ctl, dims, _ = DeviceGraph.control_block(fz.store, all_ids[:4], [4], out=staging)
+    assert ctl.base is staging or ctl is staging or np.shares_memory(ctl, staging)
+    with pytest.raises(ValueError, match="override"):
+        DeviceGraph.control_block(fz.store, all_ids, [len(all_ids)], [1])
+    with pytest.raises(ValueError, match="segment lengths"):
+        DeviceGraph.control_block(fz.store, all_ids[:5], [2, 2])
+    with pytest.raises(ValueError, match="outside the store"):
+        DeviceGraph.control_block(fz.store, np.asarray([10 ** 6], np.int32), [1])
+
+
+def test_frame_ids_equal_per_token_lookups_and_follow_the_frame():
+    """Parsing_features.frame_ids: the store id of every row's molecule, computed once per (frame, column); a batch's molecules are then
+    frame_ids[rows].  Must equal the per-SMILES dictionary path, survive new frames and not be confused by a dead frame's recycled id()."""
+    from reactranker_b200 import synthetic
+    from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features
+    ds = synthetic.make_dataset(81, [5, 3, 6, 4])
+    fz = Parsing_features(ds.mols)
+    df = ds.to_dataframe()
+    for col in ("rsmi_mapped", "psmi_mapped"):
+        ids = fz.frame_ids(df, col)
+        assert ids.dtype == np.int32 and np.array_equal(ids, fz.parsing_ids(list(df[col].values)))
+        assert fz.frame_ids(df, col) is ids                                  # cached
+    proc = DataProcessor(df)
+    for rows, scope in proc.plan_batch_reactions(batch_size=9, seed=3):
+        smiles, _, _ = proc._gather(df, rows, ["rsmi_mapped", "psmi_mapped"], "lgk", None)
+        assert np.array_equal(fz.frame_ids(df, "psmi_mapped")[rows], fz.parsing_ids(smiles[:, 1].tolist()))
+    sub = df.iloc[5:].reset_index(drop=True)
+    assert np.array_equal(fz.frame_ids(sub, "psmi_mapped"), fz.parsing_ids(list(sub["psmi_mapped"].values)))
