@@ -675,7 +675,8 @@ struct WgArgs {
   int nb;            // TMA boxes of B per stage = ceil(kt / 32)
   int k_pad;         // k rounded up to 16: the last k-tile may be narrower than kt
   int tm_a;          // first TMEM column of the A stages (accumulator below it)
-  int stages;
+  int stages;        // pipeline stages (wgrad3: slots of the raw ring)
+  int bf_stages;     // wgrad3: slots of the bf16 ring / TMEM A operand
   int m_chunk;       // rows of the reduction per blockIdx.z (multiple of WG_BK)
   float* dW;
   int lddw;
@@ -874,14 +875,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad2(const __grid_constant_
 //               X -> bf16 (hi, lo) images in the canonical MN-major 128-byte-swizzle layout (64 columns per 128-byte row, 8-row atoms)
 //   MMA       : kind::f16, A from TMEM, B MN-major from the bf16 ring; the raw slot is free again as soon as the conversion is done
 // ================================================================================================
-constexpr int W3_BKR = 32;                   // rows of the reduction per stage
-constexpr int W3_BOX = W3_BKR * 128;         // bytes of one raw TMA box [32 x 32 floats] == one bf16 MN block [32 x 64 bf16]
-constexpr int W3_A_RAW = 4 * W3_BOX;
+// The raw ring (R slots: what TMA has in flight) and the bf16 ring (SB slots: what the tensor core reads) are sized separately, and the rows
+// of the reduction per stage are a template parameter, so that the pipeline shape can be measured (scripts/bench_wgrad_cfg.sh, RR_WG3_CFG).
+// Measured on [321 778 x 304]^T [321 778 x 304] (profiles/r02_wgrad_cfg.md): 32 rows, 2 + 2 slots 273 us; 32 rows, 3 + 1 slots 330 us;
+// 16 rows with 4 + 2, 5 + 3, 6 + 2 or 5 + 2 slots 361 us each.  Ring depth changes nothing and smaller stages are slower: the kernel is not
+// waiting for HBM but paying ~830 clk of fixed cost per stage (barrier hand-offs, tcgen05.wait::st, the async-proxy fence, commit latency)
+// plus ~52 clk per row of fp32 -> bf16 conversion; 32-row stages with two slots of each ring (the most 227 KB holds) stay the default.
+constexpr int W3_A_COLS = 128;               // dZ columns per CTA == TMEM lanes
 
+template <int BKR>
 __device__ __forceinline__ uint64_t umma_desc_mn_bf16(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(W3_BOX >> 4) << 16;        // LBO: next block of 64 columns
+  d |= static_cast<uint64_t>((BKR * 128) >> 4) << 16;   // LBO: next block of 64 columns
   d |= static_cast<uint64_t>(1024 >> 4) << 32;          // SBO: next 8 rows of the reduction
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;                  // SWIZZLE_128B
@@ -891,33 +897,38 @@ __device__ __forceinline__ uint64_t umma_desc_mn_bf16(uint32_t smem_addr) {
 constexpr int W3_WORKERS = 256;   // 8 conversion warps (12 measured no faster): with 4 the fp32 -> bf16 conversion (not the MMAs) paced the kernel
 constexpr int W3_THREADS = 64 + W3_WORKERS;
 
+template <int BKR>
 __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_constant__ WgArgs g) {
+  constexpr int BOX = BKR * 128;               // bytes of one raw TMA box [BKR x 32 floats] == one bf16 MN block [BKR x 64 bf16]
+  constexpr int A_RAW = 4 * BOX;               // dZ: 128 columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int S = g.stages;
+  const int R = g.stages, SB = g.bf_stages;
   const int nblk = (g.kt + 63) / 64;                     // bf16 MN blocks per image
-  const int raw_bytes = W3_A_RAW + g.nb * W3_BOX;        // dZ | X
-  const int bf_bytes = 2 * nblk * W3_BOX;                // X hi | X lo
+  const int raw_bytes = A_RAW + g.nb * BOX;              // dZ | X
+  const int bf_bytes = 2 * nblk * BOX;                   // X hi | X lo
   uint8_t* raw0 = smem;
-  uint8_t* bf0 = smem + static_cast<size_t>(S) * raw_bytes;
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(bf0 + static_cast<size_t>(S) * bf_bytes);
-  uint64_t* raw_empty = raw_full + S;
-  uint64_t* ready = raw_empty + S;
-  uint64_t* mma_done = ready + S;
-  uint64_t* acc_bar = mma_done + S;
+  uint8_t* bf0 = smem + static_cast<size_t>(R) * raw_bytes;
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(bf0 + static_cast<size_t>(SB) * bf_bytes);
+  uint64_t* raw_empty = raw_full + R;
+  uint64_t* ready = raw_empty + R;
+  uint64_t* mma_done = ready + SB;
+  uint64_t* acc_bar = mma_done + SB;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BM, k0 = blockIdx.y * g.kt;
   const int m_beg = blockIdx.z * g.m_chunk;
   const int m_end = min(g.M, m_beg + g.m_chunk);
-  const int nst = (m_end - m_beg + W3_BKR - 1) / W3_BKR;
+  const int nst = (m_end - m_beg + BKR - 1) / BKR;
   const int width = min(g.kt, g.k_pad - k0);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < R; ++s) {
       mbar_init(raw_full + s, 1);
       mbar_init(raw_empty + s, W3_WORKERS / 32);
+    }
+    for (int s = 0; s < SB; ++s) {
       mbar_init(ready + s, W3_WORKERS / 32);
       mbar_init(mma_done + s, 1);
     }
@@ -941,14 +952,14 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
     if (lane == 0) {
       const uint32_t tx = static_cast<uint32_t>(raw_bytes);
       for (int it = 0; it < nst; ++it) {
-        const int st = it % S;
-        const uint32_t ph = (it / S) & 1;
+        const int st = it % R;
+        const uint32_t ph = (it / R) & 1;
         mbar_wait(raw_empty + st, ph ^ 1);
         uint8_t* base = raw0 + static_cast<size_t>(st) * raw_bytes;
-        const int m = m_beg + it * W3_BKR;
+        const int m = m_beg + it * BKR;
         mbar_expect_tx(raw_full + st, tx);
-        for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, raw_full + st, base + j * W3_BOX, n0 + 32 * j, m);
-        for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, raw_full + st, base + W3_A_RAW + j * W3_BOX, k0 + 32 * j, m);
+        for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, raw_full + st, base + j * BOX, n0 + 32 * j, m);
+        for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, raw_full + st, base + A_RAW + j * BOX, k0 + 32 * j, m);
       }
     }
   } else if (warp == 1) {
@@ -959,25 +970,25 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
       const uint32_t idesc1 = umma_idesc_bf16(BM, n1) | mn;
       const uint32_t idesc2 = n2 ? (umma_idesc_bf16(BM, n2) | mn) : 0u;
       for (int it = 0; it < nst; ++it) {
-        const int st = it % S;
-        const uint32_t ph = (it / S) & 1;
+        const int st = it % SB;
+        const uint32_t ph = (it / SB) & 1;
         mbar_wait(ready + st, ph);
         tc_fence_after();
-        const uint32_t b_hi = smem_u32(bf0 + static_cast<size_t>(st) * bf_bytes), b_lo = b_hi + nblk * W3_BOX;
-        const uint32_t a_hi = tmem_base + g.tm_a + st * 32, a_lo = a_hi + 16;
+        const uint32_t b_hi = smem_u32(bf0 + static_cast<size_t>(st) * bf_bytes), b_lo = b_hi + nblk * BOX;
+        const uint32_t a_hi = tmem_base + g.tm_a + st * BKR, a_lo = a_hi + BKR / 2;
         if (!(g.diag & 4)) {
 #pragma unroll
-          for (int k = 0; k < W3_BKR / 16; ++k) {
+          for (int k = 0; k < BKR / 16; ++k) {
             const uint32_t ko = k * 2048;              // next 16 rows of the reduction = two 8-row atoms
             const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            umma_bf16_ts(tmem_base, a_lo + k * 8, umma_desc_mn_bf16(b_hi + ko), idesc1, first);
-            umma_bf16_ts(tmem_base, a_hi + k * 8, umma_desc_mn_bf16(b_lo + ko), idesc1, 1u);
-            umma_bf16_ts(tmem_base, a_hi + k * 8, umma_desc_mn_bf16(b_hi + ko), idesc1, 1u);
+            umma_bf16_ts(tmem_base, a_lo + k * 8, umma_desc_mn_bf16<BKR>(b_hi + ko), idesc1, first);
+            umma_bf16_ts(tmem_base, a_hi + k * 8, umma_desc_mn_bf16<BKR>(b_lo + ko), idesc1, 1u);
+            umma_bf16_ts(tmem_base, a_hi + k * 8, umma_desc_mn_bf16<BKR>(b_hi + ko), idesc1, 1u);
             if (n2) {
-              const uint32_t bo = static_cast<uint32_t>(n1 / 64) * W3_BOX;
-              umma_bf16_ts(tmem_base + n1, a_lo + k * 8, umma_desc_mn_bf16(b_hi + bo + ko), idesc2, first);
-              umma_bf16_ts(tmem_base + n1, a_hi + k * 8, umma_desc_mn_bf16(b_lo + bo + ko), idesc2, 1u);
-              umma_bf16_ts(tmem_base + n1, a_hi + k * 8, umma_desc_mn_bf16(b_hi + bo + ko), idesc2, 1u);
+              const uint32_t bo = static_cast<uint32_t>(n1 / 64) * BOX;
+              umma_bf16_ts(tmem_base + n1, a_lo + k * 8, umma_desc_mn_bf16<BKR>(b_hi + bo + ko), idesc2, first);
+              umma_bf16_ts(tmem_base + n1, a_hi + k * 8, umma_desc_mn_bf16<BKR>(b_lo + bo + ko), idesc2, 1u);
+              umma_bf16_ts(tmem_base + n1, a_hi + k * 8, umma_desc_mn_bf16<BKR>(b_hi + bo + ko), idesc2, 1u);
             }
           }
         }
@@ -995,34 +1006,38 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
     const bool a_warp = warp < 6;                     // warps 2..5 own the four TMEM lane quadrants: dZ conversion and the final read-out
     float bsum = 0.f;
     for (int it = 0; it < nst; ++it) {
-      const int st = it % S;
-      const uint32_t ph = (it / S) & 1;
-      mbar_wait(raw_full + st, ph);
-      mbar_wait(mma_done + st, ph ^ 1);               // the MMAs of the previous lap are done with this bf16 slot and TMEM slot
+      const int rs = it % R, bs = it % SB;
+      mbar_wait(raw_full + rs, (it / R) & 1);
+      mbar_wait(mma_done + bs, ((it / SB) & 1) ^ 1);  // the MMAs of the previous lap are done with this bf16 slot and TMEM slot
       tc_fence_after();
-      const uint32_t raw = smem_u32(raw0 + static_cast<size_t>(st) * raw_bytes);
+      const uint32_t raw = smem_u32(raw0 + static_cast<size_t>(rs) * raw_bytes);
       if (a_warp && !(g.diag & 1)) {
-        const uint32_t colp = raw + quad * W3_BOX + lane * 4;
-        float a[W3_BKR];
+        const uint32_t colp = raw + quad * BOX + lane * 4;
+        float a[BKR];
 #pragma unroll
-        for (int m = 0; m < W3_BKR; ++m) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[m]) : "r"(colp + m * 128));
-        uint32_t hi[16], lo[16];
+        for (int m = 0; m < BKR; ++m) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a[m]) : "r"(colp + m * 128));
+        uint32_t hi[BKR / 2], lo[BKR / 2];
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
+        for (int m = 0; m < BKR / 2; ++m) {
           split_bf16_pair(a[2 * m], a[2 * m + 1], hi[m], lo[m]);
           bsum += a[2 * m] + a[2 * m + 1];
         }
-        const uint32_t ta = lane_addr + g.tm_a + st * 32;
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 16, lo);
+        const uint32_t ta = lane_addr + g.tm_a + bs * BKR;
+        if constexpr (BKR == 32) {
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 16, lo);
+        } else {
+          tmem_st8(ta, hi);
+          tmem_st8(ta + 8, lo);
+        }
       }
       if (!(g.diag & 2)) {
-        const uint32_t xraw = raw + W3_A_RAW;
-        const uint32_t xhi = smem_u32(bf0 + static_cast<size_t>(st) * bf_bytes), xlo = xhi + nblk * W3_BOX;
+        const uint32_t xraw = raw + A_RAW;
+        const uint32_t xhi = smem_u32(bf0 + static_cast<size_t>(bs) * bf_bytes), xlo = xhi + nblk * BOX;
         int m = wtid / G, cg = wtid - m * G;
-        for (; m < W3_BKR;) {
+        for (; m < BKR;) {
           const int jb = cg >> 2, c2 = (cg & 3) << 1, sw = m & 7;
-          const uint32_t rp = xraw + jb * W3_BOX + m * 128;
+          const uint32_t rp = xraw + jb * BOX + m * 128;
           // two 16-byte chunks of 4 floats; boxes of odd index read theirs in the opposite order: 8 consecutive lanes hit 8 distinct bank groups
           const int first = c2 + (jb & 1), second = c2 + 1 - (jb & 1);
           const float4 f0 = lds_f4(rp + ((first ^ sw) << 4)), f1 = lds_f4(rp + ((second ^ sw) << 4));
@@ -1032,7 +1047,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           split_bf16_pair(lo4.z, lo4.w, h[1], l[1]);
           split_bf16_pair(hi4.x, hi4.y, h[2], l[2]);
           split_bf16_pair(hi4.z, hi4.w, h[3], l[3]);
-          const uint32_t off = (cg >> 3) * W3_BOX + m * 128 + (((cg & 7) ^ sw) << 4);
+          const uint32_t off = (cg >> 3) * BOX + m * 128 + (((cg & 7) ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xhi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xlo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
           m += step_m;
@@ -1048,8 +1063,8 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(ready + st);
-        mbar_arrive(raw_empty + st);
+        mbar_arrive(ready + bs);
+        mbar_arrive(raw_empty + rs);
       }
     }
     if (a_warp && g.dbias != nullptr && blockIdx.y == 0 && n0 + r < g.n) atomicAdd(g.dbias + n0 + r, bsum);
@@ -1265,16 +1280,27 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   g.tm_a = g.kt <= 160 ? 160 : 320;
   // wide tiles: 16-row stages (4 x 48 KB in flight instead of 2 x 96 KB); narrow tiles fit 3+ stages of 32 rows
   if (g_bwd_bf16.load() && !getenv("RR_WG_TF32")) {
-    // 3 x bf16: raw ring (dZ 16 KB + X boxes) and bf16 ring (hi + lo images), the same number of slots each
+    // 3 x bf16: raw ring (dZ + X boxes as TMA lands them) and bf16 ring (hi + lo images + the TMEM A slots), sized separately.
+    // RR_WG3_CFG="rows per stage,raw slots,bf16 slots" overrides the default (timing experiments).
+    int bkr = 32, R = 2, SB = 2;
+    static const char* const cfg_env = getenv("RR_WG3_CFG");
+    if (cfg_env) sscanf(cfg_env, "%d,%d,%d", &bkr, &R, &SB);
+    if (bkr != 32) bkr = 16;
+    const int box = bkr * 128;
     const int nblk = (g.kt + 63) / 64;
-    const int raw_bytes = W3_A_RAW + g.nb * W3_BOX, bf_bytes = 2 * nblk * W3_BOX;
-    int S3 = (SMEM_LIMIT - 2048) / (raw_bytes + bf_bytes);
-    if (S3 > 4) S3 = 4;
-    if (S3 > (512 - g.tm_a) / 32) S3 = (512 - g.tm_a) / 32;
-    if (S3 >= 2) {
-      g.stages = S3;
-      RR_TRY(make_map(&g.tmA, dZ, M, n, lddz, W3_BKR, CU_TENSOR_MAP_SWIZZLE_NONE));
-      RR_TRY(make_map(&g.tmB, X, M, k, ldx, W3_BKR, CU_TENSOR_MAP_SWIZZLE_128B));
+    const int raw_bytes = 4 * box + g.nb * box, bf_bytes = 2 * nblk * box;
+    if (SB < 1) SB = 1;
+    if (SB > (512 - g.tm_a) / bkr) SB = (512 - g.tm_a) / bkr;
+    if (SB > 4) SB = 4;
+    while (SB > 1 && 2 * raw_bytes + SB * bf_bytes > SMEM_LIMIT - 2048) --SB;
+    int Rmax = (SMEM_LIMIT - 2048 - SB * bf_bytes) / raw_bytes;
+    if (R > Rmax) R = Rmax;
+    if (R > 8) R = 8;
+    if (R >= 2 && SB >= 1) {
+      g.stages = R;
+      g.bf_stages = SB;
+      RR_TRY(make_map(&g.tmA, dZ, M, n, lddz, bkr, CU_TENSOR_MAP_SWIZZLE_NONE));
+      RR_TRY(make_map(&g.tmB, X, M, k, ldx, bkr, CU_TENSOR_MAP_SWIZZLE_128B));
       g.M = M;
       g.n = n;
       g.k = k;
@@ -1282,24 +1308,26 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       g.dW = dW;
       g.lddw = lddw;
       g.dbias = dbias;
-      const char* de = getenv("RR_TC_DIAG");
+      static const char* const de = getenv("RR_TC_DIAG");
       g.diag = de ? atoi(de) : 0;
       const int ntiles3 = (n + BM - 1) / BM;
       int splits3 = num_sms() / (ntiles3 * ktiles);
-      const int max_splits3 = (M + 8 * W3_BKR - 1) / (8 * W3_BKR);
+      const int max_splits3 = (M + 8 * 32 - 1) / (8 * 32);
       if (splits3 > max_splits3) splits3 = max_splits3;
       if (splits3 < 1) splits3 = 1;
       int chunk3 = (M + splits3 - 1) / splits3;
-      chunk3 = (chunk3 + W3_BKR - 1) / W3_BKR * W3_BKR;
+      chunk3 = (chunk3 + 31) / 32 * 32;
       splits3 = (M + chunk3 - 1) / chunk3;
       g.m_chunk = chunk3;
       static PerDeviceOnce attr3_set;
       if (attr3_set.need()) {
-        RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr3_set.mark();
       }
-      const size_t smem3 = static_cast<size_t>(S3) * (raw_bytes + bf_bytes) + 1024 + 512;
-      RR_CUDA(launch_pdl(k_tc_wgrad3, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
+      const size_t smem3 = static_cast<size_t>(R) * raw_bytes + static_cast<size_t>(SB) * bf_bytes + 1024 + 512;
+      if (bkr == 32) RR_CUDA(launch_pdl(k_tc_wgrad3<32>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
+      else RR_CUDA(launch_pdl(k_tc_wgrad3<16>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       RR_LAUNCH_CHECK("k_tc_wgrad3");
       return RR_OK;
     }
