@@ -514,12 +514,25 @@ class _BufferPool:
         with self.lock:
             lst = self.free.setdefault(key, [])
             # a pinned staging buffer is reusable only once the asynchronous copy out of it has run (its event has completed)
-            fits = [e for e in lst if e[0].numel() >= nbytes and (e[1] is None or e[1].query())]
+            # (device blobs taken here are rewritten on the stream their previous readers ran on: stream order is enough)
+            fits = [e for e in lst if e[0].numel() >= nbytes and (key != "pinned" or e[1] is None or e[1].query())]
             if fits:
                 best = min(fits, key=lambda e: e[0].numel())
                 lst[:] = [e for e in lst if e is not best]     # identity, not tensor equality
                 return best[0]
         return make(int(nbytes * 1.0625) + 256)
+
+    def take_device(self, nbytes: int, key, make):
+        """(tensor, event | None) for a DEVICE blob that will be written on another stream than the one its previous owner read it on:
+        the event was recorded on that owner's stream when the blob came back; the writer's stream waits for it (no host wait)."""
+        with self.lock:
+            lst = self.free.setdefault(key, [])
+            fits = [e for e in lst if e[0].numel() >= nbytes]
+            if fits:
+                best = min(fits, key=lambda e: e[0].numel())
+                lst[:] = [e for e in lst if e is not best]
+                return best
+        return make(int(nbytes * 1.0625) + 256), None
 
     def give(self, t, key, event=None):
         with self.lock:
@@ -541,10 +554,25 @@ class _SharedBlob:
         p, self.p = self.p, None
         if p is not None:
             try:
-                _POOL.give(p[0], p[1])
+                # every kernel that reads the blob was enqueued (on the device's current stream) before its graphs died
+                freed = torch.cuda.Event()
+                freed.record(torch.cuda.current_stream(p[0].device))
+                _POOL.give(p[0], p[1], freed)
                 _POOL.give(p[2], "pinned", p[3])
             except Exception:      # interpreter shutdown
                 pass
+
+
+_ASM_STREAMS: dict = {}
+
+
+def _assembly_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """Side stream on which batches are assembled: the id upload and the two rr_graph_assemble launches of batch i+1 run NEXT TO the
+    kernels of step i instead of behind them (~0.15 ms of copies per step that the dense layers leave HBM bandwidth for)."""
+    s = _ASM_STREAMS.get(dev)
+    if s is None:
+        s = _ASM_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
 
 
 class DeviceGraph:
@@ -720,32 +748,48 @@ class DeviceGraph:
                 total += _align(max(nbytes, 4))
         ctl_off = [total, total + h_off[1]]
         total_all = ctl_off[1] + _align(n_ctl[1])
-        blob = _POOL.take(total_all, str(dev), lambda n: torch.empty(n, dtype=torch.uint8, device=dev))
+        blob, freed = _POOL.take_device(total_all, str(dev), lambda n: torch.empty(n, dtype=torch.uint8, device=dev))
+        main, side = torch.cuda.current_stream(dev), _assembly_stream(dev)
+        blob.record_stream(side)
+        new_upload = store.h2d_bytes_total != getattr(store, "_asm_seen_bytes", -1)
+        if new_upload:                           # the molecule store uploaded molecules (store.sync above, main stream) since the last assembly
+            uploaded = torch.cuda.Event()
+            uploaded.record(main)
         n_copy = h_off[1] + n_ctl[1]
-        blob[ctl_off[0]:ctl_off[0] + n_copy].copy_(host[:n_copy], non_blocking=True)
-        copied = torch.cuda.Event()
-        copied.record(torch.cuda.current_stream(dev))
-        shared = _SharedBlob(blob, str(dev), host, copied)
         out = []
         base = blob.data_ptr()
-        for k in (0, 1):
-            nA, nB, nM, wmax, S = dims[k]
-            g = DeviceGraph()
-            g.blob, g.host_blob, g._shared = blob, host, shared
-            g.h2d_bytes = n_ctl[k]
-            c = g.c
-            c.n_atoms, c.n_bonds, c.n_mols, c.wmax, c.n_segments = nA, nB, nM, wmax, S
-            for name, _ in DeviceGraph._sections(nA, nB, nM, wmax, S):
-                setattr(c, name, base + offs[k][name])
-            p0 = base + ctl_off[0] + h_off[k]
-            with torch.cuda.device(dev):
-                _lib.check(_lib.lib().rr_graph_assemble(ctypes.byref(store.c), nM, p0, p0 + 4 * nM, p0 + 8 * nM, p0 + 12 * nM, p0 + 16 * nM, p0 + 20 * nM,
-                                                        S, p0 + 24 * nM, p0 + 24 * nM + 4 * S, p0 + 24 * nM + 8 * S, ctypes.byref(c),
-                                                        torch.cuda.current_stream().cuda_stream))
-            g.n_atoms, g.n_bonds, g.n_mols = nA, nB, nM
-            g.real_atoms, g.real_bonds = nA - S, nB - S
-            g._offs = offs[k]
-            out.append(g)
+        with torch.cuda.stream(side):
+            if new_upload:
+                side.wait_event(uploaded)
+                store._asm_seen_bytes = store.h2d_bytes_total
+            if freed is not None:
+                side.wait_event(freed)           # the blob's previous graphs are read by kernels enqueued earlier on the main stream
+            blob[ctl_off[0]:ctl_off[0] + n_copy].copy_(host[:n_copy], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+            shared = _SharedBlob(blob, str(dev), host, copied)
+            for k in (0, 1):
+                nA, nB, nM, wmax, S = dims[k]
+                g = DeviceGraph()
+                g.blob, g.host_blob, g._shared = blob, host, shared
+                g.h2d_bytes = n_ctl[k]
+                c = g.c
+                c.n_atoms, c.n_bonds, c.n_mols, c.wmax, c.n_segments = nA, nB, nM, wmax, S
+                for name, _ in DeviceGraph._sections(nA, nB, nM, wmax, S):
+                    setattr(c, name, base + offs[k][name])
+                p0 = base + ctl_off[0] + h_off[k]
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().rr_graph_assemble(ctypes.byref(store.c), nM, p0, p0 + 4 * nM, p0 + 8 * nM, p0 + 12 * nM, p0 + 16 * nM, p0 + 20 * nM,
+                                                            S, p0 + 24 * nM, p0 + 24 * nM + 4 * S, p0 + 24 * nM + 8 * S, ctypes.byref(c), side.cuda_stream))
+                g.n_atoms, g.n_bonds, g.n_mols = nA, nB, nM
+                g.real_atoms, g.real_bonds = nA - S, nB - S
+                g._offs = offs[k]
+                out.append(g)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        # everything enqueued on the main stream FROM NOW ON sees the assembled graphs; what is already queued there (the running step)
+        # is what the assembly overlaps with
+        main.wait_event(ready)
         return out[0], out[1]
 
     @staticmethod

@@ -365,11 +365,19 @@ def test_buffer_pool_best_fit_and_event_guard():
         def query(self):
             return self.done
     ev = Ev(False)
-    pool.give(a, "p", ev)
-    c = pool.take(10, "p", make)
+    pool.give(a, "pinned", ev)
+    c = pool.take(10, "pinned", make)
     assert c is not a                      # copy still in flight: a fresh buffer instead
     ev.done = True
-    assert pool.take(10, "p", make) is a
+    assert pool.take(10, "pinned", make) is a
+    # device blobs: take() relies on stream order (no host-side wait); take_device() hands the "freed" event to the caller, whose
+    # side stream waits for it
+    ev2 = Ev(False)
+    pool.give(b, "cuda:0", ev2)
+    got, freed = pool.take_device(100, "cuda:0", make)
+    assert got is b and freed is ev2
+    fresh, none = pool.take_device(100, "cuda:0", make)
+    assert fresh is not b and none is None
 
 
 def test_train_state_round_trip_resumes_adam_and_noam(tmp_path):
