@@ -215,34 +215,43 @@ struct PadFix {
   float p, inv_keep;
   uint64_t seed, stream_id;
 };
-__global__ void k_pad_rows_linear(PadFix a) {
+// One warp per output column (grid = rows x ceil(n / 8), 8 warps per block): the k loop is unrolled into independent loads and four
+// fp64 partial sums, so a launch is a couple of microseconds (the first version, one warp per ~5 columns with a serial chain, took 20).
+__device__ __forceinline__ double pad_dot(const float* __restrict__ x, const float* __restrict__ w, int k, int lane) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int i = lane;
+  for (; i + 96 < k; i += 128) {
+    const float x0 = x[i], x1 = x[i + 32], x2 = x[i + 64], x3 = x[i + 96];
+    const float w0 = __ldg(w + i), w1 = __ldg(w + i + 32), w2 = __ldg(w + i + 64), w3 = __ldg(w + i + 96);
+    a0 = fma(static_cast<double>(x0), static_cast<double>(w0), a0);
+    a1 = fma(static_cast<double>(x1), static_cast<double>(w1), a1);
+    a2 = fma(static_cast<double>(x2), static_cast<double>(w2), a2);
+    a3 = fma(static_cast<double>(x3), static_cast<double>(w3), a3);
+  }
+  for (; i < k; i += 32) a0 = fma(static_cast<double>(x[i]), static_cast<double>(__ldg(w + i)), a0);
+  return (a0 + a1) + (a2 + a3);
+}
+__global__ void __launch_bounds__(256) k_pad_rows_linear(PadFix a) {
   const size_t row = static_cast<size_t>(__ldg(a.rows + blockIdx.x));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int c = blockIdx.y * nwarps + warp; c < a.n; c += gridDim.y * nwarps) {
-    double acc = 0.0;
-    const float* x = a.X1 + row * a.ldx1;
-    const float* w = a.W1 + static_cast<size_t>(c) * a.k1;
-    for (int k = lane; k < a.k1; k += 32) acc += static_cast<double>(x[k]) * static_cast<double>(__ldg(w + k));
-    if (a.X2) {
-      x = a.X2 + row * a.ldx2;
-      w = a.W2 + static_cast<size_t>(c) * a.k2;
-      for (int k = lane; k < a.k2; k += 32) acc += static_cast<double>(x[k]) * static_cast<double>(__ldg(w + k));
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 8 + warp;
+  if (c >= a.n) return;
+  double acc = pad_dot(a.X1 + row * a.ldx1, a.W1 + static_cast<size_t>(c) * a.k1, a.k1, lane);
+  if (a.X2) acc += pad_dot(a.X2 + row * a.ldx2, a.W2 + static_cast<size_t>(c) * a.k2, a.k2, lane);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      if (a.bias) acc += static_cast<double>(a.bias[c]);
-      if (a.resid) acc += static_cast<double>(a.resid[row * a.ldr + c]);
-      float o = static_cast<float>(acc);
-      if (a.relu) o = fmaxf(o, 0.f);
-      if (a.p > 0.f) {   // element (c & 3) of the 4-wide Philox draw the GEMM epilogue makes for this chunk (dropout4)
-        const uint4 r = philox4x32(a.seed, a.stream_id, (row * a.ldy + c) >> 2);
-        const uint32_t thr = static_cast<uint32_t>(fminf(a.p, 1.f) * 4294967295.f);
-        const uint32_t rv = (c & 3) == 0 ? r.x : ((c & 3) == 1 ? r.y : ((c & 3) == 2 ? r.z : r.w));
-        o = rv >= thr ? o * a.inv_keep : 0.f;
-      }
-      a.Y[row * a.ldy + c] = o;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (a.bias) acc += static_cast<double>(a.bias[c]);
+    if (a.resid) acc += static_cast<double>(a.resid[row * a.ldr + c]);
+    float o = static_cast<float>(acc);
+    if (a.relu) o = fmaxf(o, 0.f);
+    if (a.p > 0.f) {   // element (c & 3) of the 4-wide Philox draw the GEMM epilogue makes for this chunk (dropout4)
+      const uint4 r = philox4x32(a.seed, a.stream_id, (row * a.ldy + c) >> 2);
+      const uint32_t thr = static_cast<uint32_t>(fminf(a.p, 1.f) * 4294967295.f);
+      const uint32_t rv = (c & 3) == 0 ? r.x : ((c & 3) == 1 ? r.y : ((c & 3) == 2 ? r.z : r.w));
+      o = rv >= thr ? o * a.inv_keep : 0.f;
     }
+    a.Y[row * a.ldy + c] = o;
   }
 }
 // same argument order as linear_fwd; W1 / W2 are the raw (unsplit) packed weights
@@ -264,8 +273,7 @@ static int pad_rows_linear(const int* rows, int n_rows, int n, const float* X1, 
   a.inv_keep = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
   a.seed = seed;
   a.stream_id = stream_id;
-  const int by = n_rows >= 64 ? 1 : (n_rows >= 8 ? 2 : 8);
-  k_pad_rows_linear<<<dim3(n_rows, by), 256, 0, s>>>(a);
+  k_pad_rows_linear<<<dim3(n_rows, (n + 7) / 8), 256, 0, s>>>(a);
   RR_LAUNCH_CHECK("k_pad_rows_linear");
   return RR_OK;
 }

@@ -47,38 +47,48 @@ for k, (n, ns) in sorted(per.items(), key=lambda kv: -kv[1][1]):
 import glob
 traffic = {}
 reps = sorted(glob.glob(os.path.join(OUT, f"{R}_full_*.ncu-rep")))
-rr = []
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "sm__warps_active.avg.pct_of_peak_sustained_active"]
+
+
+def unit_bytes(v, u):
+    return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+
+def us(v, u):
+    return float(v.replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
+
+
+groups = collections.OrderedDict()          # kernel -> list of {metric: (value, unit)}: every report is read with ITS OWN header
 for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     part = list(csv.reader(raw.splitlines()))
-    rr = part if not rr else rr + part[2:]
-if rr:
-    hh, uu = rr[0], rr[1]
-    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
-            "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
-            "sm__warps_active.avg.pct_of_peak_sustained_active"]
-    idx = {w: hh.index(w) for w in want if w in hh}
+    if len(part) < 3:
+        continue
+    hh, uu = part[0], part[1]
     kn = hh.index("Kernel Name")
-
-    def unit_bytes(v, u):
-        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-    groups = collections.OrderedDict()
-    for r in rr[2:]:
-        groups.setdefault(short(r[kn]), []).append(r)
+    idx = {w: hh.index(w) for w in want if w in hh}
+    for r in part[2:]:
+        if len(r) <= kn:
+            continue
+        groups.setdefault(short(r[kn]), []).append({w: (r[i], uu[i]) for w, i in idx.items()})
+if groups:
     md += ["", f"## `--set full` captures (`gpurun_out/{R}_full_*.ncu-rep`, launches of one steady-state step of bench.py; the longest launch of each kernel is shown)", ""]
     for k, lst in groups.items():
-        durs = [float(r[idx["gpu__time_duration.sum"]].replace(",", "")) for r in lst]
+        durs = [us(*m["gpu__time_duration.sum"]) for m in lst]
         big = lst[max(range(len(lst)), key=lambda i: durs[i])]
-        rd = sum(unit_bytes(r[idx["dram__bytes_read.sum"]], uu[idx["dram__bytes_read.sum"]]) for r in lst) / len(lst)
-        wr = sum(unit_bytes(r[idx["dram__bytes_write.sum"]], uu[idx["dram__bytes_write.sum"]]) for r in lst) / len(lst)
+        rd = sum(unit_bytes(*m["dram__bytes_read.sum"]) for m in lst) / len(lst)
+        wr = sum(unit_bytes(*m["dram__bytes_write.sum"]) for m in lst) / len(lst)
         traffic[k] = {"launches_captured": len(lst), "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                       "mean_us": sum(durs) / len(durs)}
         md += [f"### `{k}`  ({len(lst)} launches captured; mean {sum(durs) / len(durs):.1f} us, DRAM {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written per launch)", "",
                "| metric | value |", "|---|---|"]
-        for w, i in idx.items():
-            md.append(f"| {w} | {big[i]} {uu[i]} |")
+        for w in want:
+            if w in big:
+                md.append(f"| {w} | {big[w][0]} {big[w][1]} |")
         md.append("")
 json.dump(traffic, open(os.path.join(PROF, f"{R}_traffic.json"), "w"), indent=1)
 open(os.path.join(PROF, f"{R}_ncu_summary.md"), "w").write("\n".join(md) + "\n")
