@@ -290,6 +290,8 @@ int rr_model_backward(const rr_model_cfg* cfg, const rr_params* w, const rr_grap
 int rr_profile_begin(void);
 int rr_profile_end(double* h_ms_by_class, int64_t* h_launches_by_class, int n_classes);
 int rr_profile_classes(void);
+/* The RR_* environment switches (kernel experiments / diagnostics) are read once, at first use; this reads them again. */
+void rr_reload_switches(void);
 /* kernels launched on this thread since the last reset (for bench.py's gpu_launches) */
 int64_t rr_launch_count(void);
 void rr_launch_count_reset(void);

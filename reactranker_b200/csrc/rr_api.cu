@@ -12,6 +12,35 @@ std::atomic<int> g_bwd_bf16{1};
 std::atomic<int> g_fwd_bf16{0};
 ProfState g_prof;
 std::mutex g_prof_mutex;
+
+static Switches g_switches;
+static std::atomic<bool> g_switches_loaded{false};
+static std::mutex g_switches_mutex;
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+void reload_switches() {
+  std::lock_guard<std::mutex> lock(g_switches_mutex);
+  Switches w;
+  const int ew = env_int("RR_TC_EW", 16);
+  w.tc_ew = (ew == 4 || ew == 8) ? ew : 16;
+  w.tc_diag = env_int("RR_TC_DIAG", 0);
+  w.tc_fake_presplit = getenv("RR_TC_FAKE_PRESPLIT") != nullptr;
+  w.wg_kt = env_int("RR_WG_KT", 0);
+  w.wg_tf32 = getenv("RR_WG_TF32") != nullptr;
+  w.wg_bkr = env_int("RR_WG_BKR", 0);
+  if (const char* c = getenv("RR_WG3_CFG")) sscanf(c, "%d,%d,%d", &w.wg3_bkr, &w.wg3_raw, &w.wg3_bf);
+  w.mp_v1 = env_int("RR_MP_V1", 0);
+  if (const char* c = getenv("RR_MP_ACC_RED")) w.mp_acc_red = c[0] != '0';
+  w.mp_consumers = env_int("RR_MP_CONSUMERS", 0);
+  g_switches = w;
+  g_switches_loaded.store(true);
+}
+const Switches& switches() {
+  if (!g_switches_loaded.load()) reload_switches();
+  return g_switches;
+}
 void prof_push(int cls, cudaEvent_t a, cudaEvent_t b) {
   std::lock_guard<std::mutex> lock(g_prof_mutex);
   ProfState& p = g_prof;
@@ -177,6 +206,7 @@ int rr_profile_end(double* ms_by_class, int64_t* launches_by_class, int n_classe
   return status;
 }
 int rr_profile_classes(void) { return rr::KC_COUNT; }
+void rr_reload_switches(void) { rr::reload_switches(); }
 int64_t rr_launch_count(void) { return rr::g_launches.load(); }
 void rr_launch_count_reset(void) { rr::g_launches.store(0); }
 

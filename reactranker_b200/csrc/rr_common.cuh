@@ -74,6 +74,17 @@ struct ProfScope {
 // 0 = fp32 SIMT GEMMs, 1 = tcgen05 3xTF32 GEMMs where the shape allows (forward + dgrad)
 extern std::atomic<int> g_gemm_mode;
 
+// Diagnostic / experiment switches from the environment (RR_TC_EW, RR_TC_DIAG, RR_TC_FAKE_PRESPLIT, RR_WG_KT, RR_WG_TF32, RR_WG_BKR, RR_WG3_CFG,
+// RR_MP_V1, RR_MP_ACC_RED, RR_MP_CONSUMERS): read ONCE, when the library is first used, not on every launch.  rr_reload_switches() reads
+// them again (tests and the micro-benchmarks flip them inside one process).
+struct Switches {
+  int tc_ew = 16, tc_diag = 0, tc_fake_presplit = 0;
+  int wg_kt = 0, wg_tf32 = 0, wg_bkr = 0, wg3_bkr = 32, wg3_raw = 2, wg3_bf = 2;
+  int mp_v1 = 0, mp_acc_red = -1, mp_consumers = 0;
+};
+const Switches& switches();
+void reload_switches();
+
 #define RR_REQUIRE(cond, ...)                                  \
   do {                                                         \
     if (!(cond)) return rr::fail(RR_ERR_INVALID, __VA_ARGS__); \

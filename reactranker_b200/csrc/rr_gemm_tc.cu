@@ -1147,11 +1147,7 @@ bool tc_linear_bf16_supported(int M, int n, int k, int ldx, int ldw) {
 }
 // epilogue warps of k_tc_gemm2: 16 (16-column sub-blocks, 704 threads at 80 registers) by default; RR_TC_EW=8 / 4 select the earlier
 // 32-column-block flavours (8 warps: -13 % forward GEMM time per step, scripts/bench_gemm.py diag)
-static int epilogue_warps() {
-  const char* e = getenv("RR_TC_EW");
-  const int v = e ? atoi(e) : 16;
-  return (v == 4 || v == 8) ? v : 16;
-}
+static int epilogue_warps() { return switches().tc_ew; }
 
 // Full-featured bf16-split linear: Y = epi(X1 W1^T + X2 W2^T) with every weight given as bf16 (hi, lo) images.
 int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t* W1hi, const uint16_t* W1lo, int ldw1, int k1, const float* X2, int ldx2,
@@ -1173,8 +1169,7 @@ int tc_linear_bf16_full(int M, int n, const float* X1, int ldx1, const uint16_t*
     g.src[1].K = k2;
   }
   g.presplit = 1;
-  const char* diag_env = getenv("RR_TC_DIAG");
-  g.diag = diag_env ? atoi(diag_env) : 0;
+  g.diag = switches().tc_diag;
   g.M = M;
   g.N = n;
   g.C = Y;
@@ -1271,21 +1266,17 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   using namespace tc;
   ProfScope prof_scope(KC_GEMM_WGRAD, s);
   WgArgs g{};
-  const char* kt_env = getenv("RR_WG_KT");
-  const int kt_cap = (kt_env && atoi(kt_env) == 160) ? 160 : MAX_NT;
+  const int kt_cap = switches().wg_kt == 160 ? 160 : MAX_NT;
   const int k_pad = (k + 15) / 16 * 16;                  // columns past k are zero-filled by TMA and never written back
   const int ktiles = (k_pad + kt_cap - 1) / kt_cap;
   g.kt = ktiles == 1 ? k_pad : kt_cap;
   g.nb = (g.kt + 31) / 32;
   g.tm_a = g.kt <= 160 ? 160 : 320;
   // wide tiles: 16-row stages (4 x 48 KB in flight instead of 2 x 96 KB); narrow tiles fit 3+ stages of 32 rows
-  if (g_bwd_bf16.load() && !getenv("RR_WG_TF32")) {
+  if (g_bwd_bf16.load() && !switches().wg_tf32) {
     // 3 x bf16: raw ring (dZ + X boxes as TMA lands them) and bf16 ring (hi + lo images + the TMEM A slots), sized separately.
     // RR_WG3_CFG="rows per stage,raw slots,bf16 slots" overrides the default (timing experiments).
-    int bkr = 32, R = 2, SB = 2;
-    static const char* const cfg_env = getenv("RR_WG3_CFG");
-    if (cfg_env) sscanf(cfg_env, "%d,%d,%d", &bkr, &R, &SB);
-    if (bkr != 32) bkr = 16;
+    int bkr = switches().wg3_bkr == 16 ? 16 : 32, R = switches().wg3_raw, SB = switches().wg3_bf;
     const int box = bkr * 128;
     const int nblk = (g.kt + 63) / 64;
     const int raw_bytes = 4 * box + g.nb * box, bf_bytes = 2 * nblk * box;
@@ -1308,8 +1299,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       g.dW = dW;
       g.lddw = lddw;
       g.dbias = dbias;
-      static const char* const de = getenv("RR_TC_DIAG");
-      g.diag = de ? atoi(de) : 0;
+      g.diag = switches().tc_diag;
       const int ntiles3 = (n + BM - 1) / BM;
       int splits3 = num_sms() / (ntiles3 * ktiles);
       const int max_splits3 = (M + 8 * 32 - 1) / (8 * 32);
@@ -1332,8 +1322,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       return RR_OK;
     }
   }
-  const char* bkr_env = getenv("RR_WG_BKR");
-  const int bkr = bkr_env ? (atoi(bkr_env) == 16 ? 16 : 32) : (g.kt > 160 ? 16 : 32);
+  const int bkr = switches().wg_bkr ? (switches().wg_bkr == 16 ? 16 : 32) : (g.kt > 160 ? 16 : 32);
   const int box = bkr * 128;
   const int stage_bytes = 4 * box + 2 * g.nb * box;
   int S = (SMEM_LIMIT - 2048) / stage_bytes;
@@ -1350,8 +1339,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   g.dW = dW;
   g.lddw = lddw;
   g.dbias = dbias;
-  const char* diag_env = getenv("RR_TC_DIAG");
-  g.diag = diag_env ? atoi(diag_env) : 0;
+  g.diag = switches().tc_diag;
   // one CTA per SM (shared memory and TMEM are both taken whole): never more CTAs than SMs, or the stragglers run as a second wave
   const int ntiles = (n + BM - 1) / BM;
   int splits = num_sms() / (ntiles * ktiles);
@@ -1388,8 +1376,7 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
               int kclass, cudaStream_t s, const float* W1lo, const float* W2lo) {
   using namespace tc;
   ProfScope prof_scope(kclass, s);
-  const char* diag_env = getenv("RR_TC_DIAG");
-  if (getenv("RR_TC_FAKE_PRESPLIT") && !W1lo) {  // timing experiments only (scripts/bench_gemm.py): wrong numerics, same traffic as pre-split weights
+  if (switches().tc_fake_presplit && !W1lo) {  // timing experiments only (scripts/bench_gemm.py): wrong numerics, same traffic as pre-split weights
     W1lo = W1;
     W2lo = W2;
   }
@@ -1397,7 +1384,7 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   const bool two = X2 && k2 > 0;
   g.nsrc = two ? 2 : 1;
   g.presplit = (W1lo != nullptr && (!two || W2lo != nullptr)) ? 1 : 0;
-  g.diag = diag_env ? atoi(diag_env) : 0;
+  g.diag = switches().tc_diag;
   RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
   RR_TRY(make_map(&g.src[0].tmB, W1, n, k1, ldw1, NT2));
   if (g.presplit) RR_TRY(make_map(&g.src[0].tmBlo, W1lo, n, k1, ldw1, NT2));

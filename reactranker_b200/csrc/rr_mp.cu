@@ -393,10 +393,7 @@ static void atom_launch_dims(int n_atoms, int ld, dim3* grid, dim3* block) {
 
 // second-generation kernels (rr_mp_pipe.cu); RR_MP_V1=1 keeps the first generation for A/B measurements
 enum { PIPE_BOND_FWD = 0, PIPE_BOND_BWD = 1, PIPE_NBR_FWD = 2, PIPE_NBR_BWD_BOND = 3, PIPE_NBR_BWD_ATOM = 4 };
-static bool use_pipe() {
-  const char* e = getenv("RR_MP_V1");
-  return !(e && e[0] == '1');
-}
+static bool use_pipe() { return switches().mp_v1 != 1; }
 
 int bond_message_fwd(const rr_graph* g, const float* m, float* pre, int hp, int relu_src, cudaStream_t s) {
   ProfScope prof_scope(KC_BOND_FWD, s);

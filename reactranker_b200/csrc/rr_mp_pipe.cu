@@ -484,8 +484,7 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
   const bool fused = y != nullptr;
   // measured (scripts/bench_mp.py): the bond-row backward gains 30 % (273 -> 190 us) from reducing into acc, the atom-row backward, whose
   // accumulator rows are one contiguous bulk copy per stage, loses 13 %: every acc element is added to exactly once, so both are deterministic
-  static const char* const red_env = getenv("RR_MP_ACC_RED");        // switches are read once, at the first launch
-  A.acc_red = red_env ? (red_env[0] != '0') : (op == BOND_BWD);
+  A.acc_red = switches().mp_acc_red >= 0 ? switches().mp_acc_red : (op == BOND_BWD);
   const bool stage_acc = fused && A.acc_mode == 2 && !A.acc_red;
   switch (op) {
     case BOND_FWD: A.n_nbr = 1; A.n_own = 0; break;
@@ -494,8 +493,7 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
     case NBR_BWD_BOND: A.n_nbr = fused ? (stage_acc ? 2 : 1) : 0; A.n_own = 1; break;
     default: A.n_nbr = 1; A.n_own = fused ? (stage_acc ? 3 : 2) : 1; break;
   }
-  static const char* const cw_env = getenv("RR_MP_CONSUMERS");
-  for (int consumers = cw_env ? atoi(cw_env) : MAX_CONSUMERS; consumers >= 256; consumers -= 256) {
+  for (int consumers = switches().mp_consumers ? switches().mp_consumers : MAX_CONSUMERS; consumers >= 256; consumers -= 256) {
     A.consumer_warps = consumers / 32;
     A.apb = consumers / cpr;
     if (A.apb > 32) A.apb = 32;

@@ -52,6 +52,7 @@ def wgrad_case(M, n, k):
 
 
 def report(name, run, flops, bytes_):
+    L.rr_reload_switches()          # pick up whatever RR_* switch the caller just set or removed
     us = timeit(run)
     print(f"{name:58s} {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s  {bytes_ / us * 1e-3:7.0f} GB/s (algorithmic)", flush=True)
 
@@ -64,6 +65,7 @@ E = os.environ
 def setenv(**kw):
     for k, v in kw.items():
         E[k] = str(v)
+    L.rr_reload_switches()          # the library reads its RR_* switches once; re-read after every change
 
 
 if which in ("all", "fwd"):

@@ -55,6 +55,7 @@ cases = [
 for v1, cw in (("1", "512"), ("0", "256"), ("0", "512")):
     os.environ["RR_MP_V1"] = v1
     os.environ["RR_MP_CONSUMERS"] = cw
+    L.rr_reload_switches()
     for name, fn, by in cases:
         us = timeit(lambda: _lib.check(fn()))
         print(f"{'gen1    ' if v1 == '1' else 'pipe' + cw + ' '} {name:32s} {us:8.1f} us  {by / us * 1e-3:7.0f} GB/s", flush=True)

@@ -48,6 +48,7 @@ def _gemm_mode_for_gpu_tests(request):
     yield
     L.rr_set_gemm_mode(1)
     L.rr_set_backward_bf16(1)
+    L.rr_reload_switches()                        # whatever RR_* switch a test monkeypatched is gone again
 
 
 @pytest.fixture(params=[0, 1], ids=["simt", "tc"])

@@ -315,8 +315,9 @@ def test_argument_errors_are_reported_not_crashed():
 def test_tcgen05_linear_matches_fp64(tc_mode, monkeypatch, ew, M, n, k1, k2):
     """tcgen05 3xTF32 forward GEMM (bias + residual + ReLU epilogue, two-source K) against an fp64 matmul:
     fp32-class accuracy, 5e-6 of the largest output.  Both epilogue flavours: 16 warps on 16-column sub-blocks (default), 8 on 32."""
-    monkeypatch.setenv("RR_TC_EW", str(ew))          # read by the launcher at every call
+    monkeypatch.setenv("RR_TC_EW", str(ew))
     L = _lib.lib()
+    L.rr_reload_switches()                           # the RR_* switches are read once; re-read them after changing the environment
     g = torch.Generator().manual_seed(M + n)
     X1, W1 = torch.randn(M, k1, generator=g), torch.randn(n, k1, generator=g) / k1 ** 0.5
     X2 = torch.randn(M, k2, generator=g) if k2 else None
@@ -341,6 +342,7 @@ def test_tcgen05_linear_matches_fp64(tc_mode, monkeypatch, ew, M, n, k1, k2):
 def test_tcgen05_and_simt_draw_the_same_dropout_mask(tc_mode, monkeypatch, ew):
     monkeypatch.setenv("RR_TC_EW", str(ew))
     L = _lib.lib()
+    L.rr_reload_switches()
     M, n, k, p = 1024, 304, 64, 0.3
     X, W = torch.randn(M, k, device=DEV), torch.randn(n, k, device=DEV)
     Yt, Ys = torch.empty(M, n, device=DEV), torch.empty(M, n, device=DEV)
@@ -506,6 +508,7 @@ def test_first_generation_gather_kernels_agree(monkeypatch):
     outs = {}
     for v1 in ("0", "1"):
         monkeypatch.setenv("RR_MP_V1", v1)
+        _lib.lib().rr_reload_switches()
         pre = torch.empty_like(m)
         am = torch.empty(b.n_atoms, hp, device=DEV)
         _lib.check(L.rr_bond_message_fwd(ctypes.byref(dg.c), m.data_ptr(), pre.data_ptr(), hp, 1, S()))
@@ -538,6 +541,7 @@ def test_row_pipeline_matches_first_generation_on_odd_shapes(monkeypatch, seed, 
     res = {}
     for v1 in ("1", "0"):
         monkeypatch.setenv("RR_MP_V1", v1)
+        _lib.lib().rr_reload_switches()
         out = {}
         t = torch.empty(B, hp, device=DEV)
         _lib.check(L.rr_bond_message_fwd(g, mB.data_ptr(), t.data_ptr(), hp, 1, S()))
