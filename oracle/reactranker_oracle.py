@@ -9,8 +9,8 @@ is missing -- there is no CPU fallback).
 Pinning: the reference ships no tests / golden vectors for this path,
 so this oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, executed in the build
 container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``; checked by
-``tests/test_oracle_golden.py`` and, when ``/root/reference`` is present, live by
-``tests/test_oracle_vs_reference.py``).
+``tests/test_oracle_golden.py`` and, wherever the reference is present, live against its own
+modules by ``tests/test_live_reference.py``).
 
 Every function cites the reference lines it restates (paths relative to the
 reference root, package ``reactranker/``).
