@@ -34,6 +34,7 @@ void reload_switches() {
   w.mp_v1 = env_int("RR_MP_V1", 0);
   if (const char* c = getenv("RR_MP_ACC_RED")) w.mp_acc_red = c[0] != '0';
   w.mp_consumers = env_int("RR_MP_CONSUMERS", 0);
+  w.mp_kstage = env_int("RR_MP_KSTAGE", 0);
   g_switches = w;
   g_switches_loaded.store(true);
 }

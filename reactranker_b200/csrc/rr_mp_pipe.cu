@@ -62,6 +62,7 @@ struct Args {
   int acc_red;      // acc += dz as a fire-and-forget vector reduction (red.global.add.v4.f32) instead of staging the accumulator rows:
                     // a third fewer bytes per stage, so twice the atoms (and 16 consumer warps) fit the ring
   int apb, stages, n_stage_total;
+  int kstage;       // neighbour rows staged per atom (<= kFast); neighbours beyond it are read straight from global memory by the consumer
   int producers, round_stages, consumer_warps;   // active producer warps, stages per producer round
   int n_nbr, n_own; // row sources per neighbour / per atom
   int stage_bytes, row_bytes;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
   const int per = A.n_stage_total / gridDim.x, rem = A.n_stage_total - per * gridDim.x;
   const int first_stage = blockIdx.x * per + min(static_cast<int>(blockIdx.x), rem);
   const int my_stages = per + (static_cast<int>(blockIdx.x) < rem ? 1 : 0);
-  const int nbr_rows_per_atom = kFast * A.n_nbr;
+  const int nbr_rows_per_atom = A.kstage * A.n_nbr;
   // stage layout: tasks [apb] | neighbour rows [apb][kFast][n_nbr] | own rows [n_own][apb]
   const int task_bytes = apb * TASK_BYTES;
   const int own_off = task_bytes + apb * nbr_rows_per_atom * A.row_bytes;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
     for (int it_base = pw * R; it_base < my_stages; it_base += NP * R) {
       const Task t = nx;
       load(it_base + NP * R, nx);
-      const int nfetch = t.valid ? min(t.deg, kFast) : 0;
+      const int nfetch = t.valid ? min(t.deg, A.kstage) : 0;
       for (int rr = 0; rr < R; ++rr) {
         const int it = it_base + rr;
         if (it >= my_stages) break;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
       if (active) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(base + task_off));
       if (q0.x & (1 << 9)) {
         const int deg = q0.x & 0xff, is_pad = (q0.x >> 8) & 1, pad_count = q0.y, prow = q0.z, a = q0.w;
-        const int nf = min(deg, kFast);
+        const int nf = min(deg, A.kstage);
         const uint32_t rows = base + rows_off;
         auto nbr = [&](int k, int j) { return lds4(rows + k * nbr_stride + j * A.row_bytes); };
         int4 q1 = make_int4(0, 0, 0, 0);     // rows this op writes: rev (BOND_FWD) or idx (BOND_BWD, NBR_BWD_BOND)
@@ -325,9 +326,9 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
               if (A.relu_src) v[k] = f4_relu(v[k]);
               acc = f4_add(acc, v[k]);
             }
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) {
+            for (int k = A.kstage; k < deg; ++k) {
               const float4 x = ld_f4(src_c + static_cast<size_t>(__ldg(ib + k)) * ld);
               acc = f4_add(acc, A.relu_src ? f4_relu(x) : x);
             }
@@ -335,10 +336,10 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
 #pragma unroll
           for (int k = 0; k < kFast; ++k)
             if (k < nf) st_f4(out_c + static_cast<size_t>(wrow[k]) * ld, f4_sub(acc, v[k]));
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
             const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) {
+            for (int k = A.kstage; k < deg; ++k) {
               const float4 x = ld_f4(src_c + static_cast<size_t>(__ldg(ib + k)) * ld);
               st_f4(out_c + static_cast<size_t>(__ldg(rb + k)) * ld, f4_sub(acc, A.relu_src ? f4_relu(x) : x));
             }
@@ -357,9 +358,9 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
               v[k] = nbr(k, 0);
               S4 = f4_add(S4, v[k]);
             }
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) S4 = f4_add(S4, ld_f4(src_c + static_cast<size_t>(__ldg(rb + k)) * ld));
+            for (int k = A.kstage; k < deg; ++k) S4 = f4_add(S4, ld_f4(src_c + static_cast<size_t>(__ldg(rb + k)) * ld));
           }
 #pragma unroll
           for (int k = 0; k < kFast; ++k)
@@ -369,10 +370,10 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
               if (FUSED) epilogue(d, nbr(k, 1), (A.acc_mode == 2 && !A.acc_red) ? nbr(k, 2) : f4_zero(), off);
               else st_f4(out_c + off, d);
             }
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
             const int* rb = g.a2b_rev + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) {
+            for (int k = A.kstage; k < deg; ++k) {
               const size_t off = static_cast<size_t>(__ldg(ib + k)) * ld;
               const float4 d = f4_sub(S4, ld_f4(src_c + static_cast<size_t>(__ldg(rb + k)) * ld));
               if (FUSED) epilogue(d, ld_f4(y_c + off), (A.acc_mode == 2 && !A.acc_red) ? ld_f4(acc_c + off) : f4_zero(), off);
@@ -390,9 +391,9 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
               const float4 x = nbr(k, 0);
               acc = f4_add(acc, A.relu_src ? f4_relu(x) : x);
             }
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* tb = (A.which ? g.a2a : g.a2b) + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) {
+            for (int k = A.kstage; k < deg; ++k) {
               const float4 x = ld_f4(src_c + static_cast<size_t>(__ldg(tb + k)) * ld);
               acc = f4_add(acc, A.relu_src ? f4_relu(x) : x);
             }
@@ -407,9 +408,9 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
               if (FUSED) epilogue(d, nbr(k, 0), (A.acc_mode == 2 && !A.acc_red) ? nbr(k, 1) : f4_zero(), off);
               else st_f4(out_c + off, d);
             }
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* ib = g.a2b + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) {
+            for (int k = A.kstage; k < deg; ++k) {
               const size_t off = static_cast<size_t>(__ldg(ib + k)) * ld;
               if (FUSED) epilogue(d, ld_f4(y_c + off), (A.acc_mode == 2 && !A.acc_red) ? ld_f4(acc_c + off) : f4_zero(), off);
               else st_f4(out_c + off, d);
@@ -421,9 +422,9 @@ __global__ void __launch_bounds__(MAX_CONSUMERS + 32 * PRODUCERS, 1) k_rowpipe(c
 #pragma unroll
           for (int k = 0; k < kFast; ++k)
             if (k < nf) acc = f4_add(acc, nbr(k, 0));
-          if (deg > kFast) {
+          if (deg > A.kstage) {
             const int* ab = g.a2a + static_cast<size_t>(a) * g.wmax;
-            for (int k = kFast; k < deg; ++k) acc = f4_add(acc, ld_f4(src_c + static_cast<size_t>(__ldg(ab + k)) * ld));
+            for (int k = A.kstage; k < deg; ++k) acc = f4_add(acc, ld_f4(src_c + static_cast<size_t>(__ldg(ab + k)) * ld));
           }
           if (!is_pad) {
             const size_t off = static_cast<size_t>(a) * ld;
@@ -482,6 +483,7 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
   if (cpr < 1 || cpr > 256 || (ld & 3)) return RR_ERR_UNSUPPORTED;
   A.row_bytes = ld * 4;
   const bool fused = y != nullptr;
+  A.kstage = (switches().mp_kstage >= 1 && switches().mp_kstage <= kFast) ? switches().mp_kstage : kFast;
   // measured (scripts/bench_mp.py): the bond-row backward gains 30 % (273 -> 190 us) from reducing into acc, the atom-row backward, whose
   // accumulator rows are one contiguous bulk copy per stage, loses 13 %: every acc element is added to exactly once, so both are deterministic
   A.acc_red = switches().mp_acc_red >= 0 ? switches().mp_acc_red : (op == BOND_BWD);
@@ -497,7 +499,7 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
     A.consumer_warps = consumers / 32;
     A.apb = consumers / cpr;
     if (A.apb > 32) A.apb = 32;
-    A.stage_bytes = A.apb * TASK_BYTES + A.apb * (kFast * A.n_nbr + A.n_own) * A.row_bytes;
+    A.stage_bytes = A.apb * TASK_BYTES + A.apb * (A.kstage * A.n_nbr + A.n_own) * A.row_bytes;
     A.stage_bytes = (A.stage_bytes + 127) / 128 * 128;
     A.stages = SMEM_BUDGET / A.stage_bytes;
     if (A.stages > MAX_STAGES) A.stages = MAX_STAGES;
