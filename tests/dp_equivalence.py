@@ -40,19 +40,28 @@ for task, task_num in (("mle", 1), ("listnet", 1), ("mle_gaussian", 2)):
     whole.backward()
     want = [p.grad.clone() for p in model.hot_parameters()]
     model.zero_grad()
-    # the product's data-parallel step
-    prepared = step.prepare(batch, fz)
-    assert prepared.groups == len(scope) and prepared.items == sum(scope) and 0 < prepared.rows < sum(scope)
-    term = step.run(prepared)
-    assert step.sync.fast_path_steps == 1 and step.sync.copy_path_steps == 0        # p.grad aliases the flat buffer: no staging copies
-    total = step.global_loss(term)
-    assert abs(total - float(whole.detach().reshape(-1)[0])) <= 1e-5 * abs(float(whole.detach().reshape(-1)[0])), (task, total, float(whole))
-    got = [p.grad for p in model.hot_parameters()]
-    # same criterion as tests/helpers.grads_close
-    gscale = max(float(w.abs().max()) for w in want)
-    worst = max(float((g - w).abs().max()) / (float(w.abs().max()) + 1e-2 * gscale) for g, w in zip(got, want))
-    assert worst < 1e-3, (task, worst)
-    worst_all = max(worst_all, worst)
+    # the product's data-parallel step, through both host paths: the gathered-SMILES tuples of generate_batch_reactions (any featuriser
+    # with the reference's interface) and the planner's row positions (what train() and bench.py feed it: per-frame id vectors + rr_batch_build)
+    rows_scope = next(iter(planner.plan_batch_reactions(batch_size=sum(sizes), seed=3)))
+    assert list(rows_scope[1]) == list(scope)
+    steps_before = 0
+    for how in ("smiles", "rows"):
+        if how == "smiles":
+            prepared = step.prepare(batch, fz)
+        else:
+            prepared = step.prepare_rows(planner, rows_scope[0], rows_scope[1], fz, ["rsmi_mapped", "psmi_mapped"], "lgk", "temp")
+        assert prepared.groups == len(scope) and prepared.items == sum(scope) and 0 < prepared.rows < sum(scope)
+        term = step.run(prepared)
+        steps_before += 1
+        assert step.sync.fast_path_steps == steps_before and step.sync.copy_path_steps == 0   # p.grad aliases the flat buffer: no staging copies
+        total = step.global_loss(term)
+        assert abs(total - float(whole.detach().reshape(-1)[0])) <= 1e-5 * abs(float(whole.detach().reshape(-1)[0])), (task, how, total, float(whole))
+        got = [p.grad for p in model.hot_parameters()]
+        # same criterion as tests/helpers.grads_close
+        gscale = max(float(w.abs().max()) for w in want)
+        worst = max(float((g - w).abs().max()) / (float(w.abs().max()) + 1e-2 * gscale) for g, w in zip(got, want))
+        assert worst < 1e-3, (task, how, worst)
+        worst_all = max(worst_all, worst)
 dist.barrier()
 if rank == 0:
     print("DP-EQUIVALENCE-OK worst rel err", worst_all)

@@ -169,3 +169,42 @@ def test_validation_metrics_on_device_match_reference_golden(two, monkeypatch):
     assert np.allclose(got, g[tag + "top_scores"], rtol=0, atol=1e-12)
     r = E.ranking_metrics(m, gpu=0, data_processor=dp, smiles2graph_dic=fz, show_info=False, smiles_list=cols, target_name="lgk", add_features_name="temp")
     assert np.allclose([r[0], r[1], r[2]] + list(r[3]), g[tag + "ranking"], rtol=1e-12, atol=1e-12)
+
+
+def test_planned_rows_path_equals_the_gathered_smiles_path():
+    """TrainStep.prepare_rows (the planner's row positions -> per-frame store-id vectors -> rr_batch_build -> pair assembly on the side
+    stream; what train() and bench.py use) builds byte-for-byte the graphs, targets and extra features that TrainStep.prepare builds from
+    the gathered (smiles, targets, scope, add_features) tuples of generate_batch_reactions, with and without reactant de-duplication;
+    the two steps then give the same loss."""
+    from reactranker_b200 import synthetic
+    from reactranker_b200.data.load_reactions import DataProcessor, Parsing_features
+    from reactranker_b200.features.featurization import DeviceGraph
+    from reactranker_b200.models.base_model import build_model
+    from reactranker_b200.train.step import TrainStep
+    ds = synthetic.make_dataset(91, [7, 5, 9, 6, 8], star_leaves_in_group={2: 6})
+    fz = Parsing_features(ds.mols)
+    proc = DataProcessor(ds.to_dataframe())
+    cols = ["rsmi_mapped", "psmi_mapped"]
+    for dropout in (0.0, 0.1):                       # 0.0: repeated reactants are encoded once (r_atom_map)
+        torch.manual_seed(1)
+        model = build_model(hidden_size=64, task_num=1, ffn_last_layer="with_softplus", add_features_dim=1, dropout=dropout).cuda(0).train()
+        opt = torch.optim.SGD(model.parameters(), lr=0.0)
+        step = TrainStep(model, opt, torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0), "mle", 0)
+        batches = list(proc.generate_batch_reactions(smiles_list=cols, target_name="lgk", batch_size=20, seed=2, add_features_name="temp"))
+        plans = list(proc.plan_batch_reactions(batch_size=20, seed=2))
+        assert len(batches) == len(plans) >= 2
+        for batch, (rows, scope) in zip(batches, plans):
+            a = step.prepare(batch, fz, device_graphs=True)
+            b = step.prepare_rows(proc, rows, scope, fz, cols, "lgk", "temp")
+            torch.cuda.synchronize()
+            assert a.scope == b.scope and (a.groups, a.items, a.rows) == (b.groups, b.items, b.rows)
+            assert torch.equal(a.targets, b.targets) and torch.equal(a.feats, b.feats)
+            for g1, g2 in ((a.r, b.r), (a.p, b.p)):
+                assert (g1.n_atoms, g1.n_bonds, g1.n_mols, g1.c.wmax, g1.c.n_segments) == (g2.n_atoms, g2.n_bonds, g2.n_mols, g2.c.wmax, g2.c.n_segments)
+                for name, nbytes in DeviceGraph._sections(g1.n_atoms, g1.n_bonds, g1.n_mols, g1.c.wmax, g1.c.n_segments):
+                    assert torch.equal(g1.blob[g1._offs[name]:g1._offs[name] + nbytes], g2.blob[g2._offs[name]:g2._offs[name] + nbytes]), name
+            assert (getattr(a.r, "atom_map", None) is None) == (dropout > 0)
+            if dropout == 0:
+                assert torch.equal(a.r.atom_map, b.r.atom_map)
+                la, lb = float(step.run(a)), float(step.run(b))
+                assert la == lb
