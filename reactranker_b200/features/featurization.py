@@ -547,16 +547,18 @@ _POOL = _BufferPool()
 class _SharedBlob:
     """Pooled device blob + pinned control buffer shared by the two DeviceGraphs of a pair: returned to the pool when both are gone."""
 
-    def __init__(self, blob, key, host, event):
-        self.p = (blob, key, host, event)
+    def __init__(self, blob, key, host, event, consumer_stream):
+        self.p = (blob, key, host, event, consumer_stream)
 
     def __del__(self):
         p, self.p = self.p, None
         if p is not None:
             try:
-                # every kernel that reads the blob was enqueued (on the device's current stream) before its graphs died
+                # every kernel that reads the blob was enqueued on the consumer stream (the stream that was current when the pair was
+                # assembled) before its graphs died -- recorded there explicitly: a garbage-collector run may call this anywhere, also
+                # while the assembly stream is current
                 freed = torch.cuda.Event()
-                freed.record(torch.cuda.current_stream(p[0].device))
+                freed.record(p[4])
                 _POOL.give(p[0], p[1], freed)
                 _POOL.give(p[2], "pinned", p[3])
             except Exception:      # interpreter shutdown
@@ -764,10 +766,15 @@ class DeviceGraph:
                 store._asm_seen_bytes = store.h2d_bytes_total
             if freed is not None:
                 side.wait_event(freed)           # the blob's previous graphs are read by kernels enqueued earlier on the main stream
+            else:
+                # a block fresh from the caching allocator may be the recycled memory of a tensor that kernels already queued on the main
+                # stream still read (the allocator only orders reuse within ONE stream): this assembly waits for them.  Only the first
+                # few batches allocate; after that the pool hands blobs back with their `freed` event.
+                side.wait_stream(main)
             blob[ctl_off[0]:ctl_off[0] + n_copy].copy_(host[:n_copy], non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(side)
-            shared = _SharedBlob(blob, str(dev), host, copied)
+            shared = _SharedBlob(blob, str(dev), host, copied, main)
             for k in (0, 1):
                 nA, nB, nM, wmax, S = dims[k]
                 g = DeviceGraph()
