@@ -35,7 +35,6 @@ void reload_switches() {
   if (const char* c = getenv("RR_MP_ACC_RED")) w.mp_acc_red = c[0] != '0';
   w.mp_consumers = env_int("RR_MP_CONSUMERS", 0);
   w.mp_kstage = env_int("RR_MP_KSTAGE", 0);
-  w.mp_moltile = env_int("RR_MP_MOLTILE", 1);
   g_switches = w;
   g_switches_loaded.store(true);
 }

@@ -80,7 +80,7 @@ extern std::atomic<int> g_gemm_mode;
 struct Switches {
   int tc_ew = 16, tc_diag = 0, tc_fake_presplit = 0;
   int wg_kt = 0, wg_tf32 = 0, wg_bkr = 0, wg3_bkr = 32, wg3_raw = 2, wg3_bf = 2;
-  int mp_v1 = 0, mp_acc_red = -1, mp_consumers = 0, mp_kstage = 0, mp_moltile = 1;
+  int mp_v1 = 0, mp_acc_red = -1, mp_consumers = 0, mp_kstage = 0;
 };
 const Switches& switches();
 void reload_switches();
@@ -216,9 +216,6 @@ int rowpipe_launch(int op, const rr_graph* g, int which, const float* src, float
                    float* acc, int acc_mode, int skip_out, cudaStream_t s);
 int pad_rows_act(float* out, const int* rows, int n_rows, int ld, const float* y, float scale, int preact, float* acc, int acc_mode, int skip_out,
                  cudaStream_t s);
-// atom-level (a2a) neighbour sums, one molecule per shared-memory tile (rr_mp_mol.cu): op 0 forward, 1 backward (+ fused epilogue when y)
-int moltile_launch(int op, const rr_graph* g, const float* src, float* out, int ld, int relu_src, const float* y, float scale, int preact, float* acc,
-                   int acc_mode, int skip_out, cudaStream_t s);
 int readout_fwd(const rr_graph*, const float*, int, int, const float*, int, float*, int, float, uint64_t, uint64_t, cudaStream_t);
 int readout_bwd(const rr_graph*, const float*, int, const float*, const float*, float*, int, float, cudaStream_t);
 int relu_bwd(long long, int, const float*, const float*, float, int, float*, float*, int, cudaStream_t);

@@ -456,10 +456,6 @@ int neighbor_sum_fwd(const rr_graph* g, int which, const float* src, float* out,
   RR_TRY(check_graph(g, ld));
   RR_REQUIRE(src && out && aligned16(src) && aligned16(out), "src/out must be non-NULL and 16-byte aligned");
   if (use_pipe()) {
-    if (which == 1) {     // atom rows: one molecule per shared-memory tile (every row read once); graphs without a molecule scope fall through
-      const int st = moltile_launch(0, g, src, out, ld, relu_src, nullptr, 1.f, 0, nullptr, 0, 0, s);
-      if (st != RR_ERR_UNSUPPORTED) return st;
-    }
     const int st = rowpipe_launch(PIPE_NBR_FWD, g, which, src, out, ld, relu_src, nullptr, 1.f, 0, nullptr, 0, 0, s);
     if (st != RR_ERR_UNSUPPORTED) return st;
   }
@@ -481,9 +477,7 @@ int neighbor_sum_bwd_act(const rr_graph* g, int which, const float* dout, float*
     ProfScope prof_scope(KC_NBR_BWD, s);
     RR_TRY(zero_rows(dsrc, pads, g->n_segments, ld, s));
     int st = RR_ERR_UNSUPPORTED;
-    if (use_pipe() && which == 1) st = moltile_launch(1, g, dout, dsrc, ld, 0, y, scale, preact, acc, acc_mode, skip_out, s);
-    if (use_pipe() && st == RR_ERR_UNSUPPORTED)
-      st = rowpipe_launch(which == 0 ? PIPE_NBR_BWD_BOND : PIPE_NBR_BWD_ATOM, g, which, dout, dsrc, ld, 0, y, scale, preact, acc, acc_mode, skip_out, s);
+    if (use_pipe()) st = rowpipe_launch(which == 0 ? PIPE_NBR_BWD_BOND : PIPE_NBR_BWD_ATOM, g, which, dout, dsrc, ld, 0, y, scale, preact, acc, acc_mode, skip_out, s);
     if (st == RR_OK) return y ? pad_rows_act(dsrc, pads, g->n_segments, ld, y, scale, preact, acc, acc_mode, skip_out, s) : RR_OK;
     if (st != RR_ERR_UNSUPPORTED) return st;
     dim3 grid, block;

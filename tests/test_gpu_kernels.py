@@ -780,62 +780,3 @@ def test_id_vector_assembly_equals_per_group_batches(dedup):
             assert torch.equal(g1.blob[o1:o1 + sizes[name]], g2.blob[o2:o2 + sizes[name]]), name
     if dedup:
         assert rg2.n_mols == 4 and torch.equal(rg1.atom_map, rg2.atom_map)
-
-
-@pytest.mark.parametrize("atoms", [(12, 28), (30, 40), (3, 4)])
-@pytest.mark.parametrize("h,segments", [(300, 1), (600, 1), (40, 3)])
-def test_molecule_tile_atom_gathers_equal_the_row_pipeline(monkeypatch, atoms, h, segments):
-    """The atom-level (a2a) neighbour sums through the molecule-tile kernels (rr_mp_mol.cu: a molecule's rows staged once in shared
-    memory) against the row pipeline (RR_MP_MOLTILE=0) and the oracle: forward (with relu-on-load), plain backward and the backward
-    fused with the ReLU / dropout epilogue in its three accumulation modes; molecules of 12-28 atoms (staged), 30-40 atoms (larger than
-    the 32-row tile for some: neighbours read from global memory) and 3-4 atoms, one and several segments, h = 300 / 600 / 40."""
-    L = _lib.lib()
-    sizes = [4, 3, 5]
-    ds = synthetic.make_dataset(23, sizes, atoms_lo=atoms[0], atoms_hi=atoms[1])
-    mols = [ds.mols[t] for t in ds.psmi]
-    if segments == 1:
-        batches = [BatchMolGraph(mols)]
-    else:
-        cuts = np.cumsum([0] + sizes)
-        batches = [BatchMolGraph(mols[cuts[i]:cuts[i + 1]]) for i in range(3)]
-    dg = DeviceGraph.from_batches(batches, DEV)
-    hp = L.rr_padded(h)
-    A = dg.n_atoms
-    src, up, y, acc0 = rand(A, hp, h, 1), rand(A, hp, h, 2), torch.relu(rand(A, hp, h, 3)), rand(A, hp, h, 4)
-    # oracle, per segment (padded a2a slots gather the segment's padding atom)
-    want_f, want_b, o = [], [], 0
-    for b in batches:
-        x = src[o:o + b.n_atoms].double().clone().requires_grad_(True)
-        out = O.gather_sum(torch.relu(x), b.get_a2a())
-        want_f.append(out.detach())
-        x2 = torch.zeros(b.n_atoms, hp, dtype=torch.double, requires_grad=True)
-        O.gather_sum(x2, b.get_a2a()).backward(up[o:o + b.n_atoms].double())
-        want_b.append(x2.grad)
-        o += b.n_atoms
-    want_f, want_b = torch.cat(want_f), torch.cat(want_b)
-    res = {}
-    for moltile in ("1", "0"):
-        monkeypatch.setenv("RR_MP_MOLTILE", moltile)
-        L.rr_reload_switches()
-        srcd, upd, yd = src.to(DEV), up.to(DEV), y.to(DEV)
-        out = torch.full((A, hp), float("nan"), device=DEV)
-        _lib.check(L.rr_neighbor_sum_fwd(ctypes.byref(dg.c), 1, srcd.data_ptr(), out.data_ptr(), hp, 1, S()))
-        close(out, want_f)
-        d = torch.full((A, hp), float("nan"), device=DEV)
-        _lib.check(L.rr_neighbor_sum_bwd(ctypes.byref(dg.c), 1, upd.data_ptr(), d.data_ptr(), hp, S()))
-        close(d, want_b)
-        fused = []
-        for acc_mode, skip_out, preact in ((1, 0, 0), (2, 0, 0), (2, 1, 1), (0, 0, 0)):
-            ysrc = src if preact else y
-            want_dz, want_acc = _act_reference(want_b, ysrc.double(), 0.8, preact, acc0.double(), acc_mode)
-            dz = torch.full((A, hp), float("nan"), device=DEV)
-            acc = acc0.to(DEV).clone()
-            _lib.check(L.rr_neighbor_sum_bwd_act(ctypes.byref(dg.c), 1, upd.data_ptr(), dz.data_ptr(), hp, ysrc.to(DEV).data_ptr(), 0.8, preact,
-                                                 acc.data_ptr() if acc_mode else None, acc_mode, skip_out, S()))
-            if not skip_out:
-                close(dz, want_dz)
-            if acc_mode:
-                close(acc, want_acc)
-            fused.append((dz.clone(), acc.clone()))
-        res[moltile] = (out.clone(), d.clone(), fused)
-    assert torch.equal(res["1"][0], res["0"][0]) or float((res["1"][0] - res["0"][0]).abs().max()) <= 2e-6 * float(want_f.abs().max())
