@@ -60,7 +60,14 @@ class GradSync:
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.model = model
-        self.numel = sum(p.numel() for p in self.params)
+        # ONE layout for both paths (every tensor starts on a 16-byte boundary, as ReactionModel's backward lays its flat buffer out):
+        # a rank whose shard is empty has no backward pass and goes through the staging bucket while its peers all-reduce their
+        # aliased buffers in place -- the collective must have the same element count on every rank
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = total
         self.flat = None
         self.fast_path_steps = 0
         self.copy_path_steps = 0
@@ -68,13 +75,13 @@ class GradSync:
     def _aliased(self):
         m = self.model
         flat = getattr(m, "_grad_flat", None) if m is not None else None
-        if flat is None:
+        if flat is None or flat.numel() != self.numel:
             return None
         hot = m.hot_parameters()
-        if len(hot) != len(self.params) or any(a is not b for a, b in zip(hot, self.params)):
+        if len(hot) != len(self.params) or any(a is not b for a, b in zip(hot, self.params)) or list(m._grad_offsets) != self.offsets:
             return None
         base = flat.data_ptr()
-        for p, off in zip(hot, m._grad_offsets):
+        for p, off in zip(hot, self.offsets):
             g = p.grad
             if g is None or not g.is_contiguous() or g.data_ptr() != base + 4 * off:
                 return None
@@ -94,11 +101,11 @@ class GradSync:
                 p.grad = torch.zeros_like(p)
         grads = [p.grad for p in self.params]
         if self.flat is None or self.flat.device != grads[0].device:
-            self.flat = torch.empty(self.numel, dtype=grads[0].dtype, device=grads[0].device)
-        views = [v.view_as(g) for v, g in zip(torch.split(self.flat, [g.numel() for g in grads]), grads)]
+            self.flat = torch.zeros(self.numel, dtype=grads[0].dtype, device=grads[0].device)      # the alignment gaps stay zero
+        views = [self.flat[o:o + g.numel()].view_as(g) for o, g in zip(self.offsets, grads)]
         torch._foreach_copy_(views, grads)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        torch._foreach_copy_(grads, views)         # copies INTO p.grad whatever its strides are
+        torch._foreach_copy_(grads, views)         # copies INTO p.grad whatever its strides are (the gaps hold sums of zeros: still zero)
 
 
 # ---- process-group plumbing for the entry points (train(), run_train(), main.py, main_ranknet.py, bench.py) ------------------------

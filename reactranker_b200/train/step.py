@@ -173,7 +173,7 @@ class TrainStep:
 
     def global_loss(self, loss: torch.Tensor) -> float:
         """The batch loss as one number on every rank (a 4-byte all-reduce; used once per epoch for logging)."""
-        v = loss.detach().reshape(-1)[:1].float().clone()
+        v = loss.detach().reshape(-1)[:1].float().to(self.dev).clone()
         if self.world > 1:
             torch.distributed.all_reduce(v, op=torch.distributed.ReduceOp.SUM, group=self.group)
         return float(v)

@@ -93,6 +93,17 @@ def _worker(rank, world, port, out):
         sync()
         assert (sync.fast_path_steps, sync.copy_path_steps) == (1, 0)
         out[("fast", rank)] = torch.cat([p.grad.reshape(-1) for p in fm.hot_parameters()]).numpy()
+        # mixed paths in ONE collective: rank 0 all-reduces its aliased buffer in place, rank 1 had an empty shard (no backward pass,
+        # p.grad is None) and goes through the staging bucket -- same layout, same element count, or NCCL / gloo would mismatch
+        torch.manual_seed(0)
+        mm = _FlatModel()
+        sm = GradSync(mm.hot_parameters(), None, mm)
+        if rank == 0:
+            ((mm.net(X).squeeze(-1) - t) ** 2).mean().backward()
+            mm.alias_grads()
+        sm()
+        assert (sm.fast_path_steps, sm.copy_path_steps) == ((1, 0) if rank == 0 else (0, 1))
+        out[("mixed", rank)] = torch.cat([p.grad.reshape(-1) for p in mm.hot_parameters()]).numpy()
         # copy path with a NON-CONTIGUOUS gradient and a missing one (empty shard): the reduced values must land in p.grad itself
         w = torch.nn.Parameter(torch.zeros(3, 4))
         w.grad = torch.full((4, 3), float(rank + 1)).t()                        # strides (1, 3)
@@ -145,6 +156,8 @@ def test_gloo_world2_inplace_flat_allreduce_and_copy_path():
     assert np.allclose(res[("fast", 0)], want, rtol=1e-5, atol=1e-7)
     for r in (0, 1):
         assert np.array_equal(res[("copy", r)][0], np.full((3, 4), 3.0)) and np.array_equal(res[("copy", r)][1], np.ones(2))
+    # rank 1 contributed zeros: both ranks hold rank 0's whole-batch gradient
+    assert np.allclose(res[("mixed", 0)], want, rtol=1e-5, atol=1e-7) and np.array_equal(res[("mixed", 0)], res[("mixed", 1)])
 
 
 def test_gloo_world2_flat_allreduce_equals_single_process():
