@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 def shard_groups(group_atoms: Sequence[int], world: int) -> List[Tuple[int, int]]:
     """Split groups 0..G-1 into ``world`` contiguous runs ``[lo, hi)`` with balanced total atom count; never splits a
-    group.  Every rank gets at least one group when G >= world; trailing ranks may be empty otherwise."""
+    group.  Every rank gets at least one group when G >= world; with fewer groups than ranks some ranks get none."""
     w = np.asarray(group_atoms, dtype=np.float64)
     G = len(w)
     if world <= 1:

@@ -77,9 +77,11 @@ whole.backward()
 want = [p.grad.clone() for p in model.hot_parameters()]
 model.zero_grad()
 prepared = step.prepare_rows(planner, rows, scope, fz, ["rsmi_mapped", "psmi_mapped"], "lgk", "temp")
-assert (prepared.rows > 0) == (rank == 0)
+mine = torch.tensor([1.0 if prepared.rows > 0 else 0.0], device=f"cuda:{local}")
+dist.all_reduce(mine)
+assert float(mine) == 1.0                                                               # exactly one rank owns the group
 step.run(prepared)
-assert (step.sync.fast_path_steps, step.sync.copy_path_steps) == ((1, 0) if rank == 0 else (0, 1))
+assert (step.sync.fast_path_steps, step.sync.copy_path_steps) == ((1, 0) if prepared.rows > 0 else (0, 1))
 gscale = max(float(w.abs().max()) for w in want)
 worst = max(float((p.grad - w).abs().max()) / (float(w.abs().max()) + 1e-2 * gscale) for p, w in zip(model.hot_parameters(), want))
 assert worst < 1e-3, ("empty shard", worst)
