@@ -255,6 +255,11 @@ typedef enum {
 /* norm: the divisor the reference applies (G, N or the window's ordered-pair count); sigma: RankNet */
 int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off,
                    float norm, float sigma, float* loss, float* dscore, void* stream);
+/* The same with the size of the largest group given (the caller has `scope` on the host): ListMLE and RankNet keep a group in shared
+ * memory and size it for max_group, up to rr_loss_max_group() = 8192 candidates.  rr_loss_fwdbwd assumes groups of at most 2048; a
+ * group larger than the capacity yields NaN in loss and dscore, never a shared-memory overrun. */
+int rr_loss_fwdbwd_ex(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off, int max_group,
+                      float norm, float sigma, float* loss, float* dscore, void* stream);
 /* largest group the segmented kernels accept */
 int rr_loss_max_group(void);
 

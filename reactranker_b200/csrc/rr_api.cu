@@ -134,6 +134,10 @@ int rr_loss_fwdbwd(int kind, int N, int G, const float* scores, const float* tar
                    float* loss, float* dscore, void* stream) {
   return rr::loss_fwdbwd(kind, N, G, scores, targets, seg_off, norm, sigma, loss, dscore, S(stream));
 }
+int rr_loss_fwdbwd_ex(int kind, int N, int G, const float* scores, const float* targets, const int32_t* seg_off, int max_group, float norm,
+                      float sigma, float* loss, float* dscore, void* stream) {
+  return rr::loss_fwdbwd(kind, N, G, scores, targets, seg_off, norm, sigma, loss, dscore, S(stream), max_group);
+}
 int rr_loss_max_group(void) { return rr::loss_max_group(); }
 int rr_rank_metrics(int N, int G, const float* scores, int score_ld, const double* targets, const int32_t* seg_off, int max_group, double ratio,
                     double* out, void* stream) {

@@ -230,7 +230,7 @@ int linear_fwd(int M, int n, const float* X1, int ldx1, const float* W1, int k1,
                const uint16_t* blo = nullptr);
 int linear_dgrad(int, int, int, const float*, int, const float*, int, float*, int, int, cudaStream_t);
 int linear_wgrad(int, int, int, const float*, int, const float*, int, float*, int, float*, cudaStream_t);
-int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t);
+int loss_fwdbwd(int, int, int, const float*, const float*, const int*, float, float, float*, float*, cudaStream_t, int max_group = 0);
 int loss_max_group();
 int rank_metrics(int, int, const float*, int, const double*, const int*, int, double, double*, cudaStream_t);
 int graph_assemble(const rr_mol_store*, int, const int*, const int*, const int*, const int*, const int*, const int*, int, const int*, const int*,

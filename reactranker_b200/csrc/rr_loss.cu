@@ -9,7 +9,8 @@
 namespace rr {
 
 constexpr int kLossThreads = 256;
-constexpr int kMaxGroup = 2048;
+constexpr int kMaxGroup = 8192;         // largest group the segmented kernels take (dynamic shared memory: 4 x 4 B x capacity for ListMLE)
+constexpr int kDefaultGroupCap = 2048;  // capacity when the caller gives no max_group hint (rr_loss_fwdbwd)
 constexpr int kMaxMetricGroup = 8192;   // 128 KB of shared doubles
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -75,15 +76,16 @@ __device__ void block_scan(float* buf, float* tmp, int n) {
 template <bool DIS>
 __global__ void __launch_bounds__(kLossThreads) k_listmle(const float* __restrict__ scores, const float* __restrict__ targets,
                                                           const int* __restrict__ seg, float inv_norm, float* __restrict__ loss,
-                                                          float* __restrict__ dscore) {
-  __shared__ float key[kMaxGroup];
-  __shared__ int id[kMaxGroup];
-  __shared__ float a[kMaxGroup];
-  __shared__ float b[kMaxGroup];
+                                                          float* __restrict__ dscore, int cap) {
+  extern __shared__ float loss_dyn[];            // key | id | a | b, `cap` entries each (cap = a power of two >= the largest group)
+  float* key = loss_dyn;
+  int* id = reinterpret_cast<int*>(loss_dyn + cap);
+  float* a = loss_dyn + 2 * cap;
+  float* b = loss_dyn + 3 * cap;
   __shared__ float red[32];
   const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
   if (n <= 0) return;
-  if (n > kMaxGroup) {   // the static shared arrays hold kMaxGroup candidates: a larger group poisons the result instead of overrunning them
+  if (n > cap) {   // the shared arrays hold `cap` candidates: a larger group poisons the result instead of overrunning them
     for (int i = threadIdx.x; i < n * (DIS ? 2 : 1); i += blockDim.x) dscore[static_cast<size_t>(o) * (DIS ? 2 : 1) + i] = CUDART_NAN_F;
     if (threadIdx.x == 0) atomicAdd(loss, CUDART_NAN_F);
     return;
@@ -419,13 +421,14 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 
 __global__ void __launch_bounds__(kLossThreads) k_ranknet(const float* __restrict__ scores, const float* __restrict__ targets,
                                                           const int* __restrict__ seg, float inv_norm, float sigma, float gfac,
-                                                          float* __restrict__ loss, float* __restrict__ dscore) {
-  __shared__ float ss[kMaxGroup];
-  __shared__ float ts[kMaxGroup];
+                                                          float* __restrict__ loss, float* __restrict__ dscore, int cap) {
+  extern __shared__ float loss_dyn[];            // ss | ts, `cap` entries each
+  float* ss = loss_dyn;
+  float* ts = loss_dyn + cap;
   __shared__ float red[32];
   const int o = seg[blockIdx.x], n = seg[blockIdx.x + 1] - o;
   if (n <= 0) return;
-  if (n > kMaxGroup) {   // as in k_listmle: NaN, never a shared-memory overrun (direct C-ABI callers bypass the Python-side check)
+  if (n > cap) {   // as in k_listmle: NaN, never a shared-memory overrun (direct C-ABI callers bypass the Python-side check)
     for (int i = threadIdx.x; i < n; i += blockDim.x) dscore[o + i] = CUDART_NAN_F;
     if (threadIdx.x == 0) atomicAdd(loss, CUDART_NAN_F);
     return;
@@ -493,10 +496,18 @@ __global__ void __launch_bounds__(kLossThreads) k_pointwise(int kind, int N, con
 }
 
 int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* targets, const int* seg_off, float norm, float sigma,
-                float* loss, float* dscore, cudaStream_t s) {
+                float* loss, float* dscore, cudaStream_t s, int max_group) {
   ProfScope prof_scope(KC_LOSS, s);
   RR_REQUIRE(N > 0 && scores && targets && loss && dscore, "loss: NULL argument or N <= 0");
   RR_REQUIRE(norm > 0.f, "loss: norm must be positive (got %g)", norm);
+  RR_REQUIRE(max_group <= kMaxGroup, "loss: groups of up to %d candidates are supported (max_group %d)", kMaxGroup, max_group);
+  // capacity of the per-group shared arrays of ListMLE / RankNet: the next power of two >= max_group (the bitonic sort pads to it);
+  // without a hint (max_group <= 0) kDefaultGroupCap.  A group larger than the capacity yields NaN, never an overrun.
+  int cap = kDefaultGroupCap;
+  if (max_group > 0) {
+    cap = 64;
+    while (cap < max_group) cap <<= 1;
+  }
   RR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
   const float inv = 1.f / norm;
   switch (kind) {
@@ -510,14 +521,23 @@ int loss_fwdbwd(int kind, int N, int G, const float* scores, const float* target
     case RR_LOSS_RANKNET_ACC:
     case RR_LOSS_DIRICHLET_UQ:
       RR_REQUIRE(G > 0 && seg_off, "loss: segmented kinds need seg_off and G > 0");
-      if (kind == RR_LOSS_LISTMLE) k_listmle<false><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
-      else if (kind == RR_LOSS_LISTMLE_DIS) k_listmle<true><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
+      {
+        static PerDeviceOnce attr_set;           // up to 128 KB of dynamic shared memory for groups of up to kMaxGroup candidates
+        if (attr_set.need()) {
+          RR_CUDA(cudaFuncSetAttribute(k_listmle<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxGroup * static_cast<int>(sizeof(float))));
+          RR_CUDA(cudaFuncSetAttribute(k_listmle<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxGroup * static_cast<int>(sizeof(float))));
+          RR_CUDA(cudaFuncSetAttribute(k_ranknet, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxGroup * static_cast<int>(sizeof(float))));
+          attr_set.mark();
+        }
+      }
+      if (kind == RR_LOSS_LISTMLE) k_listmle<false><<<G, kLossThreads, 4 * cap * sizeof(float), s>>>(scores, targets, seg_off, inv, loss, dscore, cap);
+      else if (kind == RR_LOSS_LISTMLE_DIS) k_listmle<true><<<G, kLossThreads, 4 * cap * sizeof(float), s>>>(scores, targets, seg_off, inv, loss, dscore, cap);
       else if (kind == RR_LOSS_LISTNET) k_listnet<false><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_LISTNET_DIS) k_listnet<true><<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_EVIDENTIAL) k_evidential<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, loss, dscore);
       else if (kind == RR_LOSS_DIRICHLET_UQ) k_dirichlet_uq<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
       else if (kind == RR_LOSS_LISTNET_UQ) k_listnet_uq<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, loss, dscore);
-      else k_ranknet<<<G, kLossThreads, 0, s>>>(scores, targets, seg_off, inv, sigma, kind == RR_LOSS_RANKNET_ACC ? 1.f : 2.f, loss, dscore);
+      else k_ranknet<<<G, kLossThreads, 2 * cap * sizeof(float), s>>>(scores, targets, seg_off, inv, sigma, kind == RR_LOSS_RANKNET_ACC ? 1.f : 2.f, loss, dscore, cap);
       break;
     case RR_LOSS_NIG: {            // norm = N * N (the reference's mean over the broadcast matrix); `sigma` carries lam
       RR_REQUIRE((reinterpret_cast<uintptr_t>(scores) & 15) == 0, "loss: NIG scores must be 16-byte aligned");

@@ -61,21 +61,21 @@ def segment_offsets(scope: Sequence[int], dev) -> torch.Tensor:
 
 class _LossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scores, targets, seg_off, kind: int, n_items: int, n_groups: int, norm: float, sigma: float, out_shape):
+    def forward(ctx, scores, targets, seg_off, kind: int, n_items: int, n_groups: int, norm: float, sigma: float, out_shape, max_group: int = 0):
         L = _lib.lib()
         scores_c = scores.contiguous()
         loss = torch.empty(1, dtype=torch.float32, device=scores.device)
         dscore = torch.empty_like(scores_c)
         with torch.cuda.device(scores.device):
-            _lib.check(L.rr_loss_fwdbwd(kind, n_items, n_groups, scores_c.data_ptr(), targets.data_ptr(), _lib.ptr(seg_off),
-                                        float(norm), float(sigma), loss.data_ptr(), dscore.data_ptr(), _lib.stream_ptr()))
+            _lib.check(L.rr_loss_fwdbwd_ex(kind, n_items, n_groups, scores_c.data_ptr(), targets.data_ptr(), _lib.ptr(seg_off), int(max_group),
+                                           float(norm), float(sigma), loss.data_ptr(), dscore.data_ptr(), _lib.stream_ptr()))
         ctx.save_for_backward(dscore)
         return loss.reshape(out_shape)
 
     @staticmethod
     def backward(ctx, g):
         (dscore,) = ctx.saved_tensors
-        return dscore * g.reshape(()), None, None, None, None, None, None, None, None
+        return dscore * g.reshape(()), None, None, None, None, None, None, None, None, None
 
 
 def _segmented(kind, scores, scope, targets, gpu, norm, out_shape, sigma=1.0, check_max=False):
@@ -90,7 +90,7 @@ def _segmented(kind, scores, scope, targets, gpu, norm, out_shape, sigma=1.0, ch
     if t.numel() != n_items:
         raise _lib.RRError(f"{t.numel()} targets for {n_items} scores")
     seg = segment_offsets(scope, dev)
-    return _LossFn.apply(scores.float(), t, seg, kind, n_items, len(scope), norm, sigma, out_shape)
+    return _LossFn.apply(scores.float(), t, seg, kind, n_items, len(scope), norm, sigma, out_shape, max(scope) if scope else 0)
 
 
 # ---- data-parallel normalisers -------------------------------------------------------------------------------------------------

@@ -253,6 +253,51 @@ def test_losses_match_oracle(task, kind, cols, scope):
     close(ds_, sx.grad, 2e-5)
 
 
+@pytest.mark.parametrize("task,kind", [("mle", _lib.LOSS_LISTMLE), ("evidential_ranking", _lib.LOSS_EVIDENTIAL), ("ranknet", _lib.LOSS_RANKNET)])
+@pytest.mark.parametrize("scope", [[3000, 5], [8192], [2049, 64, 1]])
+def test_large_groups_through_the_sized_entry(task, kind, scope):
+    """rr_loss_fwdbwd_ex sizes the per-group shared arrays from max_group (up to rr_loss_max_group() = 8192): groups beyond the plain
+    entry's 2048 match the fp64 oracle; the plain entry answers NaN for them (never an overrun); max_group > 8192 is refused."""
+    L = _lib.lib()
+    assert L.rr_loss_max_group() == 8192
+    N, G = sum(scope), len(scope)
+    g = torch.Generator().manual_seed(N + kind)
+    cols = 2 if task == "evidential_ranking" else 1
+    s = torch.randn(N, cols, generator=g)
+    if cols == 2:
+        s[:, 1] = torch.nn.functional.softplus(s[:, 1]) + 1e-3
+    else:
+        s = s[:, 0]
+    t = torch.randn(N, generator=g)
+    sx = s.double().requires_grad_(True)
+    if task == "ranknet":
+        total, pairs, o = 0, 0.0, 0
+        for n in scope:
+            c, npairs = O.ranknet_group_cost(sx[o:o + n], t[o:o + n].numpy())
+            if c is not None:
+                total, pairs = total + c, pairs + npairs
+            o += n
+        want, norm = total / pairs, pairs
+    else:
+        want, norm = O.loss_for_task(task, sx, scope, t.double()), G
+    want.backward(torch.ones_like(want))
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(scope)]), dtype=torch.int32, device=DEV)
+    sd, td = s.to(DEV), t.to(DEV)
+    loss, ds_ = torch.empty(1, device=DEV), torch.full_like(sd, float("nan"))
+    _lib.check(L.rr_loss_fwdbwd_ex(kind, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), max(scope), float(norm), 1.0,
+                                   loss.data_ptr(), ds_.data_ptr(), S()))
+    close(loss, want.detach().reshape(1), 5e-6)
+    close(ds_, sx.grad, 5e-5)
+    _lib.check(L.rr_loss_fwdbwd(kind, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), float(norm), 1.0, loss.data_ptr(), ds_.data_ptr(), S()))
+    torch.cuda.synchronize()
+    if task == "evidential_ranking":                            # streams its groups through registers: no capacity to exceed
+        close(loss, want.detach().reshape(1), 5e-6)
+    else:
+        assert bool(torch.isnan(loss).all()) and bool(torch.isnan(ds_[:scope[0]]).all())
+    assert L.rr_loss_fwdbwd_ex(kind, N, G, sd.data_ptr(), td.data_ptr(), seg.data_ptr(), 8193, float(norm), 1.0,
+                               loss.data_ptr(), ds_.data_ptr(), S()) != 0
+
+
 @pytest.mark.parametrize("scope", [[5, 4, 6], [64] * 4, [3, 500]])
 def test_ranknet_window_matches_oracle(scope):
     L = _lib.lib()
