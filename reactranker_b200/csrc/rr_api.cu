@@ -212,6 +212,7 @@ int rr_profile_end(double* ms_by_class, int64_t* launches_by_class, int n_classe
 }
 int rr_profile_classes(void) { return rr::KC_COUNT; }
 void rr_reload_switches(void) { rr::reload_switches(); }
+int rr_debug_wgrad_trace(unsigned long long* host_out, int n) { return rr::tc_wgrad_trace(host_out, n); }
 int64_t rr_launch_count(void) { return rr::g_launches.load(); }
 void rr_launch_count_reset(void) { rr::g_launches.store(0); }
 

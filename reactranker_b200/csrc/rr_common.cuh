@@ -79,7 +79,7 @@ extern std::atomic<int> g_gemm_mode;
 // them again (tests and the micro-benchmarks flip them inside one process).
 struct Switches {
   int tc_ew = 16, tc_diag = 0, tc_fake_presplit = 0;
-  int wg_kt = 0, wg_tf32 = 0, wg_bkr = 0, wg3_bkr = 32, wg3_raw = 2, wg3_bf = 2;
+  int wg_kt = 0, wg_tf32 = 0, wg_bkr = 0, wg3_bkr = 32, wg3_raw = 6, wg3_bf = 2;
   int mp_v1 = 0, mp_acc_red = -1, mp_consumers = 0, mp_kstage = 0;
 };
 const Switches& switches();
@@ -259,6 +259,7 @@ long long tc_dgrad_scratch_bytes(int n, int k);
 int tc_dgrad_standalone(int M, int n, int k, const float* dZ, int lddz, const float* W, int ldw, float* dX, int lddx, int accumulate, void* scratch,
                         long long scratch_bytes, cudaStream_t s);
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx);
+int tc_wgrad_trace(unsigned long long* host_out, int n);
 int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int ldx, float* dW, int lddw, float* dbias, cudaStream_t s);
 
 }  // namespace rr

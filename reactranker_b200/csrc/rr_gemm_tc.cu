@@ -682,7 +682,9 @@ struct WgArgs {
   int lddw;
   float* dbias;
   int diag;          // RR_TC_DIAG (timing experiments)
+  unsigned long long* trace;   // wgrad3, RR_TC_DIAG & 16: per-stage clock64 stamps of CTA (0,0,0) (rr_debug_wgrad_trace reads them back)
 };
+constexpr int WG_TRACE_STAGES = 96, WG_TRACE_SLOTS = 16;
 
 // MN-major tf32 operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte atomicity
 // (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1, TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 4 reduction rows x 128 B,
@@ -877,10 +879,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad2(const __grid_constant_
 // ================================================================================================
 // The raw ring (R slots: what TMA has in flight) and the bf16 ring (SB slots: what the tensor core reads) are sized separately, and the rows
 // of the reduction per stage are a template parameter, so that the pipeline shape can be measured (scripts/bench_wgrad_cfg.sh, RR_WG3_CFG).
-// Measured on [321 778 x 304]^T [321 778 x 304] (profiles/r02_wgrad_cfg.md): 32 rows, 2 + 2 slots 273 us; 32 rows, 3 + 1 slots 330 us;
-// 16 rows with 4 + 2, 5 + 3, 6 + 2 or 5 + 2 slots 361 us each.  Ring depth changes nothing and smaller stages are slower: the kernel is not
-// waiting for HBM but paying ~830 clk of fixed cost per stage (barrier hand-offs, tcgen05.wait::st, the async-proxy fence, commit latency)
-// plus ~52 clk per row of fp32 -> bf16 conversion; 32-row stages with two slots of each ring (the most 227 KB holds) stay the default.
+// Measured on [321 778 x 304]^T [321 778 x 304] (profiles/r02_wgrad_cfg.md): 32 rows, 2 + 2 slots 266-273 us; 32 rows, 3 + 1 slots 330 us;
+// 16 rows with 4 + 2, 5 + 3, 6 + 2 or 5 + 2 slots 361 us each.  The clock64 trace of one CTA (RR_TC_DIAG & 16, profiles/r02_wgrad_trace.md)
+// says why: a raw slot's turn-around is TMA issue ~1200 clk (14 boxes at the TMA unit's ~85 clk per 32-float box) + arrival ~1000 + conversion
+// ~1650 (= the stage's 212 KB of shared-memory traffic at 128 B/clk) + hand-offs ~500, and two slots make that 2212 clk per stage; 16-row
+// stages double the per-row box cost, and a third 57 KB raw slot does not fit beside two 40 KB bf16 slots.  Narrow X tiles do fit more raw
+// slots (default: up to 6), worth 6-9 % there.
 constexpr int W3_A_COLS = 128;               // dZ columns per CTA == TMEM lanes
 
 template <int BKR>
@@ -922,6 +926,10 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
   const int m_end = min(g.M, m_beg + g.m_chunk);
   const int nst = (m_end - m_beg + BKR - 1) / BKR;
   const int width = min(g.kt, g.k_pad - k0);
+  const bool tracing = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto stamp = [&](int it, int slot) {
+    if (tracing && it < WG_TRACE_STAGES) g.trace[it * WG_TRACE_SLOTS + slot] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < R; ++s) {
@@ -955,11 +963,14 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
         const int st = it % R;
         const uint32_t ph = (it / R) & 1;
         mbar_wait(raw_empty + st, ph ^ 1);
+        stamp(it, 0);
         uint8_t* base = raw0 + static_cast<size_t>(st) * raw_bytes;
         const int m = m_beg + it * BKR;
         mbar_expect_tx(raw_full + st, tx);
+        // ~85 clk per box: the TMA unit's rate for 32-float x 32-row boxes (one box per lane from 14 lanes takes exactly as long)
         for (int j = 0; j < 4; ++j) tma_load_2d(&g.tmA, raw_full + st, base + j * BOX, n0 + 32 * j, m);
         for (int j = 0; j < g.nb; ++j) tma_load_2d(&g.tmB, raw_full + st, base + A_RAW + j * BOX, k0 + 32 * j, m);
+        stamp(it, 1);
       }
     }
   } else if (warp == 1) {
@@ -974,6 +985,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
         const uint32_t ph = (it / SB) & 1;
         mbar_wait(ready + st, ph);
         tc_fence_after();
+        stamp(it, 2);
         const uint32_t b_hi = smem_u32(bf0 + static_cast<size_t>(st) * bf_bytes), b_lo = b_hi + nblk * BOX;
         const uint32_t a_hi = tmem_base + g.tm_a + st * BKR, a_lo = a_hi + BKR / 2;
         if (!(g.diag & 4)) {
@@ -993,12 +1005,14 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           }
         }
         umma_commit(mma_done + st);
+        stamp(it, 3);
       }
       umma_commit(acc_bar);
     }
   } else {
     const int wtid = threadIdx.x - 64;
     const int quad = warp & 3;
+    const int tw = (lane == 0) ? (warp == 2 ? 4 : (warp == 9 ? 10 : -1)) : -1;   // traced: one dZ + X warp, one X-only warp
     const int r = quad * 32 + lane;                    // TMEM lane == column n0 + r of dZ
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int G = g.nb * 4;                            // 8-column groups per row of the X tile (whole boxes: the padding converts zeros)
@@ -1008,8 +1022,10 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
     for (int it = 0; it < nst; ++it) {
       const int rs = it % R, bs = it % SB;
       mbar_wait(raw_full + rs, (it / R) & 1);
+      if (tw >= 0) stamp(it, tw);
       mbar_wait(mma_done + bs, ((it / SB) & 1) ^ 1);  // the MMAs of the previous lap are done with this bf16 slot and TMEM slot
       tc_fence_after();
+      if (tw >= 0) stamp(it, tw + 1);
       const uint32_t raw = smem_u32(raw0 + static_cast<size_t>(rs) * raw_bytes);
       if (a_warp && !(g.diag & 1)) {
         const uint32_t colp = raw + quad * BOX + lane * 4;
@@ -1031,6 +1047,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           tmem_st8(ta + 8, lo);
         }
       }
+      if (tw >= 0) stamp(it, tw + 2);
       if (!(g.diag & 2)) {
         const uint32_t xraw = raw + A_RAW;
         const uint32_t xhi = smem_u32(bf0 + static_cast<size_t>(bs) * bf_bytes), xlo = xhi + nblk * BOX;
@@ -1058,6 +1075,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           }
         }
       }
+      if (tw >= 0) stamp(it, tw + 3);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_proxy_async();
       tc_fence_before();
@@ -1066,6 +1084,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
         mbar_arrive(ready + bs);
         mbar_arrive(raw_empty + rs);
       }
+      if (tw >= 0) stamp(it, tw + 4);
     }
     if (a_warp && g.dbias != nullptr && blockIdx.y == 0 && n0 + r < g.n) atomicAdd(g.dbias + n0 + r, bsum);
     mbar_wait(acc_bar, 0);
@@ -1258,6 +1277,25 @@ int tc_dgrad_standalone(int M, int n, int k, const float* dZ, int lddz, const fl
                    nullptr);
 }
 
+// RR_TC_DIAG & 16: CTA (0,0,0) of every k_tc_wgrad3 launch stamps clock64 at its pipeline hand-offs (a diagnostic; see scripts/wgrad_trace.py)
+static unsigned long long* wg_trace_buffer() {
+  static unsigned long long* buf[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return nullptr;
+  if (!buf[dev] && cudaMalloc(&buf[dev], sizeof(unsigned long long) * tc::WG_TRACE_STAGES * tc::WG_TRACE_SLOTS) != cudaSuccess) buf[dev] = nullptr;
+  return buf[dev];
+}
+
+int tc_wgrad_trace(unsigned long long* host_out, int n) {
+  unsigned long long* b = wg_trace_buffer();
+  const int cap = tc::WG_TRACE_STAGES * tc::WG_TRACE_SLOTS;
+  RR_REQUIRE(b != nullptr && host_out != nullptr && n > 0 && n <= cap, "wgrad trace: no buffer or n outside [1, %d]", cap);
+  RR_CUDA(cudaDeviceSynchronize());
+  RR_CUDA(cudaMemcpy(host_out, b, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
 bool tc_wgrad_supported(int M, int n, int k, int lddz, int ldx) {
   return M > 0 && n >= 4 && k >= 4 && !(n & 3) && !(k & 3) && !(lddz & 3) && !(ldx & 3);
 }
@@ -1300,6 +1338,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       g.lddw = lddw;
       g.dbias = dbias;
       g.diag = switches().tc_diag;
+      g.trace = (g.diag & 16) ? wg_trace_buffer() : nullptr;
       const int ntiles3 = (n + BM - 1) / BM;
       int splits3 = num_sms() / (ntiles3 * ktiles);
       const int max_splits3 = (M + 8 * 32 - 1) / (8 * 32);

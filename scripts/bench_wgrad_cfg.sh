@@ -3,7 +3,7 @@
 # (the switch is read once per process).  Output: gpurun_out/wgrad_cfg.log
 out=gpurun_out/wgrad_cfg.log
 : > $out
-for cfg in 32,2,2 32,3,1 16,4,2 16,5,3 16,6,2 16,5,2; do
+for cfg in ${WG3_CFGS:-32,2,2 32,3,1 16,4,2 16,5,3 16,6,2 16,5,2}; do
   echo "== RR_WG3_CFG=$cfg" >> $out
   RR_WG3_CFG=$cfg python - >> $out 2>&1 <<'PY'
 import os, sys
