@@ -901,7 +901,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_bf16(uint32_t smem_addr) {
 constexpr int W3_WORKERS = 256;   // 8 conversion warps (12 measured no faster): with 4 the fp32 -> bf16 conversion (not the MMAs) paced the kernel
 constexpr int W3_THREADS = 64 + W3_WORKERS;
 
-template <int BKR>
+template <int BKR, bool TR = false>
 __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_constant__ WgArgs g) {
   constexpr int BOX = BKR * 128;               // bytes of one raw TMA box [BKR x 32 floats] == one bf16 MN block [BKR x 64 bf16]
   constexpr int A_RAW = 4 * BOX;               // dZ: 128 columns
@@ -926,9 +926,9 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
   const int m_end = min(g.M, m_beg + g.m_chunk);
   const int nst = (m_end - m_beg + BKR - 1) / BKR;
   const int width = min(g.kt, g.k_pad - k0);
-  const bool tracing = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  auto stamp = [&](int it, int slot) {
-    if (tracing && it < WG_TRACE_STAGES) g.trace[it * WG_TRACE_SLOTS + slot] = clock64();
+  const bool tracing = TR && g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto stamp = [&](int it, int slot) {      // TR is a separate instantiation: the stamps cost the default kernel nothing
+    if (TR && tracing && it < WG_TRACE_STAGES) g.trace[it * WG_TRACE_SLOTS + slot] = clock64();
   };
 
   if (warp == 0 && lane == 0) {
@@ -1012,7 +1012,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
   } else {
     const int wtid = threadIdx.x - 64;
     const int quad = warp & 3;
-    const int tw = (lane == 0) ? (warp == 2 ? 4 : (warp == 9 ? 10 : -1)) : -1;   // traced: one dZ + X warp, one X-only warp
+    const int tw = (TR && lane == 0) ? (warp == 2 ? 4 : (warp == 9 ? 10 : -1)) : -1;   // traced: one dZ + X warp, one X-only warp
     const int r = quad * 32 + lane;                    // TMEM lane == column n0 + r of dZ
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int G = g.nb * 4;                            // 8-column groups per row of the X tile (whole boxes: the padding converts zeros)
@@ -1022,10 +1022,10 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
     for (int it = 0; it < nst; ++it) {
       const int rs = it % R, bs = it % SB;
       mbar_wait(raw_full + rs, (it / R) & 1);
-      if (tw >= 0) stamp(it, tw);
+      if (TR && tw >= 0) stamp(it, tw);
       mbar_wait(mma_done + bs, ((it / SB) & 1) ^ 1);  // the MMAs of the previous lap are done with this bf16 slot and TMEM slot
       tc_fence_after();
-      if (tw >= 0) stamp(it, tw + 1);
+      if (TR && tw >= 0) stamp(it, tw + 1);
       const uint32_t raw = smem_u32(raw0 + static_cast<size_t>(rs) * raw_bytes);
       if (a_warp && !(g.diag & 1)) {
         const uint32_t colp = raw + quad * BOX + lane * 4;
@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           tmem_st8(ta + 8, lo);
         }
       }
-      if (tw >= 0) stamp(it, tw + 2);
+      if (TR && tw >= 0) stamp(it, tw + 2);
       if (!(g.diag & 2)) {
         const uint32_t xraw = raw + A_RAW;
         const uint32_t xhi = smem_u32(bf0 + static_cast<size_t>(bs) * bf_bytes), xlo = xhi + nblk * BOX;
@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           }
         }
       }
-      if (tw >= 0) stamp(it, tw + 3);
+      if (TR && tw >= 0) stamp(it, tw + 3);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_proxy_async();
       tc_fence_before();
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
         mbar_arrive(ready + bs);
         mbar_arrive(raw_empty + rs);
       }
-      if (tw >= 0) stamp(it, tw + 4);
+      if (TR && tw >= 0) stamp(it, tw + 4);
     }
     if (a_warp && g.dbias != nullptr && blockIdx.y == 0 && n0 + r < g.n) atomicAdd(g.dbias + n0 + r, bsum);
     mbar_wait(acc_bar, 0);
@@ -1352,10 +1352,12 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       if (attr3_set.need()) {
         RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr3_set.mark();
       }
       const size_t smem3 = static_cast<size_t>(R) * raw_bytes + static_cast<size_t>(SB) * bf_bytes + 1024 + 512;
-      if (bkr == 32) RR_CUDA(launch_pdl(k_tc_wgrad3<32>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
+      if (bkr == 32 && g.trace) RR_CUDA(launch_pdl(k_tc_wgrad3<32, true>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
+      else if (bkr == 32) RR_CUDA(launch_pdl(k_tc_wgrad3<32>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       else RR_CUDA(launch_pdl(k_tc_wgrad3<16>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       RR_LAUNCH_CHECK("k_tc_wgrad3");
       return RR_OK;
