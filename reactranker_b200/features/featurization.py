@@ -502,7 +502,8 @@ def _align(n: int, a: int = 256) -> int:
 class _BufferPool:
     """Device blobs and pinned control buffers of assembled batches, recycled when their DeviceGraph dies.  Batch sizes wander by a
     per cent from step to step; asking the allocators for a fresh, slightly larger block now and then costs a cudaMalloc / cudaHostAlloc
-    (5-25 ms) in the middle of training.  Buffers are handed out best-fit with 6 % head-room; reuse is stream-ordered (the kernels that
+    (5-25 ms) in the middle of training.  Buffers are handed out best-fit with 30 % head-room (a data-parallel shard of a few
+    large groups moves by a whole group from step to step; the blobs are a few MB); reuse is stream-ordered (the kernels that
     read the old contents were enqueued before the assembly that overwrites them)."""
 
     def __init__(self, keep: int = 8):
@@ -520,7 +521,7 @@ class _BufferPool:
                 best = min(fits, key=lambda e: e[0].numel())
                 lst[:] = [e for e in lst if e is not best]     # identity, not tensor equality
                 return best[0]
-        return make(int(nbytes * 1.0625) + 256)
+        return make(int(nbytes * 1.3) + 256)
 
     def take_device(self, nbytes: int, key, make):
         """(tensor, event | None) for a DEVICE blob that will be written on another stream than the one its previous owner read it on:
@@ -532,7 +533,7 @@ class _BufferPool:
                 best = min(fits, key=lambda e: e[0].numel())
                 lst[:] = [e for e in lst if e is not best]
                 return best
-        return make(int(nbytes * 1.0625) + 256), None
+        return make(int(nbytes * 1.3) + 256), None
 
     def give(self, t, key, event=None):
         with self.lock:

@@ -352,7 +352,7 @@ def test_buffer_pool_best_fit_and_event_guard():
         made.append(n)
         return torch.empty(n, dtype=torch.uint8)
     a = pool.take(1000, "k", make)
-    assert a.numel() >= 1000 and made == [a.numel()] and a.numel() <= 1000 * 1.07 + 256
+    assert a.numel() >= 1000 and made == [a.numel()] and a.numel() <= 1000 * 1.31 + 256
     b = pool.take(5000, "k", make)
     pool.give(a, "k")
     pool.give(b, "k")
