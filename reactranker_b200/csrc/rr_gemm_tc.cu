@@ -51,7 +51,9 @@ struct Args {
   uint64_t seed, stream_id;
   int presplit;  // B arrives as two TF32-exact images (hi, lo) made once per step by the pack kernel: no B split in the main loop
   int diag;      // RR_TC_DIAG bit mask (timing experiments only, results are wrong): 1 no A split, 2 no B split, 4 no MMA, 8 no epilogue traffic
+  unsigned long long* trace;   // RR_TC_DIAG & 16 (k_tc_gemm2<16, false, true>): clock64 stamps of CTA 0, 16 slots per work item
 };
+constexpr int G2_TRACE_ITEMS = 96, G2_TRACE_SLOTS = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -364,7 +366,7 @@ __device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
-template <int EW, bool BF>
+template <int EW, bool BF, bool TR = false>
 __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const __grid_constant__ Args g) {
   constexpr int S2 = BF ? S2_BF : tc::S2;
   constexpr int STAGE2 = BF ? STAGE2_BF : tc::STAGE2;
@@ -380,6 +382,12 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // TR: slots per work item w of CTA 0 -- 0 producer starts the item, 1 its last stage issued; 2 MMA warp has the accumulator, 3 last MMA
+  // committed; 4 first stage split by warp 2, 5 last; epilogue warp 6: 8 residual of its first sub-block requested, 9 accumulator full,
+  // 10 + j after its j-th sub-block (j < 3); epilogue warp 21: 13 accumulator full, 14 done
+  auto stamp = [&](int w, int slot) {
+    if (TR && g.trace != nullptr && blockIdx.x == 0 && w < G2_TRACE_ITEMS) g.trace[w * G2_TRACE_SLOTS + slot] = clock64();
+  };
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + NT2 - 1) / NT2;
   const int total_tiles = m_tiles * n_tiles;
   int nkb_total = 0;
@@ -417,8 +425,10 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
     if (lane == 0) {
       int it = 0;
       const uint32_t tx = static_cast<uint32_t>(A_BYTES + ((g.presplit || BF) ? 2 : 1) * B2_BYTES);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int pw = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++pw) {
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * NT2;
+        if (TR) stamp(pw, 0);
         for (int s = 0; s < g.nsrc; ++s) {
           const int nkb = (g.src[s].K + BK - 1) / BK;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -432,6 +442,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
             if (g.presplit || BF) tma_load_2d(&g.src[s].tmBlo, full + st, base + A_BYTES + B2_BYTES, kb * BK, n0);
           }
         }
+        if (TR) stamp(pw, 1);
       }
     }
   } else if (warp == 1) {
@@ -446,6 +457,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
         const uint32_t d = tmem_base + buf * NT2;
         mbar_wait(acc_empty + buf, ((w >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator
         tc_fence_after();
+        if (TR) stamp(w, 2);
         for (int kb = 0; kb < nkb_total; ++kb, ++it) {
           const int st = it % S2;
           const uint32_t ph = (it / S2) & 1;
@@ -476,6 +488,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
           umma_commit(empty + st);
         }
         umma_commit(acc_full + buf);
+        if (TR) stamp(w, 3);
       }
     }
   } else if (warp < 6) {
@@ -584,8 +597,12 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
         float4 R[4];
         int c = (eidx + w) & (EPQ - 1);                              // rotate the start so the 10 sub-blocks of a tile spread evenly over tiles
         if (c < nblk && !(g.diag & 8)) epi_issue_h(g, R, row0, n0 + 16 * c, lane);
+        const int tslot = (TR && lane == 0) ? (warp == 6 ? 8 : (warp == 21 ? 13 : -1)) : -1;
+        if (TR && tslot == 8) stamp(w, 8);
         mbar_wait(acc_full + buf, (w >> 1) & 1);
         tc_fence_after();
+        if (TR && tslot >= 0) stamp(w, tslot == 8 ? 9 : 13);
+        int tj = 0;
         if (c >= nblk) {
           tc_fence_before();
           __syncwarp();
@@ -594,6 +611,7 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
         for (; c < nblk; c += EPQ) {
           float v[16];
           tmem_ld16(taddr + 16 * c, v);
+          if (TR && tslot == 8 && tj == 0) stamp(w, 4);
           const bool last = c + EPQ >= nblk;
           if (last) {
             tc_fence_before();
@@ -602,11 +620,20 @@ __global__ void __launch_bounds__(THREADS2_BASE + 32 * EW, 1) k_tc_gemm2(const _
           }
           float4 Rn[4];
           if (!last && !(g.diag & 8)) epi_issue_h(g, Rn, row0, n0 + 16 * (c + EPQ), lane);
+          if (TR && tslot == 8 && tj == 0) stamp(w, 5);
           if (!(g.diag & 8)) epilogue_block_h(g, v, R, stage, row0, n0 + 16 * c, lane);
+          if (TR && tslot == 8 && tj == 0) stamp(w, 6);
           if (!last) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) R[i] = Rn[i];
           }
+          if (TR && tslot == 8 && tj == 0) {
+            if (__float_as_uint(R[0].x) == 0x7fc12345u) stamp(w, 15);      // consume the next block's residual: its latency ends here
+            stamp(w, 7);
+          }
+          if (TR && tslot == 8 && tj < 3) stamp(w, 10 + tj);
+          if (TR && tslot == 13 && last) stamp(w, 14);
+          ++tj;
         }
       }
     } else {
@@ -1426,6 +1453,7 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
   g.nsrc = two ? 2 : 1;
   g.presplit = (W1lo != nullptr && (!two || W2lo != nullptr)) ? 1 : 0;
   g.diag = switches().tc_diag;
+  g.trace = (g.diag & 16) ? wg_trace_buffer() : nullptr;
   RR_TRY(make_map(&g.src[0].tmA, X1, M, k1, ldx1, BM));
   RR_TRY(make_map(&g.src[0].tmB, W1, n, k1, ldw1, NT2));
   if (g.presplit) RR_TRY(make_map(&g.src[0].tmBlo, W1lo, n, k1, ldw1, NT2));
@@ -1454,13 +1482,15 @@ int tc_linear(int M, int n, const float* X1, int ldx1, const float* W1, int ldw1
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    RR_CUDA(cudaFuncSetAttribute(k_tc_gemm2<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set.mark();
   }
   const size_t smem = static_cast<size_t>(S2) * STAGE2 + 1024 + 256 + 8 * 4096;  // ring | barriers | epilogue staging
   const int ew = epilogue_warps();
   const int total_tiles = ((M + BM - 1) / BM) * ((n + NT2 - 1) / NT2);
   const int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-  if (ew == 16) RR_CUDA(launch_pdl(k_tc_gemm2<16, false>, dim3(ctas), dim3(THREADS2_BASE + 512), smem, s, g));
+  if (ew == 16 && g.trace) RR_CUDA(launch_pdl(k_tc_gemm2<16, false, true>, dim3(ctas), dim3(THREADS2_BASE + 512), smem, s, g));
+  else if (ew == 16) RR_CUDA(launch_pdl(k_tc_gemm2<16, false>, dim3(ctas), dim3(THREADS2_BASE + 512), smem, s, g));
   else if (ew == 8) RR_CUDA(launch_pdl(k_tc_gemm2<8, false>, dim3(ctas), dim3(THREADS2_BASE + 256), smem, s, g));
   else RR_CUDA(launch_pdl(k_tc_gemm2<4, false>, dim3(ctas), dim3(THREADS2_BASE + 128), smem, s, g));
   RR_LAUNCH_CHECK("k_tc_gemm2");
