@@ -79,7 +79,7 @@ extern std::atomic<int> g_gemm_mode;
 // them again (tests and the micro-benchmarks flip them inside one process).
 struct Switches {
   int tc_ew = 16, tc_diag = 0, tc_fake_presplit = 0;
-  int wg_kt = 0, wg_tf32 = 0, wg_bkr = 0, wg3_bkr = 32, wg3_raw = 6, wg3_bf = 2;
+  int wg_kt = 0, wg_tf32 = 0, wg_bkr = 0, wg3_bkr = 0, wg3_raw = 6, wg3_bf = 2;   // wg3_bkr 0: 64-row stages for narrow X tiles, 32 otherwise
   int mp_v1 = 0, mp_acc_red = -1, mp_consumers = 0, mp_kstage = 0;
 };
 const Switches& switches();

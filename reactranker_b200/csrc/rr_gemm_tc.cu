@@ -1066,7 +1066,10 @@ __global__ void __launch_bounds__(W3_THREADS, 1) k_tc_wgrad3(const __grid_consta
           bsum += a[2 * m] + a[2 * m + 1];
         }
         const uint32_t ta = lane_addr + g.tm_a + bs * BKR;
-        if constexpr (BKR == 32) {
+        if constexpr (BKR == 64) {
+          tmem_st32(ta, hi);
+          tmem_st32(ta + 32, lo);
+        } else if constexpr (BKR == 32) {
           tmem_st16(ta, hi);
           tmem_st16(ta + 16, lo);
         } else {
@@ -1341,7 +1344,12 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
   if (g_bwd_bf16.load() && !switches().wg_tf32) {
     // 3 x bf16: raw ring (dZ + X boxes as TMA lands them) and bf16 ring (hi + lo images + the TMEM A slots), sized separately.
     // RR_WG3_CFG="rows per stage,raw slots,bf16 slots" overrides the default (timing experiments).
-    int bkr = switches().wg3_bkr == 16 ? 16 : 32, R = switches().wg3_raw, SB = switches().wg3_bf;
+    // Narrow X tiles (<= 96 columns: the feature-matrix gradients W_i, W_o[:, :64], MPNDiff W_h[:, h:]) take 64 rows per stage: a stage's
+    // hand-offs and fixed conversion cost (~1400 clk, profiles/r02_wgrad_trace.md) are then paid half as often, and two 56 KB raw slots
+    // still fit.  RR_WG3_CFG's first field (16 / 32 / 64) overrides the choice.
+    int bkr = switches().wg3_bkr == 16 ? 16 : (switches().wg3_bkr == 64 ? 64 : 32), R = switches().wg3_raw, SB = switches().wg3_bf;
+    if (switches().wg3_bkr == 0) bkr = g.kt <= 96 ? 64 : 32;
+    if (bkr == 64 && g.kt > 96) bkr = 32;
     const int box = bkr * 128;
     const int nblk = (g.kt + 63) / 64;
     const int raw_bytes = 4 * box + g.nb * box, bf_bytes = 2 * nblk * box;
@@ -1372,7 +1380,7 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
       if (splits3 > max_splits3) splits3 = max_splits3;
       if (splits3 < 1) splits3 = 1;
       int chunk3 = (M + splits3 - 1) / splits3;
-      chunk3 = (chunk3 + 31) / 32 * 32;
+      chunk3 = (chunk3 + bkr - 1) / bkr * bkr;          // whole stages: a stage never reaches into the next split's rows
       splits3 = (M + chunk3 - 1) / chunk3;
       g.m_chunk = chunk3;
       static PerDeviceOnce attr3_set;
@@ -1380,11 +1388,13 @@ int tc_wgrad(int M, int n, int k, const float* dZ, int lddz, const float* X, int
         RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        RR_CUDA(cudaFuncSetAttribute(k_tc_wgrad3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr3_set.mark();
       }
       const size_t smem3 = static_cast<size_t>(R) * raw_bytes + static_cast<size_t>(SB) * bf_bytes + 1024 + 512;
       if (bkr == 32 && g.trace) RR_CUDA(launch_pdl(k_tc_wgrad3<32, true>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       else if (bkr == 32) RR_CUDA(launch_pdl(k_tc_wgrad3<32>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
+      else if (bkr == 64) RR_CUDA(launch_pdl(k_tc_wgrad3<64>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       else RR_CUDA(launch_pdl(k_tc_wgrad3<16>, dim3(ntiles3, ktiles, splits3), dim3(W3_THREADS), smem3, s, g));
       RR_LAUNCH_CHECK("k_tc_wgrad3");
       return RR_OK;
