@@ -68,7 +68,7 @@ def metric_of(wl):
     return METRIC if wl["task"] == "mle" else f"train reactions/sec, D-MPNN+{LOSS_NAME[wl['task']]}"
 
 
-_TRAFFIC_KERNELS = {"gemm_fwd": "k_tc_gemm2<16, 0>", "gemm_dgrad": "k_tc_gemm2<16, 1>", "gemm_wgrad": "k_tc_wgrad", "bond_fwd": "k_rowpipe<0", "bond_bwd": "k_rowpipe<1",
+_TRAFFIC_KERNELS = {"gemm_fwd": "k_tc_gemm2<16, 0", "gemm_dgrad": "k_tc_gemm2<16, 1", "gemm_wgrad": "k_tc_wgrad", "bond_fwd": "k_rowpipe<0", "bond_bwd": "k_rowpipe<1",
                     "nbr_fwd": "k_rowpipe<2", "nbr_bwd": "k_rowpipe<3"}
 
 

@@ -3,7 +3,7 @@
 # same command, then --set full captures of the top kernels (every replay pass saves / restores the multi-GB workspace, so a
 # handful of launches each).  Outputs land in gpurun_out/ (keep them under 64 MiB); scripts/summarise_profiles.py turns them into
 # profiles/<round>_*.  Usage: scripts/capture_profiles.sh r02
-# Launches of one training step (c5, joint encoder): 11 forward + 11 dgrad k_tc_gemm2, 15 k_tc_wgrad3, 13 k_rowpipe; the benchmark runs
+# Launches of one training step (c5, joint encoder): 11 forward + 11 dgrad k_tc_gemm2, 15 k_tc_wgrad3 (11 x <32>, 4 x <64>), 13 k_rowpipe; the benchmark runs
 # >= 3 warm-up steps first, so skipping three steps' worth of a kernel's launches lands in a steady-state step.
 set -u
 R=${1:-r02}
@@ -24,3 +24,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_rowpipe --laun
     $B --steps 1 --warmup 3 > $OUT/${R}_ncu_full_mp.log 2>&1
 tail -n 1 $OUT/${R}_ncu_full_gemm.log $OUT/${R}_ncu_full_dgrad.log $OUT/${R}_ncu_full_wgrad.log $OUT/${R}_ncu_full_mp.log
 du -sh $OUT
+# NOTE: gpurun copies back at most 64 MiB: the four --import-source captures of a whole step's launches came to 66 MB once and were lost.
+# Capture fewer launches per kernel (-c) or run the captures in two gpurun calls.
