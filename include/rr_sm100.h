@@ -297,8 +297,10 @@ int rr_profile_end(double* h_ms_by_class, int64_t* h_launches_by_class, int n_cl
 int rr_profile_classes(void);
 /* The RR_* environment switches (kernel experiments / diagnostics) are read once, at first use; this reads them again. */
 void rr_reload_switches(void);
-/* Diagnostic: with RR_TC_DIAG & 16 the first CTA of every weight-gradient launch stamps the SM clock at its pipeline hand-offs
- * (96 stages x 16 slots); this copies the first n stamps of the last launch to host_out.  scripts/wgrad_trace.py prints them. */
+/* Diagnostic: with RR_TC_DIAG & 16 the first CTA of every weight-gradient launch (k_tc_wgrad3, 32-row stages) and of every fp32-split
+ * forward launch (k_tc_gemm2) stamps the SM clock at its pipeline hand-offs into one device buffer (96 stages or work items x 16 slots);
+ * this synchronises the device and copies the first n stamps of the last such launch to host_out.  scripts/wgrad_trace.py and
+ * scripts/gemm_trace.py print them; the slot meanings are listed there and next to the kernels. */
 int rr_debug_wgrad_trace(unsigned long long* host_out, int n);
 /* kernels launched on this thread since the last reset (for bench.py's gpu_launches) */
 int64_t rr_launch_count(void);
