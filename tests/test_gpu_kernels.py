@@ -298,6 +298,27 @@ def test_large_groups_through_the_sized_entry(task, kind, scope):
                                loss.data_ptr(), ds_.data_ptr(), S()) != 0
 
 
+def test_loss_modules_take_groups_beyond_2048():
+    """The Python loss layer passes the batch's largest group down (rr_loss_fwdbwd_ex): MLEloss on a 3000-candidate group matches the fp64
+    oracle in value and gradient; a group beyond rr_loss_max_group() is refused with RRError before any launch."""
+    from reactranker_b200.train.loss import MLEloss
+    scope = [3000, 40, 7]
+    N = sum(scope)
+    g = torch.Generator().manual_seed(5)
+    s, t = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    sx = s.double().requires_grad_(True)
+    want = O.listmle_loss(sx, scope, t.double())
+    want.backward()
+    sd = s.to(DEV).requires_grad_(True)
+    loss = MLEloss()(sd, scope, t, 0)
+    loss.backward()
+    close(loss.detach().reshape(1), want.detach().reshape(1), 5e-6)
+    close(sd.grad, sx.grad, 5e-5)
+    big = [9000]
+    with pytest.raises(_lib.RRError):
+        MLEloss()(torch.zeros(9000, device=DEV), big, torch.zeros(9000), 0)
+
+
 @pytest.mark.parametrize("scope", [[5, 4, 6], [64] * 4, [3, 500]])
 def test_ranknet_window_matches_oracle(scope):
     L = _lib.lib()
